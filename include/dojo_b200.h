@@ -1,0 +1,176 @@
+/*
+ * dojo_b200.h -- C-ABI of the B200-native batched Dojo step.
+ *
+ * The reference (dojo-sim/Dojo.jl @ be7b518) has no FFI boundary of its own: it is pure Julia.
+ * The drop-in boundary is therefore *defined* here at the level of the Julia methods that enter
+ * and leave the per-timestep hot path.  Each entry point names the reference
+ * method it replaces (file:line relative to the reference repository root):
+ *
+ *   dojo_create / dojo_destroy   <- Mechanism(origin, bodies, joints, contacts; timestep,
+ *                                   input_scaling, gravity)        src/mechanism/constructor.jl:46-84
+ *                                   (the live Julia Mechanism is flattened into DojoMechanismDesc)
+ *   dojo_step                    <- step!(mechanism, z, u; opts)   src/simulation/step.jl:11-30
+ *                                   = set_maximal_state! (src/mechanism/set.jl:10-26)
+ *                                   + set_input!          (src/mechanism/set.jl:40-53)
+ *                                   + mehrotra!           (src/solver/mehrotra.jl:9-73)
+ *                                   + update_state!       (src/bodies/set.jl:22-36)
+ *                                   + get_next_state      (src/mechanism/get.jl:126-134)
+ *   dojo_step_grad               <- get_maximal_gradients!(mechanism, z, u; opts)
+ *                                                                  src/gradients/state.jl:69-126
+ *   dojo_rollout                 <- simulate!(mechanism, steps, storage, control!)
+ *                                                                  src/simulation/simulate.jl:16-36
+ *   DojoSolverOptions            <- SolverOptions{T}               src/solver/options.jl:16-26
+ *
+ * All arrays are fp64.  Batched arrays are column-major [feature x B] exactly as a Julia
+ * Matrix{Float64}(feature, B) is laid out, i.e. environment e owns the contiguous slice
+ * [e*feature, (e+1)*feature).  Per body the maximal state is packed as the reference packs it
+ * (src/mechanism/get.jl:107-134): [x2(3) v15(3) q2(s,v1,v2,v3) w15(3)].
+ * Gradients use the 12-per-body attitude-reduced packing [x(3) v(3) phi(3) w(3)]
+ * (src/gradients/state.jl:102-123), column-major [12Nb x 12Nb] and [12Nb x nu] per environment.
+ *
+ * Buffers passed to dojo_step / dojo_step_grad / dojo_rollout may be HOST or DEVICE pointers
+ * (detected with cudaPointerGetAttributes); host buffers are staged through pinned memory and
+ * copied inside the call.  The *_async variants take device pointers only and a cudaStream_t
+ * (passed as void*), do not synchronise, and are what a resident-data caller uses.
+ *
+ * Return value: 0 on success, negative DOJO_E* on API misuse / CUDA failure (message via
+ * dojo_last_error).  Per-environment solver outcomes never abort the batch; they are reported in
+ * status[B]: 0 success, 1 :failed (max_iter reached, src/solver/mehrotra.jl:13,30,72),
+ * 2 excessive angular velocity (the reference throws: src/solver/line_search.jl:18-20),
+ * 3 non-finite iterate.
+ */
+#ifndef DOJO_B200_H
+#define DOJO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOJO_OK 0
+#define DOJO_EINVAL (-1)      /* bad argument / unsupported mechanism */
+#define DOJO_ECUDA (-2)       /* CUDA runtime failure */
+#define DOJO_ENOMEM (-3)      /* mechanism does not fit the per-environment shared-memory budget */
+#define DOJO_ENODEVICE (-4)   /* no CUDA device: there is NO CPU fallback in this library */
+
+#define DOJO_STATUS_SUCCESS 0
+#define DOJO_STATUS_FAILED 1
+#define DOJO_STATUS_EXCESSIVE_OMEGA 2
+#define DOJO_STATUS_NONFINITE 3
+
+/* flags */
+#define DOJO_FLAG_Q1_LITERAL_RETURN 1u /* reproduce step!'s double-advanced return value */
+
+/* Body: src/bodies/constructor.jl:13-27 (mass, inertia) */
+typedef struct {
+  double mass;
+  double inertia[9]; /* row-major 3x3, body frame */
+} DojoBodyDesc;
+
+/* One half of a JointConstraint: Translational / Rotational
+ * (src/joints/translational/constructor.jl:19-31, src/joints/rotational/constructor.jl:19-31). */
+typedef struct {
+  int32_t nlambda;         /* N_lambda: number of constrained axes, 0..3 */
+  int32_t nlimits;         /* Nb/2: 0, or 3-nlambda when every free axis is limited (joints/limits.jl) */
+  double axis_mask[9];     /* rows V1,V2,V3 (joints/orthogonal.jl:1-12); masks per joints/joint.jl:56-64 */
+  double spring, damper;
+  double spring_offset[3]; /* first 3-nlambda entries used */
+  double limit_lo[3], limit_hi[3];
+} DojoJointElementDesc;
+
+/* JointConstraint: src/joints/constraints.jl:17-86 */
+typedef struct {
+  int32_t parent_body;          /* 0-based body index, -1 = origin */
+  int32_t child_body;           /* 0-based body index */
+  double vertex_parent[3];      /* translational.vertices[1], parent frame */
+  double vertex_child[3];       /* translational.vertices[2], child frame */
+  double orientation_offset[4]; /* rotational.orientation_offset (s,v1,v2,v3) */
+  DojoJointElementDesc tra, rot;
+} DojoJointDesc;
+
+/* ContactConstraint{NonlinearContact} + SphereHalfSpaceCollision
+ * (src/contacts/nonlinear.jl:12-48, src/contacts/collisions/sphere_halfspace.jl:11-24). */
+typedef struct {
+  int32_t type;        /* 2 = nonlinear (second-order cone); 0 impact / 1 linear are not implemented */
+  int32_t parent_body; /* 0-based body index; child is always the origin half-space */
+  double friction_coefficient;
+  double tangent[6];   /* contact_tangent, row-major 2x3 */
+  double normal[3];    /* contact_normal */
+  double origin[3];    /* contact_origin (body frame) */
+  double radius;       /* contact_radius */
+  double offset[3];    /* contact_offset */
+} DojoContactDesc;
+
+/* Flattened Mechanism.  Node ids follow the reference (src/mechanism/id.jl:5-13):
+ * joints 1..Ne, bodies Ne+1..Ne+Nb, contacts after; solution/residual vectors are ordered
+ * joints | bodies [v25;w25] | contacts [s;gamma] (src/gradients/finite_difference.jl:1-18).
+ * Inputs u are ordered by joint, [tra free axes; rot free axes] each (src/mechanism/set.jl:40-53). */
+typedef struct {
+  int32_t num_bodies, num_joints, num_contacts;
+  double timestep, input_scaling, gravity[3];
+  const DojoBodyDesc* bodies;
+  const DojoJointDesc* joints;
+  const DojoContactDesc* contacts;
+} DojoMechanismDesc;
+
+/* SolverOptions: src/solver/options.jl:16-26 (ls_scale is carried but, as in the reference, never read) */
+typedef struct {
+  double rtol, btol, ls_scale;
+  int32_t max_iter, max_ls;
+  double undercut;
+  int32_t no_progress_max;
+  double no_progress_undercut;
+  int32_t verbose;
+} DojoSolverOptions;
+
+typedef struct DojoHandle DojoHandle;
+
+void dojo_default_options(DojoSolverOptions* opts);
+
+/* device: CUDA device ordinal (>= 0).  max_batch: largest B that will be passed. */
+int dojo_create(const DojoMechanismDesc* desc, int device, int max_batch, DojoHandle** out);
+int dojo_destroy(DojoHandle* h);
+const char* dojo_last_error(const DojoHandle* h); /* h may be NULL: last create error */
+
+/* sizes derived from the descriptor */
+int dojo_num_state(const DojoHandle* h);    /* 13 Nb */
+int dojo_num_input(const DojoHandle* h);    /* nu */
+int dojo_num_residual(const DojoHandle* h); /* Nres */
+int dojo_num_grad_state(const DojoHandle* h); /* 12 Nb */
+int dojo_shared_bytes_per_env(const DojoHandle* h);
+
+/* One step! for B environments.  Z [13Nb x B], U [nu x B], Fext nullable [6Nb x B]
+ * ([F(3); tau(3)] per body: State.Fext / State.τext), Z_next [13Nb x B],
+ * sol nullable [Nres x B] (final solution: joint impulses | v25,w25 | s,gamma),
+ * status [B], iters [B] (Newton iterations taken), both nullable. */
+int dojo_step(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U,
+              const double* Fext, double* Z_next, double* sol, int32_t* status, int32_t* iters,
+              uint32_t flags);
+int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ,
+                    const double* dU, const double* dFext, double* dZ_next, double* dsol,
+                    int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
+
+/* step! + consistent IFT gradients at the solution (get_maximal_gradients evaluated
+ * right after mehrotra!, before update_state!).  dFz [12Nb x 12Nb x B], dFu [12Nb x nu x B]. */
+int dojo_step_grad(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z,
+                   const double* U, const double* Fext, double* Z_next, double* Fz, double* Fu,
+                   int32_t* status, int32_t* iters, uint32_t flags);
+int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ,
+                         const double* dU, const double* dFext, double* dZ_next, double* dFz,
+                         double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags,
+                         void* cuda_stream);
+
+/* simulate!: T steps with the state resident on the device.  U is [nu x B x T] (step-major) or
+ * NULL (zero input); Z_traj nullable [13Nb x B x T] receives the state after every step
+ * (Storage, src/simulation/storage.jl:15-42); Z_final [13Nb x B]; status_any [B] = max status. */
+int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0,
+                 const double* U, double* Z_final, double* Z_traj, int32_t* status_any);
+
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+int64_t dojo_launch_count(const DojoHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOJO_B200_H */
