@@ -1,0 +1,514 @@
+// dojo_b200.cu -- C-ABI (include/dojo_b200.h) + kernel entry points of the B200-native Dojo step.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC  (see build.py)
+// There is NO CPU fallback in this library: dojo_create fails with DOJO_ENODEVICE without a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dojo_b200.h"
+#include "dojo_kernels.cuh"
+
+using namespace dj;
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------------------------
+struct StepArgs {
+  Plan plan;
+  Options opts;
+  int B;
+  int max_child_color, max_contact_color;
+  const double* Z;
+  const double* U;
+  const double* Fext;
+  double* Zn;
+  double* sol;
+  int32_t* status;
+  int32_t* iters;
+  uint32_t flags;
+  int* counter;  // dynamic work queue over environments
+};
+
+// epilogue: update_state! + get_next_state (bodies/set.jl:22-36, mechanism/get.jl:126-134).  The default output is the
+// mechanism's state after the step, (x3, v25, q3, w25); DOJO_FLAG_Q1_LITERAL_RETURN reproduces step!'s literal return
+// value, which advances the configuration a second time.
+DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
+  const Plan& P = *c.P;
+  if (c.lane < P.Nb) {
+    Kin k = body_kin(c, c.lane, 0.0);
+    V3 x3 = k.x3;
+    Quat q3 = k.q3;
+    if (q1_literal) { x3 = x3 + P.h * k.v; q3 = qmul(q3, qmap(k.w, P.h)); }
+    double* o = zn + 13 * c.lane;
+    o[0] = x3.x; o[1] = x3.y; o[2] = x3.z;
+    o[3] = k.v.x; o[4] = k.v.y; o[5] = k.v.z;
+    o[6] = q3.s; o[7] = q3.x; o[8] = q3.y; o[9] = q3.z;
+    o[10] = k.w.x; o[11] = k.w.y; o[12] = k.w.z;
+  }
+}
+
+__global__ void __launch_bounds__(32) dojo_step_kernel(const StepArgs a) {
+  extern __shared__ double arena[];
+  Ctx c;
+  c.A = arena;
+  c.P = &a.plan;
+  c.lane = threadIdx.x;
+  c.mu = 0.0;
+  const Plan& P = a.plan;
+  for (;;) {
+    int e = 0;
+    if (c.lane == 0) e = atomicAdd(a.counter, 1);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= a.B) break;
+    const double* z = a.Z + (size_t)e * P.nz;
+    const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
+    const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
+    prologue(c, z, u, fx, a.max_child_color, a.max_contact_color);
+    int iters = 0;
+    int status = mehrotra(c, a.opts, a.max_child_color, a.max_contact_color, &iters);
+    epilogue(c, a.Zn + (size_t)e * P.nz, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+    if (a.sol)
+      for (int t = c.lane; t < P.nres; t += 32) a.sol[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
+    if (c.lane == 0) {
+      if (a.status) a.status[e] = status;
+      if (a.iters) a.iters[e] = iters;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------
+struct DojoHandle {
+  int device = 0;
+  int max_batch = 0;
+  int sm_count = 0;
+  int envs_per_sm = 1;
+  Plan plan;  // device pointers inside
+  int max_child_color = 0, max_contact_color = 0;
+  size_t arena_bytes = 0;
+  BodyDev* d_bodies = nullptr;
+  JointDev* d_joints = nullptr;
+  ContactDev* d_contacts = nullptr;
+  ElimStep* d_steps = nullptr;
+  int* d_counter = nullptr;
+  // staging for host-pointer calls
+  double *d_Z = nullptr, *d_U = nullptr, *d_F = nullptr, *d_Zn = nullptr, *d_sol = nullptr;
+  int32_t *d_status = nullptr, *d_iters = nullptr;
+  double *p_in = nullptr, *p_out = nullptr;  // pinned
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  std::string err;
+};
+
+static std::string g_create_error;
+
+#define CUDA_TRY(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                       \
+      return DOJO_ECUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+extern "C" void dojo_default_options(DojoSolverOptions* o) {
+  o->rtol = 1.0e-6; o->btol = 1.0e-4; o->ls_scale = 0.5; o->max_iter = 50; o->max_ls = 10;
+  o->undercut = INFINITY; o->no_progress_max = 3; o->no_progress_undercut = 10.0; o->verbose = 0;
+}
+
+static void pad_mask(const DojoJointElementDesc& e, double* C, double* A) {
+  // joints/joint.jl:56-64 (constraint_mask / nullspace_mask), zero-padded to 3 rows
+  std::memset(C, 0, 9 * sizeof(double));
+  std::memset(A, 0, 9 * sizeof(double));
+  const double* V1 = e.axis_mask; const double* V2 = e.axis_mask + 3; const double* V3_ = e.axis_mask + 6;
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  switch (e.nlambda) {
+    case 0: std::memcpy(A, I3, sizeof(I3)); break;
+    case 1: std::memcpy(C, V3_, 3 * sizeof(double)); std::memcpy(A, V1, 3 * sizeof(double)); std::memcpy(A + 3, V2, 3 * sizeof(double)); break;
+    case 2: std::memcpy(C, V1, 3 * sizeof(double)); std::memcpy(C + 3, V2, 3 * sizeof(double)); std::memcpy(A, V3_, 3 * sizeof(double)); break;
+    case 3: std::memcpy(C, I3, sizeof(I3)); break;
+  }
+}
+
+extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch, DojoHandle** out) {
+  g_create_error.clear();
+  if (!d || !out || max_batch <= 0) { g_create_error = "dojo_create: bad arguments"; return DOJO_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    g_create_error = "dojo_create: no usable CUDA device (this library has no CPU fallback)";
+    return DOJO_ENODEVICE;
+  }
+  const int Nb = d->num_bodies, Ne = d->num_joints, Ni = d->num_contacts;
+  auto fail = [&](const char* msg) { g_create_error = std::string("dojo_create: ") + msg; return DOJO_EINVAL; };
+  if (Nb < 1 || Nb > 32 || Ne > 32 || Ni > 32) return fail("this build supports up to 32 bodies / 32 joints / 32 contacts per mechanism");
+  // ---- topology checks: tree with exactly one parent joint per body
+  std::vector<int> parent_joint(Nb, -1);
+  for (int j = 0; j < Ne; ++j) {
+    const DojoJointDesc& jd = d->joints[j];
+    if (jd.child_body < 0 || jd.child_body >= Nb || jd.parent_body < -1 || jd.parent_body >= Nb) return fail("joint body index out of range");
+    if (parent_joint[jd.child_body] >= 0) return fail("loop-closure joints are not supported yet (each body needs exactly one parent joint)");
+    parent_joint[jd.child_body] = j;
+    if (jd.tra.nlimits != 0) return fail("translational joint limits are not supported yet");
+    if ((jd.tra.nlambda < 3) && (jd.tra.spring != 0.0 || jd.tra.damper != 0.0)) return fail("translational springs / dampers are not supported yet");
+    if (jd.rot.nlimits != 0 && jd.rot.nlimits != 3 - jd.rot.nlambda) return fail("rotational limits must cover every free axis");
+  }
+  for (int b = 0; b < Nb; ++b) if (parent_joint[b] < 0) return fail("every body needs a parent joint (use a Floating joint to the origin)");
+  for (int c = 0; c < Ni; ++c) {
+    if (d->contacts[c].type != 2) return fail("only NonlinearContact (type 2) is implemented");
+    if (d->contacts[c].parent_body < 0 || d->contacts[c].parent_body >= Nb) return fail("contact body index out of range");
+  }
+
+  DojoHandle* h = new DojoHandle();
+  h->device = device;
+  h->max_batch = max_batch;
+  cudaSetDevice(device);
+
+  // ---- solution layout: joints | bodies | contacts (gradients/finite_difference.jl:1-18)
+  std::vector<JointDev> joints(Ne);
+  std::vector<BodyDev> bodies(Nb);
+  std::vector<ContactDev> contacts(Ni);
+  int off = 0, uoff = 0;
+  for (int j = 0; j < Ne; ++j) {
+    const DojoJointDesc& jd = d->joints[j];
+    JointDev& J = joints[j];
+    std::memset(&J, 0, sizeof(J));
+    J.parent = jd.parent_body; J.child = jd.child_body;
+    J.nl_t = jd.tra.nlambda; J.nl_r = jd.rot.nlambda; J.nb2_r = jd.rot.nlimits; J.nb_r = 2 * J.nb2_r;
+    J.row_r = J.nl_t;
+    J.n = J.nl_t + J.nl_r + 2 * J.nb_r;
+    J.sol_off = off; off += J.n;
+    J.nfree_t = 3 - J.nl_t; J.nfree_r = 3 - J.nl_r;
+    J.u_off = uoff; uoff += J.nfree_t + J.nfree_r;
+    std::memcpy(J.pa, jd.vertex_parent, sizeof(J.pa));
+    std::memcpy(J.pb, jd.vertex_child, sizeof(J.pb));
+    std::memcpy(J.qoff, jd.orientation_offset, sizeof(J.qoff));
+    pad_mask(jd.tra, J.Ct, J.At);
+    pad_mask(jd.rot, J.Cr, J.Ar);
+    J.spring_r = (jd.rot.nlambda < 3) ? jd.rot.spring : 0.0;
+    J.damper_r = (jd.rot.nlambda < 3) ? jd.rot.damper : 0.0;
+    for (int i = 0; i < 3; ++i) { J.spring_off_r[i] = jd.rot.spring_offset[i]; J.lo[i] = jd.rot.limit_lo[i]; J.hi[i] = jd.rot.limit_hi[i]; }
+    if (J.n > 16) { delete h; return fail("joint impulse dimension > 16 is not supported"); }
+  }
+  const int nu = uoff;
+  for (int b = 0; b < Nb; ++b) {
+    BodyDev& B = bodies[b];
+    std::memset(&B, 0, sizeof(B));
+    B.mass = d->bodies[b].mass;
+    std::memcpy(B.J, d->bodies[b].inertia, sizeof(B.J));
+    B.sol_off = off; off += 6;
+  }
+  for (int c = 0; c < Ni; ++c) {
+    const DojoContactDesc& cd = d->contacts[c];
+    ContactDev& C = contacts[c];
+    std::memset(&C, 0, sizeof(C));
+    C.body = cd.parent_body; C.mu = cd.friction_coefficient; C.radius = cd.radius;
+    std::memcpy(C.n, cd.normal, sizeof(C.n)); std::memcpy(C.t, cd.tangent, sizeof(C.t));
+    std::memcpy(C.o, cd.origin, sizeof(C.o)); std::memcpy(C.off, cd.offset, sizeof(C.off));
+    C.sol_off = off; off += 8;
+  }
+  const int nres = off;
+
+  // ---- arena layout: [sol | rhs | sav | body state | body cst | constant blocks | re-zeroed matrix region]
+  Plan& P = h->plan;
+  std::memset(&P, 0, sizeof(P));
+  P.Nb = Nb; P.Ne = Ne; P.Ni = Ni; P.nres = nres; P.nu = nu; P.nz = 13 * Nb;
+  P.h = d->timestep; P.input_scaling = d->input_scaling;
+  std::memcpy(P.g, d->gravity, sizeof(P.g));
+  int a = 0;
+  P.sol_off = a; a += nres;
+  P.rhs_off = a; a += nres;
+  P.sav_off = a; a += nres;
+  for (int b = 0; b < Nb; ++b) { bodies[b].st_off = a; a += 7; }
+  for (int b = 0; b < Nb; ++b) { bodies[b].cst_off = a; a += 6; }
+  for (int j = 0; j < Ne; ++j) {  // constant (per step) blocks
+    JointDev& J = joints[j];
+    J.Lc_off = a; a += 6 * J.n;
+    if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.n; } else J.Gp_off = -1;
+  }
+  P.mat_off = a;
+  for (int b = 0; b < Nb; ++b) { bodies[b].D_off = a; a += 36; }
+  for (int j = 0; j < Ne; ++j) {
+    JointDev& J = joints[j];
+    J.D_off = a; a += J.n * J.n;
+    J.Uc_off = a; a += 6 * J.n;
+    if (J.parent >= 0) {
+      J.Up_off = a; a += 6 * J.n;
+      J.Lp_off = a; a += 6 * J.n;
+      if (J.damper_r != 0.0) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
+    } else { J.Up_off = J.Lp_off = J.BBpc_off = J.BBcp_off = -1; }
+  }
+  for (int c = 0; c < Ni; ++c) {
+    ContactDev& C = contacts[c];
+    C.D_off = a; a += 64;
+    C.U_off = a; a += 24;
+    C.L_off = a; a += 48;
+  }
+  P.mat_len = a - P.mat_off;
+  P.arena_len = a;
+  h->arena_bytes = (size_t)a * sizeof(double);
+
+  // ---- colours (deterministic accumulation order)
+  {
+    std::vector<int> nchild(Nb, 0), ncont(Nb, 0);
+    for (int j = 0; j < Ne; ++j) if (joints[j].parent >= 0) { joints[j].color_parent = nchild[joints[j].parent]++; }
+    for (int c = 0; c < Ni; ++c) contacts[c].color = ncont[contacts[c].body]++;
+    h->max_child_color = 0; h->max_contact_color = 0;
+    for (int b = 0; b < Nb; ++b) { h->max_child_color = std::max(h->max_child_color, nchild[b]); h->max_contact_color = std::max(h->max_contact_color, ncont[b]); }
+  }
+
+  // ---- elimination order: post-order over the body tree; contacts of b, then b, then its parent joint
+  //      (contacts into bodies, bodies into their parent joint, joints into the parent body: SURVEY.md Appendix C)
+  std::vector<ElimStep> steps;
+  {
+    std::vector<char> done(Nb, 0);
+    struct Rec {
+      const std::vector<JointDev>& joints; const std::vector<BodyDev>& bodies; const std::vector<ContactDev>& contacts;
+      const std::vector<int>& pj; std::vector<char>& done; std::vector<ElimStep>& steps; int Ne, Ni;
+      void visit(int b) {
+        done[b] = 1;
+        for (int j = 0; j < Ne; ++j) if (joints[j].parent == b && !done[joints[j].child]) visit(joints[j].child);
+        const BodyDev& B = bodies[b];
+        for (int c = 0; c < Ni; ++c) {
+          if (contacts[c].body != b) continue;
+          const ContactDev& C = contacts[c];
+          ElimStep s; std::memset(&s, 0, sizeof(s));
+          s.d_off = C.D_off; s.n = 8; s.vec_off = C.sol_off; s.nnb = 1;
+          s.nb[0].n = 6; s.nb[0].vec_off = B.sol_off; s.nb[0].L_off = C.L_off; s.nb[0].U_off = C.U_off; s.nb[0].U_k = 4; s.nb[0].U_row = 4;
+          s.tgt[0][0] = B.D_off;
+          steps.push_back(s);
+        }
+        const JointDev& J = joints[pj[b]];
+        {  // the body: neighbours = parent joint (if it has impulses) and, with dampers, the parent body
+          ElimStep s; std::memset(&s, 0, sizeof(s));
+          s.d_off = B.D_off; s.n = 6; s.vec_off = B.sol_off; s.nnb = 0;
+          int ij = -1, ip = -1;
+          if (J.n > 0) {
+            ij = s.nnb++;
+            s.nb[ij].n = J.n; s.nb[ij].vec_off = J.sol_off; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+          }
+          if (J.parent >= 0 && J.BBpc_off >= 0) {
+            ip = s.nnb++;
+            const BodyDev& Pb = bodies[J.parent];
+            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
+          }
+          if (ij >= 0) s.tgt[ij][ij] = J.D_off;
+          if (ip >= 0) s.tgt[ip][ip] = bodies[J.parent].D_off;
+          if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off; s.tgt[ip][ij] = J.Lp_off; }
+          steps.push_back(s);
+        }
+        if (J.n > 0) {  // the parent joint: neighbour = parent body
+          ElimStep s; std::memset(&s, 0, sizeof(s));
+          s.d_off = J.D_off; s.n = J.n; s.vec_off = J.sol_off; s.nnb = 0;
+          if (J.parent >= 0) {
+            const BodyDev& Pb = bodies[J.parent];
+            s.nnb = 1;
+            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.n; s.nb[0].U_row = 0;
+            s.tgt[0][0] = Pb.D_off;
+          }
+          steps.push_back(s);
+        }
+      }
+    } rec{joints, bodies, contacts, parent_joint, done, steps, Ne, Ni};
+    for (int j = 0; j < Ne; ++j) if (joints[j].parent < 0 && !done[joints[j].child]) rec.visit(joints[j].child);
+    for (int b = 0; b < Nb; ++b) if (!done[b]) { delete h; return fail("mechanism is not a tree rooted at the origin"); }
+  }
+  P.nsteps = (int)steps.size();
+
+  // ---- device resources
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; g_create_error = "cudaGetDeviceProperties failed"; return DOJO_ECUDA; }
+  h->sm_count = prop.multiProcessorCount;
+  if (h->arena_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+    delete h;
+    g_create_error = "dojo_create: mechanism does not fit the per-environment shared-memory arena";
+    return DOJO_ENOMEM;
+  }
+  auto upload = [&](const void* src, size_t bytes, void** dst) -> bool {
+    if (bytes == 0) { *dst = nullptr; return true; }
+    if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok = upload(bodies.data(), sizeof(BodyDev) * Nb, (void**)&h->d_bodies) && upload(joints.data(), sizeof(JointDev) * Ne, (void**)&h->d_joints) &&
+            upload(contacts.data(), sizeof(ContactDev) * Ni, (void**)&h->d_contacts) && upload(steps.data(), sizeof(ElimStep) * steps.size(), (void**)&h->d_steps);
+  ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+  if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
+  P.bodies = h->d_bodies; P.joints = h->d_joints; P.contacts = h->d_contacts; P.steps = h->d_steps;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel, 32, h->arena_bytes);
+  h->envs_per_sm = std::max(1, occ);
+  *out = h;
+  return DOJO_OK;
+}
+
+extern "C" int dojo_destroy(DojoHandle* h) {
+  if (!h) return DOJO_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_bodies); cudaFree(h->d_joints); cudaFree(h->d_contacts); cudaFree(h->d_steps); cudaFree(h->d_counter);
+  cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
+  if (h->p_in) cudaFreeHost(h->p_in);
+  if (h->p_out) cudaFreeHost(h->p_out);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DOJO_OK;
+}
+
+extern "C" const char* dojo_last_error(const DojoHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int dojo_num_state(const DojoHandle* h) { return h->plan.nz; }
+extern "C" int dojo_num_input(const DojoHandle* h) { return h->plan.nu; }
+extern "C" int dojo_num_residual(const DojoHandle* h) { return h->plan.nres; }
+extern "C" int dojo_num_grad_state(const DojoHandle* h) { return 12 * h->plan.Nb; }
+extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->arena_bytes; }
+extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
+
+static Options make_options(const DojoSolverOptions* o) {
+  DojoSolverOptions d;
+  if (!o) { dojo_default_options(&d); o = &d; }
+  Options r;
+  r.rtol = o->rtol; r.btol = o->btol; r.undercut = o->undercut; r.no_progress_undercut = o->no_progress_undercut;
+  r.max_iter = o->max_iter; r.max_ls = o->max_ls; r.no_progress_max = o->no_progress_max;
+  return r;
+}
+
+extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
+                               double* dZn, double* dsol, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+  if (!h || B <= 0 || !dZ || !dZn) { if (h) h->err = "dojo_step_async: bad arguments"; return DOJO_EINVAL; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  StepArgs a;
+  a.plan = h->plan; a.opts = make_options(opts); a.B = B;
+  a.max_child_color = h->max_child_color; a.max_contact_color = h->max_contact_color;
+  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
+  a.counter = h->d_counter;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  int grid = std::min(B, h->sm_count * h->envs_per_sm);
+  dojo_step_kernel<<<grid, 32, h->arena_bytes, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_staging(DojoHandle* h) {
+  if (h->d_Z) return DOJO_OK;
+  const Plan& P = h->plan;
+  size_t B = h->max_batch;
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_Z, B * P.nz * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_U, std::max<size_t>(1, B * P.nu) * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_F, B * 6 * P.Nb * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_Zn, B * P.nz * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_sol, B * P.nres * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_status, B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_iters, B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMallocHost((void**)&h->p_in, B * (P.nz + P.nu + 6 * P.Nb) * sizeof(double)));
+  CUDA_TRY(h, cudaMallocHost((void**)&h->p_out, B * (P.nz + P.nres + 1) * sizeof(double)));
+  return DOJO_OK;
+}
+
+// Host- or device-pointer entry: host buffers are staged through pinned memory, copies are part of the call.
+extern "C" int dojo_step(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, const double* Fext, double* Zn,
+                         double* sol, int32_t* status, int32_t* iters, uint32_t flags) {
+  if (!h || B <= 0 || B > h->max_batch || !Z || !Zn) { if (h) h->err = "dojo_step: bad arguments (B must be in 1..max_batch)"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Plan& P = h->plan;
+  if (is_device_ptr(Z)) {  // resident data: launch on the handle's stream and wait
+    int rc = dojo_step_async(h, opts, B, Z, U, Fext, Zn, sol, status, iters, flags, h->stream);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = h->stream;
+  double* pz = h->p_in;
+  double* pu = pz + (size_t)B * P.nz;
+  double* pf = pu + (size_t)B * P.nu;
+  std::memcpy(pz, Z, (size_t)B * P.nz * sizeof(double));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, pz, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (U && P.nu > 0) {
+    std::memcpy(pu, U, (size_t)B * P.nu * sizeof(double));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_U, pu, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  if (Fext) {
+    std::memcpy(pf, Fext, (size_t)B * 6 * P.Nb * sizeof(double));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_F, pf, (size_t)B * 6 * P.Nb * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  rc = dojo_step_async(h, opts, B, h->d_Z, (U && P.nu > 0) ? h->d_U : nullptr, Fext ? h->d_F : nullptr, h->d_Zn, sol ? h->d_sol : nullptr, h->d_status,
+                       h->d_iters, flags, s);
+  if (rc != DOJO_OK) return rc;
+  double* po = h->p_out;
+  double* ps = po + (size_t)B * P.nz;
+  int32_t* pi = (int32_t*)(ps + (size_t)B * P.nres);
+  CUDA_TRY(h, cudaMemcpyAsync(po, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (sol) CUDA_TRY(h, cudaMemcpyAsync(ps, h->d_sol, (size_t)B * P.nres * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  std::memcpy(Zn, po, (size_t)B * P.nz * sizeof(double));
+  if (sol) std::memcpy(sol, ps, (size_t)B * P.nres * sizeof(double));
+  if (status) { CUDA_TRY(h, cudaMemcpy(pi, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost)); std::memcpy(status, pi, B * sizeof(int32_t)); }
+  if (iters) { CUDA_TRY(h, cudaMemcpy(pi, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost)); std::memcpy(iters, pi, B * sizeof(int32_t)); }
+  return DOJO_OK;
+}
+
+// simulate!: T steps with the state resident on the device (simulation/simulate.jl:16-36)
+extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0, const double* U, double* Z_final, double* Z_traj,
+                            int32_t* status_any) {
+  if (!h || B <= 0 || B > h->max_batch || T <= 0 || !Z0 || !Z_final) { if (h) h->err = "dojo_rollout: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  const size_t zbytes = (size_t)B * P.nz * sizeof(double), ubytes = (size_t)B * P.nu * sizeof(double);
+  const bool dev_io = is_device_ptr(Z0);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z0, zbytes, cudaMemcpyDefault, s));
+  std::vector<int32_t> worst(B, 0), st(B, 0);
+  double* cur = h->d_Z;
+  double* nxt = h->d_Zn;
+  for (int t = 0; t < T; ++t) {
+    const double* du = nullptr;
+    if (U && P.nu > 0) {
+      if (dev_io) du = U + (size_t)t * B * P.nu;
+      else { CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U + (size_t)t * B * P.nu, ubytes, cudaMemcpyDefault, s)); du = h->d_U; }
+    }
+    rc = dojo_step_async(h, opts, B, cur, du, nullptr, nxt, nullptr, h->d_status, nullptr, 0, s);
+    if (rc != DOJO_OK) return rc;
+    if (Z_traj) CUDA_TRY(h, cudaMemcpyAsync(Z_traj + (size_t)t * B * P.nz, nxt, zbytes, cudaMemcpyDefault, s));
+    if (status_any) {
+      CUDA_TRY(h, cudaMemcpyAsync(st.data(), h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));
+      for (int e = 0; e < B; ++e) worst[e] = std::max(worst[e], st[e]);
+    }
+    std::swap(cur, nxt);
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(Z_final, cur, zbytes, cudaMemcpyDefault, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (status_any) std::memcpy(status_any, worst.data(), B * sizeof(int32_t));
+  return DOJO_OK;
+}
+
+// gradients: implemented in dojo_grad.cu
+extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions*, int, const double*, const double*, const double*, double*, double*, double*,
+                                    int32_t*, int32_t*, uint32_t, void*) {
+  if (h) h->err = "dojo_step_grad_async: not implemented yet";
+  return DOJO_EINVAL;
+}
+extern "C" int dojo_step_grad(DojoHandle* h, const DojoSolverOptions*, int, const double*, const double*, const double*, double*, double*, double*, int32_t*,
+                              int32_t*, uint32_t) {
+  if (h) h->err = "dojo_step_grad: not implemented yet";
+  return DOJO_EINVAL;
+}

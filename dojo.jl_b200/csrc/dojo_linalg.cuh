@@ -1,0 +1,128 @@
+// dojo_linalg.cuh -- warp-cooperative block linear algebra on the per-environment shared-memory arena.
+//
+// One warp owns one environment's block-sparse KKT system.  The factorisation is the block LDU of
+// GraphBasedSystems.jl (external dependency of the reference; call sites src/solver/mehrotra.jl:36-37,49):
+// nodes are eliminated leaves -> root, diagonal blocks are inverted explicitly (Gauss-Jordan with partial
+// pivoting inside the block, the whole block living in registers, one column per lane), off-diagonal
+// blocks are updated with warp-wide small GEMMs whose output elements are spread over the lanes.
+//
+//   for c in elimination order, N(c) = later-eliminated neighbours (<= 2 for tree mechanisms):
+//       Dinv_c  = inv(D_c)                                  (in place)
+//       L~_ic   = M_ic * Dinv_c            for i in N(c)     (in place; the column blocks of c)
+//       M_ij   -= L~_ic * M_cj             for i, j in N(c)  (the row blocks M_cj of c are left untouched)
+//   solve:  forward  z_i -= L~_ic z_c      backward  x_c = Dinv_c (z_c - sum_j M_cj x_j)
+#pragma once
+#include "dojo_math.cuh"
+
+namespace dj {
+
+// In-place inverse of an n x n row-major block (leading dimension ld) held in shared memory.
+// Lanes 0..n-1 own the columns of A, lanes n..2n-1 the columns of the identity that becomes A^{-1}.
+// Returns false (warp-uniform) if a zero / non-finite pivot is met.
+template <int N>
+DJ_DEV bool block_inverse_t(double* A, int ld, int lane) {
+  static_assert(2 * N <= 32, "block too large for the one-column-per-lane inverse");
+  double a[N];
+  const bool left = lane < N;
+  const int col = left ? lane : lane - N;
+  const bool active = lane < 2 * N;
+#pragma unroll
+  for (int r = 0; r < N; ++r) a[r] = active ? (left ? A[r * ld + col] : (r == col ? 1.0 : 0.0)) : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    // pivot search in column k (owned by lane k)
+    int p = k;
+    double best = fabs(a[k]);
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      double v = fabs(a[r]);
+      if (v > best) { best = v; p = r; }
+    }
+    p = __shfl_sync(0xffffffffu, p, k);
+    best = __shfl_sync(0xffffffffu, best, k);
+    if (!(best > 0.0) || !(best < 1e300)) ok = false;
+    // swap rows k and p (predicated, static indices)
+    double akp = a[k];
+#pragma unroll
+    for (int r = k + 1; r < N; ++r)
+      if (r == p) { double t = a[r]; a[r] = akp; akp = t; }
+    a[k] = akp;
+    double piv = __shfl_sync(0xffffffffu, a[k], k);
+    double inv = 1.0 / piv;
+    a[k] *= inv;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      if (r == k) continue;
+      double f = __shfl_sync(0xffffffffu, a[r], k);
+      a[r] -= f * a[k];
+    }
+  }
+  __syncwarp();
+  if (active && !left) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) A[r * ld + col] = a[r];
+  }
+  __syncwarp();
+  return ok;
+}
+
+DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
+  switch (n) {
+    case 1: return block_inverse_t<1>(A, ld, lane);
+    case 2: return block_inverse_t<2>(A, ld, lane);
+    case 3: return block_inverse_t<3>(A, ld, lane);
+    case 4: return block_inverse_t<4>(A, ld, lane);
+    case 5: return block_inverse_t<5>(A, ld, lane);
+    case 6: return block_inverse_t<6>(A, ld, lane);
+    case 7: return block_inverse_t<7>(A, ld, lane);
+    case 8: return block_inverse_t<8>(A, ld, lane);
+    case 9: return block_inverse_t<9>(A, ld, lane);
+    case 10: return block_inverse_t<10>(A, ld, lane);
+    case 11: return block_inverse_t<11>(A, ld, lane);
+    case 12: return block_inverse_t<12>(A, ld, lane);
+    case 13: return block_inverse_t<13>(A, ld, lane);
+    case 14: return block_inverse_t<14>(A, ld, lane);
+    case 15: return block_inverse_t<15>(A, ld, lane);
+    case 16: return block_inverse_t<16>(A, ld, lane);
+    default: return false;
+  }
+}
+
+// L (m x n, row-major) <- L * Dinv (n x n), in place.  Output elements are spread over the lanes; everything is
+// computed into registers before anything is written back (a row of L is both input and output).
+DJ_DEV void right_multiply_inplace(double* L, const double* Dinv, int m, int n, int lane) {
+  const int total = m * n;  // <= 256
+  double out[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    int e = lane + 32 * p;
+    double acc = 0.0;
+    if (e < total) {
+      int i = e / n, j = e - i * n;
+      for (int k = 0; k < n; ++k) acc += L[i * n + k] * Dinv[k * n + j];
+    }
+    out[p] = acc;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    int e = lane + 32 * p;
+    if (e < total) L[e] = out[p];
+  }
+  __syncwarp();
+}
+
+// C (ni x nj, ld = nj) -= A (ni x k, ld = lda) * B (k x nj, ld = nj)
+DJ_DEV void schur_update(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int lane) {
+  const int total = ni * nj;
+  for (int e = lane; e < total; e += 32) {
+    int i = e / nj, j = e - i * nj;
+    double acc = 0.0;
+    for (int t = 0; t < k; ++t) acc += A[i * lda + t] * B[t * nj + j];
+    C[e] -= acc;
+  }
+  __syncwarp();
+}
+
+}  // namespace dj

@@ -1,0 +1,182 @@
+"""ctypes binding of the product library libdojo_b200.so (include/dojo_b200.h).
+
+This is the ONLY compute path of the package: if the CUDA library is missing or no CUDA device is
+present, construction fails loudly (RuntimeError) -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .mechanism import Mechanism
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdojo_b200.so")
+
+DOJO_FLAG_Q1_LITERAL_RETURN = 1
+STATUS = {0: "success", 1: "failed", 2: "excessive_angular_velocity", 3: "nonfinite"}
+
+EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_error", "dojo_num_state", "dojo_num_input",
+           "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env", "dojo_step", "dojo_step_async",
+           "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_launch_count"]
+
+_lib = None
+
+
+def load_library():
+    """Load libdojo_b200.so (built in-tree by build.py).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  dojo.jl_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = capi.c_double_p, capi.c_int32_p, C.c_void_p
+    op = C.POINTER(capi.DojoSolverOptions)
+    L.dojo_default_options.argtypes = [op]
+    L.dojo_create.argtypes = [C.POINTER(capi.DojoMechanismDesc), C.c_int, C.c_int, C.POINTER(vp)]
+    L.dojo_create.restype = C.c_int
+    L.dojo_destroy.argtypes = [vp]
+    L.dojo_last_error.argtypes = [vp]
+    L.dojo_last_error.restype = C.c_char_p
+    for n in ("dojo_num_state", "dojo_num_input", "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = C.c_int
+    L.dojo_launch_count.argtypes = [vp]
+    L.dojo_launch_count.restype = C.c_int64
+    L.dojo_step.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
+    L.dojo_step.restype = C.c_int
+    L.dojo_step_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.dojo_step_async.restype = C.c_int
+    L.dojo_step_grad.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
+    L.dojo_step_grad.restype = C.c_int
+    L.dojo_step_grad_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.dojo_step_grad_async.restype = C.c_int
+    L.dojo_rollout.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.dojo_rollout.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _p(a):
+    """numpy array / int (device pointer) / None -> c_void_p"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+class BatchedStepper:
+    """A mechanism bound to one GPU: the handle of include/dojo_b200.h.
+
+    Host arrays are [B, feature] C-contiguous numpy arrays, i.e. exactly the column-major
+    [feature x B] Julia matrices of the ABI.  Device buffers are passed as integer pointers
+    (``tensor.data_ptr()``) to the *_device methods together with a CUDA stream handle.
+    """
+
+    def __init__(self, mech: Mechanism, max_batch: int, device: int = 0):
+        self.mech = mech
+        self.L = load_library()
+        desc, keep = capi.flatten(mech)
+        h = C.c_void_p()
+        rc = self.L.dojo_create(C.byref(desc), int(device), int(max_batch), C.byref(h))
+        if rc != 0:
+            msg = self.L.dojo_last_error(None).decode()
+            raise RuntimeError(f"dojo_create failed ({rc}): {msg}")
+        self.h = h
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self.nz = self.L.dojo_num_state(h)
+        self.nu = self.L.dojo_num_input(h)
+        self.nres = self.L.dojo_num_residual(h)
+        self.ngrad = self.L.dojo_num_grad_state(h)
+        assert (self.nz, self.nu, self.nres) == (mech.nz, mech.nu, mech.nres)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dojo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.L.dojo_last_error(self.h).decode()}")
+
+    @property
+    def shared_bytes_per_env(self) -> int:
+        return self.L.dojo_shared_bytes_per_env(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.dojo_launch_count(self.h))
+
+    # ------------------------------------------------------------------ host buffers
+    def step(self, Z, U=None, opts: Optional[capi.DojoSolverOptions] = None, fext=None, flags: int = 0, return_sol: bool = False):
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        assert Z.shape[1] == self.nz
+        U = np.zeros((B, self.nu)) if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        assert U.shape == (B, self.nu)
+        if fext is not None:
+            fext = np.ascontiguousarray(fext, dtype=np.float64).reshape(B, 6 * self.mech.Nb)
+        Zn = np.empty_like(Z)
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        sol = np.empty((B, self.nres)) if return_sol else None
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step(self.h, C.byref(o), B, _p(Z), _p(U), _p(fext), _p(Zn), _p(sol), _p(status), _p(iters), flags)
+        self._check(rc, "dojo_step")
+        return (Zn, status, iters, sol) if return_sol else (Zn, status, iters)
+
+    def step_grad(self, Z, U=None, opts=None, flags: int = 0):
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        U = np.zeros((B, self.nu)) if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        Zn = np.empty_like(Z)
+        ng = self.ngrad
+        Fz = np.empty((B, ng, ng))   # per env column-major [ng x ng]  ==  Fz[e].T is the Jacobian
+        Fu = np.empty((B, self.nu, ng))
+        status = np.zeros(B, dtype=np.int32)
+        iters = np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_grad(self.h, C.byref(o), B, _p(Z), _p(U), None, _p(Zn), _p(Fz), _p(Fu), _p(status), _p(iters), flags)
+        self._check(rc, "dojo_step_grad")
+        return Zn, np.transpose(Fz, (0, 2, 1)), np.transpose(Fu, (0, 2, 1)), status, iters
+
+    def rollout(self, Z0, U=None, T: int = 1, opts=None, record: bool = False):
+        Z0 = np.ascontiguousarray(np.atleast_2d(Z0), dtype=np.float64)
+        B = Z0.shape[0]
+        if U is not None:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+            assert U.shape == (T, B, self.nu)
+        Zf = np.empty_like(Z0)
+        traj = np.empty((T, B, self.nz)) if record else None
+        st = np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_rollout(self.h, C.byref(o), B, int(T), _p(Z0), _p(U), _p(Zf), _p(traj), _p(st))
+        self._check(rc, "dojo_rollout")
+        return (Zf, st, traj) if record else (Zf, st)
+
+    # ------------------------------------------------------------------ device buffers (resident data)
+    def step_device(self, dZ: int, dU: Optional[int], dZn: int, B: int, opts=None, dstatus: Optional[int] = None, diters: Optional[int] = None,
+                    dsol: Optional[int] = None, dfext: Optional[int] = None, flags: int = 0, stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_async(self.h, C.byref(o), int(B), _p(dZ), _p(dU), _p(dfext), _p(dZn), _p(dsol), _p(dstatus), _p(diters), flags,
+                                    C.c_void_p(int(stream)))
+        self._check(rc, "dojo_step_async")
+
+    def step_grad_device(self, dZ: int, dU: Optional[int], dZn: int, dFz: int, dFu: int, B: int, opts=None, dstatus=None, diters=None, flags: int = 0,
+                         stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_grad_async(self.h, C.byref(o), int(B), _p(dZ), _p(dU), None, _p(dZn), _p(dFz), _p(dFu), _p(dstatus), _p(diters), flags,
+                                         C.c_void_p(int(stream)))
+        self._check(rc, "dojo_step_grad_async")

@@ -1,0 +1,147 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI, against the CPU
+oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star: fp64 tolerance, identical contact modes):
+  * same status for every environment;
+  * environments whose Newton-iteration count equals the oracle's:  |z_next - z_oracle|_inf <= 1e-8 and an identical
+    contact-mode bitmap (gamma_1 > s_1 per contact);
+  * iteration counts may differ for a small fraction of environments (a rounding-level flip of a line-search /
+    convergence comparison, SURVEY.md §7 hard part 2); those must still agree to solver tolerance.
+"""
+import numpy as np
+import pytest
+
+import dojo_jl_b200 as dj
+from dojo_jl_b200 import capi
+from conftest import jittered_states, random_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL_SAME_PATH = 1e-8
+TOL_SOLVER = 5e-3
+
+
+def _contact_modes(mech, sol):
+    off = mech.contact_sol_offset(0) if mech.Ni else 0
+    s = sol[:, off:].reshape(sol.shape[0], mech.Ni, 8)
+    return s[:, :, 4] > s[:, :, 0]
+
+
+def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03):
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(seed)
+    Z = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
+    stepper = BatchedStepper(mech, B)
+    oracle = Oracle(mech, opts)
+    total = mismatched = 0
+    for t in range(T):
+        U = random_inputs(mech, B, rng, scale)
+        Zg, sg, ig, solg = stepper.step(Z, U, opts=opts, return_sol=True)
+        Zo = np.empty_like(Z)
+        so, io = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        solo = np.empty((B, mech.nres))
+        for e in range(B):
+            Zo[e], so[e], io[e], solo[e] = oracle.step(Z[e], U[e], return_sol=True)
+        assert (sg == so).all(), f"{name} step {t}: status differs"
+        same = ig == io
+        err = np.abs(Zg - Zo).max(axis=1)
+        assert err[same].max(initial=0.0) <= TOL_SAME_PATH, f"{name} step {t}: {err[same].max()}"
+        assert err.max() <= TOL_SOLVER, f"{name} step {t}: {err.max()}"
+        if mech.Ni:
+            assert (_contact_modes(mech, solg)[same] == _contact_modes(mech, solo)[same]).all()
+        total += B
+        mismatched += int((~same).sum())
+        Z = Zo
+    assert mismatched <= max_mismatch * total, f"{name}: {mismatched}/{total} environments took a different iteration count"
+    return mismatched, total
+
+
+def test_pendulum_1000_steps():
+    """BASELINE config C0: pendulum, 1 env, 1000 steps."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism("pendulum")
+    stepper, oracle = BatchedStepper(mech, 1), Oracle(mech)
+    zg = zo = mech.z0.copy()
+    for _ in range(1000):
+        zg = stepper.step(zg[None], np.zeros((1, 1)))[0][0]
+        zo, _, _ = oracle.step(zo, np.zeros(1))
+    assert np.abs(zg - zo).max() < 1e-9
+
+
+def test_rollout_matches_stepwise():
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(3)
+    B, T = 16, 6
+    Z0 = jittered_states(mech, B, rng)
+    U = np.stack([random_inputs(mech, B, rng) for _ in range(T)])
+    stepper = BatchedStepper(mech, B)
+    Zf, st, traj = stepper.rollout(Z0, U, T, record=True)
+    Z = Z0
+    for t in range(T):
+        Z, s, _ = stepper.step(Z, U[t])
+        assert np.array_equal(traj[t], Z)
+    assert np.array_equal(Zf, Z)
+
+
+@pytest.mark.parametrize("name,B,T,scale", [("ant", 96, 25, 1.0), ("quadruped", 64, 30, 2.0), ("atlas", 48, 20, 5.0)])
+def test_step_parity(name, B, T, scale):
+    _compare_rollout(name, B, T, seed=7, scale=scale)
+
+
+def test_step_parity_tight_tolerances():
+    _compare_rollout("ant", 48, 12, seed=11, scale=1.0, opts=capi.solver_options(rtol=1e-9, btol=1e-9), max_mismatch=0.1)
+
+
+def test_q1_literal_return_flag():
+    """step! returns a double-advanced configuration; flag bit0 reproduces it."""
+    from dojo_jl_b200.solver import BatchedStepper, DOJO_FLAG_Q1_LITERAL_RETURN
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism("ant")
+    z, u = mech.z0.copy(), np.zeros(mech.nu)
+    zg = BatchedStepper(mech, 1).step(z[None], u[None], flags=DOJO_FLAG_Q1_LITERAL_RETURN)[0][0]
+    zo, _, _ = Oracle(mech).step(z, u, flags=1)
+    assert np.abs(zg - zo).max() < 1e-10
+    zt, _, _ = Oracle(mech).step(z, u)
+    assert np.abs(zo - zt).max() > 1e-4  # the literal return differs from the true next state
+
+
+def test_external_force():
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(5)
+    B = 8
+    Z = jittered_states(mech, B, rng)
+    U = random_inputs(mech, B, rng)
+    F = rng.normal(0, 1.0, (B, 6 * mech.Nb))
+    Zg, sg, _ = BatchedStepper(mech, B).step(Z, U, fext=F)
+    o = Oracle(mech)
+    for e in range(B):
+        zo, so, _ = o.step(Z[e], U[e], fext=np.ascontiguousarray(F[e]))
+        assert np.abs(Zg[e] - zo).max() < 1e-8
+
+
+def test_full_size_invariants():
+    """BASELINE config C1 size (ant, B = 4096): size-independent properties -- unit quaternions, finite output,
+    determinism (bit-identical repeat), batch-permutation equivariance."""
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(9)
+    B = 4096
+    Z = jittered_states(mech, 64, rng)[rng.integers(0, 64, B)]
+    Z[:, 2] += rng.uniform(-0.05, 0.2, B)
+    U = random_inputs(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Z1, s1, i1 = stepper.step(Z, U)
+    Z2, s2, i2 = stepper.step(Z, U)
+    assert np.array_equal(Z1, Z2) and np.array_equal(i1, i2)
+    assert np.isfinite(Z1).all() and (s1 == 0).mean() > 0.99
+    q = Z1.reshape(B, mech.Nb, 13)[:, :, 6:10]
+    assert np.abs(np.linalg.norm(q, axis=2) - 1).max() < 1e-12
+    perm = rng.permutation(B)
+    Z3, _, _ = stepper.step(Z[perm], U[perm])
+    assert np.array_equal(Z3, Z1[perm])
