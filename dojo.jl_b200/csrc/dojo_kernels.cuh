@@ -16,6 +16,12 @@
 //   update_state! + get_next_state  bodies/set.jl:22-36, mechanism/get.jl:126-134 -> epilogue()
 #pragma once
 #include "dojo_linalg.cuh"
+
+#ifndef DJ_NOINLINE_BIG
+#define DJ_BIG __device__ __forceinline__
+#else
+#define DJ_BIG __device__ __noinline__
+#endif
 #include "dojo_plan.h"
 
 namespace dj {
@@ -139,7 +145,7 @@ DJ_DEV void rotvec_attitude_jacobians(const JointDev& jd, const JointGeom& g, M3
 // ------------------------------------------------------------------------------------------------------------
 // Prologue: set_maximal_state!, set_input!, explicit spring impulses, joint impulse maps (constant over the solve)
 // ------------------------------------------------------------------------------------------------------------
-DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext,
+DJ_BIG void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext,
                      int max_child_color, int max_contact_color) {
   const Plan& P = *c.P;
   double* A = c.A;
@@ -296,7 +302,7 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
 // residual is dead at that point).  Returns the residual / bilinear violations (solver/violations.jl).
 // ------------------------------------------------------------------------------------------------------------
 template <bool JAC>
-DJ_DEV void evaluate(Ctx& c, double f, int res_off, int max_child_color, int max_contact_color, double& rvio, double& bvio) {
+DJ_BIG void evaluate(Ctx& c, double f, int res_off, int max_child_color, int max_contact_color, double& rvio, double& bvio) {
   const Plan& P = *c.P;
   double* A = c.A;
   const int lane = c.lane;
@@ -643,7 +649,7 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, int max_child_color, int max
 // ------------------------------------------------------------------------------------------------------------
 // Block LDU (GraphBasedSystems.ldu_factorization! / ldu_backsubstitution!)
 // ------------------------------------------------------------------------------------------------------------
-DJ_DEV bool factorize(Ctx& c) {
+DJ_BIG bool factorize(Ctx& c) {
   const Plan& P = *c.P;
   double* A = c.A;
   bool ok = true;
@@ -661,7 +667,7 @@ DJ_DEV bool factorize(Ctx& c) {
 }
 
 // x <- KKT^{-1} x for the vector at arena offset vec_off (solution ordering)
-DJ_DEV void solve(Ctx& c, int vec_off) {
+DJ_BIG void solve(Ctx& c, int vec_off) {
   const Plan& P = *c.P;
   double* A = c.A;
   double* x = A + vec_off;

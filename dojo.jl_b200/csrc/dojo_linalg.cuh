@@ -14,13 +14,19 @@
 #pragma once
 #include "dojo_math.cuh"
 
+#ifndef DJ_NOINLINE_LA
+#define DJ_LA __device__ __forceinline__
+#else
+#define DJ_LA __device__ __noinline__
+#endif
+
 namespace dj {
 
 // In-place inverse of an n x n row-major block (leading dimension ld) held in shared memory.
 // Lanes 0..n-1 own the columns of A, lanes n..2n-1 the columns of the identity that becomes A^{-1}.
 // Returns false (warp-uniform) if a zero / non-finite pivot is met.
 template <int N>
-DJ_DEV bool block_inverse_t(double* A, int ld, int lane) {
+DJ_LA bool block_inverse_t(double* A, int ld, int lane) {
   static_assert(2 * N <= 32, "block too large for the one-column-per-lane inverse");
   double a[N];
   const bool left = lane < N;
@@ -89,9 +95,12 @@ DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Generic (runtime-size) fallbacks
+// ---------------------------------------------------------------------------------------------------------
 // L (m x n, row-major) <- L * Dinv (n x n), in place.  Output elements are spread over the lanes; everything is
 // computed into registers before anything is written back (a row of L is both input and output).
-DJ_DEV void right_multiply_inplace(double* L, const double* Dinv, int m, int n, int lane) {
+__device__ __noinline__ void right_multiply_generic(double* L, const double* Dinv, int m, int n, int lane) {
   const int total = m * n;  // <= 256
   double out[8];
 #pragma unroll
@@ -114,7 +123,7 @@ DJ_DEV void right_multiply_inplace(double* L, const double* Dinv, int m, int n, 
 }
 
 // C (ni x nj, ld = nj) -= A (ni x k, ld = lda) * B (k x nj, ld = nj)
-DJ_DEV void schur_update(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int lane) {
+__device__ __noinline__ void schur_generic(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int lane) {
   const int total = ni * nj;
   for (int e = lane; e < total; e += 32) {
     int i = e / nj, j = e - i * nj;
@@ -123,6 +132,79 @@ DJ_DEV void schur_update(double* C, const double* A, int lda, const double* B, i
     C[e] -= acc;
   }
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-size kernels: fully unrolled, immediate shared-memory offsets, each lane owns a 1 x 3 strip of the output
+// (one load of A feeds three FMAs with independent accumulators).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStrip = 3;
+
+template <int M, int N>
+DJ_LA void right_multiply_t(double* L, const double* Dinv, int lane) {
+  constexpr int SPR = (N + kStrip - 1) / kStrip;
+  constexpr int NS = M * SPR;
+  static_assert(NS <= 32, "single pass only");
+  const int i = lane / SPR, js = (lane - i * SPR) * kStrip;
+  double acc[kStrip] = {0.0, 0.0, 0.0};
+  if (lane < NS) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double a = L[i * N + k];
+#pragma unroll
+      for (int c = 0; c < kStrip; ++c)
+        if (js + c < N) acc[c] += a * Dinv[k * N + js + c];
+    }
+  }
+  __syncwarp();
+  if (lane < NS) {
+#pragma unroll
+    for (int c = 0; c < kStrip; ++c)
+      if (js + c < N) L[i * N + js + c] = acc[c];
+  }
+  __syncwarp();
+}
+
+template <int NI, int K, int NJ>
+DJ_LA void schur_t(double* C, const double* A, int lda, const double* B, int lane) {
+  constexpr int SPR = (NJ + kStrip - 1) / kStrip;
+  constexpr int NS = NI * SPR;
+  static_assert(NS <= 32, "single pass only");
+  if (lane < NS) {
+    const int i = lane / SPR, js = (lane - i * SPR) * kStrip;
+    double acc[kStrip] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      double a = A[i * lda + t];
+#pragma unroll
+      for (int c = 0; c < kStrip; ++c)
+        if (js + c < NJ) acc[c] += a * B[t * NJ + js + c];
+    }
+#pragma unroll
+    for (int c = 0; c < kStrip; ++c)
+      if (js + c < NJ) C[i * NJ + js + c] -= acc[c];
+  }
+  __syncwarp();
+}
+
+#define DJ_RM_CASE(M, N) case (M) * 32 + (N): right_multiply_t<M, N>(L, Dinv, lane); return;
+DJ_DEV void right_multiply_inplace(double* L, const double* Dinv, int m, int n, int lane) {
+  switch (m * 32 + n) {
+    DJ_RM_CASE(6, 8) DJ_RM_CASE(6, 6) DJ_RM_CASE(5, 6) DJ_RM_CASE(9, 6) DJ_RM_CASE(6, 5) DJ_RM_CASE(6, 9)
+    DJ_RM_CASE(3, 6) DJ_RM_CASE(6, 3)
+    default: right_multiply_generic(L, Dinv, m, n, lane);
+  }
+}
+#define DJ_SC_CASE(NI, K, NJ) case ((NI) * 32 + (K)) * 32 + (NJ): schur_t<NI, K, NJ>(C, A, lda, B, lane); return;
+DJ_DEV void schur_update(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int lane) {
+  switch ((ni * 32 + k) * 32 + nj) {
+    DJ_SC_CASE(6, 4, 6)
+    DJ_SC_CASE(6, 6, 6)
+    DJ_SC_CASE(5, 6, 5) DJ_SC_CASE(5, 6, 6) DJ_SC_CASE(6, 6, 5) DJ_SC_CASE(6, 5, 6)
+    DJ_SC_CASE(9, 6, 9) DJ_SC_CASE(9, 6, 6) DJ_SC_CASE(6, 6, 9) DJ_SC_CASE(6, 9, 6)
+    DJ_SC_CASE(3, 6, 3) DJ_SC_CASE(3, 6, 6) DJ_SC_CASE(6, 6, 3) DJ_SC_CASE(6, 3, 6)
+    default: schur_generic(C, A, lda, B, ni, k, nj, lane);
+  }
 }
 
 }  // namespace dj

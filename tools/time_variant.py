@@ -1,0 +1,28 @@
+"""Time one build variant: python tools/time_variant.py <lib.so> mech B steps  (DOJO_B200_LIB overrides the library path)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import dojo_jl_b200 as dj
+from dojo_jl_b200 import solver
+solver.LIB_PATH = os.path.abspath(sys.argv[1])
+from dojo_jl_b200.solver import BatchedStepper
+import bench
+name, B, steps = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+mech = dj.get_mechanism(name)
+Z0, rng = bench.synthetic_batch(mech, B, 0xD0D0 + 1)
+U = torch.from_numpy(bench.random_inputs(mech, rng, 20 + steps, B, bench.SCALE[name])).cuda()
+s = BatchedStepper(mech, B)
+Za = torch.from_numpy(Z0).cuda(); Zb = torch.empty_like(Za)
+it = torch.zeros(B, dtype=torch.int32, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+for t in range(20):
+    s.step_device(Za.data_ptr(), U[t].data_ptr(), Zb.data_ptr(), B, stream=st); Za, Zb = Zb, Za
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+its = 0
+for t in range(20, 20 + steps):
+    s.step_device(Za.data_ptr(), U[t].data_ptr(), Zb.data_ptr(), B, diters=it.data_ptr(), stream=st); Za, Zb = Zb, Za
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(f"{os.path.basename(sys.argv[1]):20s} {name} B={B}: {ms:8.3f} ms/step  {B/ms*1e3:10.0f} env-steps/s  smem/env {s.shared_bytes_per_env}  checksum {float(Za.sum()):.9f}")
