@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -22,7 +23,6 @@ struct StepArgs {
   Plan plan;
   Options opts;
   int B;
-  int max_child_color, max_contact_color;
   const double* Z;
   const double* U;
   const double* Fext;
@@ -32,6 +32,7 @@ struct StepArgs {
   int32_t* iters;
   uint32_t flags;
   int* counter;  // dynamic work queue over environments
+  unsigned long long* prof;  // DJ_PROFILE builds: cycle counters [eval_jac, eval_ls, factorize, solve, misc]
 };
 
 // epilogue: update_state! + get_next_state (bodies/set.jl:22-36, mechanism/get.jl:126-134).  The default output is the
@@ -39,12 +40,12 @@ struct StepArgs {
 // value, which advances the configuration a second time.
 DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
   const Plan& P = *c.P;
-  if (c.lane < P.Nb) {
-    Kin k = body_kin(c, c.lane, 0.0);
+  if (c.tid < P.Nb) {
+    Kin k = body_kin(c, c.tid, 0.0);
     V3 x3 = k.x3;
     Quat q3 = k.q3;
     if (q1_literal) { x3 = x3 + P.h * k.v; q3 = qmul(q3, qmap(k.w, P.h)); }
-    double* o = zn + 13 * c.lane;
+    double* o = zn + 13 * c.tid;
     o[0] = x3.x; o[1] = x3.y; o[2] = x3.z;
     o[3] = k.v.x; o[4] = k.v.y; o[5] = k.v.z;
     o[6] = q3.s; o[7] = q3.x; o[8] = q3.y; o[9] = q3.z;
@@ -52,34 +53,50 @@ DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
   }
 }
 
-__global__ void __launch_bounds__(32) dojo_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
   extern __shared__ double arena[];
+  __shared__ int s_env;
   Ctx c;
   c.A = arena;
   c.P = &a.plan;
-  c.lane = threadIdx.x;
+  c.tid = threadIdx.x;
+  c.nthreads = blockDim.x;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
   c.mu = 0.0;
+#ifdef DJ_PROFILE
+  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = 0; c.t_last = clock64();
+#endif
   const Plan& P = a.plan;
   for (;;) {
-    int e = 0;
-    if (c.lane == 0) e = atomicAdd(a.counter, 1);
-    e = __shfl_sync(0xffffffffu, e, 0);
+    if (c.tid == 0) s_env = atomicAdd(a.counter, 1);  // dynamic work queue: iteration counts differ between environments
+    __syncthreads();
+    const int e = s_env;
+    __syncthreads();
     if (e >= a.B) break;
+    DJ_TICK(c, t_misc)
     const double* z = a.Z + (size_t)e * P.nz;
     const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
     const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
-    prologue(c, z, u, fx, a.max_child_color, a.max_contact_color);
+    prologue(c, z, u, fx);
     int iters = 0;
-    int status = mehrotra(c, a.opts, a.max_child_color, a.max_contact_color, &iters);
+    int status = mehrotra(c, a.opts, &iters);
     epilogue(c, a.Zn + (size_t)e * P.nz, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
     if (a.sol)
-      for (int t = c.lane; t < P.nres; t += 32) a.sol[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
-    if (c.lane == 0) {
+      for (int t = c.tid; t < P.nres; t += c.nthreads) a.sol[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
+    if (c.tid == 0) {
       if (a.status) a.status[e] = status;
       if (a.iters) a.iters[e] = iters;
     }
-    __syncwarp();
+    __syncthreads();
   }
+#ifdef DJ_PROFILE
+  DJ_TICK(c, t_misc)
+  if (c.tid == 0 && a.prof) {
+    atomicAdd(a.prof + 0, (unsigned long long)c.t_eval_jac); atomicAdd(a.prof + 1, (unsigned long long)c.t_eval_ls);
+    atomicAdd(a.prof + 2, (unsigned long long)c.t_fact); atomicAdd(a.prof + 3, (unsigned long long)c.t_solve); atomicAdd(a.prof + 4, (unsigned long long)c.t_misc);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -91,13 +108,17 @@ struct DojoHandle {
   int sm_count = 0;
   int envs_per_sm = 1;
   Plan plan;  // device pointers inside
-  int max_child_color = 0, max_contact_color = 0;
+  int nw = 4;  // warps per environment
   size_t arena_bytes = 0;
   BodyDev* d_bodies = nullptr;
   JointDev* d_joints = nullptr;
   ContactDev* d_contacts = nullptr;
   ElimStep* d_steps = nullptr;
+  int* d_sched = nullptr;
+  int* d_ilist = nullptr;
+  WarpRole* d_roles = nullptr;
   int* d_counter = nullptr;
+  unsigned long long* d_prof = nullptr;
   // staging for host-pointer calls
   double *d_Z = nullptr, *d_U = nullptr, *d_F = nullptr, *d_Zn = nullptr, *d_sol = nullptr;
   int32_t *d_status = nullptr, *d_iters = nullptr;
@@ -215,24 +236,36 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   }
   const int nres = off;
 
-  // ---- arena layout: [sol | rhs | sav | body state | body cst | constant blocks | re-zeroed matrix region]
+  // ---- warps per environment
+  int nw = 4;
+  if (const char* e = getenv("DOJO_B200_WARPS")) nw = atoi(e);
+  if (nw != 1 && nw != 2 && nw != 4 && nw != 8) nw = 4;
+  h->nw = nw;
+
+  // ---- arena layout: [sol | rhs | sav | reduction scratch | body state | body cst | joint slots | constant blocks |
+  //                     re-zeroed region: contact slots, scratch records, matrix blocks]
   Plan& P = h->plan;
   std::memset(&P, 0, sizeof(P));
-  P.Nb = Nb; P.Ne = Ne; P.Ni = Ni; P.nres = nres; P.nu = nu; P.nz = 13 * Nb;
+  P.Nb = Nb; P.Ne = Ne; P.Ni = Ni; P.nres = nres; P.nu = nu; P.nz = 13 * Nb; P.nw = nw;
   P.h = d->timestep; P.input_scaling = d->input_scaling;
   std::memcpy(P.g, d->gravity, sizeof(P.g));
   int a = 0;
   P.sol_off = a; a += nres;
   P.rhs_off = a; a += nres;
   P.sav_off = a; a += nres;
+  P.red_off = a; a += 3 * nw + 1;
   for (int b = 0; b < Nb; ++b) { bodies[b].st_off = a; a += 7; }
   for (int b = 0; b < Nb; ++b) { bodies[b].cst_off = a; a += 6; }
-  for (int j = 0; j < Ne; ++j) {  // constant (per step) blocks
+  for (int j = 0; j < Ne; ++j) {  // joint contribution slots (also used by the prologue) and constant (per step) blocks
     JointDev& J = joints[j];
+    J.slot_c = a; a += kSlot;
+    if (J.parent >= 0) { J.slot_p = a; a += kSlot; } else J.slot_p = -1;
     J.Lc_off = a; a += 6 * J.n;
     if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.n; } else J.Gp_off = -1;
   }
   P.mat_off = a;
+  for (int c = 0; c < Ni; ++c) { contacts[c].slot = a; a += kSlot; }
+  for (int j = 0; j < Ne; ++j) { if (joints[j].parent >= 0) { joints[j].S_off = a; a += kScratch; } else joints[j].S_off = -1; }
   for (int b = 0; b < Nb; ++b) { bodies[b].D_off = a; a += 36; }
   for (int j = 0; j < Ne; ++j) {
     JointDev& J = joints[j];
@@ -254,72 +287,142 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   P.arena_len = a;
   h->arena_bytes = (size_t)a * sizeof(double);
 
-  // ---- colours (deterministic accumulation order)
-  {
-    std::vector<int> nchild(Nb, 0), ncont(Nb, 0);
-    for (int j = 0; j < Ne; ++j) if (joints[j].parent >= 0) { joints[j].color_parent = nchild[joints[j].parent]++; }
-    for (int c = 0; c < Ni; ++c) contacts[c].color = ncont[contacts[c].body]++;
-    h->max_child_color = 0; h->max_contact_color = 0;
-    for (int b = 0; b < Nb; ++b) { h->max_child_color = std::max(h->max_child_color, nchild[b]); h->max_contact_color = std::max(h->max_contact_color, ncont[b]); }
+  // ---- gather lists (deterministic accumulation order): contacts of b, its parent joint (child side), its child joints
+  std::vector<int> ilist;
+  for (int b = 0; b < Nb; ++b) {
+    bodies[b].g_off = (int)ilist.size();
+    for (int c = 0; c < Ni; ++c) if (contacts[c].body == b) ilist.push_back(contacts[c].slot);
+    ilist.push_back(joints[parent_joint[b]].slot_c);
+    for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(joints[j].slot_p);
+    bodies[b].g_cnt = (int)ilist.size() - bodies[b].g_off;
   }
 
-  // ---- elimination order: post-order over the body tree; contacts of b, then b, then its parent joint
+  // ---- roles: which warp evaluates which nodes (one lane per node)
+  std::vector<WarpRole> roles(nw);
+  {
+    for (auto& r : roles) std::memset(&r, 0, sizeof(r));
+    auto add = [&](int w, int type, int first, int count) {
+      if (count <= 0) return;
+      WarpRole& r = roles[w];
+      r.type[r.npass] = type; r.first[r.npass] = first; r.count[r.npass] = count; r.npass++;
+    };
+    if (nw == 1) { add(0, ROLE_BODY, 0, Nb); add(0, ROLE_CONTACT, 0, Ni); add(0, ROLE_JOINT, 0, Ne); }
+    else if (nw == 2) { add(0, ROLE_BODY, 0, Nb); add(0, ROLE_CONTACT, 0, Ni); add(1, ROLE_JOINT, 0, Ne); }
+    else if (nw == 4) { add(0, ROLE_BODY, 0, Nb); add(1, ROLE_CONTACT, 0, Ni); int hj = (Ne + 1) / 2; add(2, ROLE_JOINT, 0, hj); add(3, ROLE_JOINT, hj, Ne - hj); }
+    else {
+      int hb = (Nb + 1) / 2, hc = (Ni + 1) / 2, qj = (Ne + 3) / 4;
+      add(0, ROLE_BODY, 0, hb); add(1, ROLE_BODY, hb, Nb - hb);
+      add(2, ROLE_CONTACT, 0, hc); add(3, ROLE_CONTACT, hc, Ni - hc);
+      for (int q = 0; q < 4; ++q) add(4 + q, ROLE_JOINT, q * qj, std::max(0, std::min(qj, Ne - q * qj)));
+    }
+  }
+
+  // ---- elimination steps with heights; a parent body's diagonal / vector updates go to the joint's scratch record
   //      (contacts into bodies, bodies into their parent joint, joints into the parent body: SURVEY.md Appendix C)
-  std::vector<ElimStep> steps;
+  struct HStep { ElimStep s; int height; int group; double cost; };
+  std::vector<HStep> hs;
+  std::vector<int> body_height(Nb, 0);
   {
     std::vector<char> done(Nb, 0);
     struct Rec {
-      const std::vector<JointDev>& joints; const std::vector<BodyDev>& bodies; const std::vector<ContactDev>& contacts;
-      const std::vector<int>& pj; std::vector<char>& done; std::vector<ElimStep>& steps; int Ne, Ni;
-      void visit(int b) {
+      std::vector<JointDev>& joints; std::vector<BodyDev>& bodies; std::vector<ContactDev>& contacts;
+      const std::vector<int>& pj; std::vector<char>& done; std::vector<HStep>& hs; std::vector<int>& ilist; int Ne, Ni;
+      int visit(int b) {  // returns the height of the parent-joint step of b (or of b if the joint has no impulses)
         done[b] = 1;
-        for (int j = 0; j < Ne; ++j) if (joints[j].parent == b && !done[joints[j].child]) visit(joints[j].child);
+        int hb = 0;
+        std::vector<int> fold;
+        for (int j = 0; j < Ne; ++j)
+          if (joints[j].parent == b && !done[joints[j].child]) {
+            int hc = visit(joints[j].child);
+            hb = std::max(hb, hc + 1);
+            fold.push_back(joints[j].S_off);
+          }
         const BodyDev& B = bodies[b];
         for (int c = 0; c < Ni; ++c) {
           if (contacts[c].body != b) continue;
           const ContactDev& C = contacts[c];
-          ElimStep s; std::memset(&s, 0, sizeof(s));
+          HStep h; std::memset(&h, 0, sizeof(h));
+          ElimStep& s = h.s;
           s.d_off = C.D_off; s.n = 8; s.vec_off = C.sol_off; s.nnb = 1;
-          s.nb[0].n = 6; s.nb[0].vec_off = B.sol_off; s.nb[0].L_off = C.L_off; s.nb[0].U_off = C.U_off; s.nb[0].U_k = 4; s.nb[0].U_row = 4;
+          s.nb[0].n = 6; s.nb[0].vec_off = B.sol_off; s.nb[0].fwd_abs = -1; s.nb[0].L_off = C.L_off; s.nb[0].U_off = C.U_off; s.nb[0].U_k = 4; s.nb[0].U_row = 4;
           s.tgt[0][0] = B.D_off;
-          steps.push_back(s);
+          h.height = 0; h.group = b; h.cost = 3.0;
+          hs.push_back(h);
+          hb = std::max(hb, 1);
         }
         const JointDev& J = joints[pj[b]];
         {  // the body: neighbours = parent joint (if it has impulses) and, with dampers, the parent body
-          ElimStep s; std::memset(&s, 0, sizeof(s));
+          HStep h; std::memset(&h, 0, sizeof(h));
+          ElimStep& s = h.s;
           s.d_off = B.D_off; s.n = 6; s.vec_off = B.sol_off; s.nnb = 0;
+          s.fold_off = (int)ilist.size(); s.fold_cnt = (int)fold.size();
+          for (int f : fold) ilist.push_back(f);
           int ij = -1, ip = -1;
           if (J.n > 0) {
             ij = s.nnb++;
-            s.nb[ij].n = J.n; s.nb[ij].vec_off = J.sol_off; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+            s.nb[ij].n = J.n; s.nb[ij].vec_off = J.sol_off; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
           }
           if (J.parent >= 0 && J.BBpc_off >= 0) {
             ip = s.nnb++;
             const BodyDev& Pb = bodies[J.parent];
-            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
+            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].fwd_abs = J.S_off + 36; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
           }
           if (ij >= 0) s.tgt[ij][ij] = J.D_off;
-          if (ip >= 0) s.tgt[ip][ip] = bodies[J.parent].D_off;
+          if (ip >= 0) s.tgt[ip][ip] = J.S_off;
           if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off; s.tgt[ip][ij] = J.Lp_off; }
-          steps.push_back(s);
+          h.height = hb; h.group = -1; h.cost = 4.0 + J.n * 0.3;
+          hs.push_back(h);
         }
+        int hj = hb;
         if (J.n > 0) {  // the parent joint: neighbour = parent body
-          ElimStep s; std::memset(&s, 0, sizeof(s));
+          HStep h; std::memset(&h, 0, sizeof(h));
+          ElimStep& s = h.s;
           s.d_off = J.D_off; s.n = J.n; s.vec_off = J.sol_off; s.nnb = 0;
           if (J.parent >= 0) {
             const BodyDev& Pb = bodies[J.parent];
             s.nnb = 1;
-            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.n; s.nb[0].U_row = 0;
-            s.tgt[0][0] = Pb.D_off;
+            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.n; s.nb[0].U_row = 0;
+            s.tgt[0][0] = J.S_off;
           }
-          steps.push_back(s);
+          hj = hb + 1;
+          h.height = hj; h.group = -1; h.cost = 2.0 + J.n * 0.4;
+          hs.push_back(h);
         }
+        return hj;
       }
-    } rec{joints, bodies, contacts, parent_joint, done, steps, Ne, Ni};
+    } rec{joints, bodies, contacts, parent_joint, done, hs, ilist, Ne, Ni};
     for (int j = 0; j < Ne; ++j) if (joints[j].parent < 0 && !done[joints[j].child]) rec.visit(joints[j].child);
     for (int b = 0; b < Nb; ++b) if (!done[b]) { delete h; return fail("mechanism is not a tree rooted at the origin"); }
   }
-  P.nsteps = (int)steps.size();
+  // ---- schedule: phase = height; the steps of a phase are independent and are spread over the warps (contacts of one
+  //      body stay on one warp, they update the same diagonal block)
+  int nphase = 0;
+  for (auto& x : hs) nphase = std::max(nphase, x.height + 1);
+  std::vector<ElimStep> steps;
+  std::vector<int> sched((size_t)nphase * nw * 2, 0);
+  for (int ph = 0; ph < nphase; ++ph) {
+    std::vector<std::vector<int>> per_warp(nw);
+    std::vector<double> load(nw, 0.0);
+    std::vector<int> group_warp(Nb, -1);
+    for (int i = 0; i < (int)hs.size(); ++i) {
+      if (hs[i].height != ph) continue;
+      int w;
+      if (hs[i].group >= 0 && group_warp[hs[i].group] >= 0) w = group_warp[hs[i].group];
+      else {
+        w = 0;
+        for (int k = 1; k < nw; ++k) if (load[k] < load[w]) w = k;
+        if (hs[i].group >= 0) group_warp[hs[i].group] = w;
+      }
+      per_warp[w].push_back(i);
+      load[w] += hs[i].cost;
+    }
+    for (int w = 0; w < nw; ++w) {
+      sched[2 * (ph * nw + w)] = (int)steps.size();
+      sched[2 * (ph * nw + w) + 1] = (int)per_warp[w].size();
+      for (int i : per_warp[w]) steps.push_back(hs[i].s);
+    }
+  }
+  P.nphase = nphase;
 
   // ---- device resources
   cudaDeviceProp prop;
@@ -336,15 +439,19 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
   bool ok = upload(bodies.data(), sizeof(BodyDev) * Nb, (void**)&h->d_bodies) && upload(joints.data(), sizeof(JointDev) * Ne, (void**)&h->d_joints) &&
-            upload(contacts.data(), sizeof(ContactDev) * Ni, (void**)&h->d_contacts) && upload(steps.data(), sizeof(ElimStep) * steps.size(), (void**)&h->d_steps);
+            upload(contacts.data(), sizeof(ContactDev) * Ni, (void**)&h->d_contacts) && upload(steps.data(), sizeof(ElimStep) * steps.size(), (void**)&h->d_steps) &&
+            upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
+            upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_prof, 8 * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
   P.bodies = h->d_bodies; P.joints = h->d_joints; P.contacts = h->d_contacts; P.steps = h->d_steps;
+  P.sched = h->d_sched; P.ilist = h->d_ilist; P.roles = h->d_roles;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel, 32, h->arena_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel, 32 * h->nw, h->arena_bytes);
   h->envs_per_sm = std::max(1, occ);
   *out = h;
   return DOJO_OK;
@@ -354,6 +461,7 @@ extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_bodies); cudaFree(h->d_joints); cudaFree(h->d_contacts); cudaFree(h->d_steps); cudaFree(h->d_counter);
+  cudaFree(h->d_sched); cudaFree(h->d_ilist); cudaFree(h->d_roles);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
   if (h->p_out) cudaFreeHost(h->p_out);
@@ -369,6 +477,12 @@ extern "C" int dojo_num_residual(const DojoHandle* h) { return h->plan.nres; }
 extern "C" int dojo_num_grad_state(const DojoHandle* h) { return 12 * h->plan.Nb; }
 extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->arena_bytes; }
 extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
+// debugging aid (DJ_PROFILE builds): cycle counters accumulated by thread 0 of every CTA; out[5]
+extern "C" int dojo_debug_cycles(DojoHandle* h, unsigned long long* out) {
+  cudaMemcpy(out, h->d_prof, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long));
+  return DOJO_OK;
+}
 
 static Options make_options(const DojoSolverOptions* o) {
   DojoSolverOptions d;
@@ -386,12 +500,12 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   CUDA_TRY(h, cudaSetDevice(h->device));
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
-  a.max_child_color = h->max_child_color; a.max_contact_color = h->max_contact_color;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
   a.counter = h->d_counter;
+  a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   int grid = std::min(B, h->sm_count * h->envs_per_sm);
-  dojo_step_kernel<<<grid, 32, h->arena_bytes, s>>>(a);
+  dojo_step_kernel<<<grid, 32 * h->nw, h->arena_bytes, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;

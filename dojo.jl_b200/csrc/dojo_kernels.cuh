@@ -1,13 +1,13 @@
 // dojo_kernels.cuh -- the per-timestep hot path as one persistent sm_100a kernel.
 //
-// One warp owns one environment.  The environment's whole interior-point problem (solution vector, residuals,
-// block-sparse KKT matrix) lives in that warp's shared-memory arena for the duration of the step; HBM is touched
-// only to read z, u (and Fext) at the start and to write z_next (and status / iters / sol / gradients) at the end.
+// One CTA (nw warps) owns one environment.  The environment's whole interior-point problem (solution vector,
+// residuals, block-sparse KKT matrix) lives in the CTA's shared-memory arena for the duration of the step; HBM is
+// touched only to read z, u (and Fext) at the start and to write z_next (and status / iters / sol / gradients) at the end.
 //
 // Reference call stack restated here (file:line relative to the reference's src/):
-//   step!                 simulation/step.jl:11-30      -> step_env()
-//   set_maximal_state!    mechanism/set.jl:10-26        -> prologue_bodies()
-//   set_input!            mechanism/set.jl:40-53        -> prologue_joints() (input / spring impulses, impulse maps)
+//   step!                 simulation/step.jl:11-30      -> dojo_step_kernel
+//   set_maximal_state!    mechanism/set.jl:10-26        -> prologue()
+//   set_input!            mechanism/set.jl:40-53        -> prologue() (input / spring impulses, impulse maps)
 //   mehrotra!             solver/mehrotra.jl:9-73       -> mehrotra()
 //   set_entries!          solver/linear_system.jl:1-17  -> evaluate<true>()   (residual + KKT blocks)
 //   residual_violation / bilinear_violation  solver/violations.jl -> evaluate<false>() (line search)
@@ -16,12 +16,6 @@
 //   update_state! + get_next_state  bodies/set.jl:22-36, mechanism/get.jl:126-134 -> epilogue()
 #pragma once
 #include "dojo_linalg.cuh"
-
-#ifndef DJ_NOINLINE_BIG
-#define DJ_BIG __device__ __forceinline__
-#else
-#define DJ_BIG __device__ __noinline__
-#endif
 #include "dojo_plan.h"
 
 namespace dj {
@@ -37,14 +31,65 @@ DJ_DEV M33 ldm33(const double* p) {
     for (int j = 0; j < 3; ++j) r.m[i][j] = p[3 * i + j];
   return r;
 }
+DJ_DEV void stm33(double* p, const M33& a) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p[3 * i + j] = a.m[i][j];
+}
 DJ_DEV Quat ldq(const double* p) { return Quat{p[0], p[1], p[2], p[3]}; }
 
 struct Ctx {
-  double* A;  // this warp's arena
+  double* A;  // this environment's arena
   const Plan* P;
-  int lane;
+  int tid, nthreads, warp, lane;
   double mu;
+#ifdef DJ_PROFILE
+  long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_last;
+#endif
 };
+#ifdef DJ_PROFILE
+#define DJ_TICK(c, field) { long long _t = clock64(); (c).field += _t - (c).t_last; (c).t_last = _t; }
+#else
+#define DJ_TICK(c, field)
+#endif
+
+// CTA-wide reductions (deterministic: per-warp shuffles, then a fixed-order combine of the nw partials)
+DJ_DEV void block_nanmax2(const Ctx& c, double& a, double& b) {
+  double* red = c.A + c.P->red_off;
+  a = warp_nanmax(a);
+  b = warp_nanmax(b);
+  if (c.P->nw == 1) return;
+  if (c.lane == 0) { red[2 * c.warp] = a; red[2 * c.warp + 1] = b; }
+  __syncthreads();
+  a = red[0]; b = red[1];
+  for (int w = 1; w < c.P->nw; ++w) { a = nanmax(a, red[2 * w]); b = nanmax(b, red[2 * w + 1]); }
+  __syncthreads();
+}
+DJ_DEV double block_min(const Ctx& c, double a) {
+  double* red = c.A + c.P->red_off;
+  a = warp_min(a);
+  if (c.P->nw == 1) return a;
+  if (c.lane == 0) red[c.warp] = a;
+  __syncthreads();
+  a = red[0];
+  for (int w = 1; w < c.P->nw; ++w) a = fmin(a, red[w]);
+  __syncthreads();
+  return a;
+}
+DJ_DEV void block_sum3(const Ctx& c, double& a, double& b, double& d) {
+  double* red = c.A + c.P->red_off;
+  a = warp_sum(a); b = warp_sum(b); d = warp_sum(d);
+  if (c.P->nw == 1) return;
+  if (c.lane == 0) { red[3 * c.warp] = a; red[3 * c.warp + 1] = b; red[3 * c.warp + 2] = d; }
+  __syncthreads();
+  a = red[0]; b = red[1]; d = red[2];
+  for (int w = 1; w < c.P->nw; ++w) { a += red[3 * w]; b += red[3 * w + 1]; d += red[3 * w + 2]; }
+  __syncthreads();
+}
+
+// node index handled by this lane for role pass p (or -1)
+DJ_DEV int role_item(const WarpRole& r, int p, int lane) { return lane < r.count[p] ? r.first[p] + lane : -1; }
 
 // kinematic state of one body at the candidate solution sol + f * delta
 struct Kin {
@@ -119,10 +164,9 @@ DJ_DEV JointGeom joint_geom(const JointDev& jd, V3 xa, Quat qa, const M33& Ra, V
 DJ_DEV void rotvec_attitude_jacobians(const JointDev& jd, const JointGeom& g, M33& Tp, M33& Tc) {
   M34 drv = drotation_vector_dq(g.qr);
   V3 vr = qvec(g.qr);
-  // child: d qr = [ -vr' ; s I + skew(vr) ] d
-  // parent: d qr = [ vr' Roff' ; -(s I - skew(vr)) Roff' ] d
+  // child: d qr = [ -vr' ; s I + skew(vr) ] d          parent: d qr = [ vr' Roff' ; -(s I - skew(vr)) Roff' ] d
   M33 Rofft = transpose(rotmat(ldq(jd.qoff)));
-  V3 srow_p = vtmul(vr, Rofft);  // vr' * Roff'  (row vector)
+  V3 srow_p = vtmul(vr, Rofft);
   V3 srow_c = -vr;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -134,24 +178,107 @@ DJ_DEV void rotvec_attitude_jacobians(const JointDev& jd, const JointGeom& g, M3
   }
 }
 
-// accumulate helper: colour-ordered, deterministic accumulation of per-joint / per-contact contributions into
-// per-body storage (no atomics: the order of floating-point additions is fixed, so results are reproducible)
-#define DJ_COLOR_LOOP(maxc, mycolor, active, body)          \
-  for (int _col = 0; _col < (maxc); ++_col) {               \
-    if ((active) && (mycolor) == _col) { body; }            \
-    __syncwarp();                                           \
-  }
+DJ_DEV void write_slot(double* s, V3 f, V3 t, const M33& K) { st3(s, f); st3(s + 3, t); stm33(s + 6, K); }
 
 // ------------------------------------------------------------------------------------------------------------
 // Prologue: set_maximal_state!, set_input!, explicit spring impulses, joint impulse maps (constant over the solve)
 // ------------------------------------------------------------------------------------------------------------
-DJ_BIG void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext,
-                     int max_child_color, int max_contact_color) {
+DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int lane = c.lane;
+  const JointDev& jd = P.joints[j];
+  V3 cl_p = v3zero(), ca_p = v3zero(), cl_c = v3zero(), ca_c = v3zero();  // [JF2; Jtau2] + spring impulses
+  Kin ka = body_kin(c, jd.parent, 0.0), kb = body_kin(c, jd.child, 0.0);
+  M33 Ra = rotmat(ka.q2), Rb = rotmat(kb.q2);
+  JointGeom g = joint_geom(jd, ka.x2, ka.q2, Ra, kb.x2, kb.q2, Rb);
+  M33 Roff = rotmat(ldq(jd.qoff));
+  M33 Rrel_t = transpose(Rb) * Ra;  // R(qb^-1 qa)
+  // inputs (joints/joint.jl:96-99, translational/input.jl:5-27, rotational/input.jl:5-17)
+  if (u) {
+    V3 it = v3zero(), ir = v3zero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nfree_t) it += u[jd.u_off + i] * ld3(jd.At + 3 * i);
+      if (i < jd.nfree_r) ir += u[jd.u_off + jd.nfree_t + i] * ld3(jd.Ar + 3 * i);
+    }
+    it = P.input_scaling * it;
+    ir = P.input_scaling * ir;
+    // translational: JF += X' input ; Jtau += (1/2 Q' input) / 2
+    cl_p += tmul(g.Xp, it); ca_p += 0.25 * tmul(g.Qtp, it);
+    cl_c += tmul(g.Xc, it); ca_c += 0.25 * tmul(g.Qtc, it);
+    // rotational: parent -R(qoff) tau, child R(qb^-1 qa qoff) tau
+    V3 tp = Roff * ir;
+    ca_p -= tp;
+    ca_c += Rrel_t * tp;
+  }
+  // rotational spring (rotational/springs.jl:5-38), explicit at (x2, q2)
+  if (jd.spring_r != 0.0 && jd.nfree_r > 0) {
+    V3 rv = rotation_vector(g.qr);
+    V3 force = v3zero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < jd.nfree_r) {
+        V3 a = ld3(jd.Ar + 3 * i);
+        force += (-jd.spring_r * (jd.spring_off_r[i] - dot(a, rv))) * a;
+      }
+    V3 tp = P.h * (Roff * force);
+    ca_p += tp;
+    ca_c -= Rrel_t * tp;
+  }
+  write_slot(A + jd.slot_c, cl_c, ca_c, m33zero());
+  if (jd.parent >= 0) write_slot(A + jd.slot_p, cl_p, ca_p, m33zero());
+  // impulse maps at the current configuration (joints/joint.jl:67-93, joints/impulses.jl:4-7): 6 x n
+  for (int side = 0; side < 2; ++side) {
+    const bool par = (side == 0);
+    if (par && jd.parent < 0) continue;
+    double* G = A + (par ? jd.Gp_off : jd.Lc_off);
+    const double sgn = par ? 1.0 : -1.0;  // the child block stores L = -G directly
+    const M33& X = par ? g.Xp : g.Xc;
+    const M33& Qt = par ? g.Qtp : g.Qtc;
+    const M33& Qr = par ? g.Qrp : g.Qrc;
+    const int n = jd.n;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nl_t) {  // translational lambda column i
+        V3 ci = ld3(jd.Ct + 3 * i);
+        V3 f = tmul(X, ci), t = 0.5 * tmul(Qt, ci);
+        int col = i;
+        G[0 * n + col] = sgn * f.x; G[1 * n + col] = sgn * f.y; G[2 * n + col] = sgn * f.z;
+        G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
+      }
+      if (i < jd.nb2_r) {  // limit duals: s columns are zero, gamma_upper = -A', gamma_lower = +A'
+        V3 ai = ld3(jd.Ar + 3 * i);
+        V3 t = 0.5 * tmul(Qr, ai);
+        int cs_u = jd.row_r + i, cs_l = jd.row_r + jd.nb2_r + i;
+        int cu = jd.row_r + jd.nb_r + i, cl = jd.row_r + jd.nb_r + jd.nb2_r + i;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { G[r * n + cs_u] = 0.0; G[r * n + cs_l] = 0.0; }
+        G[0 * n + cu] = 0.0; G[1 * n + cu] = 0.0; G[2 * n + cu] = 0.0;
+        G[3 * n + cu] = -sgn * t.x; G[4 * n + cu] = -sgn * t.y; G[5 * n + cu] = -sgn * t.z;
+        G[0 * n + cl] = 0.0; G[1 * n + cl] = 0.0; G[2 * n + cl] = 0.0;
+        G[3 * n + cl] = sgn * t.x; G[4 * n + cl] = sgn * t.y; G[5 * n + cl] = sgn * t.z;
+      }
+      if (i < jd.nl_r) {  // rotational lambda column i
+        V3 ci = ld3(jd.Cr + 3 * i);
+        V3 t = 0.5 * tmul(Qr, ci);
+        int col = jd.row_r + 2 * jd.nb_r + i;
+        G[0 * n + col] = 0.0; G[1 * n + col] = 0.0; G[2 * n + col] = 0.0;
+        G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
+      }
+    }
+  }
+  // reset! (joints/constraints.jl:440-448): s = gamma = 1, lambda = 0
+  double* so = A + P.sol_off + jd.sol_off;
+  for (int i = 0; i < jd.n; ++i) so[i] = 0.0;
+  for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.row_r + i] = 1.0;
+}
+
+DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const WarpRole& role = P.roles[c.warp];
   // coalesced read of z: [x2(3) v15(3) q2(4) w15(3)] per body (mechanism/set.jl:10-26)
-  for (int t = lane; t < P.nz; t += 32) {
+  for (int t = c.tid; t < P.nz; t += c.nthreads) {
     int b = t / 13, k = t - 13 * b;
     double val = z[t];
     const BodyDev& bd = P.bodies[b];
@@ -160,140 +287,49 @@ DJ_BIG void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
     else if (k < 10) A[bd.st_off + 3 + (k - 6)] = val;
     else A[P.sol_off + bd.sol_off + 3 + (k - 10)] = val;
   }
-  __syncwarp();
-  // bodies: constant part of the discrete Euler-Lagrange residual (integrators/constraint.jl:14-25)
-  if (lane < P.Nb) {
-    const BodyDev& bd = P.bodies[lane];
-    const double* so = A + P.sol_off + bd.sol_off;
-    V3 v15 = ld3(so), w15 = ld3(so + 3);
-    M33 J = ldm33(bd.J);
-    V3 F = v3zero(), tau = v3zero();
-    if (fext) { F = ld3(fext + 6 * lane); tau = ld3(fext + 6 * lane + 3); }
-    V3 g = ld3(P.g);
-    V3 lin = (-bd.mass) * v15 - P.h * (bd.mass * g + F);
-    double n0 = 0.5 * P.h * sqrt(4.0 / (P.h * P.h) - dot(w15, w15));
-    V3 Jw = J * w15;
-    V3 ang = (-1.0) * (n0 * Jw - (0.5 * P.h) * cross(w15, Jw)) - P.h * tau;
-    st3(A + bd.cst_off, lin);
-    st3(A + bd.cst_off + 3, ang);
-  }
-  __syncwarp();
-  // joints
-  const bool jact = lane < P.Ne;
-  V3 cl_p = v3zero(), ca_p = v3zero(), cl_c = v3zero(), ca_c = v3zero();  // contributions to cst (to subtract)
-  int jparent = -1, jchild = 0, jcolor = 0;
-  if (jact) {
-    const JointDev& jd = P.joints[lane];
-    jparent = jd.parent; jchild = jd.child; jcolor = jd.color_parent;
-    Kin ka = body_kin(c, jd.parent, 0.0), kb = body_kin(c, jd.child, 0.0);
-    M33 Ra = rotmat(ka.q2), Rb = rotmat(kb.q2);
-    JointGeom g = joint_geom(jd, ka.x2, ka.q2, Ra, kb.x2, kb.q2, Rb);
-    M33 Roff = rotmat(ldq(jd.qoff));
-    M33 Rrel_t = transpose(Rb) * Ra;  // R(qb^-1 qa)
-    // inputs (joints/joint.jl:96-99, translational/input.jl:5-27, rotational/input.jl:5-17)
-    if (u) {
-      V3 it = v3zero(), ir = v3zero();
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < jd.nfree_t) it += u[jd.u_off + i] * ld3(jd.At + 3 * i);
-        if (i < jd.nfree_r) ir += u[jd.u_off + jd.nfree_t + i] * ld3(jd.Ar + 3 * i);
-      }
-      it = P.input_scaling * it;
-      ir = P.input_scaling * ir;
-      // translational: JF += X' input ; Jtau += (1/2 Q' input) / 2
-      cl_p += tmul(g.Xp, it); ca_p += 0.25 * tmul(g.Qtp, it);
-      cl_c += tmul(g.Xc, it); ca_c += 0.25 * tmul(g.Qtc, it);
-      // rotational
-      V3 tp = Roff * ir;
-      ca_p -= tp;
-      ca_c += Rrel_t * tp;
-    }
-    // rotational spring (rotational/springs.jl:5-38), explicit at (x2, q2)
-    if (jd.spring_r != 0.0 && jd.nfree_r > 0) {
-      V3 rv = rotation_vector(g.qr);
-      V3 force = v3zero();
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (i < jd.nfree_r) {
-          V3 a = ld3(jd.Ar + 3 * i);
-          force += (-jd.spring_r * (jd.spring_off_r[i] - dot(a, rv))) * a;
-        }
-      V3 tp = P.h * (Roff * force);
-      ca_p += tp;
-      ca_c -= Rrel_t * tp;
-    }
-    // impulse maps at the current configuration (joints/joint.jl:67-93, joints/impulses.jl:4-7): 6 x n
-    for (int side = 0; side < 2; ++side) {
-      const bool par = (side == 0);
-      if (par && jd.parent < 0) continue;
-      double* G = A + (par ? jd.Gp_off : jd.Lc_off);
-      const double sgn = par ? 1.0 : -1.0;  // the child block stores L = -G directly
-      const M33& X = par ? g.Xp : g.Xc;
-      const M33& Qt = par ? g.Qtp : g.Qtc;
-      const M33& Qr = par ? g.Qrp : g.Qrc;
-      const int n = jd.n;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < jd.nl_t) {  // translational lambda column i
-          V3 ci = ld3(jd.Ct + 3 * i);
-          V3 f = tmul(X, ci), t = 0.5 * tmul(Qt, ci);
-          int col = i;
-          G[0 * n + col] = sgn * f.x; G[1 * n + col] = sgn * f.y; G[2 * n + col] = sgn * f.z;
-          G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
-        }
-        if (i < jd.nb2_r) {  // limit duals: s columns are zero, gamma_upper = -A', gamma_lower = +A'
-          V3 ai = ld3(jd.Ar + 3 * i);
-          V3 t = 0.5 * tmul(Qr, ai);
-          int cs_u = jd.row_r + i, cs_l = jd.row_r + jd.nb2_r + i;
-          int cu = jd.row_r + jd.nb_r + i, cl = jd.row_r + jd.nb_r + jd.nb2_r + i;
-#pragma unroll
-          for (int r = 0; r < 6; ++r) { G[r * n + cs_u] = 0.0; G[r * n + cs_l] = 0.0; }
-          G[0 * n + cu] = 0.0; G[1 * n + cu] = 0.0; G[2 * n + cu] = 0.0;
-          G[3 * n + cu] = -sgn * t.x; G[4 * n + cu] = -sgn * t.y; G[5 * n + cu] = -sgn * t.z;
-          G[0 * n + cl] = 0.0; G[1 * n + cl] = 0.0; G[2 * n + cl] = 0.0;
-          G[3 * n + cl] = sgn * t.x; G[4 * n + cl] = sgn * t.y; G[5 * n + cl] = sgn * t.z;
-        }
-        if (i < jd.nl_r) {  // rotational lambda column i
-          V3 ci = ld3(jd.Cr + 3 * i);
-          V3 t = 0.5 * tmul(Qr, ci);
-          int col = jd.row_r + 2 * jd.nb_r + i;
-          G[0 * n + col] = 0.0; G[1 * n + col] = 0.0; G[2 * n + col] = 0.0;
-          G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
-        }
-      }
+  __syncthreads();
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_BODY) {  // constant part of the discrete Euler-Lagrange residual (integrators/constraint.jl:14-25)
+      const BodyDev& bd = P.bodies[idx];
+      const double* so = A + P.sol_off + bd.sol_off;
+      V3 v15 = ld3(so), w15 = ld3(so + 3);
+      M33 J = ldm33(bd.J);
+      V3 F = v3zero(), tau = v3zero();
+      if (fext) { F = ld3(fext + 6 * idx); tau = ld3(fext + 6 * idx + 3); }
+      V3 g = ld3(P.g);
+      V3 lin = (-bd.mass) * v15 - P.h * (bd.mass * g + F);
+      double n0 = 0.5 * P.h * sqrt(4.0 / (P.h * P.h) - dot(w15, w15));
+      V3 Jw = J * w15;
+      V3 ang = (-1.0) * (n0 * Jw - (0.5 * P.h) * cross(w15, Jw)) - P.h * tau;
+      st3(A + bd.cst_off, lin);
+      st3(A + bd.cst_off + 3, ang);
+    } else if (role.type[p] == ROLE_JOINT) {
+      prologue_joint(c, idx, u);
+    } else {  // reset! + initialize! (contacts/constraints.jl:79-86, solver/initialization.jl:7-48)
+      double* so = A + P.sol_off + P.contacts[idx].sol_off;
+      const double v0 = 1.0 + 0.5 * 1.0 * 1.0 / (1.0 + 1e-20);  // neutral (1,1,0,0) pushed to 1.5 by the Mehrotra-style start
+      so[0] = v0; so[1] = v0; so[2] = 0.0; so[3] = 0.0;
+      so[4] = v0; so[5] = v0; so[6] = 0.0; so[7] = 0.0;
     }
   }
-  __syncwarp();
-  // cst -= [JF2; Jtau2] + spring impulses (child side first: one parent joint per body, then coloured parent sides)
-  if (jact) {
-    const BodyDev& bc = P.bodies[jchild];
-    double* cst = A + bc.cst_off;
-    add3(cst, -cl_c);
-    add3(cst + 3, -ca_c);
+  __syncthreads();
+  // cst -= [JF2; Jtau2] + spring impulses, gathered per body in a fixed order
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0 || role.type[p] != ROLE_BODY) continue;
+    const BodyDev& bd = P.bodies[idx];
+    double* cst = A + bd.cst_off;
+    for (int g = 0; g < bd.g_cnt; ++g) {
+      const int so = P.ilist[bd.g_off + g];
+      if (so >= P.mat_off) continue;  // contact slots carry nothing in the prologue (joint slots sit below mat_off)
+      const double* s = A + so;
+      add3(cst, -ld3(s));
+      add3(cst + 3, -ld3(s + 3));
+    }
   }
-  __syncwarp();
-  DJ_COLOR_LOOP(max_child_color, jcolor, jact && jparent >= 0, {
-    double* cst = A + P.bodies[jparent].cst_off;
-    add3(cst, -cl_p);
-    add3(cst + 3, -ca_p);
-  })
-  // reset! + initialize! (joints/constraints.jl:440-448, contacts/constraints.jl:79-86, solver/initialization.jl:7-48)
-  if (jact) {
-    const JointDev& jd = P.joints[lane];
-    double* so = A + P.sol_off + jd.sol_off;
-    for (int i = 0; i < jd.n; ++i) so[i] = 0.0;
-    for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.row_r + i] = 1.0;
-  }
-  if (lane < P.Ni) {
-    const ContactDev& cd = P.contacts[lane];
-    double* so = A + P.sol_off + cd.sol_off;
-    // neutral vector (1,1,0,0) pushed by the Mehrotra-style initialisation: 1 + 0.5 * 1 * 1 / (1 + 1e-20) = 1.5
-    const double v0 = 1.0 + 0.5 * 1.0 * 1.0 / (1.0 + 1e-20);
-    so[0] = v0; so[1] = v0; so[2] = 0.0; so[3] = 0.0;
-    so[4] = v0; so[5] = v0; so[6] = 0.0; so[7] = 0.0;
-  }
-  __syncwarp();
-  (void)max_contact_color;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -301,416 +337,437 @@ DJ_BIG void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
 // Residual entries are written to `res` (= rhs when assembling, = sav during the line search, whose saved
 // residual is dead at that point).  Returns the residual / bilinear violations (solver/violations.jl).
 // ------------------------------------------------------------------------------------------------------------
-template <bool JAC>
-DJ_BIG void evaluate(Ctx& c, double f, int res_off, int max_child_color, int max_contact_color, double& rvio, double& bvio) {
+DJ_DEV void eval_body(Ctx& c, const bool JAC, int idx, double f, double* res) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int lane = c.lane;
-  double* res = A + res_off;
+  const BodyDev& bd = P.bodies[idx];
+  Kin k = body_kin(c, idx, f);
+  M33 J = ldm33(bd.J);
+  const double* cst = A + bd.cst_off;
+  double m0 = 0.5 * P.h * sqrt(4.0 / (P.h * P.h) - dot(k.w, k.w));
+  V3 Jw = J * k.w;
+  V3 dlin = bd.mass * k.v + ld3(cst);
+  V3 dang = m0 * Jw + (0.5 * P.h) * cross(k.w, Jw) + ld3(cst + 3);
+  st3(res + bd.sol_off, -dlin);
+  st3(res + bd.sol_off + 3, -dang);
+  if (JAC) {
+    double* D = A + bd.D_off;
+    D[0] = bd.mass + kReg; D[7] = bd.mass + kReg; D[14] = bd.mass + kReg;
+    V3 dm0 = (-(0.25 * P.h * P.h) / m0) * k.w;
+    M33 dR = outer(Jw, dm0) + m0 * J + (0.5 * P.h) * (skew(k.w) * J - skew(Jw));
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] = dR.m[i][j] + (i == j ? kReg : 0.0);
+  }
+}
+
+// contacts (contacts/nonlinear.jl:50-97, contacts/contact.jl:37-155, collisions/sphere_halfspace.jl)
+DJ_DEV void eval_contact(Ctx& c, const bool JAC, int idx, double f, double* res, double& rv, double& bv) {
+  const Plan& P = *c.P;
+  double* A = c.A;
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
-  double rv = 0.0, bv = 0.0;
-
-  if (JAC) {  // all KKT blocks are rewritten: zero the matrix region cooperatively, then scatter the non-zeros
-    for (int t = lane; t < P.mat_len; t += 32) A[P.mat_off + t] = 0.0;
-    __syncwarp();
+  const ContactDev& cd = P.contacts[idx];
+  V3 F = v3zero(), tau = v3zero();
+  M33 KE = m33zero();
+  {
+  Kin k = body_kin(c, cd.body, f);
+  double s[4], g[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[i] = sol[cd.sol_off + i];
+    g[i] = sol[cd.sol_off + 4 + i];
+    if (f != 0.0) { s[i] += f * dl[cd.sol_off + i]; g[i] += f * dl[cd.sol_off + 4 + i]; }
   }
+  V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3), o = ld3(cd.o), off = ld3(cd.off);
+  V3 ow = k.R3 * o;
+  V3 rc = ow - off - cd.radius * n;
+  double phi = dot(n, k.x3 + ow - off) - cd.radius;
+  V3 ww = k.R3 * k.w;
+  V3 vc = k.v + cross(ww, rc);
+  double r4 = phi - s[0];
+  double r5 = cd.mu * g[0] - g[1];
+  double r6 = dot(t0, vc) - s[2];
+  double r7 = dot(t1, vc) - s[3];
+  double c0 = g[0] * s[0];
+  double c1 = g[1] * s[1] + g[2] * s[2] + g[3] * s[3];
+  double c2 = g[1] * s[2] + s[1] * g[2];
+  double c3 = g[1] * s[3] + s[1] * g[3];
+  rv = nanmax(nanmax(fabs(r4), fabs(r5)), nanmax(fabs(r6), fabs(r7)));
+  bv = nanmax(nanmax(fabs(c0), fabs(c1)), nanmax(fabs(c2), fabs(c3)));
+  double* rr = res + cd.sol_off;
+  rr[0] = -(c0 - c.mu); rr[1] = -(c1 - c.mu); rr[2] = -c2; rr[3] = -c3;
+  rr[4] = -r4; rr[5] = -r5; rr[6] = -r6; rr[7] = -r7;
+  F = g[0] * n + g[2] * t0 + g[3] * t1;
+  tau = tmul(k.R3, cross(rc, F));
+  if (JAC) {
+    double* D = A + cd.D_off;
+    double g0 = g[0] + kReg, g1 = g[1] + kReg, s0 = s[0] + kReg, s1 = s[1] + kReg;
+    D[0 * 8 + 0] = g0; D[0 * 8 + 4] = s0;
+    D[1 * 8 + 1] = g1; D[1 * 8 + 2] = g[2]; D[1 * 8 + 3] = g[3];
+    D[2 * 8 + 1] = g[2]; D[2 * 8 + 2] = g1;
+    D[3 * 8 + 1] = g[3]; D[3 * 8 + 3] = g1;
+    D[1 * 8 + 5] = s1; D[1 * 8 + 6] = s[2]; D[1 * 8 + 7] = s[3];
+    D[2 * 8 + 5] = s[2]; D[2 * 8 + 6] = s1;
+    D[3 * 8 + 5] = s[3]; D[3 * 8 + 7] = s1;
+    D[4 * 8 + 0] = -1.0; D[6 * 8 + 2] = -1.0; D[7 * 8 + 3] = -1.0;
+    D[5 * 8 + 4] = cd.mu; D[5 * 8 + 5] = -1.0;
+    // U (4 x 6) = rows 4..7 of the contact's row block [0; constraint_jacobian_velocity]: local rows 0, 2, 3
+    double* U = A + cd.U_off;
+    M33 R3so = k.R3 * skew(o);
+    V3 nphi = (-2.0) * vtmul(n, R3so);       // n' * (-2 R3 skew(o))
+    V3 r4w = vtmul(nphi, k.E);
+    U[0 * 6 + 0] = P.h * n.x; U[0 * 6 + 1] = P.h * n.y; U[0 * 6 + 2] = P.h * n.z;
+    U[0 * 6 + 3] = r4w.x; U[0 * 6 + 4] = r4w.y; U[0 * 6 + 5] = r4w.z;
+    M33 dvc_dw = (-1.0) * (skew(rc) * k.R3);
+    M33 dvc_dd = 2.0 * (skew(rc) * (k.R3 * skew(k.w))) - 2.0 * (skew(ww) * R3so);
+    M33 W = dvc_dw + dvc_dd * k.E;
+    V3 r6w = vtmul(t0, W), r7w = vtmul(t1, W);
+    U[2 * 6 + 0] = t0.x; U[2 * 6 + 1] = t0.y; U[2 * 6 + 2] = t0.z;
+    U[2 * 6 + 3] = r6w.x; U[2 * 6 + 4] = r6w.y; U[2 * 6 + 5] = r6w.z;
+    U[3 * 6 + 0] = t1.x; U[3 * 6 + 1] = t1.y; U[3 * 6 + 2] = t1.z;
+    U[3 * 6 + 3] = r7w.x; U[3 * 6 + 4] = r7w.y; U[3 * 6 + 5] = r7w.z;
+    // L (6 x 8) = [0 | -G], G = [X; R3' skew(rc) X], X = [n' 0 t0' t1']
+    double* L = A + cd.L_off;
+    V3 qn = tmul(k.R3, cross(rc, n)), q0 = tmul(k.R3, cross(rc, t0)), q1 = tmul(k.R3, cross(rc, t1));
+    L[0 * 8 + 4] = -n.x; L[1 * 8 + 4] = -n.y; L[2 * 8 + 4] = -n.z; L[3 * 8 + 4] = -qn.x; L[4 * 8 + 4] = -qn.y; L[5 * 8 + 4] = -qn.z;
+    L[0 * 8 + 6] = -t0.x; L[1 * 8 + 6] = -t0.y; L[2 * 8 + 6] = -t0.z; L[3 * 8 + 6] = -q0.x; L[4 * 8 + 6] = -q0.y; L[5 * 8 + 6] = -q0.z;
+    L[0 * 8 + 7] = -t1.x; L[1 * 8 + 7] = -t1.y; L[2 * 8 + 7] = -t1.z; L[3 * 8 + 7] = -q1.x; L[4 * 8 + 7] = -q1.y; L[5 * 8 + 7] = -q1.z;
+    // d(G gamma)/d attitude, torque rows only: 2 skew(tau) + 2 R3' skew(F) R3 skew(o)
+    M33 K = 2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so));
+    KE = K * k.E;
+  }
+  }
+  write_slot(A + cd.slot, F, tau, KE);
+}
 
-  // ---- bodies (integrators/constraint.jl:1-66)
-  if (lane < P.Nb) {
-    const BodyDev& bd = P.bodies[lane];
-    Kin k = body_kin(c, lane, f);
-    M33 J = ldm33(bd.J);
-    const double* cst = A + bd.cst_off;
-    double m0 = 0.5 * P.h * sqrt(4.0 / (P.h * P.h) - dot(k.w, k.w));
-    V3 Jw = J * k.w;
-    V3 dlin = bd.mass * k.v + ld3(cst);
-    V3 dang = m0 * Jw + (0.5 * P.h) * cross(k.w, Jw) + ld3(cst + 3);
-    st3(res + bd.sol_off, -dlin);
-    st3(res + bd.sol_off + 3, -dang);
+// joints (joints/constraints.jl:114-299, joints/joint.jl, joints/limits.jl, rotational/dampers.jl)
+DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, double& rv, double& bv) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const double* sol = A + P.sol_off;
+  const double* dl = A + P.rhs_off;
+  const JointDev& jd = P.joints[idx];
+  V3 fl_p = v3zero(), fa_p = v3zero(), fl_c = v3zero(), fa_c = v3zero();  // G * eta (+ damper impulses)
+  M33 Kaa = m33zero(), Kcc = m33zero();                                     // damper d(tau)/d(w) on the diagonal blocks
+  bool has_damper = false;
+  (void)has_damper;
+  {
+    Kin ka = body_kin(c, jd.parent, f), kb = body_kin(c, jd.child, f);
+  JointGeom g = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
+  const int n = jd.n;
+  double* rr = res + jd.sol_off;
+  const double* so = sol + jd.sol_off;
+  const double* dd = dl + jd.sol_off;
+  double* Uc = A + jd.Uc_off;
+  double* Up = (jd.parent >= 0) ? A + jd.Up_off : nullptr;
+  double* D = A + jd.D_off;
+  // translational equality rows: C_t e_t
+  V3 QEp = v3zero();
+  M33 QtpE, QtcE, QrpE, QrcE;
+  if (JAC) { QtpE = g.Qtp * ka.E; QtcE = g.Qtc * kb.E; QrpE = g.Qrp * ka.E; QrcE = g.Qrc * kb.E; }
+  (void)QEp;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nl_t) {
+      V3 ci = ld3(jd.Ct + 3 * i);
+      double gi = dot(ci, g.et);
+      rr[i] = -gi;
+      rv = nanmax(rv, fabs(gi));
+      if (JAC) {
+        D[i * n + i] = kReg;
+        V3 ux = P.h * vtmul(ci, g.Xc), uw = vtmul(ci, QtcE);
+        st3(Uc + i * 6, ux); st3(Uc + i * 6 + 3, uw);
+        if (Up) {
+          V3 px = P.h * vtmul(ci, g.Xp), pw = vtmul(ci, QtpE);
+          st3(Up + i * 6, px); st3(Up + i * 6 + 3, pw);
+        }
+      }
+    }
+  }
+  // rotational limits: rows [s.gamma - mu (Nb); s_u - (hi - theta); s_l - (theta - lo)]
+  if (jd.nb2_r > 0) {
+    V3 rvq = rotation_vector(g.qr);
+    M33 Tp, Tc;
     if (JAC) {
-      double* D = A + bd.D_off;
-      D[0] = bd.mass + kReg; D[7] = bd.mass + kReg; D[14] = bd.mass + kReg;
-      V3 dm0 = (-(0.25 * P.h * P.h) / m0) * k.w;
-      M33 dR = outer(Jw, dm0) + m0 * J + (0.5 * P.h) * (skew(k.w) * J - skew(Jw));
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] = dR.m[i][j] + (i == j ? kReg : 0.0);
+      rotvec_attitude_jacobians(jd, g, Tp, Tc);
+      Tp = Tp * ka.E;
+      Tc = Tc * kb.E;
     }
-  }
-  __syncwarp();
-
-  // ---- contacts (contacts/nonlinear.jl:50-97, contacts/contact.jl:37-155, collisions/sphere_halfspace.jl)
-  {
-    const bool act = lane < P.Ni;
-    V3 F = v3zero(), tau = v3zero();
-    M33 KE = m33zero();
-    int body = 0, color = 0;
-    if (act) {
-      const ContactDev& cd = P.contacts[lane];
-      body = cd.body; color = cd.color;
-      Kin k = body_kin(c, cd.body, f);
-      double s[4], g[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        s[i] = sol[cd.sol_off + i];
-        g[i] = sol[cd.sol_off + 4 + i];
-        if (f != 0.0) { s[i] += f * dl[cd.sol_off + i]; g[i] += f * dl[cd.sol_off + 4 + i]; }
-      }
-      V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3), o = ld3(cd.o), off = ld3(cd.off);
-      V3 ow = k.R3 * o;
-      V3 rc = ow - off - cd.radius * n;
-      double phi = dot(n, k.x3 + ow - off) - cd.radius;
-      V3 ww = k.R3 * k.w;
-      V3 vc = k.v + cross(ww, rc);
-      double r4 = phi - s[0];
-      double r5 = cd.mu * g[0] - g[1];
-      double r6 = dot(t0, vc) - s[2];
-      double r7 = dot(t1, vc) - s[3];
-      double c0 = g[0] * s[0];
-      double c1 = g[1] * s[1] + g[2] * s[2] + g[3] * s[3];
-      double c2 = g[1] * s[2] + s[1] * g[2];
-      double c3 = g[1] * s[3] + s[1] * g[3];
-      rv = nanmax(nanmax(fabs(r4), fabs(r5)), nanmax(fabs(r6), fabs(r7)));
-      bv = nanmax(nanmax(fabs(c0), fabs(c1)), nanmax(fabs(c2), fabs(c3)));
-      double* rr = res + cd.sol_off;
-      rr[0] = -(c0 - c.mu); rr[1] = -(c1 - c.mu); rr[2] = -c2; rr[3] = -c3;
-      rr[4] = -r4; rr[5] = -r5; rr[6] = -r6; rr[7] = -r7;
-      F = g[0] * n + g[2] * t0 + g[3] * t1;
-      tau = tmul(k.R3, cross(rc, F));
-      if (JAC) {
-        double* D = A + cd.D_off;
-        double g0 = g[0] + kReg, g1 = g[1] + kReg, s0 = s[0] + kReg, s1 = s[1] + kReg;
-        D[0 * 8 + 0] = g0; D[0 * 8 + 4] = s0;
-        D[1 * 8 + 1] = g1; D[1 * 8 + 2] = g[2]; D[1 * 8 + 3] = g[3];
-        D[2 * 8 + 1] = g[2]; D[2 * 8 + 2] = g1;
-        D[3 * 8 + 1] = g[3]; D[3 * 8 + 3] = g1;
-        D[1 * 8 + 5] = s1; D[1 * 8 + 6] = s[2]; D[1 * 8 + 7] = s[3];
-        D[2 * 8 + 5] = s[2]; D[2 * 8 + 6] = s1;
-        D[3 * 8 + 5] = s[3]; D[3 * 8 + 7] = s1;
-        D[4 * 8 + 0] = -1.0; D[6 * 8 + 2] = -1.0; D[7 * 8 + 3] = -1.0;
-        D[5 * 8 + 4] = cd.mu; D[5 * 8 + 5] = -1.0;
-        // U (4 x 6) = rows 4..7 of the contact's row block [0; constraint_jacobian_velocity]: local rows 0, 2, 3
-        double* U = A + cd.U_off;
-        M33 R3so = k.R3 * skew(o);
-        V3 nphi = (-2.0) * vtmul(n, R3so);       // n' * (-2 R3 skew(o))
-        V3 r4w = vtmul(nphi, k.E);
-        U[0 * 6 + 0] = P.h * n.x; U[0 * 6 + 1] = P.h * n.y; U[0 * 6 + 2] = P.h * n.z;
-        U[0 * 6 + 3] = r4w.x; U[0 * 6 + 4] = r4w.y; U[0 * 6 + 5] = r4w.z;
-        M33 dvc_dw = (-1.0) * (skew(rc) * k.R3);
-        M33 dvc_dd = 2.0 * (skew(rc) * (k.R3 * skew(k.w))) - 2.0 * (skew(ww) * R3so);
-        M33 W = dvc_dw + dvc_dd * k.E;
-        V3 r6w = vtmul(t0, W), r7w = vtmul(t1, W);
-        U[2 * 6 + 0] = t0.x; U[2 * 6 + 1] = t0.y; U[2 * 6 + 2] = t0.z;
-        U[2 * 6 + 3] = r6w.x; U[2 * 6 + 4] = r6w.y; U[2 * 6 + 5] = r6w.z;
-        U[3 * 6 + 0] = t1.x; U[3 * 6 + 1] = t1.y; U[3 * 6 + 2] = t1.z;
-        U[3 * 6 + 3] = r7w.x; U[3 * 6 + 4] = r7w.y; U[3 * 6 + 5] = r7w.z;
-        // L (6 x 8) = [0 | -G], G = [X; R3' skew(rc) X], X = [n' 0 t0' t1']
-        double* L = A + cd.L_off;
-        V3 qn = tmul(k.R3, cross(rc, n)), q0 = tmul(k.R3, cross(rc, t0)), q1 = tmul(k.R3, cross(rc, t1));
-        L[0 * 8 + 4] = -n.x; L[1 * 8 + 4] = -n.y; L[2 * 8 + 4] = -n.z; L[3 * 8 + 4] = -qn.x; L[4 * 8 + 4] = -qn.y; L[5 * 8 + 4] = -qn.z;
-        L[0 * 8 + 6] = -t0.x; L[1 * 8 + 6] = -t0.y; L[2 * 8 + 6] = -t0.z; L[3 * 8 + 6] = -q0.x; L[4 * 8 + 6] = -q0.y; L[5 * 8 + 6] = -q0.z;
-        L[0 * 8 + 7] = -t1.x; L[1 * 8 + 7] = -t1.y; L[2 * 8 + 7] = -t1.z; L[3 * 8 + 7] = -q1.x; L[4 * 8 + 7] = -q1.y; L[5 * 8 + 7] = -q1.z;
-        // d(G gamma)/d attitude, torque rows only: 2 skew(tau) + 2 R3' skew(F) R3 skew(o)
-        M33 K = 2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so));
-        KE = K * k.E;
-      }
-    }
-    __syncwarp();
-    DJ_COLOR_LOOP(max_contact_color, color, act, {
-      const BodyDev& bd = P.bodies[body];
-      add3(res + bd.sol_off, F);
-      add3(res + bd.sol_off + 3, tau);
-      if (JAC) {
-        double* D = A + bd.D_off;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] -= KE.m[i][j];
-      }
-    })
-  }
-
-  // ---- joints (joints/constraints.jl:114-299, joints/joint.jl, joints/limits.jl, rotational/dampers.jl)
-  {
-    const bool act = lane < P.Ne;
-    V3 fl_p = v3zero(), fa_p = v3zero(), fl_c = v3zero(), fa_c = v3zero();  // G * eta (+ damper impulses)
-    M33 Kaa = m33zero(), Kcc = m33zero();                                     // damper d(tau)/d(w) on the diagonal blocks
-    int jparent = -1, jchild = 0, jcolor = 0;
-    bool has_damper = false;
-    if (act) {
-      const JointDev& jd = P.joints[lane];
-      jparent = jd.parent; jchild = jd.child; jcolor = jd.color_parent;
-      Kin ka = body_kin(c, jd.parent, f), kb = body_kin(c, jd.child, f);
-      JointGeom g = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
-      const int n = jd.n;
-      double* rr = res + jd.sol_off;
-      const double* so = sol + jd.sol_off;
-      const double* dd = dl + jd.sol_off;
-      double* Uc = A + jd.Uc_off;
-      double* Up = (jd.parent >= 0) ? A + jd.Up_off : nullptr;
-      double* D = A + jd.D_off;
-      // translational equality rows: C_t e_t
-      V3 QEp = v3zero();
-      M33 QtpE, QtcE, QrpE, QrcE;
-      if (JAC) { QtpE = g.Qtp * ka.E; QtcE = g.Qtc * kb.E; QrpE = g.Qrp * ka.E; QrcE = g.Qrc * kb.E; }
-      (void)QEp;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < jd.nl_t) {
-          V3 ci = ld3(jd.Ct + 3 * i);
-          double gi = dot(ci, g.et);
-          rr[i] = -gi;
-          rv = nanmax(rv, fabs(gi));
-          if (JAC) {
-            D[i * n + i] = kReg;
-            V3 ux = P.h * vtmul(ci, g.Xc), uw = vtmul(ci, QtcE);
-            st3(Uc + i * 6, ux); st3(Uc + i * 6 + 3, uw);
-            if (Up) {
-              V3 px = P.h * vtmul(ci, g.Xp), pw = vtmul(ci, QtpE);
-              st3(Up + i * 6, px); st3(Up + i * 6 + 3, pw);
-            }
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nb2_r) {
+        V3 ai = ld3(jd.Ar + 3 * i);
+        double th = dot(ai, rvq);
+        const int is_u = jd.row_r + i, is_l = jd.row_r + jd.nb2_r + i;
+        const int ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+        double su = so[is_u], sl = so[is_l], gu = so[ig_u], gl = so[ig_l];
+        if (f != 0.0) { su += f * dd[is_u]; sl += f * dd[is_l]; gu += f * dd[ig_u]; gl += f * dd[ig_l]; }
+        bv = nanmax(bv, nanmax(fabs(su * gu), fabs(sl * gl)));
+        rr[is_u] = -(su * gu - c.mu);
+        rr[is_l] = -(sl * gl - c.mu);
+        rr[ig_u] = -(su - (jd.hi[i] - th));   // slack rows sit after the Nb complementarity rows
+        rr[ig_l] = -(sl - (th - jd.lo[i]));
+        if (JAC) {
+          D[is_u * n + is_u] = gu + kReg; D[is_u * n + ig_u] = su + kReg;
+          D[is_l * n + is_l] = gl + kReg; D[is_l * n + ig_l] = sl + kReg;
+          D[ig_u * n + is_u] = 1.0;
+          D[ig_l * n + is_l] = 1.0;
+          V3 tc = vtmul(ai, Tc);
+          st3(Uc + ig_u * 6 + 3, tc);
+          st3(Uc + ig_l * 6 + 3, -tc);
+          if (Up) {
+            V3 tp = vtmul(ai, Tp);
+            st3(Up + ig_u * 6 + 3, tp);
+            st3(Up + ig_l * 6 + 3, -tp);
           }
         }
       }
-      // rotational limits: rows [s.gamma - mu (Nb); s_u - (hi - theta); s_l - (theta - lo)]
-      if (jd.nb2_r > 0) {
-        V3 rvq = rotation_vector(g.qr);
-        M33 Tp, Tc;
-        if (JAC) {
-          rotvec_attitude_jacobians(jd, g, Tp, Tc);
-          Tp = Tp * ka.E;
-          Tc = Tc * kb.E;
-        }
+    }
+  }
+  // rotational equality rows: C_r vec(qr)
+  V3 er = qvec(g.qr);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nl_r) {
+      V3 ci = ld3(jd.Cr + 3 * i);
+      const int row = jd.row_r + 2 * jd.nb_r + i;
+      double gi = dot(ci, er);
+      rr[row] = -gi;
+      rv = nanmax(rv, fabs(gi));
+      if (JAC) {
+        D[row * n + row] = kReg;
+        st3(Uc + row * 6 + 3, vtmul(ci, QrcE));
+        if (Up) st3(Up + row * 6 + 3, vtmul(ci, QrpE));
+      }
+    }
+  }
+  // impulses on the two bodies: G * eta with the pristine maps (child: Lc = -G_c, parent: Gp)
+  {
+    const double* Lc = A + jd.Lc_off;
+    const double* Gp = (jd.parent >= 0) ? A + jd.Gp_off : nullptr;
+    double ac[6] = {0, 0, 0, 0, 0, 0}, ap[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      double e = so[i];
+      if (f != 0.0) e += f * dd[i];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        ac[r] -= Lc[r * n + i] * e;
+        if (Gp) ap[r] += Gp[r * n + i] * e;
+      }
+    }
+    fl_c = v3(ac[0], ac[1], ac[2]); fa_c = v3(ac[3], ac[4], ac[5]);
+    fl_p = v3(ap[0], ap[1], ap[2]); fa_p = v3(ap[3], ap[4], ap[5]);
+    if (JAC && Gp) {  // parent-side lower block is consumed by the factorisation: refresh it from the pristine copy
+      double* Lp = A + jd.Lp_off;
+      for (int i = 0; i < 6 * n; ++i) Lp[i] = -Gp[i];
+    }
+  }
+  // rotational damper (rotational/dampers.jl:4-27,66-84; rotational/minimal.jl:103-118,151-174)
+  if (jd.damper_r != 0.0 && jd.nfree_r > 0) {
+    has_damper = true;
+    Quat r = qmul(qinv(ka.q2), kb.q2);           // relative orientation at the current step
+    Quat ma = qmap(ka.w, P.h), mb = qmap(kb.w, P.h);
+    Quat left = qmul(mb, qconj(r));               // w = mb (x) r^-1 (x) conj(ma) (x) r   (unit r)
+    left = qmul(mb, qinv(r));
+    Quat rest = qmul(qmul(qinv(r), qconj(ma)), r);
+    Quat wq = qmul(mb, rest);
+    V3 rvd = rotation_vector(wq);
+    M33 AtA = m33zero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < jd.nfree_r) { V3 a = ld3(jd.Ar + 3 * i); AtA = AtA + outer(a, a); }
+    M33 Roff = rotmat(ldq(jd.qoff));
+    M33 Rr = rotmat(r);
+    M33 B = jd.damper_r * (Roff * AtA);
+    V3 ta = B * rvd;
+    V3 tb = (-1.0) * tmul(Rr, ta);
+    fa_p += ta;  // d -= damper_impulses  =>  res += impulses
+    fa_c += tb;
+    if (JAC) {
+      M34 drv = drotation_vector_dq(wq);
+      M33 dwa, dwb;  // d rotvec / d w_a, d w_b
+      double m0a = ma.s, m0b = mb.s;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        V3 ek = v3(kx == 0 ? 1.0 : 0.0, kx == 1 ? 1.0 : 0.0, kx == 2 ? 1.0 : 0.0);
+        Quat dmb = Quat{-(0.25 * P.h * P.h) * comp(kb.w, kx) / m0b, 0.5 * P.h * ek.x, 0.5 * P.h * ek.y, 0.5 * P.h * ek.z};
+        Quat dma = Quat{-(0.25 * P.h * P.h) * comp(ka.w, kx) / m0a, 0.5 * P.h * ek.x, 0.5 * P.h * ek.y, 0.5 * P.h * ek.z};
+        Quat cb = qmul(dmb, rest);
+        Quat ca = qmul(qmul(left, qconj(dma)), r);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          if (i < jd.nb2_r) {
-            V3 ai = ld3(jd.Ar + 3 * i);
-            double th = dot(ai, rvq);
-            const int is_u = jd.row_r + i, is_l = jd.row_r + jd.nb2_r + i;
-            const int ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-            double su = so[is_u], sl = so[is_l], gu = so[ig_u], gl = so[ig_l];
-            if (f != 0.0) { su += f * dd[is_u]; sl += f * dd[is_l]; gu += f * dd[ig_u]; gl += f * dd[ig_l]; }
-            bv = nanmax(bv, nanmax(fabs(su * gu), fabs(sl * gl)));
-            rr[is_u] = -(su * gu - c.mu);
-            rr[is_l] = -(sl * gl - c.mu);
-            rr[ig_u] = -(su - (jd.hi[i] - th));   // slack rows sit after the Nb complementarity rows
-            rr[ig_l] = -(sl - (th - jd.lo[i]));
-            if (JAC) {
-              D[is_u * n + is_u] = gu + kReg; D[is_u * n + ig_u] = su + kReg;
-              D[is_l * n + is_l] = gl + kReg; D[is_l * n + ig_l] = sl + kReg;
-              D[ig_u * n + is_u] = 1.0;
-              D[ig_l * n + is_l] = 1.0;
-              V3 tc = vtmul(ai, Tc);
-              st3(Uc + ig_u * 6 + 3, tc);
-              st3(Uc + ig_l * 6 + 3, -tc);
-              if (Up) {
-                V3 tp = vtmul(ai, Tp);
-                st3(Up + ig_u * 6 + 3, tp);
-                st3(Up + ig_l * 6 + 3, -tp);
-              }
-            }
-          }
+          dwb.m[i][kx] = drv.m[i][0] * cb.s + drv.m[i][1] * cb.x + drv.m[i][2] * cb.y + drv.m[i][3] * cb.z;
+          dwa.m[i][kx] = drv.m[i][0] * ca.s + drv.m[i][1] * ca.x + drv.m[i][2] * ca.y + drv.m[i][3] * ca.z;
         }
       }
-      // rotational equality rows: C_r vec(qr)
-      V3 er = qvec(g.qr);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < jd.nl_r) {
-          V3 ci = ld3(jd.Cr + 3 * i);
-          const int row = jd.row_r + 2 * jd.nb_r + i;
-          double gi = dot(ci, er);
-          rr[row] = -gi;
-          rv = nanmax(rv, fabs(gi));
-          if (JAC) {
-            D[row * n + row] = kReg;
-            st3(Uc + row * 6 + 3, vtmul(ci, QrcE));
-            if (Up) st3(Up + row * 6 + 3, vtmul(ci, QrpE));
-          }
-        }
-      }
-      // impulses on the two bodies: G * eta with the pristine maps (child: Lc = -G_c, parent: Gp)
-      {
-        const double* Lc = A + jd.Lc_off;
-        const double* Gp = (jd.parent >= 0) ? A + jd.Gp_off : nullptr;
-        double ac[6] = {0, 0, 0, 0, 0, 0}, ap[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < n; ++i) {
-          double e = so[i];
-          if (f != 0.0) e += f * dd[i];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            ac[r] -= Lc[r * n + i] * e;
-            if (Gp) ap[r] += Gp[r * n + i] * e;
-          }
-        }
-        fl_c = v3(ac[0], ac[1], ac[2]); fa_c = v3(ac[3], ac[4], ac[5]);
-        fl_p = v3(ap[0], ap[1], ap[2]); fa_p = v3(ap[3], ap[4], ap[5]);
-        if (JAC && Gp) {  // parent-side lower block is consumed by the factorisation: refresh it from the pristine copy
-          double* Lp = A + jd.Lp_off;
-          for (int i = 0; i < 6 * n; ++i) Lp[i] = -Gp[i];
-        }
-      }
-      // rotational damper (rotational/dampers.jl:4-27,66-84; rotational/minimal.jl:103-118,151-174)
-      if (jd.damper_r != 0.0 && jd.nfree_r > 0) {
-        has_damper = true;
-        Quat r = qmul(qinv(ka.q2), kb.q2);           // relative orientation at the current step
-        Quat ma = qmap(ka.w, P.h), mb = qmap(kb.w, P.h);
-        Quat left = qmul(mb, qconj(r));               // w = mb (x) r^-1 (x) conj(ma) (x) r   (unit r)
-        left = qmul(mb, qinv(r));
-        Quat rest = qmul(qmul(qinv(r), qconj(ma)), r);
-        Quat wq = qmul(mb, rest);
-        V3 rvd = rotation_vector(wq);
-        M33 AtA = m33zero();
+      M33 Ka = B * dwa, Kb = B * dwb;              // d tau_a / d w_a, d tau_a / d w_b
+      M33 Rrt = transpose(Rr);
+      Kaa = Ka;                                    // D_parent -= Ka
+      Kcc = (-1.0) * (Rrt * Kb);                   // d tau_b / d w_b ; D_child -= Kcc
+      if (jd.parent >= 0 && jd.BBpc_off >= 0) {
+        double* Bpc = A + jd.BBpc_off;
+        double* Bcp = A + jd.BBcp_off;
+        M33 Kca = (-1.0) * (Rrt * Ka);             // d tau_b / d w_a
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          if (i < jd.nfree_r) { V3 a = ld3(jd.Ar + 3 * i); AtA = AtA + outer(a, a); }
-        M33 Roff = rotmat(ldq(jd.qoff));
-        M33 Rr = rotmat(r);
-        M33 B = jd.damper_r * (Roff * AtA);
-        V3 ta = B * rvd;
-        V3 tb = (-1.0) * tmul(Rr, ta);
-        fa_p += ta;  // d -= damper_impulses  =>  res += impulses
-        fa_c += tb;
-        if (JAC) {
-          M34 drv = drotation_vector_dq(wq);
-          M33 dwa, dwb;  // d rotvec / d w_a, d w_b
-          double m0a = ma.s, m0b = mb.s;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            V3 ek = v3(kx == 0 ? 1.0 : 0.0, kx == 1 ? 1.0 : 0.0, kx == 2 ? 1.0 : 0.0);
-            Quat dmb = Quat{-(0.25 * P.h * P.h) * comp(kb.w, kx) / m0b, 0.5 * P.h * ek.x, 0.5 * P.h * ek.y, 0.5 * P.h * ek.z};
-            Quat dma = Quat{-(0.25 * P.h * P.h) * comp(ka.w, kx) / m0a, 0.5 * P.h * ek.x, 0.5 * P.h * ek.y, 0.5 * P.h * ek.z};
-            Quat cb = qmul(dmb, rest);
-            Quat ca = qmul(qmul(left, qconj(dma)), r);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              dwb.m[i][kx] = drv.m[i][0] * cb.s + drv.m[i][1] * cb.x + drv.m[i][2] * cb.y + drv.m[i][3] * cb.z;
-              dwa.m[i][kx] = drv.m[i][0] * ca.s + drv.m[i][1] * ca.x + drv.m[i][2] * ca.y + drv.m[i][3] * ca.z;
-            }
+          for (int j2 = 0; j2 < 3; ++j2) {
+            Bpc[(3 + i) * 6 + 3 + j2] = -Kb.m[i][j2];
+            Bcp[(3 + i) * 6 + 3 + j2] = -Kca.m[i][j2];
           }
-          M33 Ka = B * dwa, Kb = B * dwb;              // d tau_a / d w_a, d tau_a / d w_b
-          M33 Rrt = transpose(Rr);
-          Kaa = Ka;                                    // D_parent -= Ka
-          Kcc = (-1.0) * (Rrt * Kb);                   // d tau_b / d w_b ; D_child -= Kcc
-          if (jd.parent >= 0 && jd.BBpc_off >= 0) {
-            double* Bpc = A + jd.BBpc_off;
-            double* Bcp = A + jd.BBcp_off;
-            M33 Kca = (-1.0) * (Rrt * Ka);             // d tau_b / d w_a
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j2 = 0; j2 < 3; ++j2) {
-                Bpc[(3 + i) * 6 + 3 + j2] = -Kb.m[i][j2];
-                Bcp[(3 + i) * 6 + 3 + j2] = -Kca.m[i][j2];
-              }
-          }
-        }
       }
     }
-    __syncwarp();
-    if (act) {  // child side: exactly one parent joint per body
-      const BodyDev& bc = P.bodies[jchild];
-      add3(res + bc.sol_off, fl_c);
-      add3(res + bc.sol_off + 3, fa_c);
-      if (JAC && has_damper) {
-        double* D = A + bc.D_off;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) D[(3 + i) * 6 + 3 + j2] -= Kcc.m[i][j2];
-      }
-    }
-    __syncwarp();
-    DJ_COLOR_LOOP(max_child_color, jcolor, act && jparent >= 0, {
-      const BodyDev& bp = P.bodies[jparent];
-      add3(res + bp.sol_off, fl_p);
-      add3(res + bp.sol_off + 3, fa_p);
-      if (JAC && has_damper) {
-        double* D = A + bp.D_off;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) D[(3 + i) * 6 + 3 + j2] -= Kaa.m[i][j2];
-      }
-    })
   }
-  // body residual norms (all contributions are in)
-  if (lane < P.Nb) {
-    const double* rb = res + P.bodies[lane].sol_off;
+  }
+  write_slot(A + jd.slot_c, fl_c, fa_c, Kcc);
+  if (jd.parent >= 0) write_slot(A + jd.slot_p, fl_p, fa_p, Kaa);
+}
+
+DJ_DEV void evaluate(Ctx& c, const bool JAC, double f, int res_off, double& rvio, double& bvio) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  double* res = A + res_off;
+  const WarpRole& role = P.roles[c.warp];
+  double rv = 0.0, bv = 0.0;
+  if (JAC) {  // all KKT blocks are rewritten: zero the matrix region cooperatively, then scatter the non-zeros
+    for (int t = c.tid; t < P.mat_len; t += c.nthreads) A[P.mat_off + t] = 0.0;
+    __syncthreads();
+  }
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_BODY) eval_body(c, JAC, idx, f, res);
+    else if (role.type[p] == ROLE_CONTACT) eval_contact(c, JAC, idx, f, res, rv, bv);
+    else eval_joint(c, JAC, idx, f, res, rv, bv);
+  }
+  __syncthreads();
+  // gather the impulse contributions of the incident joints / contacts into the body rows (fixed order)
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0 || role.type[p] != ROLE_BODY) continue;
+    const BodyDev& bd = P.bodies[idx];
+    double* rb = res + bd.sol_off;
+    double* D = A + bd.D_off;
+    for (int g = 0; g < bd.g_cnt; ++g) {
+      const double* s = A + P.ilist[bd.g_off + g];
+      add3(rb, ld3(s));
+      add3(rb + 3, ld3(s + 3));
+      if (JAC) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] -= s[6 + 3 * i + j];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 6; ++i) rv = nanmax(rv, fabs(rb[i]));
   }
-  rvio = warp_nanmax(rv);
-  bvio = warp_nanmax(bv);
+  block_nanmax2(c, rv, bv);
+  rvio = rv;
+  bvio = bv;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Block LDU (GraphBasedSystems.ldu_factorization! / ldu_backsubstitution!)
+// Block LDU (GraphBasedSystems.ldu_factorization! / ldu_backsubstitution!), phase-parallel over the warps
 // ------------------------------------------------------------------------------------------------------------
-DJ_BIG bool factorize(Ctx& c) {
+DJ_DEV bool factorize(Ctx& c) {
   const Plan& P = *c.P;
   double* A = c.A;
   bool ok = true;
-  for (int s = 0; s < P.nsteps; ++s) {
-    const ElimStep& st = P.steps[s];
-    double* Dc = A + st.d_off;
-    ok = block_inverse(Dc, st.n, st.n, c.lane) && ok;                                                  // D_c <- D_c^-1
-    for (int i = 0; i < st.nnb; ++i) right_multiply_inplace(A + st.nb[i].L_off, Dc, st.nb[i].n, st.n, c.lane);  // L~_ic = M_ic D_c^-1
-    for (int i = 0; i < st.nnb; ++i)
-      for (int j = 0; j < st.nnb; ++j)                                                                  // M_ij -= L~_ic M_cj
-        schur_update(A + st.tgt[i][j], A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
-                     st.nb[j].n, c.lane);
+  for (int ph = 0; ph < P.nphase; ++ph) {
+    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    for (int s = s0; s < s0 + sn; ++s) {
+      const ElimStep& st = P.steps[s];
+      double* Dc = A + st.d_off;
+      if (st.fold_cnt > 0) {  // fold the children's scratch updates into D_c
+        for (int t = c.lane; t < st.n * st.n; t += 32) {
+          double acc = Dc[t];
+          for (int k = 0; k < st.fold_cnt; ++k) acc += A[P.ilist[st.fold_off + k] + t];
+          Dc[t] = acc;
+        }
+        __syncwarp();
+      }
+      ok = block_inverse(Dc, st.n, st.n, c.lane) && ok;                                                  // D_c <- D_c^-1
+      for (int i = 0; i < st.nnb; ++i) right_multiply_inplace(A + st.nb[i].L_off, Dc, st.nb[i].n, st.n, c.lane);  // L~_ic = M_ic D_c^-1
+      for (int i = 0; i < st.nnb; ++i)
+        for (int j = 0; j < st.nnb; ++j)                                                                  // M_ij -= L~_ic M_cj
+          schur_update(A + st.tgt[i][j], A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
+                       st.nb[j].n, c.lane);
+    }
+    __syncthreads();
   }
-  return ok;
+  return __syncthreads_and(ok ? 1 : 0) != 0;
 }
 
 // x <- KKT^{-1} x for the vector at arena offset vec_off (solution ordering)
-DJ_BIG void solve(Ctx& c, int vec_off) {
+DJ_DEV void solve(Ctx& c, int vec_off) {
   const Plan& P = *c.P;
   double* A = c.A;
   double* x = A + vec_off;
   const int lane = c.lane;
   const int half = lane >> 4, li = lane & 15;
-  for (int s = 0; s < P.nsteps; ++s) {  // forward: z_i -= L~_ic z_c   (lanes [0,16) serve nb[0], [16,32) nb[1])
-    const ElimStep& st = P.steps[s];
-    const double* xc = x + st.vec_off;
-    if (half < st.nnb && li < st.nb[half].n) {
-      const ElimNb& nb = st.nb[half];
-      const double* L = A + nb.L_off;
-      double acc = 0.0;
-      for (int k = 0; k < st.n; ++k) acc += L[li * st.n + k] * xc[k];
-      x[nb.vec_off + li] -= acc;
-    }
-    __syncwarp();
-  }
-  for (int s = P.nsteps - 1; s >= 0; --s) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
-    const ElimStep& st = P.steps[s];
-    const double* Dc = A + st.d_off;
-    double* xc = x + st.vec_off;
-    if (st.nnb > 0) {
-      if (lane < st.n) {
-        double acc = 0.0;
-        for (int j = 0; j < st.nnb; ++j) {
-          const ElimNb& nb = st.nb[j];
-          int r = lane - nb.U_row;
-          if (r >= 0 && r < nb.U_k) {
-            const double* U = A + nb.U_off;
-            const double* xj = x + nb.vec_off;
-            for (int k = 0; k < nb.n; ++k) acc += U[r * nb.n + k] * xj[k];
+  for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c   (lanes [0,16) serve nb[0], [16,32) nb[1])
+    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    for (int s = s0; s < s0 + sn; ++s) {
+      const ElimStep& st = P.steps[s];
+      double* xc = x + st.vec_off;
+      if (st.fold_cnt > 0) {  // fold (and clear) the children's forward updates of this body
+        if (lane < st.n) {
+          double acc = xc[lane];
+          for (int k = 0; k < st.fold_cnt; ++k) {
+            double* v = A + P.ilist[st.fold_off + k] + 36;
+            acc += v[lane];
+            v[lane] = 0.0;
           }
+          xc[lane] = acc;
         }
-        xc[lane] -= acc;
+        __syncwarp();
+      }
+      if (half < st.nnb && li < st.nb[half].n) {
+        const ElimNb& nb = st.nb[half];
+        const double* L = A + nb.L_off;
+        double acc = 0.0;
+        for (int k = 0; k < st.n; ++k) acc += L[li * st.n + k] * xc[k];
+        double* tgt = nb.fwd_abs >= 0 ? A + nb.fwd_abs : x + nb.vec_off;
+        tgt[li] -= acc;
       }
       __syncwarp();
     }
-    double acc = 0.0;
-    if (lane < st.n)
-      for (int k = 0; k < st.n; ++k) acc += Dc[lane * st.n + k] * xc[k];
-    __syncwarp();
-    if (lane < st.n) xc[lane] = acc;
-    __syncwarp();
+    __syncthreads();
+  }
+  for (int ph = P.nphase - 1; ph >= 0; --ph) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
+    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    for (int s = s0 + sn - 1; s >= s0; --s) {
+      const ElimStep& st = P.steps[s];
+      const double* Dc = A + st.d_off;
+      double* xc = x + st.vec_off;
+      if (st.nnb > 0) {
+        if (lane < st.n) {
+          double acc = 0.0;
+          for (int j = 0; j < st.nnb; ++j) {
+            const ElimNb& nb = st.nb[j];
+            int r = lane - nb.U_row;
+            if (r >= 0 && r < nb.U_k) {
+              const double* U = A + nb.U_off;
+              const double* xj = x + nb.vec_off;
+              for (int k = 0; k < nb.n; ++k) acc += U[r * nb.n + k] * xj[k];
+            }
+          }
+          xc[lane] -= acc;
+        }
+        __syncwarp();
+      }
+      double acc = 0.0;
+      if (lane < st.n)
+        for (int k = 0; k < st.n; ++k) acc += Dc[lane * st.n + k] * xc[k];
+      __syncwarp();
+      if (lane < st.n) xc[lane] = acc;
+      __syncwarp();
+    }
+    __syncthreads();
   }
 }
 
@@ -734,23 +791,27 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
   const Plan& P = *c.P;
   const double* sol = c.A + P.sol_off;
   const double* dl = c.A + P.rhs_off;
+  const WarpRole& role = P.roles[c.warp];
   double a = 1.0;
-  if (c.lane < P.Ni) {
-    const ContactDev& cd = P.contacts[c.lane];
-    const double* s = sol + cd.sol_off;
-    const double* g = s + 4;
-    const double* ds = dl + cd.sol_off;
-    const double* dg = ds + 4;
-    a = fmin(a, ort_step(s[0], ds[0], tau_ort));
-    a = fmin(a, ort_step(g[0], dg[0], tau_ort));
-    a = fmin(a, soc_step(s[1], s[2], s[3], ds[1], ds[2], ds[3], tau_soc));
-    a = fmin(a, soc_step(g[1], g[2], g[3], dg[1], dg[2], dg[3], tau_soc));
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_CONTACT) {
+      const ContactDev& cd = P.contacts[idx];
+      const double* s = sol + cd.sol_off;
+      const double* g = s + 4;
+      const double* ds = dl + cd.sol_off;
+      const double* dg = ds + 4;
+      a = fmin(a, ort_step(s[0], ds[0], tau_ort));
+      a = fmin(a, ort_step(g[0], dg[0], tau_ort));
+      a = fmin(a, soc_step(s[1], s[2], s[3], ds[1], ds[2], ds[3], tau_soc));
+      a = fmin(a, soc_step(g[1], g[2], g[3], dg[1], dg[2], dg[3], tau_soc));
+    } else if (role.type[p] == ROLE_JOINT) {
+      const JointDev& jd = P.joints[idx];
+      for (int i = 0; i < 2 * jd.nb_r; ++i) a = fmin(a, ort_step(sol[jd.sol_off + jd.row_r + i], dl[jd.sol_off + jd.row_r + i], tau_ort));
+    }
   }
-  if (c.lane < P.Ne) {
-    const JointDev& jd = P.joints[c.lane];
-    for (int i = 0; i < 2 * jd.nb_r; ++i) a = fmin(a, ort_step(sol[jd.sol_off + jd.row_r + i], dl[jd.sol_off + jd.row_r + i], tau_ort));
-  }
-  return warp_min(a);
+  return block_min(c, a);
 }
 
 // centering! (solver/centering.jl:1-48)
@@ -758,27 +819,31 @@ DJ_DEV void centering(Ctx& c, double aaff, double& nu, double& nuaff) {
   const Plan& P = *c.P;
   const double* sol = c.A + P.sol_off;
   const double* dl = c.A + P.rhs_off;
+  const WarpRole& role = P.roles[c.warp];
   double sn = 0.0, sa = 0.0, cnt = 0.0;
-  if (c.lane < P.Ni) {
-    const ContactDev& cd = P.contacts[c.lane];
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_CONTACT) {
+      const ContactDev& cd = P.contacts[idx];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double s = sol[cd.sol_off + i], g = sol[cd.sol_off + 4 + i];
-      sn += s * g;
-      sa += (s + aaff * dl[cd.sol_off + i]) * (g + aaff * dl[cd.sol_off + 4 + i]);
+      for (int i = 0; i < 4; ++i) {
+        double s = sol[cd.sol_off + i], g = sol[cd.sol_off + 4 + i];
+        sn += s * g;
+        sa += (s + aaff * dl[cd.sol_off + i]) * (g + aaff * dl[cd.sol_off + 4 + i]);
+      }
+      cnt += 2.0;  // cone_degree(NonlinearContact) (contacts/nonlinear.jl:101)
+    } else if (role.type[p] == ROLE_JOINT) {
+      const JointDev& jd = P.joints[idx];
+      for (int i = 0; i < jd.nb_r; ++i) {
+        int is = jd.sol_off + jd.row_r + i, ig = is + jd.nb_r;
+        sn += sol[is] * sol[ig];
+        sa += (sol[is] + aaff * dl[is]) * (sol[ig] + aaff * dl[ig]);
+      }
+      cnt += (double)jd.nb_r;
     }
-    cnt += 2.0;  // cone_degree(NonlinearContact) (contacts/nonlinear.jl:101)
   }
-  if (c.lane < P.Ne) {
-    const JointDev& jd = P.joints[c.lane];
-    for (int i = 0; i < jd.nb_r; ++i) {
-      int is = jd.sol_off + jd.row_r + i, ig = is + jd.nb_r;
-      sn += sol[is] * sol[ig];
-      sa += (sol[is] + aaff * dl[is]) * (sol[ig] + aaff * dl[ig]);
-    }
-    cnt += (double)jd.nb_r;
-  }
-  sn = warp_sum(sn); sa = warp_sum(sa); cnt = warp_sum(cnt);
+  block_sum3(c, sn, sa, cnt);
   nu = sn / cnt;
   nuaff = sa / cnt;
 }
@@ -788,99 +853,115 @@ DJ_DEV void correction(Ctx& c) {
   const Plan& P = *c.P;
   const double* dl = c.A + P.rhs_off;
   double* sav = c.A + P.sav_off;
-  if (c.lane < P.Ni) {
-    const ContactDev& cd = P.contacts[c.lane];
-    const double* ds = dl + cd.sol_off;
-    const double* dg = ds + 4;
-    double* r = sav + cd.sol_off;
-    r[0] += -ds[0] * dg[0] + c.mu;
-    r[1] += -(ds[1] * dg[1] + ds[2] * dg[2] + ds[3] * dg[3]) + c.mu;
-    r[2] += -(ds[1] * dg[2] + dg[1] * ds[2]);
-    r[3] += -(ds[1] * dg[3] + dg[1] * ds[3]);
-  }
-  if (c.lane < P.Ne) {
-    const JointDev& jd = P.joints[c.lane];
-    for (int i = 0; i < jd.nb_r; ++i) {
-      int is = jd.sol_off + jd.row_r + i;
-      sav[is] += -dl[is] * dl[is + jd.nb_r] + c.mu;
+  const WarpRole& role = P.roles[c.warp];
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_CONTACT) {
+      const ContactDev& cd = P.contacts[idx];
+      const double* ds = dl + cd.sol_off;
+      const double* dg = ds + 4;
+      double* r = sav + cd.sol_off;
+      r[0] += -ds[0] * dg[0] + c.mu;
+      r[1] += -(ds[1] * dg[1] + ds[2] * dg[2] + ds[3] * dg[3]) + c.mu;
+      r[2] += -(ds[1] * dg[2] + dg[1] * ds[2]);
+      r[3] += -(ds[1] * dg[3] + dg[1] * ds[3]);
+    } else if (role.type[p] == ROLE_JOINT) {
+      const JointDev& jd = P.joints[idx];
+      for (int i = 0; i < jd.nb_r; ++i) {
+        int is = jd.sol_off + jd.row_r + i;
+        sav[is] += -dl[is] * dl[is + jd.nb_r] + c.mu;
+      }
     }
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // mehrotra! (solver/mehrotra.jl:9-73).  Returns the status code; *iters = Newton iterations taken.
 // ------------------------------------------------------------------------------------------------------------
-DJ_DEV int mehrotra(Ctx& c, const Options& o, int mcc, int mkc, int* iters) {
+DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int lane = c.lane;
   int status = 1;
   c.mu = 0.0;
   double mutarget = 0.0;
   int no_progress = 0;
   double undercut = o.undercut;
-  double rvio, bvio;
-  evaluate<true>(c, 0.0, P.rhs_off, mcc, mkc, rvio, bvio);
+  double rvio = 0.0, bvio = 0.0;
   int ndone = 0;
-  for (int n = 1; n <= o.max_iter; ++n) {
-    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
-    ndone = n;
-    // affine direction (Quirk Q3: the rhs was assembled with the previous mutarget)
-    for (int t = lane; t < P.nres; t += 32) A[P.sav_off + t] = A[P.rhs_off + t];  // pull_residual!
-    __syncwarp();
-    if (!factorize(c)) { status = 3; break; }
-    solve(c, P.rhs_off);
-    double aaff = cone_line_search(c, 0.95, 0.95);
-    double nu, nuaff;
-    centering(c, aaff, nu, nuaff);
-    double ratio = nuaff / (nu + 1e-20);
-    double sig = (ratio != ratio) ? ratio : fmin(fmax(ratio, 0.0), 1.0);
-    sig = sig * sig * sig;
-    double sn = sig * nu;
-    mutarget = (sn != sn) ? sn : fmax(sn, o.btol / undercut);
-    c.mu = mutarget;
-    correction(c);
-    for (int t = lane; t < P.nres; t += 32) A[P.rhs_off + t] = A[P.sav_off + t];  // push_residual!
-    __syncwarp();
-    solve(c, P.rhs_off);
-    double mx = fmax(rvio, bvio);
-    double tau = fmax(0.95, 1.0 - mx * mx);
-    double alpha = cone_line_search(c, tau, fmin(tau, 0.95));
-    // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
-    double rv = 0.0, bv = 0.0, fsel = alpha;
-    {
-      double fk = alpha;
-      for (int k = 0; k < o.max_ls; ++k) {
-        fsel = fk;
-        evaluate<false>(c, fk, P.sav_off, mcc, mkc, rv, bv);
-        if ((rv > rvio) && (bv > bvio)) fk *= 0.5;
-        else break;
-      }
-    }
-    bool made = (!(rv < o.rtol) && (rv < 0.8 * rvio)) || (!(bv < o.btol) && (bv < 0.8 * bvio));
-    no_progress = made ? max(no_progress - 1, 0) : no_progress + 1;
-    rvio = rv; bvio = bv;
-    if (no_progress >= o.no_progress_max) undercut *= o.no_progress_undercut;
-    // update! : commit the accepted candidate (with the angular-velocity clip of candidate_step!)
-    {
+  // The loop is written so that every large routine (evaluate, factorize, solve, cone_line_search) has exactly ONE call
+  // site: the kernel is instruction-cache bound, duplicated inlined bodies cost more than the extra control flow.
+  //   mode 0: set_entries! at the current iterate (first pass: also yields the initial violations)
+  //   mode 1: line-search trial at sol + fk * delta
+  int mode = 0;
+  double fk = 0.0, fsel = 0.0;
+  int ls_k = 0;
+  bool first = true;
+  for (;;) {
+    double rv, bv;
+    DJ_TICK(c, t_misc)
+    evaluate(c, mode == 0, fk, mode == 0 ? P.rhs_off : P.sav_off, rv, bv);
+    if (mode == 0) DJ_TICK(c, t_eval_jac) else DJ_TICK(c, t_eval_ls)
+    if (mode == 1) {
+      // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
+      fsel = fk;
+      if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) { fk *= 0.5; ls_k += 1; continue; }
+      bool made = (!(rv < o.rtol) && (rv < 0.8 * rvio)) || (!(bv < o.btol) && (bv < 0.8 * bvio));
+      no_progress = made ? max(no_progress - 1, 0) : no_progress + 1;
+      rvio = rv; bvio = bv;
+      if (no_progress >= o.no_progress_max) undercut *= o.no_progress_undercut;
+      // update! : commit the accepted candidate (with the angular-velocity clip of candidate_step!)
       double* sol = A + P.sol_off;
       const double* dl = A + P.rhs_off;
       if (fsel != 0.0) {
-        for (int t = lane; t < P.nres; t += 32) sol[t] += fsel * dl[t];
-        __syncwarp();
-        if (lane < P.Nb) {
-          double* w = sol + P.bodies[lane].sol_off + 3;
+        for (int t = c.tid; t < P.nres; t += c.nthreads) sol[t] += fsel * dl[t];
+        __syncthreads();
+        if (c.tid < P.Nb) {
+          double* w = sol + P.bodies[c.tid].sol_off + 3;
           double wmax = 3.9 / (P.h * P.h);
           double wd = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
           if (wd > wmax) { double k = wmax / wd; w[0] *= k; w[1] *= k; w[2] *= k; }
         }
-        __syncwarp();
+        __syncthreads();
+      }
+      mode = 0; fk = 0.0;
+      continue;  // set_entries! at the new iterate (mu = mutarget)
+    }
+    // mode 0: the system is assembled
+    if (first) { rvio = rv; bvio = bv; first = false; }
+    if ((rvio != rvio) || (bvio != bvio)) { status = 3; break; }
+    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
+    if (ndone >= o.max_iter) break;
+    ndone += 1;
+    for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.sav_off + t] = A[P.rhs_off + t];  // pull_residual!
+    __syncthreads();
+    DJ_TICK(c, t_misc)
+    if (!factorize(c)) { status = 3; break; }
+    DJ_TICK(c, t_fact)
+    double alpha = 1.0;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: affine direction (Quirk Q3: rhs carries the previous mutarget); pass 1: corrected
+      DJ_TICK(c, t_misc)
+      solve(c, P.rhs_off);
+      DJ_TICK(c, t_solve)
+      double mx = fmax(rvio, bvio);
+      double tau = (pass == 0) ? 0.95 : fmax(0.95, 1.0 - mx * mx);
+      alpha = cone_line_search(c, tau, fmin(tau, 0.95));
+      if (pass == 0) {
+        double nu, nuaff;
+        centering(c, alpha, nu, nuaff);
+        double ratio = nuaff / (nu + 1e-20);
+        double sig = (ratio != ratio) ? ratio : fmin(fmax(ratio, 0.0), 1.0);
+        sig = sig * sig * sig;
+        double sn = sig * nu;
+        mutarget = (sn != sn) ? sn : fmax(sn, o.btol / undercut);
+        c.mu = mutarget;
+        correction(c);
+        for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.rhs_off + t] = A[P.sav_off + t];  // push_residual!
+        __syncthreads();
       }
     }
-    double r2, b2;
-    evaluate<true>(c, 0.0, P.rhs_off, mcc, mkc, r2, b2);  // set_entries! at the new iterate (mu = mutarget)
-    if ((rvio != rvio) || (bvio != bvio)) { status = 3; break; }
+    mode = 1; fk = alpha; ls_k = 0;
   }
   *iters = ndone;
   return status;

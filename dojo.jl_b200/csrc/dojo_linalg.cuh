@@ -73,6 +73,51 @@ DJ_LA bool block_inverse_t(double* A, int ld, int lane) {
   return ok;
 }
 
+// n <= 16 fallback: embed the block into a 16 x 16 matrix padded with the identity
+DJ_DEV bool block_inverse_pad16(double* A, int n, int ld, int lane) {
+  double a[16];
+  const bool left = lane < 16;
+  const int col = lane & 15;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) a[r] = left ? ((r < n && col < n) ? A[r * ld + col] : (r == col ? 1.0 : 0.0)) : (r == col ? 1.0 : 0.0);
+  bool ok = true;
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) {
+    int p = 0;
+    double best = -1.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double v = fabs(a[r]);
+      if (r >= k && v > best) { best = v; p = r; }
+    }
+    p = __shfl_sync(0xffffffffu, p, k);
+    best = __shfl_sync(0xffffffffu, best, k);
+    if (!(best > 0.0) || !(best < 1e300)) ok = false;
+    double ak = 0.0, ap = 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { if (r == k) ak = a[r]; if (r == p) ap = a[r]; }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { if (r == k) a[r] = ap; else if (r == p) a[r] = ak; }
+    double piv = __shfl_sync(0xffffffffu, ap, k);
+    double akk = ap * (1.0 / piv);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double f = __shfl_sync(0xffffffffu, a[r], k);
+      a[r] = (r == k) ? akk : a[r] - f * akk;
+    }
+  }
+  __syncwarp();
+  if (!left && col < n) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < n) A[r * ld + col] = a[r];
+  }
+  __syncwarp();
+  return ok;
+}
+
+// Runtime-size fallback: the augmented matrix lives in registers of a 16-column template; only used for block
+// sizes outside the specialised set below.
 DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
   switch (n) {
     case 1: return block_inverse_t<1>(A, ld, lane);
@@ -81,17 +126,10 @@ DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
     case 4: return block_inverse_t<4>(A, ld, lane);
     case 5: return block_inverse_t<5>(A, ld, lane);
     case 6: return block_inverse_t<6>(A, ld, lane);
-    case 7: return block_inverse_t<7>(A, ld, lane);
     case 8: return block_inverse_t<8>(A, ld, lane);
     case 9: return block_inverse_t<9>(A, ld, lane);
-    case 10: return block_inverse_t<10>(A, ld, lane);
-    case 11: return block_inverse_t<11>(A, ld, lane);
-    case 12: return block_inverse_t<12>(A, ld, lane);
-    case 13: return block_inverse_t<13>(A, ld, lane);
-    case 14: return block_inverse_t<14>(A, ld, lane);
-    case 15: return block_inverse_t<15>(A, ld, lane);
-    case 16: return block_inverse_t<16>(A, ld, lane);
-    default: return false;
+    case 7: return block_inverse_t<7>(A, ld, lane);
+    default: return block_inverse_pad16(A, n, ld, lane);
   }
 }
 

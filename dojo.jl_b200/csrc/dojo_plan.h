@@ -1,12 +1,24 @@
 // dojo_plan.h -- flattened, device-resident description of one mechanism ("plan").
 // Built once on the host in dojo_create() from the DojoMechanismDesc (include/dojo_b200.h), read-only on
 // the device.  All *_off fields are offsets (in doubles) into the per-environment shared-memory arena.
+//
+// Execution model: one CTA (nw warps) owns one environment.
+//   * assembly / residual evaluation: warps take ROLES (bodies, contacts, joints), one lane per node; per-node
+//     contributions to body rows go through 15-double "slots" that the body lanes gather in a fixed order
+//     (deterministic floating-point summation order, no atomics);
+//   * block LDU: elimination steps are grouped in PHASES by height in the elimination tree; the steps of one
+//     phase are independent (updates of a parent body go to a per-joint scratch record that the parent folds in
+//     when its own turn comes) and are spread over the warps; one CTA barrier separates phases.
 #pragma once
 #include <stdint.h>
 
 namespace dj {
 
 constexpr double kReg = 1.0e-10;  // REG, src/Dojo.jl:4
+constexpr int kSlot = 15;         // contribution record: force(3) torque(3) K(3x3)
+constexpr int kScratch = 42;      // parent-update scratch record: S(6x6) v(6)
+
+enum RoleType { ROLE_BODY = 0, ROLE_CONTACT = 1, ROLE_JOINT = 2 };
 
 struct BodyDev {
   double mass;
@@ -15,6 +27,7 @@ struct BodyDev {
   int st_off;   // x2(3), q2(4)
   int cst_off;  // constant part of the dynamics residual for this step (6)
   int D_off;    // 6x6 diagonal block
+  int g_off, g_cnt;  // gather list (Plan::ilist): arena offsets of the slots contributing to this body, fixed order
 };
 
 struct JointDev {
@@ -32,7 +45,8 @@ struct JointDev {
   int Up_off, Lp_off, Gp_off;   // same for the parent body (-1 when the parent is the origin); Lp is consumed by the
                                 // factorisation and refreshed from the pristine impulse map Gp at every assembly
   int BBpc_off, BBcp_off;       // (parent,child) / (child,parent) 6x6 blocks, -1 without dampers
-  int color_parent;             // index of this joint among its parent's child joints
+  int slot_c, slot_p;           // contribution slots for the child / parent body (slot_p = -1 for the origin)
+  int S_off;                    // scratch record receiving this joint's (and its child body's) updates of the parent body
 };
 
 struct ContactDev {
@@ -40,12 +54,13 @@ struct ContactDev {
   double mu, radius;
   double n[3], t[6], o[3], off[3];
   int D_off, U_off, L_off;  // 8x8 ; (contact,body) rows 4..7: 4x6 ; (body,contact) 6x8
-  int color;                // index among the contacts of the same body
+  int slot;
 };
 
 // One elimination step of the block LDU (GraphBasedSystems ldu_factorization!)
 struct ElimNb {
   int n, vec_off;   // neighbour dimension / offset of its entry in the solution-ordered vectors
+  int fwd_abs;      // >= 0: absolute arena offset that receives the forward-substitution update instead of vec_off (scratch v)
   int L_off;        // M_{nb,c}: n_nb x n_c   (overwritten by M_{nb,c} * Dinv_c)
   int U_off, U_k;   // M_{c,nb}: rows [U_row, U_row + U_k) of c, U_k x n_nb (never written by the factorisation)
   int U_row;
@@ -54,19 +69,29 @@ struct ElimStep {
   int d_off, n, vec_off;
   int nnb;
   ElimNb nb[2];
-  int tgt[2][2];  // M_{nb_i, nb_j}
+  int tgt[2][2];           // M_{nb_i, nb_j} (the parent body's diagonal is redirected to the joint's scratch record)
+  int fold_off, fold_cnt;  // scratch records (Plan::ilist) folded into (D_c, z_c) before c is eliminated
+};
+
+struct WarpRole {
+  int npass;
+  int type[3], first[3], count[3];
 };
 
 struct Plan {
   int Nb, Ne, Ni, nres, nu, nz;
-  int nsteps;
+  int nw;       // warps per environment
+  int nphase;   // elimination phases
   double h, input_scaling, g[3];
   // arena layout (doubles)
-  int sol_off, rhs_off, sav_off, mat_off, mat_len, arena_len;  // [mat_off, mat_off + mat_len) is re-zeroed at every assembly
+  int sol_off, rhs_off, sav_off, red_off, mat_off, mat_len, arena_len;  // [mat_off, mat_off + mat_len) is re-zeroed at every assembly
   const BodyDev* bodies;
   const JointDev* joints;
   const ContactDev* contacts;
   const ElimStep* steps;
+  const int* sched;   // [nphase][nw][2] = (first step, count)
+  const int* ilist;   // gather / fold lists
+  const WarpRole* roles;  // [nw]
 };
 
 struct Options {
