@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
   c.mu = 0.0;
 #ifdef DJ_PROFILE
   c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = 0; c.t_last = clock64();
+  c.f_fold = c.f_inv = c.f_rm = c.f_schur = c.f_bar = 0;
 #endif
   const Plan& P = a.plan;
   for (;;) {
@@ -82,8 +83,20 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
     int iters = 0;
     int status = mehrotra(c, a.opts, &iters);
     epilogue(c, a.Zn + (size_t)e * P.nz, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
-    if (a.sol)
-      for (int t = c.tid; t < P.nres; t += c.nthreads) a.sol[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
+    if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
+      double* so = a.sol + (size_t)e * P.nres;
+      const int first_body = P.bodies[0].sol_off;
+      for (int t = c.tid; t < P.nres; t += c.nthreads)
+        if (t >= first_body) so[t] = c.A[P.sol_off + t];
+      if (c.tid < P.Ne) {
+        const JointDev& jd = P.joints[c.tid];
+        const double* src = c.A + P.sol_off + jd.sol_off;
+        double* dst = so + jd.sol_off;
+        for (int i = 0; i < jd.nl_t; ++i) dst[i] = src[i];
+        for (int i = 0; i < 2 * jd.nb_r; ++i) dst[jd.nl_t + i] = src[jd.ne + i];
+        for (int i = 0; i < jd.nl_r; ++i) dst[jd.nl_t + 2 * jd.nb_r + i] = src[jd.nl_t + i];
+      }
+    }
     if (c.tid == 0) {
       if (a.status) a.status[e] = status;
       if (a.iters) a.iters[e] = iters;
@@ -95,6 +108,8 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
   if (c.tid == 0 && a.prof) {
     atomicAdd(a.prof + 0, (unsigned long long)c.t_eval_jac); atomicAdd(a.prof + 1, (unsigned long long)c.t_eval_ls);
     atomicAdd(a.prof + 2, (unsigned long long)c.t_fact); atomicAdd(a.prof + 3, (unsigned long long)c.t_solve); atomicAdd(a.prof + 4, (unsigned long long)c.t_misc);
+    atomicAdd(a.prof + 5, (unsigned long long)c.f_fold); atomicAdd(a.prof + 6, (unsigned long long)c.f_inv); atomicAdd(a.prof + 7, (unsigned long long)c.f_rm);
+    atomicAdd(a.prof + 8, (unsigned long long)c.f_schur); atomicAdd(a.prof + 9, (unsigned long long)c.f_bar);
   }
 #endif
 }
@@ -202,8 +217,8 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     std::memset(&J, 0, sizeof(J));
     J.parent = jd.parent_body; J.child = jd.child_body;
     J.nl_t = jd.tra.nlambda; J.nl_r = jd.rot.nlambda; J.nb2_r = jd.rot.nlimits; J.nb_r = 2 * J.nb2_r;
-    J.row_r = J.nl_t;
-    J.n = J.nl_t + J.nl_r + 2 * J.nb_r;
+    J.ne = J.nl_t + J.nl_r;
+    J.n = J.ne + 2 * J.nb_r;
     J.sol_off = off; off += J.n;
     J.nfree_t = 3 - J.nl_t; J.nfree_r = 3 - J.nl_r;
     J.u_off = uoff; uoff += J.nfree_t + J.nfree_r;
@@ -215,7 +230,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     J.spring_r = (jd.rot.nlambda < 3) ? jd.rot.spring : 0.0;
     J.damper_r = (jd.rot.nlambda < 3) ? jd.rot.damper : 0.0;
     for (int i = 0; i < 3; ++i) { J.spring_off_r[i] = jd.rot.spring_offset[i]; J.lo[i] = jd.rot.limit_lo[i]; J.hi[i] = jd.rot.limit_hi[i]; }
-    if (J.n > 16) { delete h; return fail("joint impulse dimension > 16 is not supported"); }
+    if (J.nb2_r > 3) { delete h; return fail("too many limited axes"); }
   }
   const int nu = uoff;
   for (int b = 0; b < Nb; ++b) {
@@ -237,9 +252,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   const int nres = off;
 
   // ---- warps per environment
-  int nw = 4;
+  int nw = 2;  // measured on B200 (ant, quadruped, atlas): 2 warps per environment beat 1, 4 and 8
   if (const char* e = getenv("DOJO_B200_WARPS")) nw = atoi(e);
-  if (nw != 1 && nw != 2 && nw != 4 && nw != 8) nw = 4;
+  if (nw != 1 && nw != 2 && nw != 4 && nw != 8) nw = 2;
   h->nw = nw;
 
   // ---- arena layout: [sol | rhs | sav | reduction scratch | body state | body cst | joint slots | constant blocks |
@@ -260,28 +275,30 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     JointDev& J = joints[j];
     J.slot_c = a; a += kSlot;
     if (J.parent >= 0) { J.slot_p = a; a += kSlot; } else J.slot_p = -1;
-    J.Lc_off = a; a += 6 * J.n;
-    if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.n; } else J.Gp_off = -1;
+    J.Lc_off = a; a += 6 * J.ne;
+    if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.ne; } else J.Gp_off = -1;
+    J.lim_off = a; a += kLim * J.nb2_r;
+  }
+  for (int c = 0; c < Ni; ++c) {  // contact records survive the assembly (used by condense / recover)
+    ContactDev& C = contacts[c];
+    C.slot = a; a += kSlotC;
+    C.J_off = a; a += 24;
+    C.G_off = a; a += 24;
+    C.rec_off = a; a += 3;
   }
   P.mat_off = a;
-  for (int c = 0; c < Ni; ++c) { contacts[c].slot = a; a += kSlot; }
   for (int j = 0; j < Ne; ++j) { if (joints[j].parent >= 0) { joints[j].S_off = a; a += kScratch; } else joints[j].S_off = -1; }
   for (int b = 0; b < Nb; ++b) { bodies[b].D_off = a; a += 36; }
   for (int j = 0; j < Ne; ++j) {
     JointDev& J = joints[j];
-    J.D_off = a; a += J.n * J.n;
-    J.Uc_off = a; a += 6 * J.n;
+    J.D_off = a; a += J.ne * J.ne;
+    J.Uc_off = a; a += 6 * J.ne;
     if (J.parent >= 0) {
-      J.Up_off = a; a += 6 * J.n;
-      J.Lp_off = a; a += 6 * J.n;
-      if (J.damper_r != 0.0) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
+      J.Up_off = a; a += 6 * J.ne;
+      J.Lp_off = a; a += 6 * J.ne;
+      // body-body coupling exists with dampers and with (condensed) joint limits
+      if (J.damper_r != 0.0 || J.nb2_r > 0) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
     } else { J.Up_off = J.Lp_off = J.BBpc_off = J.BBcp_off = -1; }
-  }
-  for (int c = 0; c < Ni; ++c) {
-    ContactDev& C = contacts[c];
-    C.D_off = a; a += 64;
-    C.U_off = a; a += 24;
-    C.L_off = a; a += 48;
   }
   P.mat_len = a - P.mat_off;
   P.arena_len = a;
@@ -292,6 +309,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   for (int b = 0; b < Nb; ++b) {
     bodies[b].g_off = (int)ilist.size();
     for (int c = 0; c < Ni; ++c) if (contacts[c].body == b) ilist.push_back(contacts[c].slot);
+    bodies[b].g_ncontact = (int)ilist.size() - bodies[b].g_off;
     ilist.push_back(joints[parent_joint[b]].slot_c);
     for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(joints[j].slot_p);
     bodies[b].g_cnt = (int)ilist.size() - bodies[b].g_off;
@@ -338,18 +356,6 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
             fold.push_back(joints[j].S_off);
           }
         const BodyDev& B = bodies[b];
-        for (int c = 0; c < Ni; ++c) {
-          if (contacts[c].body != b) continue;
-          const ContactDev& C = contacts[c];
-          HStep h; std::memset(&h, 0, sizeof(h));
-          ElimStep& s = h.s;
-          s.d_off = C.D_off; s.n = 8; s.vec_off = C.sol_off; s.nnb = 1;
-          s.nb[0].n = 6; s.nb[0].vec_off = B.sol_off; s.nb[0].fwd_abs = -1; s.nb[0].L_off = C.L_off; s.nb[0].U_off = C.U_off; s.nb[0].U_k = 4; s.nb[0].U_row = 4;
-          s.tgt[0][0] = B.D_off;
-          h.height = 0; h.group = b; h.cost = 3.0;
-          hs.push_back(h);
-          hb = std::max(hb, 1);
-        }
         const JointDev& J = joints[pj[b]];
         {  // the body: neighbours = parent joint (if it has impulses) and, with dampers, the parent body
           HStep h; std::memset(&h, 0, sizeof(h));
@@ -358,9 +364,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
           s.fold_off = (int)ilist.size(); s.fold_cnt = (int)fold.size();
           for (int f : fold) ilist.push_back(f);
           int ij = -1, ip = -1;
-          if (J.n > 0) {
+          if (J.ne > 0) {
             ij = s.nnb++;
-            s.nb[ij].n = J.n; s.nb[ij].vec_off = J.sol_off; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+            s.nb[ij].n = J.ne; s.nb[ij].vec_off = J.sol_off; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
           }
           if (J.parent >= 0 && J.BBpc_off >= 0) {
             ip = s.nnb++;
@@ -370,22 +376,22 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
           if (ij >= 0) s.tgt[ij][ij] = J.D_off;
           if (ip >= 0) s.tgt[ip][ip] = J.S_off;
           if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off; s.tgt[ip][ij] = J.Lp_off; }
-          h.height = hb; h.group = -1; h.cost = 4.0 + J.n * 0.3;
+          h.height = hb; h.group = -1; h.cost = 4.0 + J.ne * 0.3;
           hs.push_back(h);
         }
         int hj = hb;
-        if (J.n > 0) {  // the parent joint: neighbour = parent body
+        if (J.ne > 0) {  // the parent joint: neighbour = parent body
           HStep h; std::memset(&h, 0, sizeof(h));
           ElimStep& s = h.s;
-          s.d_off = J.D_off; s.n = J.n; s.vec_off = J.sol_off; s.nnb = 0;
+          s.d_off = J.D_off; s.n = J.ne; s.vec_off = J.sol_off; s.nnb = 0;
           if (J.parent >= 0) {
             const BodyDev& Pb = bodies[J.parent];
             s.nnb = 1;
-            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.n; s.nb[0].U_row = 0;
+            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.ne; s.nb[0].U_row = 0;
             s.tgt[0][0] = J.S_off;
           }
           hj = hb + 1;
-          h.height = hj; h.group = -1; h.cost = 2.0 + J.n * 0.4;
+          h.height = hj; h.group = -1; h.cost = 2.0 + J.ne * 0.4;
           hs.push_back(h);
         }
         return hj;
@@ -443,7 +449,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
             upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
             upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&h->d_prof, 8 * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
@@ -479,8 +485,8 @@ extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->a
 extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
 // debugging aid (DJ_PROFILE builds): cycle counters accumulated by thread 0 of every CTA; out[5]
 extern "C" int dojo_debug_cycles(DojoHandle* h, unsigned long long* out) {
-  cudaMemcpy(out, h->d_prof, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  cudaMemset(h->d_prof, 0, 8 * sizeof(unsigned long long));
+  cudaMemcpy(out, h->d_prof, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long));
   return DOJO_OK;
 }
 

@@ -46,12 +46,15 @@ struct Ctx {
   double mu;
 #ifdef DJ_PROFILE
   long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_last;
+  long long f_fold, f_inv, f_rm, f_schur, f_bar, f_last;
 #endif
 };
 #ifdef DJ_PROFILE
 #define DJ_TICK(c, field) { long long _t = clock64(); (c).field += _t - (c).t_last; (c).t_last = _t; }
+#define DJ_FTICK(c, field) { long long _t = clock64(); (c).field += _t - (c).f_last; (c).f_last = _t; }
 #else
-#define DJ_TICK(c, field)
+#define DJ_TICK(c, field) {}
+#define DJ_FTICK(c, field) {}
 #endif
 
 // CTA-wide reductions (deterministic: per-warp shuffles, then a fixed-order combine of the nw partials)
@@ -227,7 +230,8 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
   }
   write_slot(A + jd.slot_c, cl_c, ca_c, m33zero());
   if (jd.parent >= 0) write_slot(A + jd.slot_p, cl_p, ca_p, m33zero());
-  // impulse maps at the current configuration (joints/joint.jl:67-93, joints/impulses.jl:4-7): 6 x n
+  // impulse maps at the current configuration (joints/joint.jl:67-93, joints/impulses.jl:4-7): 6 x ne for the equality
+  // multipliers; the limit duals act through +-(1/2 Qr' A_i) on the torque rows only (kept per limited axis: tP, tC)
   for (int side = 0; side < 2; ++side) {
     const bool par = (side == 0);
     if (par && jd.parent < 0) continue;
@@ -236,7 +240,7 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
     const M33& X = par ? g.Xp : g.Xc;
     const M33& Qt = par ? g.Qtp : g.Qtc;
     const M33& Qr = par ? g.Qrp : g.Qrc;
-    const int n = jd.n;
+    const int n = jd.ne;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if (i < jd.nl_t) {  // translational lambda column i
@@ -246,31 +250,23 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
         G[0 * n + col] = sgn * f.x; G[1 * n + col] = sgn * f.y; G[2 * n + col] = sgn * f.z;
         G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
       }
-      if (i < jd.nb2_r) {  // limit duals: s columns are zero, gamma_upper = -A', gamma_lower = +A'
-        V3 ai = ld3(jd.Ar + 3 * i);
-        V3 t = 0.5 * tmul(Qr, ai);
-        int cs_u = jd.row_r + i, cs_l = jd.row_r + jd.nb2_r + i;
-        int cu = jd.row_r + jd.nb_r + i, cl = jd.row_r + jd.nb_r + jd.nb2_r + i;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) { G[r * n + cs_u] = 0.0; G[r * n + cs_l] = 0.0; }
-        G[0 * n + cu] = 0.0; G[1 * n + cu] = 0.0; G[2 * n + cu] = 0.0;
-        G[3 * n + cu] = -sgn * t.x; G[4 * n + cu] = -sgn * t.y; G[5 * n + cu] = -sgn * t.z;
-        G[0 * n + cl] = 0.0; G[1 * n + cl] = 0.0; G[2 * n + cl] = 0.0;
-        G[3 * n + cl] = sgn * t.x; G[4 * n + cl] = sgn * t.y; G[5 * n + cl] = sgn * t.z;
-      }
       if (i < jd.nl_r) {  // rotational lambda column i
         V3 ci = ld3(jd.Cr + 3 * i);
         V3 t = 0.5 * tmul(Qr, ci);
-        int col = jd.row_r + 2 * jd.nb_r + i;
+        int col = jd.nl_t + i;
         G[0 * n + col] = 0.0; G[1 * n + col] = 0.0; G[2 * n + col] = 0.0;
         G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
+      }
+      if (i < jd.nb2_r) {  // G[:, gamma_upper_i] = -[0; t], G[:, gamma_lower_i] = +[0; t],  t = 1/2 Qr' A_i
+        V3 t = 0.5 * tmul(Qr, ld3(jd.Ar + 3 * i));
+        st3(A + jd.lim_off + kLim * i + (par ? 6 : 9), t);
       }
     }
   }
   // reset! (joints/constraints.jl:440-448): s = gamma = 1, lambda = 0
   double* so = A + P.sol_off + jd.sol_off;
-  for (int i = 0; i < jd.n; ++i) so[i] = 0.0;
-  for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.row_r + i] = 1.0;
+  for (int i = 0; i < jd.ne; ++i) so[i] = 0.0;
+  for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.ne + i] = 1.0;
 }
 
 DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext) {
@@ -321,10 +317,8 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
     if (idx < 0 || role.type[p] != ROLE_BODY) continue;
     const BodyDev& bd = P.bodies[idx];
     double* cst = A + bd.cst_off;
-    for (int g = 0; g < bd.g_cnt; ++g) {
-      const int so = P.ilist[bd.g_off + g];
-      if (so >= P.mat_off) continue;  // contact slots carry nothing in the prologue (joint slots sit below mat_off)
-      const double* s = A + so;
+    for (int g = bd.g_ncontact; g < bd.g_cnt; ++g) {  // joint slots only: contacts carry nothing in the prologue
+      const double* s = A + P.ilist[bd.g_off + g];
       add3(cst, -ld3(s));
       add3(cst + 3, -ld3(s + 3));
     }
@@ -337,7 +331,8 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
 // Residual entries are written to `res` (= rhs when assembling, = sav during the line search, whose saved
 // residual is dead at that point).  Returns the residual / bilinear violations (solver/violations.jl).
 // ------------------------------------------------------------------------------------------------------------
-DJ_DEV void eval_body(Ctx& c, const bool JAC, int idx, double f, double* res) {
+template <bool JAC>
+DJ_DEV void eval_body(Ctx& c, int idx, double f, double* res) {
   const Plan& P = *c.P;
   double* A = c.A;
   const BodyDev& bd = P.bodies[idx];
@@ -362,16 +357,48 @@ DJ_DEV void eval_body(Ctx& c, const bool JAC, int idx, double f, double* res) {
   }
 }
 
+// Closed-form solve of the contact diagonal block  D_c y = t  (contacts/nonlinear.jl:78-97), y = [ds(4); dgamma(4)]:
+//   rows 0-3 (complementarity): g1' ys1 + s1' yg1 = t0 ;  Arw(g') [ys2 ys3 ys4] + Arw(s') [yg2 yg3 yg4] = t1..t3
+//   rows 4-7 (constraint)     : -ys1 = t4 ; mu yg1 - yg2 = t5 ; -ys3 = t6 ; -ys4 = t7
+// with the REG-shifted s' = s + REG (1,1,0,0), g' likewise.  Three pivots: s1', s2' and p = g2' - (s3 g3 + s4 g4)/s2',
+// all positive while the iterate is strictly inside the cones (the fraction-to-boundary rule keeps it there).
+// This is the elimination of the contact node that the reference's LDU performs first (contacts are the leaves of the
+// elimination tree), done per lane in closed form instead of a pivoted 8 x 8 inverse.
+struct ContactBlock {
+  double s1, s2, s3, s4, g1, g2, g3, g4, mu;  // shifted values
+  double r_s1, r_s2, r_p;                      // reciprocals of the pivots
+};
+DJ_DEV ContactBlock contact_block(const double* s, const double* g, double mu) {
+  ContactBlock b;
+  b.s1 = s[0] + kReg; b.s2 = s[1] + kReg; b.s3 = s[2]; b.s4 = s[3];
+  b.g1 = g[0] + kReg; b.g2 = g[1] + kReg; b.g3 = g[2]; b.g4 = g[3];
+  b.mu = mu;
+  b.r_s1 = 1.0 / b.s1;
+  b.r_s2 = 1.0 / b.s2;
+  b.r_p = 1.0 / (b.g2 - (b.s3 * b.g3 + b.s4 * b.g4) * b.r_s2);
+  return b;
+}
+DJ_DEV void contact_solve(const ContactBlock& b, const double* t, double* y) {
+  const double ys1 = -t[4], ys3 = -t[6], ys4 = -t[7];
+  const double yg1 = (t[0] - b.g1 * ys1) * b.r_s1;
+  const double yg2 = b.mu * yg1 - t[5];
+  const double a3 = t[2] - b.g2 * ys3 - b.s3 * yg2;
+  const double a4 = t[3] - b.g2 * ys4 - b.s4 * yg2;
+  const double ys2 = (t[1] - b.g3 * ys3 - b.g4 * ys4 - b.s2 * yg2 - (b.s3 * a3 + b.s4 * a4) * b.r_s2) * b.r_p;
+  y[0] = ys1; y[1] = ys2; y[2] = ys3; y[3] = ys4;
+  y[4] = yg1; y[5] = yg2;
+  y[6] = (a3 - b.g3 * ys2) * b.r_s2;
+  y[7] = (a4 - b.g4 * ys2) * b.r_s2;
+}
+
 // contacts (contacts/nonlinear.jl:50-97, contacts/contact.jl:37-155, collisions/sphere_halfspace.jl)
-DJ_DEV void eval_contact(Ctx& c, const bool JAC, int idx, double f, double* res, double& rv, double& bv) {
+template <bool JAC>
+DJ_DEV void eval_contact(Ctx& c, int idx, double f, double* res, double& rv, double& bv) {
   const Plan& P = *c.P;
   double* A = c.A;
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
   const ContactDev& cd = P.contacts[idx];
-  V3 F = v3zero(), tau = v3zero();
-  M33 KE = m33zero();
-  {
   Kin k = body_kin(c, cd.body, f);
   double s[4], g[4];
 #pragma unroll
@@ -394,80 +421,102 @@ DJ_DEV void eval_contact(Ctx& c, const bool JAC, int idx, double f, double* res,
   double c1 = g[1] * s[1] + g[2] * s[2] + g[3] * s[3];
   double c2 = g[1] * s[2] + s[1] * g[2];
   double c3 = g[1] * s[3] + s[1] * g[3];
-  rv = nanmax(nanmax(fabs(r4), fabs(r5)), nanmax(fabs(r6), fabs(r7)));
-  bv = nanmax(nanmax(fabs(c0), fabs(c1)), nanmax(fabs(c2), fabs(c3)));
+  rv = nanmax(rv, nanmax(nanmax(fabs(r4), fabs(r5)), nanmax(fabs(r6), fabs(r7))));
+  bv = nanmax(bv, nanmax(nanmax(fabs(c0), fabs(c1)), nanmax(fabs(c2), fabs(c3))));
   double* rr = res + cd.sol_off;
   rr[0] = -(c0 - c.mu); rr[1] = -(c1 - c.mu); rr[2] = -c2; rr[3] = -c3;
   rr[4] = -r4; rr[5] = -r5; rr[6] = -r6; rr[7] = -r7;
-  F = g[0] * n + g[2] * t0 + g[3] * t1;
-  tau = tmul(k.R3, cross(rc, F));
+  V3 F = g[0] * n + g[2] * t0 + g[3] * t1;       // X gamma, X = [n' 0 t0' t1']
+  V3 tau = tmul(k.R3, cross(rc, F));              // R3' (rc x F)
+  st3(A + cd.slot, F);
+  st3(A + cd.slot + 3, tau);
   if (JAC) {
-    double* D = A + cd.D_off;
-    double g0 = g[0] + kReg, g1 = g[1] + kReg, s0 = s[0] + kReg, s1 = s[1] + kReg;
-    D[0 * 8 + 0] = g0; D[0 * 8 + 4] = s0;
-    D[1 * 8 + 1] = g1; D[1 * 8 + 2] = g[2]; D[1 * 8 + 3] = g[3];
-    D[2 * 8 + 1] = g[2]; D[2 * 8 + 2] = g1;
-    D[3 * 8 + 1] = g[3]; D[3 * 8 + 3] = g1;
-    D[1 * 8 + 5] = s1; D[1 * 8 + 6] = s[2]; D[1 * 8 + 7] = s[3];
-    D[2 * 8 + 5] = s[2]; D[2 * 8 + 6] = s1;
-    D[3 * 8 + 5] = s[3]; D[3 * 8 + 7] = s1;
-    D[4 * 8 + 0] = -1.0; D[6 * 8 + 2] = -1.0; D[7 * 8 + 3] = -1.0;
-    D[5 * 8 + 4] = cd.mu; D[5 * 8 + 5] = -1.0;
-    // U (4 x 6) = rows 4..7 of the contact's row block [0; constraint_jacobian_velocity]: local rows 0, 2, 3
-    double* U = A + cd.U_off;
+    // J (4 x 6): d(constraint rows)/d(v25, w25); rows (phi - s1, mu g1 - g2 [zero], vt1 - s3, vt2 - s4)
+    double* Jm = A + cd.J_off;
     M33 R3so = k.R3 * skew(o);
-    V3 nphi = (-2.0) * vtmul(n, R3so);       // n' * (-2 R3 skew(o))
+    V3 nphi = (-2.0) * vtmul(n, R3so);  // n' * (-2 R3 skew(o))
     V3 r4w = vtmul(nphi, k.E);
-    U[0 * 6 + 0] = P.h * n.x; U[0 * 6 + 1] = P.h * n.y; U[0 * 6 + 2] = P.h * n.z;
-    U[0 * 6 + 3] = r4w.x; U[0 * 6 + 4] = r4w.y; U[0 * 6 + 5] = r4w.z;
+    V3 hn = P.h * n;
     M33 dvc_dw = (-1.0) * (skew(rc) * k.R3);
     M33 dvc_dd = 2.0 * (skew(rc) * (k.R3 * skew(k.w))) - 2.0 * (skew(ww) * R3so);
-    M33 W = dvc_dw + dvc_dd * k.E;
-    V3 r6w = vtmul(t0, W), r7w = vtmul(t1, W);
-    U[2 * 6 + 0] = t0.x; U[2 * 6 + 1] = t0.y; U[2 * 6 + 2] = t0.z;
-    U[2 * 6 + 3] = r6w.x; U[2 * 6 + 4] = r6w.y; U[2 * 6 + 5] = r6w.z;
-    U[3 * 6 + 0] = t1.x; U[3 * 6 + 1] = t1.y; U[3 * 6 + 2] = t1.z;
-    U[3 * 6 + 3] = r7w.x; U[3 * 6 + 4] = r7w.y; U[3 * 6 + 5] = r7w.z;
-    // L (6 x 8) = [0 | -G], G = [X; R3' skew(rc) X], X = [n' 0 t0' t1']
-    double* L = A + cd.L_off;
+    M33 W3 = dvc_dw + dvc_dd * k.E;
+    V3 r6w = vtmul(t0, W3), r7w = vtmul(t1, W3);
+    st3(Jm + 0, hn); st3(Jm + 3, r4w);
+    st3(Jm + 6, v3zero()); st3(Jm + 9, v3zero());
+    st3(Jm + 12, t0); st3(Jm + 15, r6w);
+    st3(Jm + 18, t1); st3(Jm + 21, r7w);
+    // G (6 x 4) = [X; R3' skew(rc) X]
+    double* Gm = A + cd.G_off;
     V3 qn = tmul(k.R3, cross(rc, n)), q0 = tmul(k.R3, cross(rc, t0)), q1 = tmul(k.R3, cross(rc, t1));
-    L[0 * 8 + 4] = -n.x; L[1 * 8 + 4] = -n.y; L[2 * 8 + 4] = -n.z; L[3 * 8 + 4] = -qn.x; L[4 * 8 + 4] = -qn.y; L[5 * 8 + 4] = -qn.z;
-    L[0 * 8 + 6] = -t0.x; L[1 * 8 + 6] = -t0.y; L[2 * 8 + 6] = -t0.z; L[3 * 8 + 6] = -q0.x; L[4 * 8 + 6] = -q0.y; L[5 * 8 + 6] = -q0.z;
-    L[0 * 8 + 7] = -t1.x; L[1 * 8 + 7] = -t1.y; L[2 * 8 + 7] = -t1.z; L[3 * 8 + 7] = -q1.x; L[4 * 8 + 7] = -q1.y; L[5 * 8 + 7] = -q1.z;
-    // d(G gamma)/d attitude, torque rows only: 2 skew(tau) + 2 R3' skew(F) R3 skew(o)
+    const double Gc[6][4] = {{n.x, 0.0, t0.x, t1.x}, {n.y, 0.0, t0.y, t1.y}, {n.z, 0.0, t0.z, t1.z},
+                             {qn.x, 0.0, q0.x, q1.x}, {qn.y, 0.0, q0.y, q1.y}, {qn.z, 0.0, q0.z, q1.z}};
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) Gm[r * 4 + cc] = Gc[r][cc];
+    // condensation onto the body:  dgamma = w0 - W J dv,  W = (D_c^-1)[gamma rows, constraint columns]  =>  D_b += G W J
+    ContactBlock cb = contact_block(s, g, cd.mu);
+    double Wm[4][4];
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      if (kx == 1) continue;  // J row 1 is zero
+      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8];
+      t[4 + kx] = 1.0;
+      contact_solve(cb, t, y);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) Wm[r][kx] = y[4 + r];
+    }
+    const double Jr0[6] = {hn.x, hn.y, hn.z, r4w.x, r4w.y, r4w.z};
+    const double Jr2[6] = {t0.x, t0.y, t0.z, r6w.x, r6w.y, r6w.z};
+    const double Jr3[6] = {t1.x, t1.y, t1.z, r7w.x, r7w.y, r7w.z};
+    double WJ[4][6];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) WJ[r][cc] = Wm[r][0] * Jr0[cc] + Wm[r][2] * Jr2[cc] + Wm[r][3] * Jr3[cc];
+    // d(G gamma)/d attitude, torque rows only: 2 skew(tau) + 2 R3' skew(F) R3 skew(o)   (impulse_map_jacobian)
     M33 K = 2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so));
-    KE = K * k.E;
+    M33 KE = K * k.E;
+    double* slotK = A + cd.slot + 6;  // the body does D_b -= slotK:  slotK = KE (angular block) - G W J
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        double v = -(Gc[r][0] * WJ[0][cc] + Gc[r][2] * WJ[2][cc] + Gc[r][3] * WJ[3][cc]);
+        if (r >= 3 && cc >= 3) v += KE.m[r - 3][cc - 3];
+        slotK[r * 6 + cc] = v;
+      }
   }
-  }
-  write_slot(A + cd.slot, F, tau, KE);
 }
 
 // joints (joints/constraints.jl:114-299, joints/joint.jl, joints/limits.jl, rotational/dampers.jl)
-DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, double& rv, double& bv) {
+// The limit slacks / duals (4 per limited axis) are condensed out analytically:
+//   comp:  g' ds + s' dg = rc ;  slack_u: ds_u + a.dw = rs_u ;  slack_l: ds_l - a.dw = rs_l   (a.dw = aP.dw_p + aC.dw_c)
+//   =>  dg_u - dg_l = c0 + (k_u + k_l) a.dw,   k = g'/s',  c0 = (rc_u - g_u' rs_u)/s_u' - (rc_l - g_l' rs_l)/s_l'
+// and the bodies see  L dgamma = +-t (dg_u - dg_l): a rank-one coupling t (k_u + k_l) a' on the angular blocks.
+template <bool JAC>
+DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, double& bv) {
   const Plan& P = *c.P;
   double* A = c.A;
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
   const JointDev& jd = P.joints[idx];
   V3 fl_p = v3zero(), fa_p = v3zero(), fl_c = v3zero(), fa_c = v3zero();  // G * eta (+ damper impulses)
-  M33 Kaa = m33zero(), Kcc = m33zero();                                     // damper d(tau)/d(w) on the diagonal blocks
-  bool has_damper = false;
-  (void)has_damper;
-  {
-    Kin ka = body_kin(c, jd.parent, f), kb = body_kin(c, jd.child, f);
+  M33 Kaa = m33zero(), Kcc = m33zero();                                     // D_parent -= Kaa, D_child -= Kcc (angular blocks)
+  M33 Bpc = m33zero(), Bcp = m33zero();                                     // (parent,child) / (child,parent) angular blocks
+  bool coupled = false;
+  Kin ka = body_kin(c, jd.parent, f), kb = body_kin(c, jd.child, f);
   JointGeom g = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
-  const int n = jd.n;
+  const int n = jd.ne;
   double* rr = res + jd.sol_off;
   const double* so = sol + jd.sol_off;
   const double* dd = dl + jd.sol_off;
   double* Uc = A + jd.Uc_off;
   double* Up = (jd.parent >= 0) ? A + jd.Up_off : nullptr;
   double* D = A + jd.D_off;
-  // translational equality rows: C_t e_t
-  V3 QEp = v3zero();
   M33 QtpE, QtcE, QrpE, QrcE;
   if (JAC) { QtpE = g.Qtp * ka.E; QtcE = g.Qtc * kb.E; QrpE = g.Qrp * ka.E; QrcE = g.Qrc * kb.E; }
-  (void)QEp;
+  // translational equality rows: C_t e_t
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nl_t) {
@@ -477,52 +526,8 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
       rv = nanmax(rv, fabs(gi));
       if (JAC) {
         D[i * n + i] = kReg;
-        V3 ux = P.h * vtmul(ci, g.Xc), uw = vtmul(ci, QtcE);
-        st3(Uc + i * 6, ux); st3(Uc + i * 6 + 3, uw);
-        if (Up) {
-          V3 px = P.h * vtmul(ci, g.Xp), pw = vtmul(ci, QtpE);
-          st3(Up + i * 6, px); st3(Up + i * 6 + 3, pw);
-        }
-      }
-    }
-  }
-  // rotational limits: rows [s.gamma - mu (Nb); s_u - (hi - theta); s_l - (theta - lo)]
-  if (jd.nb2_r > 0) {
-    V3 rvq = rotation_vector(g.qr);
-    M33 Tp, Tc;
-    if (JAC) {
-      rotvec_attitude_jacobians(jd, g, Tp, Tc);
-      Tp = Tp * ka.E;
-      Tc = Tc * kb.E;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (i < jd.nb2_r) {
-        V3 ai = ld3(jd.Ar + 3 * i);
-        double th = dot(ai, rvq);
-        const int is_u = jd.row_r + i, is_l = jd.row_r + jd.nb2_r + i;
-        const int ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-        double su = so[is_u], sl = so[is_l], gu = so[ig_u], gl = so[ig_l];
-        if (f != 0.0) { su += f * dd[is_u]; sl += f * dd[is_l]; gu += f * dd[ig_u]; gl += f * dd[ig_l]; }
-        bv = nanmax(bv, nanmax(fabs(su * gu), fabs(sl * gl)));
-        rr[is_u] = -(su * gu - c.mu);
-        rr[is_l] = -(sl * gl - c.mu);
-        rr[ig_u] = -(su - (jd.hi[i] - th));   // slack rows sit after the Nb complementarity rows
-        rr[ig_l] = -(sl - (th - jd.lo[i]));
-        if (JAC) {
-          D[is_u * n + is_u] = gu + kReg; D[is_u * n + ig_u] = su + kReg;
-          D[is_l * n + is_l] = gl + kReg; D[is_l * n + ig_l] = sl + kReg;
-          D[ig_u * n + is_u] = 1.0;
-          D[ig_l * n + is_l] = 1.0;
-          V3 tc = vtmul(ai, Tc);
-          st3(Uc + ig_u * 6 + 3, tc);
-          st3(Uc + ig_l * 6 + 3, -tc);
-          if (Up) {
-            V3 tp = vtmul(ai, Tp);
-            st3(Up + ig_u * 6 + 3, tp);
-            st3(Up + ig_l * 6 + 3, -tp);
-          }
-        }
+        st3(Uc + i * 6, P.h * vtmul(ci, g.Xc)); st3(Uc + i * 6 + 3, vtmul(ci, QtcE));
+        if (Up) { st3(Up + i * 6, P.h * vtmul(ci, g.Xp)); st3(Up + i * 6 + 3, vtmul(ci, QtpE)); }
       }
     }
   }
@@ -532,18 +537,60 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nl_r) {
       V3 ci = ld3(jd.Cr + 3 * i);
-      const int row = jd.row_r + 2 * jd.nb_r + i;
+      const int row = jd.nl_t + i;
       double gi = dot(ci, er);
       rr[row] = -gi;
       rv = nanmax(rv, fabs(gi));
       if (JAC) {
         D[row * n + row] = kReg;
-        st3(Uc + row * 6 + 3, vtmul(ci, QrcE));
-        if (Up) st3(Up + row * 6 + 3, vtmul(ci, QrpE));
+        st3(Uc + row * 6, v3zero()); st3(Uc + row * 6 + 3, vtmul(ci, QrcE));
+        if (Up) { st3(Up + row * 6, v3zero()); st3(Up + row * 6 + 3, vtmul(ci, QrpE)); }
       }
     }
   }
-  // impulses on the two bodies: G * eta with the pristine maps (child: Lc = -G_c, parent: Gp)
+  // rotational limits: rows [s.gamma - mu (Nb); s_u - (hi - theta); s_l - (theta - lo)]   (joints/limits.jl:1-29)
+  if (jd.nb2_r > 0) {
+    V3 rvq = rotation_vector(g.qr);
+    M33 Tp, Tc;
+    if (JAC) {
+      rotvec_attitude_jacobians(jd, g, Tp, Tc);
+      Tp = Tp * ka.E;
+      Tc = Tc * kb.E;
+      coupled = true;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nb2_r) {
+        V3 ai = ld3(jd.Ar + 3 * i);
+        double th = dot(ai, rvq);
+        const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i;
+        const int ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+        double su = so[is_u], sl = so[is_l], gu = so[ig_u], gl = so[ig_l];
+        if (f != 0.0) { su += f * dd[is_u]; sl += f * dd[is_l]; gu += f * dd[ig_u]; gl += f * dd[ig_l]; }
+        bv = nanmax(bv, nanmax(fabs(su * gu), fabs(sl * gl)));
+        rr[is_u] = -(su * gu - c.mu);          // complementarity rows
+        rr[is_l] = -(sl * gl - c.mu);
+        rr[ig_u] = -(su - (jd.hi[i] - th));    // slack rows (stored at the gamma positions)
+        rr[ig_l] = -(sl - (th - jd.lo[i]));
+        double* lim = A + jd.lim_off + kLim * i;
+        V3 tP = ld3(lim + 6), tC = ld3(lim + 9);
+        // impulses of the limit duals: G[:, gamma_u] = -t, G[:, gamma_l] = +t
+        fa_p += (gl - gu) * tP;
+        fa_c += (gl - gu) * tC;
+        if (JAC) {
+          V3 aP = vtmul(ai, Tp), aC = vtmul(ai, Tc);
+          st3(lim, aP); st3(lim + 3, aC);
+          double kk = (gu + kReg) / (su + kReg) + (gl + kReg) / (sl + kReg);
+          // body rows gain  t kk (aP.dw_p + aC.dw_c)  =>  D_parent += kk tP aP', (p,c) += kk tP aC', ...
+          Kaa = Kaa - kk * outer(tP, aP);
+          Kcc = Kcc - kk * outer(tC, aC);
+          Bpc = Bpc + kk * outer(tP, aC);
+          Bcp = Bcp + kk * outer(tC, aP);
+        }
+      }
+    }
+  }
+  // impulses of the equality multipliers on the two bodies: G * lambda with the pristine maps (child: Lc = -G_c, parent: Gp)
   {
     const double* Lc = A + jd.Lc_off;
     const double* Gp = (jd.parent >= 0) ? A + jd.Gp_off : nullptr;
@@ -557,8 +604,8 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
         if (Gp) ap[r] += Gp[r * n + i] * e;
       }
     }
-    fl_c = v3(ac[0], ac[1], ac[2]); fa_c = v3(ac[3], ac[4], ac[5]);
-    fl_p = v3(ap[0], ap[1], ap[2]); fa_p = v3(ap[3], ap[4], ap[5]);
+    fl_c += v3(ac[0], ac[1], ac[2]); fa_c += v3(ac[3], ac[4], ac[5]);
+    fl_p += v3(ap[0], ap[1], ap[2]); fa_p += v3(ap[3], ap[4], ap[5]);
     if (JAC && Gp) {  // parent-side lower block is consumed by the factorisation: refresh it from the pristine copy
       double* Lp = A + jd.Lp_off;
       for (int i = 0; i < 6 * n; ++i) Lp[i] = -Gp[i];
@@ -566,11 +613,9 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
   }
   // rotational damper (rotational/dampers.jl:4-27,66-84; rotational/minimal.jl:103-118,151-174)
   if (jd.damper_r != 0.0 && jd.nfree_r > 0) {
-    has_damper = true;
     Quat r = qmul(qinv(ka.q2), kb.q2);           // relative orientation at the current step
     Quat ma = qmap(ka.w, P.h), mb = qmap(kb.w, P.h);
-    Quat left = qmul(mb, qconj(r));               // w = mb (x) r^-1 (x) conj(ma) (x) r   (unit r)
-    left = qmul(mb, qinv(r));
+    Quat left = qmul(mb, qinv(r));                // w = mb (x) r^-1 (x) conj(ma) (x) r
     Quat rest = qmul(qmul(qinv(r), qconj(ma)), r);
     Quat wq = qmul(mb, rest);
     V3 rvd = rotation_vector(wq);
@@ -586,6 +631,7 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
     fa_p += ta;  // d -= damper_impulses  =>  res += impulses
     fa_c += tb;
     if (JAC) {
+      coupled = true;
       M34 drv = drotation_vector_dq(wq);
       M33 dwa, dwb;  // d rotvec / d w_a, d w_b
       double m0a = ma.s, m0b = mb.s;
@@ -604,28 +650,118 @@ DJ_DEV void eval_joint(Ctx& c, const bool JAC, int idx, double f, double* res, d
       }
       M33 Ka = B * dwa, Kb = B * dwb;              // d tau_a / d w_a, d tau_a / d w_b
       M33 Rrt = transpose(Rr);
-      Kaa = Ka;                                    // D_parent -= Ka
-      Kcc = (-1.0) * (Rrt * Kb);                   // d tau_b / d w_b ; D_child -= Kcc
-      if (jd.parent >= 0 && jd.BBpc_off >= 0) {
-        double* Bpc = A + jd.BBpc_off;
-        double* Bcp = A + jd.BBcp_off;
-        M33 Kca = (-1.0) * (Rrt * Ka);             // d tau_b / d w_a
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j2 = 0; j2 < 3; ++j2) {
-            Bpc[(3 + i) * 6 + 3 + j2] = -Kb.m[i][j2];
-            Bcp[(3 + i) * 6 + 3 + j2] = -Kca.m[i][j2];
-          }
-      }
+      Kaa = Kaa + Ka;                              // D_parent -= d tau_a / d w_a
+      Kcc = Kcc - Rrt * Kb;                        // D_child  -= d tau_b / d w_b = -(Rr' Kb)
+      Bpc = Bpc - Kb;                              // (parent,child) = -d tau_a / d w_b
+      Bcp = Bcp + Rrt * Ka;                        // (child,parent) = -d tau_b / d w_a = +Rr' Ka
     }
   }
+  if (JAC && coupled && jd.parent >= 0 && jd.BBpc_off >= 0) {
+    double* Mpc = A + jd.BBpc_off;
+    double* Mcp = A + jd.BBcp_off;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2) {
+        Mpc[(3 + i) * 6 + 3 + j2] = Bpc.m[i][j2];
+        Mcp[(3 + i) * 6 + 3 + j2] = Bcp.m[i][j2];
+      }
   }
   write_slot(A + jd.slot_c, fl_c, fa_c, Kcc);
   if (jd.parent >= 0) write_slot(A + jd.slot_p, fl_p, fa_p, Kaa);
 }
 
-DJ_DEV void evaluate(Ctx& c, const bool JAC, double f, int res_off, double& rvio, double& bvio) {
+// condense_rhs / recover: the per-solve halves of the analytic condensation.  `x` is a right-hand side in solution
+// ordering.  condense_rhs writes each node's contribution to its bodies' rows into the slots (gathered by the bodies
+// right after); recover overwrites the condensed-out entries of x with the step (ds, dgamma) once dv is known.
+DJ_DEV void condense_contact(Ctx& c, int idx, const double* x) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const ContactDev& cd = P.contacts[idx];
+  const double* so = A + P.sol_off + cd.sol_off;
+  ContactBlock cb = contact_block(so, so + 4, cd.mu);
+  double y[8];
+  contact_solve(cb, x + cd.sol_off, y);  // w0 = y[4:8]:  r_b += G w0
+  const double* G = A + cd.G_off;
+  double o[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) o[r] = G[r * 4 + 0] * y[4] + G[r * 4 + 2] * y[6] + G[r * 4 + 3] * y[7];
+  double* s = A + cd.slot;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) s[r] = o[r];
+}
+DJ_DEV void recover_contact(Ctx& c, int idx, double* x) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const ContactDev& cd = P.contacts[idx];
+  const double* so = A + P.sol_off + cd.sol_off;
+  ContactBlock cb = contact_block(so, so + 4, cd.mu);
+  const double* J = A + cd.J_off;
+  const double* dv = x + P.bodies[cd.body].sol_off;
+  double t[8], y[8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) t[r] = x[cd.sol_off + r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += J[r * 6 + k] * dv[k];
+    t[4 + r] = x[cd.sol_off + 4 + r] - acc;
+  }
+  contact_solve(cb, t, y);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) x[cd.sol_off + r] = y[r];
+}
+DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const JointDev& jd = P.joints[idx];
+  V3 tp = v3zero(), tc = v3zero();
+  const double* so = A + P.sol_off + jd.sol_off;
+  const double* xr = x + jd.sol_off;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nb2_r) {
+      const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
+      double c0 = (xr[is_u] - gu * xr[ig_u]) / su - (xr[is_l] - gl * xr[ig_l]) / sl;
+      const double* lim = A + jd.lim_off + kLim * i;
+      tp -= c0 * ld3(lim + 6);  // body rows: t (dg_u - dg_l) moves to the right-hand side
+      tc -= c0 * ld3(lim + 9);
+    }
+  }
+  double* sc = A + jd.slot_c;
+  st3(sc, v3zero()); st3(sc + 3, tc);
+  if (jd.parent >= 0) { double* sp = A + jd.slot_p; st3(sp, v3zero()); st3(sp + 3, tp); }
+}
+DJ_DEV void recover_joint(Ctx& c, int idx, double* x) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const JointDev& jd = P.joints[idx];
+  if (jd.nb2_r == 0) return;
+  const double* so = A + P.sol_off + jd.sol_off;
+  double* xr = x + jd.sol_off;
+  V3 wp = (jd.parent >= 0) ? ld3(x + P.bodies[jd.parent].sol_off + 3) : v3zero();
+  V3 wc = ld3(x + P.bodies[jd.child].sol_off + 3);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nb2_r) {
+      const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
+      const double* lim = A + jd.lim_off + kLim * i;
+      double adw = dot(ld3(lim), wp) + dot(ld3(lim + 3), wc);
+      double rc_u = xr[is_u], rc_l = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
+      double ds_u = rs_u - adw, ds_l = rs_l + adw;
+      xr[is_u] = ds_u;
+      xr[is_l] = ds_l;
+      xr[ig_u] = (rc_u - gu * ds_u) / su;
+      xr[ig_l] = (rc_l - gl * ds_l) / sl;
+    }
+  }
+}
+
+template <bool JAC>
+DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) {
   const Plan& P = *c.P;
   double* A = c.A;
   double* res = A + res_off;
@@ -638,9 +774,9 @@ DJ_DEV void evaluate(Ctx& c, const bool JAC, double f, int res_off, double& rvio
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
-    if (role.type[p] == ROLE_BODY) eval_body(c, JAC, idx, f, res);
-    else if (role.type[p] == ROLE_CONTACT) eval_contact(c, JAC, idx, f, res, rv, bv);
-    else eval_joint(c, JAC, idx, f, res, rv, bv);
+    if (role.type[p] == ROLE_BODY) eval_body<JAC>(c, idx, f, res);
+    else if (role.type[p] == ROLE_CONTACT) eval_contact<JAC>(c, idx, f, res, rv, bv);
+    else eval_joint<JAC>(c, idx, f, res, rv, bv);
   }
   __syncthreads();
   // gather the impulse contributions of the incident joints / contacts into the body rows (fixed order)
@@ -655,10 +791,15 @@ DJ_DEV void evaluate(Ctx& c, const bool JAC, double f, int res_off, double& rvio
       add3(rb, ld3(s));
       add3(rb + 3, ld3(s + 3));
       if (JAC) {
+        if (g < bd.g_ncontact) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < 36; ++i) D[i] -= s[6 + i];
+        } else {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] -= s[6 + 3 * i + j];
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) D[(3 + i) * 6 + 3 + j] -= s[6 + 3 * i + j];
+        }
       }
     }
 #pragma unroll
@@ -677,6 +818,9 @@ DJ_DEV bool factorize(Ctx& c) {
   const Plan& P = *c.P;
   double* A = c.A;
   bool ok = true;
+#ifdef DJ_PROFILE
+  c.f_last = clock64();
+#endif
   for (int ph = 0; ph < P.nphase; ++ph) {
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0; s < s0 + sn; ++s) {
@@ -690,14 +834,19 @@ DJ_DEV bool factorize(Ctx& c) {
         }
         __syncwarp();
       }
+      DJ_FTICK(c, f_fold)
       ok = block_inverse(Dc, st.n, st.n, c.lane) && ok;                                                  // D_c <- D_c^-1
+      DJ_FTICK(c, f_inv)
       for (int i = 0; i < st.nnb; ++i) right_multiply_inplace(A + st.nb[i].L_off, Dc, st.nb[i].n, st.n, c.lane);  // L~_ic = M_ic D_c^-1
+      DJ_FTICK(c, f_rm)
       for (int i = 0; i < st.nnb; ++i)
         for (int j = 0; j < st.nnb; ++j)                                                                  // M_ij -= L~_ic M_cj
           schur_update(A + st.tgt[i][j], A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
                        st.nb[j].n, c.lane);
+      DJ_FTICK(c, f_schur)
     }
     __syncthreads();
+    DJ_FTICK(c, f_bar)
   }
   return __syncthreads_and(ok ? 1 : 0) != 0;
 }
@@ -709,6 +858,27 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
   double* x = A + vec_off;
   const int lane = c.lane;
   const int half = lane >> 4, li = lane & 15;
+  const WarpRole& role = P.roles[c.warp];
+  // condense the right-hand side of the contact / joint-limit rows onto the body rows
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_CONTACT) condense_contact(c, idx, x);
+    else if (role.type[p] == ROLE_JOINT) condense_joint(c, idx, x);
+  }
+  __syncthreads();
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, lane);
+    if (idx < 0 || role.type[p] != ROLE_BODY) continue;
+    const BodyDev& bd = P.bodies[idx];
+    double* xb = x + bd.sol_off;
+    for (int g = 0; g < bd.g_cnt; ++g) {
+      const double* s = A + P.ilist[bd.g_off + g];
+      add3(xb, ld3(s));
+      add3(xb + 3, ld3(s + 3));
+    }
+  }
+  __syncthreads();
   for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c   (lanes [0,16) serve nb[0], [16,32) nb[1])
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0; s < s0 + sn; ++s) {
@@ -769,6 +939,14 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     }
     __syncthreads();
   }
+  // recover the condensed-out steps (ds, dgamma) of the contacts and joint limits
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_CONTACT) recover_contact(c, idx, x);
+    else if (role.type[p] == ROLE_JOINT) recover_joint(c, idx, x);
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -808,7 +986,7 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
       a = fmin(a, soc_step(g[1], g[2], g[3], dg[1], dg[2], dg[3], tau_soc));
     } else if (role.type[p] == ROLE_JOINT) {
       const JointDev& jd = P.joints[idx];
-      for (int i = 0; i < 2 * jd.nb_r; ++i) a = fmin(a, ort_step(sol[jd.sol_off + jd.row_r + i], dl[jd.sol_off + jd.row_r + i], tau_ort));
+      for (int i = 0; i < 2 * jd.nb_r; ++i) a = fmin(a, ort_step(sol[jd.sol_off + jd.ne + i], dl[jd.sol_off + jd.ne + i], tau_ort));
     }
   }
   return block_min(c, a);
@@ -836,7 +1014,7 @@ DJ_DEV void centering(Ctx& c, double aaff, double& nu, double& nuaff) {
     } else if (role.type[p] == ROLE_JOINT) {
       const JointDev& jd = P.joints[idx];
       for (int i = 0; i < jd.nb_r; ++i) {
-        int is = jd.sol_off + jd.row_r + i, ig = is + jd.nb_r;
+        int is = jd.sol_off + jd.ne + i, ig = is + jd.nb_r;
         sn += sol[is] * sol[ig];
         sa += (sol[is] + aaff * dl[is]) * (sol[ig] + aaff * dl[ig]);
       }
@@ -869,7 +1047,7 @@ DJ_DEV void correction(Ctx& c) {
     } else if (role.type[p] == ROLE_JOINT) {
       const JointDev& jd = P.joints[idx];
       for (int i = 0; i < jd.nb_r; ++i) {
-        int is = jd.sol_off + jd.row_r + i;
+        int is = jd.sol_off + jd.ne + i;
         sav[is] += -dl[is] * dl[is + jd.nb_r] + c.mu;
       }
     }
@@ -901,8 +1079,9 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
   for (;;) {
     double rv, bv;
     DJ_TICK(c, t_misc)
-    evaluate(c, mode == 0, fk, mode == 0 ? P.rhs_off : P.sav_off, rv, bv);
-    if (mode == 0) DJ_TICK(c, t_eval_jac) else DJ_TICK(c, t_eval_ls)
+    if (mode == 0) evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
+    else evaluate<false>(c, fk, P.sav_off, rv, bv);
+    if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
     if (mode == 1) {
       // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
       fsel = fk;

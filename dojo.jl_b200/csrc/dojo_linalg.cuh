@@ -73,6 +73,42 @@ DJ_LA bool block_inverse_t(double* A, int ld, int lane) {
   return ok;
 }
 
+// Gauss-Jordan inverse WITHOUT pivoting for the blocks of the condensed KKT system: body blocks (mass matrix plus
+// contact / limit / damper terms) and joint blocks (REG I + U D_b^-1 G, a J M^-1 J' form) have safely non-zero
+// diagonals in elimination order; the blocks that needed pivoting (contact and limit complementarity rows) are
+// condensed out analytically.  A vanishing / non-finite pivot is reported (status 3), never silently used.
+template <int N>
+DJ_LA bool block_inverse_nopivot_t(double* A, int ld, int lane) {
+  static_assert(2 * N <= 32, "block too large for the one-column-per-lane inverse");
+  double a[N];
+  const bool left = lane < N;
+  const int col = left ? lane : lane - N;
+  const bool active = lane < 2 * N;
+#pragma unroll
+  for (int r = 0; r < N; ++r) a[r] = active ? (left ? A[r * ld + col] : (r == col ? 1.0 : 0.0)) : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double piv = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(fabs(piv) > 1e-300) || !(fabs(piv) < 1e300)) ok = false;
+    double akk = a[k] * (1.0 / piv);
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      if (r == k) continue;
+      double f = __shfl_sync(0xffffffffu, a[r], k);
+      a[r] -= f * akk;
+    }
+    a[k] = akk;
+  }
+  __syncwarp();
+  if (active && !left) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) A[r * ld + col] = a[r];
+  }
+  __syncwarp();
+  return ok;
+}
+
 // n <= 16 fallback: embed the block into a 16 x 16 matrix padded with the identity
 DJ_DEV bool block_inverse_pad16(double* A, int n, int ld, int lane) {
   double a[16];
@@ -120,16 +156,13 @@ DJ_DEV bool block_inverse_pad16(double* A, int n, int ld, int lane) {
 // sizes outside the specialised set below.
 DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
   switch (n) {
-    case 1: return block_inverse_t<1>(A, ld, lane);
-    case 2: return block_inverse_t<2>(A, ld, lane);
-    case 3: return block_inverse_t<3>(A, ld, lane);
-    case 4: return block_inverse_t<4>(A, ld, lane);
-    case 5: return block_inverse_t<5>(A, ld, lane);
-    case 6: return block_inverse_t<6>(A, ld, lane);
-    case 8: return block_inverse_t<8>(A, ld, lane);
-    case 9: return block_inverse_t<9>(A, ld, lane);
-    case 7: return block_inverse_t<7>(A, ld, lane);
-    default: return block_inverse_pad16(A, n, ld, lane);
+    case 1: return block_inverse_nopivot_t<1>(A, ld, lane);
+    case 2: return block_inverse_nopivot_t<2>(A, ld, lane);
+    case 3: return block_inverse_nopivot_t<3>(A, ld, lane);
+    case 4: return block_inverse_nopivot_t<4>(A, ld, lane);
+    case 5: return block_inverse_nopivot_t<5>(A, ld, lane);
+    case 6: return block_inverse_nopivot_t<6>(A, ld, lane);
+    default: return false;  // joint equality blocks are at most 6 x 6
   }
 }
 

@@ -15,8 +15,10 @@
 namespace dj {
 
 constexpr double kReg = 1.0e-10;  // REG, src/Dojo.jl:4
-constexpr int kSlot = 15;         // contribution record: force(3) torque(3) K(3x3)
+constexpr int kSlot = 15;         // joint contribution record: force(3) torque(3) K(3x3, angular-angular block)
+constexpr int kSlotC = 42;        // contact contribution record: force(3) torque(3) K(6x6)
 constexpr int kScratch = 42;      // parent-update scratch record: S(6x6) v(6)
+constexpr int kLim = 12;          // per limited axis: aP(3) aC(3) (d theta / d w, assembly) tP(3) tC(3) (impulse map, per step)
 
 enum RoleType { ROLE_BODY = 0, ROLE_CONTACT = 1, ROLE_JOINT = 2 };
 
@@ -27,19 +29,23 @@ struct BodyDev {
   int st_off;   // x2(3), q2(4)
   int cst_off;  // constant part of the dynamics residual for this step (6)
   int D_off;    // 6x6 diagonal block
-  int g_off, g_cnt;  // gather list (Plan::ilist): arena offsets of the slots contributing to this body, fixed order
+  int g_off, g_cnt, g_ncontact;  // gather list (Plan::ilist): arena offsets of the slots contributing to this body in a fixed
+                                 // order; the first g_ncontact entries are contact slots (kSlotC), the rest joint slots (kSlot)
 };
 
 struct JointDev {
   int parent, child;  // body indices, parent = -1 for the origin
   int n, sol_off;     // impulse dimension / offset inside the solution vector
+  int ne;             // equality multipliers nl_t + nl_r: the joint's node in the condensed KKT system
   int nl_t, nl_r, nb2_r, nb_r;  // constrained axes (tra, rot), rotational limits Nb/2 and Nb
-  int row_r;          // first row of the rotational element inside the joint vector (= nl_t)
+  // DEVICE layout of the joint's entries in sol / rhs / sav:  [ tra eq (nl_t) | rot eq (nl_r) | s (nb_r) | gamma (nb_r) ]
+  // (the reference orders them [tra eq | s | gamma | rot eq]; the permutation is applied when `sol` is written out)
+  int lim_off;        // nb2_r records of kLim doubles
   int nfree_t, nfree_r, u_off;
   double pa[3], pb[3], qoff[4];
   double Ct[9], At[9], Cr[9], Ar[9];  // constraint / nullspace masks, zero-padded to 3 rows (joints/joint.jl:56-64)
   double spring_r, damper_r, spring_off_r[3], lo[3], hi[3];
-  int D_off;                    // n x n
+  int D_off;                    // ne x ne (limit slacks / duals are condensed out analytically)
   int Uc_off, Lc_off;           // (joint,child) n x 6, rewritten every assembly ; (child,joint) 6 x n = -G_c, constant over the
                                 // solve and never written by the factorisation (lives in the constant region of the arena)
   int Up_off, Lp_off, Gp_off;   // same for the parent body (-1 when the parent is the origin); Lp is consumed by the
@@ -53,7 +59,7 @@ struct ContactDev {
   int body, sol_off;  // [s(4); gamma(4)] inside the solution vector
   double mu, radius;
   double n[3], t[6], o[3], off[3];
-  int D_off, U_off, L_off;  // 8x8 ; (contact,body) rows 4..7: 4x6 ; (body,contact) 6x8
+  int J_off, G_off, rec_off;  // J = d(constraint)/d(v25,w25) 4x6 ; G = impulse map 6x4 ; 3 reciprocals of the closed-form block solve
   int slot;
 };
 

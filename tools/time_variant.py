@@ -28,8 +28,8 @@ ms = e0.elapsed_time(e1) / steps
 print(f"{os.path.basename(sys.argv[1]):20s} {name} B={B}: {ms:8.3f} ms/step  {B/ms*1e3:10.0f} env-steps/s  smem/env {s.shared_bytes_per_env}  checksum {float(Za.sum()):.9f}")
 if os.environ.get("DJ_PROF"):
     import ctypes as C
-    out = (C.c_ulonglong * 5)()
+    out = (C.c_ulonglong * 10)()
     s.L.dojo_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]
     s.L.dojo_debug_cycles(s.h, out)
     tot = sum(out)
-    print("   cycles/env-step: " + "  ".join(f"{n}={v/ (B*(20+steps)):.0f}" for n, v in zip(("eval_jac","eval_ls","fact","solve","misc"), out)), f"(sum {tot/(B*(20+steps)):.0f})")
+    print("   cycles/env-step: " + "  ".join(f"{n}={v/ (B*(20+steps)):.0f}" for n, v in zip(("eval_jac","eval_ls","fact","solve","misc","f_fold","f_inv","f_rm","f_schur","f_bar"), out)))
