@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/dojo_b200.h"
-#include "dojo_kernels.cuh"
+#include "dojo_grad.cuh"
 
 using namespace dj;
 
@@ -30,6 +30,8 @@ struct StepArgs {
   double* sol;
   int32_t* status;
   int32_t* iters;
+  double* Fz;  // gradients (GRAD kernels): [12Nb x 12Nb x B], [12Nb x nu x B], column-major per environment
+  double* Fu;
   uint32_t flags;
   int* counter;  // dynamic work queue over environments
   unsigned long long* prof;  // DJ_PROFILE builds: cycle counters [eval_jac, eval_ls, factorize, solve, misc]
@@ -53,6 +55,7 @@ DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
   }
 }
 
+template <bool GRAD>
 __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
   extern __shared__ double arena[];
   __shared__ int s_env;
@@ -79,10 +82,15 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
     const double* z = a.Z + (size_t)e * P.nz;
     const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
     const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
-    prologue(c, z, u, fx);
+    prologue(c, z, u, fx, GRAD);
     int iters = 0;
     int status = mehrotra(c, a.opts, &iters);
     epilogue(c, a.Zn + (size_t)e * P.nz, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+    if (GRAD) {
+      const size_t ng = 12 * (size_t)P.Nb;
+      __syncthreads();
+      if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu) && status == 0) status = 3;
+    }
     if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
       double* so = a.sol + (size_t)e * P.nres;
       const int first_body = P.bodies[0].sol_off;
@@ -124,7 +132,11 @@ struct DojoHandle {
   int envs_per_sm = 1;
   Plan plan;  // device pointers inside
   int nw = 4;  // warps per environment
-  size_t arena_bytes = 0;
+  size_t arena_bytes = 0, grad_bytes = 0;
+  int envs_per_sm_grad = 1;
+  int* d_ucol = nullptr;
+  double *d_Fz = nullptr, *d_Fu = nullptr;  // staging for host-pointer gradient calls (grad_chunk environments)
+  int grad_chunk = 0;
   BodyDev* d_bodies = nullptr;
   JointDev* d_joints = nullptr;
   ContactDev* d_contacts = nullptr;
@@ -304,6 +316,35 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   P.arena_len = a;
   h->arena_bytes = (size_t)a * sizeof(double);
 
+  // ---- gradient workspace (appended to the arena; only the gradient kernel allocates it)
+  std::vector<int> ucol;
+  {
+    int r = 0;
+    for (int j = 0; j < Ne; ++j) { joints[j].r_off = r; r += joints[j].ne; }
+    for (int b = 0; b < Nb; ++b) { bodies[b].r_off = r; r += 6; }
+    P.n_red = r;
+    P.ncol = 12 * Nb + nu;
+    for (int j = 0; j < Ne; ++j)
+      for (int k = 0; k < joints[j].nfree_t + joints[j].nfree_r; ++k) { ucol.push_back(j); ucol.push_back(k); }
+    for (int pass = 0; pass < 4; ++pass) {
+      P.ch = 32 >> pass;  // 32, 16, 8, 4 columns per chunk
+      int g = P.arena_len;
+      for (int b = 0; b < Nb; ++b) { bodies[b].gb_off = g; g += 30; }
+      for (int c = 0; c < Ni; ++c) { contacts[c].gc_off = g; g += 36; }
+      for (int j = 0; j < Ne; ++j) {
+        JointDev& J = joints[j];
+        J.gj_off = g; g += 12 * J.ne + 144 + 12 * (J.nfree_t + J.nfree_r);
+        if (J.parent >= 0) { J.gv_off = g; g += 6 * P.ch; } else J.gv_off = -1;
+      }
+      P.gvec_off = g; g += P.n_red * P.ch;
+      P.grad_len = g;
+      // prefer two environments per SM; large mechanisms (atlas) shrink the chunk until one environment fits
+      if ((size_t)g * sizeof(double) <= 113 * 1024) break;
+      if (pass >= 1 && (size_t)P.arena_len * sizeof(double) > 100 * 1024 && (size_t)g * sizeof(double) <= 225 * 1024) break;
+    }
+    h->grad_bytes = (size_t)P.grad_len * sizeof(double);
+  }
+
   // ---- gather lists (deterministic accumulation order): contacts of b, its parent joint (child side), its child joints
   std::vector<int> ilist;
   for (int b = 0; b < Nb; ++b) {
@@ -313,6 +354,16 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     ilist.push_back(joints[parent_joint[b]].slot_c);
     for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(joints[j].slot_p);
     bodies[b].g_cnt = (int)ilist.size() - bodies[b].g_off;
+  }
+
+  for (int b = 0; b < Nb; ++b) {  // adjacency for the gradient pass
+    bodies[b].pjoint = parent_joint[b];
+    bodies[b].cj_off = (int)ilist.size();
+    for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(j);
+    bodies[b].cj_cnt = (int)ilist.size() - bodies[b].cj_off;
+    bodies[b].ct_off = (int)ilist.size();
+    for (int c = 0; c < Ni; ++c) if (contacts[c].body == b) ilist.push_back(c);
+    bodies[b].ct_cnt = (int)ilist.size() - bodies[b].ct_off;
   }
 
   // ---- roles: which warp evaluates which nodes (one lane per node)
@@ -348,30 +399,33 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
       int visit(int b) {  // returns the height of the parent-joint step of b (or of b if the joint has no impulses)
         done[b] = 1;
         int hb = 0;
-        std::vector<int> fold;
+        std::vector<int> fold, gfold;
         for (int j = 0; j < Ne; ++j)
           if (joints[j].parent == b && !done[joints[j].child]) {
             int hc = visit(joints[j].child);
             hb = std::max(hb, hc + 1);
             fold.push_back(joints[j].S_off);
+            gfold.push_back(joints[j].gv_off);
           }
         const BodyDev& B = bodies[b];
         const JointDev& J = joints[pj[b]];
         {  // the body: neighbours = parent joint (if it has impulses) and, with dampers, the parent body
           HStep h; std::memset(&h, 0, sizeof(h));
           ElimStep& s = h.s;
-          s.d_off = B.D_off; s.n = 6; s.vec_off = B.sol_off; s.nnb = 0;
+          s.d_off = B.D_off; s.n = 6; s.vec_off = B.sol_off; s.r_off = B.r_off; s.nnb = 0;
           s.fold_off = (int)ilist.size(); s.fold_cnt = (int)fold.size();
           for (int f : fold) ilist.push_back(f);
+          s.gfold_off = (int)ilist.size();
+          for (int f : gfold) ilist.push_back(f);
           int ij = -1, ip = -1;
           if (J.ne > 0) {
             ij = s.nnb++;
-            s.nb[ij].n = J.ne; s.nb[ij].vec_off = J.sol_off; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+            s.nb[ij].n = J.ne; s.nb[ij].vec_off = J.sol_off; s.nb[ij].r_off = J.r_off; s.nb[ij].gv_off = -1; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
           }
           if (J.parent >= 0 && J.BBpc_off >= 0) {
             ip = s.nnb++;
             const BodyDev& Pb = bodies[J.parent];
-            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].fwd_abs = J.S_off + 36; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
+            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].r_off = Pb.r_off; s.nb[ip].gv_off = J.gv_off; s.nb[ip].fwd_abs = J.S_off + 36; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
           }
           if (ij >= 0) s.tgt[ij][ij] = J.D_off;
           if (ip >= 0) s.tgt[ip][ip] = J.S_off;
@@ -383,11 +437,11 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
         if (J.ne > 0) {  // the parent joint: neighbour = parent body
           HStep h; std::memset(&h, 0, sizeof(h));
           ElimStep& s = h.s;
-          s.d_off = J.D_off; s.n = J.ne; s.vec_off = J.sol_off; s.nnb = 0;
+          s.d_off = J.D_off; s.n = J.ne; s.vec_off = J.sol_off; s.r_off = J.r_off; s.nnb = 0;
           if (J.parent >= 0) {
             const BodyDev& Pb = bodies[J.parent];
             s.nnb = 1;
-            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.ne; s.nb[0].U_row = 0;
+            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].r_off = Pb.r_off; s.nb[0].gv_off = J.gv_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.ne; s.nb[0].U_row = 0;
             s.tgt[0][0] = J.S_off;
           }
           hj = hb + 1;
@@ -447,18 +501,24 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   bool ok = upload(bodies.data(), sizeof(BodyDev) * Nb, (void**)&h->d_bodies) && upload(joints.data(), sizeof(JointDev) * Ne, (void**)&h->d_joints) &&
             upload(contacts.data(), sizeof(ContactDev) * Ni, (void**)&h->d_contacts) && upload(steps.data(), sizeof(ElimStep) * steps.size(), (void**)&h->d_steps) &&
             upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
-            upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles);
+            upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles) && upload(ucol.data(), sizeof(int) * ucol.size(), (void**)&h->d_ucol);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&h->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(dojo_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+  const bool grad_fits = h->grad_bytes <= (size_t)prop.sharedMemPerBlockOptin;
+  if (grad_fits) {
+    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_bytes) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+  } else h->grad_bytes = 0;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
   P.bodies = h->d_bodies; P.joints = h->d_joints; P.contacts = h->d_contacts; P.steps = h->d_steps;
-  P.sched = h->d_sched; P.ilist = h->d_ilist; P.roles = h->d_roles;
+  P.sched = h->d_sched; P.ilist = h->d_ilist; P.roles = h->d_roles; P.ucol = h->d_ucol;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel, 32 * h->nw, h->arena_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<false>, 32 * h->nw, h->arena_bytes);
   h->envs_per_sm = std::max(1, occ);
+  if (h->grad_bytes) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<true>, 32 * h->nw, h->grad_bytes); h->envs_per_sm_grad = std::max(1, occ); }
   *out = h;
   return DOJO_OK;
 }
@@ -467,7 +527,7 @@ extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_bodies); cudaFree(h->d_joints); cudaFree(h->d_contacts); cudaFree(h->d_steps); cudaFree(h->d_counter);
-  cudaFree(h->d_sched); cudaFree(h->d_ilist); cudaFree(h->d_roles);
+  cudaFree(h->d_sched); cudaFree(h->d_ilist); cudaFree(h->d_roles); cudaFree(h->d_ucol); cudaFree(h->d_Fz); cudaFree(h->d_Fu);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
   if (h->p_out) cudaFreeHost(h->p_out);
@@ -507,11 +567,12 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
+  a.Fz = nullptr; a.Fu = nullptr;
   a.counter = h->d_counter;
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   int grid = std::min(B, h->sm_count * h->envs_per_sm);
-  dojo_step_kernel<<<grid, 32 * h->nw, h->arena_bytes, s>>>(a);
+  dojo_step_kernel<false><<<grid, 32 * h->nw, h->arena_bytes, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
@@ -622,13 +683,61 @@ extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B,
 }
 
 // gradients: implemented in dojo_grad.cu
-extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions*, int, const double*, const double*, const double*, double*, double*, double*,
-                                    int32_t*, int32_t*, uint32_t, void*) {
-  if (h) h->err = "dojo_step_grad_async: not implemented yet";
-  return DOJO_EINVAL;
+extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
+                                    double* dZn, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+  if (!h || B <= 0 || !dZ || !dZn || !dFz || !dFu) { if (h) h->err = "dojo_step_grad_async: bad arguments"; return DOJO_EINVAL; }
+  if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  StepArgs a;
+  a.plan = h->plan; a.opts = make_options(opts); a.B = B;
+  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.status = dstatus; a.iters = diters; a.flags = flags;
+  a.Fz = dFz; a.Fu = dFu;
+  a.counter = h->d_counter;
+  a.prof = h->d_prof;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  int grid = std::min(B, h->sm_count * h->envs_per_sm_grad);
+  dojo_step_kernel<true><<<grid, 32 * h->nw, h->grad_bytes, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
 }
-extern "C" int dojo_step_grad(DojoHandle* h, const DojoSolverOptions*, int, const double*, const double*, const double*, double*, double*, double*, int32_t*,
-                              int32_t*, uint32_t) {
-  if (h) h->err = "dojo_step_grad: not implemented yet";
-  return DOJO_EINVAL;
+
+// Host- or device-pointer entry.  Host buffers are processed in chunks (the Jacobians are large: (12Nb)^2 doubles per env).
+extern "C" int dojo_step_grad(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, const double* Fext, double* Zn,
+                              double* Fz, double* Fu, int32_t* status, int32_t* iters, uint32_t flags) {
+  if (!h || B <= 0 || B > h->max_batch || !Z || !Zn || !Fz || !Fu) { if (h) h->err = "dojo_step_grad: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Plan& P = h->plan;
+  if (is_device_ptr(Z)) {
+    int rc = dojo_step_grad_async(h, opts, B, Z, U, Fext, Zn, Fz, Fu, status, iters, flags, h->stream);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const size_t ng = 12 * (size_t)P.Nb, fz = ng * ng, fu = ng * P.nu;
+  if (!h->d_Fz) {
+    h->grad_chunk = (int)std::max<size_t>(1, std::min<size_t>(h->max_batch, (size_t(256) << 20) / ((fz + fu) * sizeof(double))));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_Fz, (size_t)h->grad_chunk * fz * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_Fu, std::max<size_t>(1, (size_t)h->grad_chunk * fu) * sizeof(double)));
+  }
+  cudaStream_t s = h->stream;
+  for (int e0 = 0; e0 < B; e0 += h->grad_chunk) {
+    const int nb = std::min(h->grad_chunk, B - e0);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z + (size_t)e0 * P.nz, (size_t)nb * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (U && P.nu > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U + (size_t)e0 * P.nu, (size_t)nb * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (Fext) CUDA_TRY(h, cudaMemcpyAsync(h->d_F, Fext + (size_t)e0 * 6 * P.Nb, (size_t)nb * 6 * P.Nb * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = dojo_step_grad_async(h, opts, nb, h->d_Z, (U && P.nu > 0) ? h->d_U : nullptr, Fext ? h->d_F : nullptr, h->d_Zn, h->d_Fz, h->d_Fu, h->d_status, h->d_iters,
+                              flags, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(Zn + (size_t)e0 * P.nz, h->d_Zn, (size_t)nb * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(Fz + (size_t)e0 * fz, h->d_Fz, (size_t)nb * fz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (fu) CUDA_TRY(h, cudaMemcpyAsync(Fu + (size_t)e0 * fu, h->d_Fu, (size_t)nb * fu * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(h, cudaMemcpyAsync(status + e0, h->d_status, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + e0, h->d_iters, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+  }
+  return DOJO_OK;
 }

@@ -1,0 +1,496 @@
+// dojo_grad.cuh -- implicit-function-theorem gradients of the step (K2).
+//
+// Reference: get_maximal_gradients (gradients/state.jl:78-126) evaluated at the solution right after mehrotra!, before
+// update_state! (the consistent variant), with the data Jacobian of gradients/data.jl restricted to the
+// state / control columns [x2 v15 phi2 w15] per body and the joint inputs (state.jl:92-93).
+//
+//   d w / d theta = KKT^-1 * d(rhs)/d theta          (state.jl:99 solves the dense system; the reference leaves
+//                                                     "use pre-factorization" as a TODO -- here the block-LDU factor
+//                                                     of the step's own KKT matrix is reused)
+//
+// Work split:  (1) roles (one lane per node) write the sparse data-Jacobian blocks, already condensed onto the body /
+// joint-equality rows exactly like the right-hand sides of the solver; (2) the factorisation of the final KKT matrix;
+// (3) columns are processed in chunks of `ch`, ONE LANE PER COLUMN: each lane builds its right-hand side from the
+// blocks, runs the forward / backward substitution for its own column (matrix entries are warp-broadcast reads, the
+// column vectors are stored [row][lane], bank-conflict free) and applies the chain rule to (x3, q3) (state.jl:104-123).
+// The elimination phases are spread over the warps as in the solver.
+//
+// Everything is in attitude (body-frame) form: a perturbation q (x) (1, d).  The reference's attjac'd 6x6 blocks
+// (joints/*/impulses.jl impulse_transform_jacobian, springs.jl / dampers.jl *_jacobian_configuration, contacts/contact.jl
+// impulse_map_jacobian, integrators/integrator.jl integrator_jacobian_configuration) are re-derived in closed form.
+// As in the reference, d(input impulse)/d(configuration) is NOT part of the data Jacobian (gradients/data.jl has no
+// such term; test/data.jl runs with zero inputs).
+#pragma once
+#include "dojo_kernels.cuh"
+
+namespace dj {
+
+DJ_DEV void st_block33(double* B, int ld, int r0, int c0, const M33& m, double sgn = 1.0) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) B[(r0 + i) * ld + c0 + j] = sgn * m.m[i][j];
+}
+DJ_DEV void add_block33(double* B, int ld, int r0, int c0, const M33& m, double sgn = 1.0) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) B[(r0 + i) * ld + c0 + j] += sgn * m.m[i][j];
+}
+DJ_DEV M33 transport(V3 w, double h) { return transpose(rotmat(qmap(w, h))); }  // d phi3 / d phi2 = R(m)'
+
+// ---------------------------------------------------------------------------------------------------------
+// (1) data-Jacobian blocks
+// ---------------------------------------------------------------------------------------------------------
+DJ_DEV void grad_body(Ctx& c, int idx) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const BodyDev& bd = P.bodies[idx];
+  // the v15 / w15 columns need (x1, q1), i.e. the *initial* velocities: recovered from the constant residual part
+  // cst is not invertible for that -> the kernel keeps w15 in the body record (written by the prologue)
+  double* rec = A + bd.gb_off;
+  V3 w15 = ld3(rec + 27);
+  M33 J = ldm33(bd.J);
+  double n0 = 0.5 * P.h * sqrt(4.0 / (P.h * P.h) - dot(w15, w15));
+  V3 Jw = J * w15;
+  // -d(D1q)/d w15 = d/dw [ n0 J w - (h/2) w x J w ]       (gradients/data.jl:31-36)
+  V3 dn0 = (-(0.25 * P.h * P.h) / n0) * w15;
+  M33 dW = outer(Jw, dn0) + n0 * J - (0.5 * P.h) * (skew(w15) * J - skew(Jw));
+  stm33(rec, dW);
+  Kin k = body_kin(c, idx, 0.0);
+  stm33(rec + 9, transport(k.w, P.h));
+  stm33(rec + 18, k.E);
+}
+
+DJ_DEV void grad_contact(Ctx& c, int idx) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const ContactDev& cd = P.contacts[idx];
+  const double* so = A + P.sol_off + cd.sol_off;
+  Kin k = body_kin(c, cd.body, 0.0);
+  V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3), o = ld3(cd.o), off = ld3(cd.off);
+  V3 ow = k.R3 * o;
+  V3 rc = ow - off - cd.radius * n;
+  V3 ww = k.R3 * k.w;
+  const double* g = so + 4;
+  V3 F = g[0] * n + g[2] * t0 + g[3] * t1;
+  V3 tau = tmul(k.R3, cross(rc, F));
+  M33 R3so = k.R3 * skew(o);
+  M33 Mqq = transport(k.w, P.h);
+  // contact rows:  Zc = -d(constraint)/d(x3, phi3) * blkdiag(I, Mqq)   (gradients/data.jl:194-205, contacts/contact.jl:9-35)
+  V3 nphi = vtmul((-2.0) * vtmul(n, R3so), Mqq);
+  M33 dvc_dd = (2.0 * (skew(rc) * (k.R3 * skew(k.w))) - 2.0 * (skew(ww) * R3so)) * Mqq;
+  V3 v0 = vtmul(t0, dvc_dd), v1 = vtmul(t1, dvc_dd);
+  const double Zc0[6] = {-n.x, -n.y, -n.z, -nphi.x, -nphi.y, -nphi.z};
+  const double Zc2[6] = {0, 0, 0, -v0.x, -v0.y, -v0.z};
+  const double Zc3[6] = {0, 0, 0, -v1.x, -v1.y, -v1.z};
+  // condensation (as for the solver's right-hand sides): body rows += G W Zc
+  ContactBlock cb = contact_block(so, g, cd.mu);
+  double Wm[4][4];
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    if (kx == 1) continue;
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8];
+    t[4 + kx] = 1.0;
+    contact_solve(cb, t, y);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Wm[r][kx] = y[4 + r];
+  }
+  double WZ[4][6];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) WZ[r][cc] = Wm[r][0] * Zc0[cc] + Wm[r][2] * Zc2[cc] + Wm[r][3] * Zc3[cc];
+  const double* G = A + cd.G_off;
+  // body rows: + d(G gamma)/d(x3, phi3) * blkdiag(I, Mqq): torque rows, attitude columns only   (gradients/data.jl:126-135)
+  M33 K = (2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so))) * Mqq;
+  double* CB = A + cd.gc_off;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+      double v = G[r * 4 + 0] * WZ[0][cc] + G[r * 4 + 2] * WZ[2][cc] + G[r * 4 + 3] * WZ[3][cc];
+      if (r >= 3 && cc >= 3) v += K.m[r - 3][cc - 3];
+      CB[r * 6 + cc] = v;
+    }
+}
+
+// record layout of a joint (doubles): RJp[ne*6] RJc[ne*6] BPp[36] BPc[36] BCp[36] BCc[36] Up[6*nu] Uc[6*nu]
+DJ_DEV void grad_joint(Ctx& c, int idx) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const JointDev& jd = P.joints[idx];
+  const int ne = jd.ne, nuj = jd.nfree_t + jd.nfree_r;
+  double* RJp = A + jd.gj_off;
+  double* RJc = RJp + 6 * ne;
+  double* BPp = RJc + 6 * ne;
+  double* BPc = BPp + 36;
+  double* BCp = BPc + 36;
+  double* BCc = BCp + 36;
+  double* Up = BCc + 36;
+  double* Uc = Up + 6 * nuj;
+  for (int i = 0; i < 144; ++i) BPp[i] = 0.0;
+  const double* so = A + P.sol_off + jd.sol_off;
+  Kin ka = body_kin(c, jd.parent, 0.0), kb = body_kin(c, jd.child, 0.0);
+  M33 Ma = (jd.parent >= 0) ? transport(ka.w, P.h) : m33ident();
+  M33 Mb = transport(kb.w, P.h);
+  // ---- joint rows: -d g / d(x3, phi3) * blkdiag(I, Mqq)        (gradients/data.jl:4-14)
+  JointGeom g3 = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
+  {
+    M33 QtpM = g3.Qtp * Ma, QtcM = g3.Qtc * Mb, QrpM = g3.Qrp * Ma, QrcM = g3.Qrc * Mb;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nl_t) {
+        V3 ci = ld3(jd.Ct + 3 * i);
+        st3(RJp + i * 6, -vtmul(ci, g3.Xp)); st3(RJp + i * 6 + 3, -vtmul(ci, QtpM));
+        st3(RJc + i * 6, -vtmul(ci, g3.Xc)); st3(RJc + i * 6 + 3, -vtmul(ci, QtcM));
+      }
+      if (i < jd.nl_r) {
+        V3 ci = ld3(jd.Cr + 3 * i);
+        const int row = jd.nl_t + i;
+        st3(RJp + row * 6, v3zero()); st3(RJp + row * 6 + 3, -vtmul(ci, QrpM));
+        st3(RJc + row * 6, v3zero()); st3(RJc + row * 6 + 3, -vtmul(ci, QrcM));
+      }
+    }
+  }
+  // ---- geometry at the current configuration (impulse maps, springs, dampers)
+  M33 Ra = rotmat(ka.q2), Rb = rotmat(kb.q2);
+  JointGeom g2 = joint_geom(jd, ka.x2, ka.q2, Ra, kb.x2, kb.q2, Rb);
+  M33 Roff = rotmat(ldq(jd.qoff));
+  V3 vr = qvec(g2.qr);
+  const double s0 = g2.qr.s;
+  // projected impulses: p_t = C_t' lambda_t ;  p_r = C_r' lambda_r + sum_i (gamma_l - gamma_u) A_i
+  V3 pt = v3zero(), pr = v3zero();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nl_t) pt += so[i] * ld3(jd.Ct + 3 * i);
+    if (i < jd.nl_r) pr += so[jd.nl_t + i] * ld3(jd.Cr + 3 * i);
+    if (i < jd.nb2_r) pr += (so[ne + jd.nb_r + jd.nb2_r + i] - so[ne + jd.nb_r + i]) * ld3(jd.Ar + 3 * i);
+  }
+  // translational impulses (translational/impulses.jl:9-45):  F_p = -Ra p, F_c = Ra p, tau_p = p x (e + pa), tau_c = pb x (Rb' Ra p)
+  {
+    V3 pb = ld3(jd.pb);
+    M33 Rasp = Ra * skew(pt);
+    add_block33(BPp, 6, 0, 3, Rasp, 2.0);    // dF_p / d phi_a
+    add_block33(BCp, 6, 0, 3, Rasp, -2.0);   // dF_c / d phi_a
+    M33 sp = skew(pt);
+    add_block33(BPp, 6, 3, 0, sp * g2.Xp); add_block33(BPp, 6, 3, 3, sp * g2.Qtp);
+    add_block33(BPc, 6, 3, 0, sp * g2.Xc); add_block33(BPc, 6, 3, 3, sp * g2.Qtc);
+    M33 RbtRa = transpose(Rb) * Ra;
+    add_block33(BCp, 6, 3, 3, skew(pb) * (RbtRa * sp), -2.0);
+    add_block33(BCc, 6, 3, 3, skew(pb) * skew(RbtRa * pt), 2.0);
+  }
+  // rotational impulses (rotational/impulses.jl:9-38): tau_c = 1/2 (s p - v x p), tau_p = -1/2 Roff (s p + v x p)
+  {
+    M33 sp = skew(pr);
+    V3 Rv = Roff * vr;
+    M33 dc_b = 0.5 * (outer(pr, -vr) + sp * g2.Qrc);       // d tau_c / d phi_b
+    M33 dc_a = 0.5 * (outer(pr, Rv) + sp * g2.Qrp);        // d tau_c / d phi_a
+    M33 dp_b = (-0.5) * (Roff * (outer(pr, -vr) - sp * g2.Qrc));
+    M33 dp_a = (-0.5) * (Roff * (outer(pr, Rv) - sp * g2.Qrp));
+    add_block33(BCc, 6, 3, 3, dc_b); add_block33(BCp, 6, 3, 3, dc_a);
+    add_block33(BPc, 6, 3, 3, dp_b); add_block33(BPp, 6, 3, 3, dp_a);
+    (void)s0;
+  }
+  Quat r = qmul(qinv(ka.q2), kb.q2);
+  M33 Rr = rotmat(r), Rrt = transpose(Rr);
+  M33 AtA = m33zero();
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < jd.nfree_r) { V3 a = ld3(jd.Ar + 3 * i); AtA = AtA + outer(a, a); }
+  // rotational spring (rotational/springs.jl:44-84): tau_p = h Roff f, f = -k sum (th0_i - a_i.rv) a_i, tau_c = -R(r)' tau_p
+  if (jd.spring_r != 0.0 && jd.nfree_r > 0) {
+    M33 Tp, Tc;
+    rotvec_attitude_jacobians(jd, g2, Tp, Tc);
+    V3 rv = rotation_vector(g2.qr);
+    V3 force = v3zero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < jd.nfree_r) { V3 a = ld3(jd.Ar + 3 * i); force += (-jd.spring_r * (jd.spring_off_r[i] - dot(a, rv))) * a; }
+    V3 tp = P.h * (Roff * force);
+    V3 tc = (-1.0) * (Rrt * tp);
+    M33 Bs = (P.h * jd.spring_r) * (Roff * AtA);
+    M33 dpa = Bs * Tp, dpb = Bs * Tc;
+    add_block33(BPp, 6, 3, 3, dpa); add_block33(BPc, 6, 3, 3, dpb);
+    add_block33(BCp, 6, 3, 3, (-1.0) * (Rrt * dpa) + 2.0 * (Rrt * skew(tp)));
+    add_block33(BCc, 6, 3, 3, (-1.0) * (Rrt * dpb) + 2.0 * skew(tc));
+  }
+  // rotational damper (rotational/dampers.jl:33-64): tau_a = c Roff A'A rotvec(w), w = mb r^-1 conj(ma) r, tau_b = -R(r)' tau_a
+  if (jd.damper_r != 0.0 && jd.nfree_r > 0) {
+    Quat ma = qmap(ka.w, P.h), mb = qmap(kb.w, P.h);
+    Quat rinv = qinv(r);
+    Quat rest = qmul(qmul(rinv, qconj(ma)), r);
+    Quat wq = qmul(mb, rest);
+    M33 B = jd.damper_r * (Roff * AtA);
+    V3 ta = B * rotation_vector(wq);
+    V3 tb = (-1.0) * (Rrt * ta);
+    M34 drv = drotation_vector_dq(wq);
+    Quat mbr = qmul(mb, rinv);             // mb r^-1
+    Quat cmar = qmul(qconj(ma), r);        // conj(ma) r
+    M33 dwa, dwb;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      Quat e = Quat{0.0, kx == 0 ? 1.0 : 0.0, kx == 1 ? 1.0 : 0.0, kx == 2 ? 1.0 : 0.0};
+      // r -> r (1, d):   dw = -mb (0,d) rest + w (0,d)
+      Quat db = Quat{0, 0, 0, 0};
+      {
+        Quat t1 = qmul(qmul(mb, e), rest), t2 = qmul(wq, e);
+        db = Quat{t2.s - t1.s, t2.x - t1.x, t2.y - t1.y, t2.z - t1.z};
+      }
+      // qa -> qa (1, d): r -> (1,-d) r:  dw = mb r^-1 (0,d) conj(ma) r - mb r^-1 conj(ma) (0,d) r
+      Quat da;
+      {
+        Quat t1 = qmul(qmul(mbr, e), cmar), t2 = qmul(qmul(qmul(mbr, qconj(ma)), e), r);
+        da = Quat{t1.s - t2.s, t1.x - t2.x, t1.y - t2.y, t1.z - t2.z};
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dwb.m[i][kx] = drv.m[i][0] * db.s + drv.m[i][1] * db.x + drv.m[i][2] * db.y + drv.m[i][3] * db.z;
+        dwa.m[i][kx] = drv.m[i][0] * da.s + drv.m[i][1] * da.x + drv.m[i][2] * da.y + drv.m[i][3] * da.z;
+      }
+    }
+    M33 dta_a = B * dwa, dta_b = B * dwb;
+    add_block33(BPp, 6, 3, 3, dta_a); add_block33(BPc, 6, 3, 3, dta_b);
+    add_block33(BCp, 6, 3, 3, (-1.0) * (Rrt * dta_a) + 2.0 * (Rrt * skew(ta)));
+    add_block33(BCc, 6, 3, 3, (-1.0) * (Rrt * dta_b) + 2.0 * skew(tb));
+  }
+  // joint limits, condensed: slack rows -+(A_i Theta Mqq) -> body rows -kk t (abar_p d phi_a + abar_c d phi_b)
+  if (jd.nb2_r > 0) {
+    M33 Tp, Tc;
+    rotvec_attitude_jacobians(jd, g3, Tp, Tc);
+    Tp = Tp * Ma;
+    Tc = Tc * Mb;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nb2_r) {
+        V3 ai = ld3(jd.Ar + 3 * i);
+        V3 ap = vtmul(ai, Tp), ac = vtmul(ai, Tc);
+        const int is_u = ne + i, is_l = ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+        double kk = (so[ig_u] + kReg) / (so[is_u] + kReg) + (so[ig_l] + kReg) / (so[is_l] + kReg);
+        const double* lim = A + jd.lim_off + kLim * i;
+        V3 tP = ld3(lim + 6), tC = ld3(lim + 9);
+        add_block33(BPp, 6, 3, 3, outer(tP, ap), -kk); add_block33(BPc, 6, 3, 3, outer(tP, ac), -kk);
+        add_block33(BCp, 6, 3, 3, outer(tC, ap), -kk); add_block33(BCc, 6, 3, 3, outer(tC, ac), -kk);
+      }
+    }
+  }
+  // inputs (gradients/data.jl:137-150, translational/input.jl:33-44, rotational/input.jl:23-39)
+  {
+    int col = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nfree_t) {
+        V3 a = P.input_scaling * ld3(jd.At + 3 * i);
+        V3 fp = tmul(g2.Xp, a), tp = 0.25 * tmul(g2.Qtp, a), fc = tmul(g2.Xc, a), tc = 0.25 * tmul(g2.Qtc, a);
+        Up[0 * nuj + col] = fp.x; Up[1 * nuj + col] = fp.y; Up[2 * nuj + col] = fp.z; Up[3 * nuj + col] = tp.x; Up[4 * nuj + col] = tp.y; Up[5 * nuj + col] = tp.z;
+        Uc[0 * nuj + col] = fc.x; Uc[1 * nuj + col] = fc.y; Uc[2 * nuj + col] = fc.z; Uc[3 * nuj + col] = tc.x; Uc[4 * nuj + col] = tc.y; Uc[5 * nuj + col] = tc.z;
+        col++;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nfree_r) {
+        V3 a = P.input_scaling * ld3(jd.Ar + 3 * i);
+        V3 tp = (-1.0) * (Roff * a);
+        V3 tc = Rrt * (Roff * a);
+        Up[0 * nuj + col] = 0; Up[1 * nuj + col] = 0; Up[2 * nuj + col] = 0; Up[3 * nuj + col] = tp.x; Up[4 * nuj + col] = tp.y; Up[5 * nuj + col] = tp.z;
+        Uc[0 * nuj + col] = 0; Uc[1 * nuj + col] = 0; Uc[2 * nuj + col] = 0; Uc[3 * nuj + col] = tc.x; Uc[4 * nuj + col] = tc.y; Uc[5 * nuj + col] = tc.z;
+        col++;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (3) columns: right-hand side, substitution, chain rule.  One lane per column; `V` = column vectors [n_red][ch].
+// ---------------------------------------------------------------------------------------------------------
+DJ_DEV void add_col6(double* V, int ch, int lane, int r_off, const double* B, int ld, int col) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) V[(r_off + r) * ch + lane] += B[r * ld + col];
+}
+
+DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const int ch = P.ch;
+  for (int r = 0; r < P.n_red; ++r) V[r * ch + lane] = 0.0;
+  if (col < 12 * P.Nb) {
+    const int b = col / 12, k = col - 12 * b;
+    const BodyDev& bd = P.bodies[b];
+    if (k >= 3 && k < 6) {  // v15 column: m I on the linear rows (gradients/data.jl:30)
+      V[(bd.r_off + (k - 3)) * ch + lane] = bd.mass;
+    } else if (k >= 9) {    // w15 column
+      const double* dW = A + bd.gb_off;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) V[(bd.r_off + 3 + r) * ch + lane] = dW[r * 3 + (k - 9)];
+    } else {                // x2 (k < 3) or phi2 (6 <= k < 9) column
+      const int cc = k < 3 ? k : k - 3;
+      const JointDev& pj = P.joints[bd.pjoint];
+      {  // parent joint: this body is the child
+        const double* RJc = A + pj.gj_off + 6 * pj.ne;
+        const double* BPc = RJc + 6 * pj.ne + 36;
+        const double* BCc = BPc + 72;
+        for (int r = 0; r < pj.ne; ++r) V[(pj.r_off + r) * ch + lane] += RJc[r * 6 + cc];
+        add_col6(V, ch, lane, bd.r_off, BCc, 6, cc);
+        if (pj.parent >= 0) add_col6(V, ch, lane, P.bodies[pj.parent].r_off, BPc, 6, cc);
+      }
+      for (int q = 0; q < bd.cj_cnt; ++q) {  // child joints: this body is the parent
+        const JointDev& cj = P.joints[P.ilist[bd.cj_off + q]];
+        const double* RJp = A + cj.gj_off;
+        const double* BPp = RJp + 12 * cj.ne;
+        const double* BCp = BPp + 72;
+        for (int r = 0; r < cj.ne; ++r) V[(cj.r_off + r) * ch + lane] += RJp[r * 6 + cc];
+        add_col6(V, ch, lane, bd.r_off, BPp, 6, cc);
+        add_col6(V, ch, lane, P.bodies[cj.child].r_off, BCp, 6, cc);
+      }
+      for (int q = 0; q < bd.ct_cnt; ++q) add_col6(V, ch, lane, bd.r_off, A + P.contacts[P.ilist[bd.ct_off + q]].gc_off, 6, cc);
+    }
+  } else {  // input column
+    const int ui = col - 12 * P.Nb;
+    const JointDev& jd = P.joints[P.ucol[2 * ui]];
+    const int dof = P.ucol[2 * ui + 1], nuj = jd.nfree_t + jd.nfree_r;
+    const double* Up = A + jd.gj_off + 12 * jd.ne + 144;
+    const double* Uc = Up + 6 * nuj;
+    if (jd.parent >= 0) add_col6(V, ch, lane, P.bodies[jd.parent].r_off, Up, nuj, dof);
+    add_col6(V, ch, lane, P.bodies[jd.child].r_off, Uc, nuj, dof);
+  }
+}
+
+// forward / backward substitution of the block LDU for one column per lane
+DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const int ch = P.ch, lane = c.lane;
+  for (int ph = 0; ph < P.nphase; ++ph) {
+    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    for (int s = s0; s < s0 + sn; ++s) {
+      const ElimStep& st = P.steps[s];
+      if (!active) continue;
+      double zc[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) zc[k] = (k < st.n) ? V[(st.r_off + k) * ch + lane] : 0.0;
+      if (st.fold_cnt > 0) {
+        for (int q = 0; q < st.fold_cnt; ++q) {
+          double* v = A + P.ilist[st.gfold_off + q];
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (k < st.n) { zc[k] += v[k * ch + lane]; v[k * ch + lane] = 0.0; }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < st.n) V[(st.r_off + k) * ch + lane] = zc[k];
+      }
+      for (int j = 0; j < st.nnb; ++j) {
+        const ElimNb& nb = st.nb[j];
+        const double* L = A + nb.L_off;
+        double* tgt = nb.gv_off >= 0 ? A + nb.gv_off : V + nb.r_off * ch;
+        for (int i = 0; i < nb.n; ++i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (k < st.n) acc += L[i * st.n + k] * zc[k];
+          tgt[i * ch + lane] -= acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int ph = P.nphase - 1; ph >= 0; --ph) {
+    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    for (int s = s0 + sn - 1; s >= s0; --s) {
+      const ElimStep& st = P.steps[s];
+      if (!active) continue;
+      double t[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) t[k] = (k < st.n) ? V[(st.r_off + k) * ch + lane] : 0.0;
+      for (int j = 0; j < st.nnb; ++j) {
+        const ElimNb& nb = st.nb[j];
+        const double* U = A + nb.U_off;
+        const double* xj = V + nb.r_off * ch;
+        for (int kk = 0; kk < nb.n; ++kk) {
+          double xv = xj[kk * ch + lane];
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+            if (r < st.n) t[r] -= U[r * nb.n + kk] * xv;
+        }
+      }
+      const double* Dc = A + st.d_off;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        if (r < st.n) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            if (k < st.n) acc += Dc[r * st.n + k] * t[k];
+          V[(st.r_off + r) * ch + lane] = acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// chain rule to (x3, v25, phi3, w25) and write the column (gradients/state.jl:104-123)
+DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, double* __restrict__ Fz, double* __restrict__ Fu) {
+  const Plan& P = *c.P;
+  const double* A = c.A;
+  const int ch = P.ch, ng = 12 * P.Nb;
+  double* out = col < ng ? Fz + (size_t)col * ng : Fu + (size_t)(col - ng) * ng;
+  for (int b = 0; b < P.Nb; ++b) {
+    const BodyDev& bd = P.bodies[b];
+    const double* rec = A + bd.gb_off;
+    V3 dv = v3(V[(bd.r_off + 0) * ch + lane], V[(bd.r_off + 1) * ch + lane], V[(bd.r_off + 2) * ch + lane]);
+    V3 dw = v3(V[(bd.r_off + 3) * ch + lane], V[(bd.r_off + 4) * ch + lane], V[(bd.r_off + 5) * ch + lane]);
+    V3 dx = P.h * dv;
+    V3 dphi = ldm33(rec + 18) * dw;  // E dw
+    if (col < ng && col / 12 == b) {
+      const int k = col - 12 * b;
+      if (k < 3) { if (k == 0) dx.x += 1.0; else if (k == 1) dx.y += 1.0; else dx.z += 1.0; }
+      else if (k >= 6 && k < 9) {
+        const double* M = rec + 9;
+        dphi.x += M[0 * 3 + (k - 6)]; dphi.y += M[1 * 3 + (k - 6)]; dphi.z += M[2 * 3 + (k - 6)];
+      }
+    }
+    double* o = out + 12 * b;
+    o[0] = dx.x; o[1] = dx.y; o[2] = dx.z;
+    o[3] = dv.x; o[4] = dv.y; o[5] = dv.z;
+    o[6] = dphi.x; o[7] = dphi.y; o[8] = dphi.z;
+    o[9] = dw.x; o[10] = dw.y; o[11] = dw.z;
+  }
+}
+
+// the whole gradient pass for one environment; the KKT blocks of the final iterate must be assembled (unfactorised)
+DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const WarpRole& role = P.roles[c.warp];
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = role_item(role, p, c.lane);
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_BODY) grad_body(c, idx);
+    else if (role.type[p] == ROLE_CONTACT) grad_contact(c, idx);
+    else grad_joint(c, idx);
+  }
+  // per-column forward scratch must start from zero
+  for (int j = c.tid; j < P.Ne; j += c.nthreads)
+    if (P.joints[j].gv_off >= 0)
+      for (int t = 0; t < 6 * P.ch; ++t) A[P.joints[j].gv_off + t] = 0.0;
+  __syncthreads();
+  bool ok = factorize(c);
+  double* V = A + P.gvec_off;
+  for (int c0 = 0; c0 < P.ncol; c0 += P.ch) {
+    // every warp works on the same chunk (the elimination phases are spread over the warps); the right-hand sides
+    // are built by warp 0 .. nw-1 in slices of the chunk
+    for (int l = c.tid; l < P.ch; l += c.nthreads)
+      if (c0 + l < P.ncol) grad_build_rhs(c, V, c0 + l, l);
+    __syncthreads();
+    const bool active = c.lane < P.ch && c0 + c.lane < P.ncol;
+    grad_solve_columns(c, V, active);
+    for (int l = c.tid; l < P.ch; l += c.nthreads)
+      if (c0 + l < P.ncol) grad_write_column(c, V, c0 + l, l, Fz, Fu);
+    __syncthreads();
+  }
+  return ok;
+}
+
+}  // namespace dj

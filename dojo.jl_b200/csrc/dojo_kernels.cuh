@@ -269,7 +269,7 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
   for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.ne + i] = 1.0;
 }
 
-DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext) {
+DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext, const bool grad) {
   const Plan& P = *c.P;
   double* A = c.A;
   const WarpRole& role = P.roles[c.warp];
@@ -301,6 +301,7 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
       V3 ang = (-1.0) * (n0 * Jw - (0.5 * P.h) * cross(w15, Jw)) - P.h * tau;
       st3(A + bd.cst_off, lin);
       st3(A + bd.cst_off + 3, ang);
+      if (grad) st3(A + bd.gb_off + 27, w15);  // gradient pass: the w15 column needs the initial angular velocity
     } else if (role.type[p] == ROLE_JOINT) {
       prologue_joint(c, idx, u);
     } else {  // reset! + initialize! (contacts/constraints.jl:79-86, solver/initialization.jl:7-48)

@@ -31,6 +31,12 @@ struct BodyDev {
   int D_off;    // 6x6 diagonal block
   int g_off, g_cnt, g_ncontact;  // gather list (Plan::ilist): arena offsets of the slots contributing to this body in a fixed
                                  // order; the first g_ncontact entries are contact slots (kSlotC), the rest joint slots (kSlot)
+  // gradient pass (dojo_grad.cuh)
+  int pjoint;              // parent joint index
+  int cj_off, cj_cnt;      // child joints (Plan::ilist)
+  int ct_off, ct_cnt;      // contacts (Plan::ilist)
+  int r_off;               // offset of this body's 6 rows in the reduced (condensed) right-hand sides
+  int gb_off;              // body record: d(w15 column)(9) Mqq(9) E(9)
 };
 
 struct JointDev {
@@ -53,6 +59,10 @@ struct JointDev {
   int BBpc_off, BBcp_off;       // (parent,child) / (child,parent) 6x6 blocks, -1 without dampers
   int slot_c, slot_p;           // contribution slots for the child / parent body (slot_p = -1 for the origin)
   int S_off;                    // scratch record receiving this joint's (and its child body's) updates of the parent body
+  // gradient pass
+  int r_off;                    // offset of the ne equality rows in the reduced right-hand sides
+  int gj_off;                   // joint record: RJp(ne x 6) RJc(ne x 6) BPp BPc BCp BCc (6x6 each) Up(6 x nu_j) Uc(6 x nu_j)
+  int gv_off;                   // per-column forward scratch v (6 x CH) inside the gradient workspace (-1 for the origin)
 };
 
 struct ContactDev {
@@ -61,11 +71,14 @@ struct ContactDev {
   double n[3], t[6], o[3], off[3];
   int J_off, G_off, rec_off;  // J = d(constraint)/d(v25,w25) 4x6 ; G = impulse map 6x4 ; 3 reciprocals of the closed-form block solve
   int slot;
+  int gc_off;                 // gradient pass: condensed body block CB (6x6)
 };
 
 // One elimination step of the block LDU (GraphBasedSystems ldu_factorization!)
 struct ElimNb {
   int n, vec_off;   // neighbour dimension / offset of its entry in the solution-ordered vectors
+  int r_off;        // same in the reduced right-hand sides of the gradient pass
+  int gv_off;       // >= 0: per-column forward scratch (gradient pass) instead of r_off
   int fwd_abs;      // >= 0: absolute arena offset that receives the forward-substitution update instead of vec_off (scratch v)
   int L_off;        // M_{nb,c}: n_nb x n_c   (overwritten by M_{nb,c} * Dinv_c)
   int U_off, U_k;   // M_{c,nb}: rows [U_row, U_row + U_k) of c, U_k x n_nb (never written by the factorisation)
@@ -73,6 +86,8 @@ struct ElimNb {
 };
 struct ElimStep {
   int d_off, n, vec_off;
+  int r_off;               // reduced offset (gradient pass)
+  int gfold_off;           // gradient pass: Plan::ilist offsets of the children's per-column scratch v (fold_cnt entries)
   int nnb;
   ElimNb nb[2];
   int tgt[2][2];           // M_{nb_i, nb_j} (the parent body's diagonal is redirected to the joint's scratch record)
@@ -98,6 +113,13 @@ struct Plan {
   const int* sched;   // [nphase][nw][2] = (first step, count)
   const int* ilist;   // gather / fold lists
   const WarpRole* roles;  // [nw]
+  // gradient pass
+  int n_red;            // rows of the condensed system (6 Nb + sum ne)
+  int ncol;             // 12 Nb + nu
+  int ch;               // columns solved per chunk (one lane per column)
+  int gvec_off;         // [n_red][ch] column vectors
+  int grad_len;         // arena length with the gradient workspace
+  const int* ucol;      // [nu][2] = (joint, dof) of every input column
 };
 
 struct Options {

@@ -149,3 +149,35 @@ def test_full_size_invariants():
     perm = rng.permutation(B)
     Z3, _, _ = stepper.step(Z[perm], U[perm])
     assert np.array_equal(Z3, Z1[perm])
+
+
+@pytest.mark.parametrize("name,T,scale", [("pendulum", 3, 1.0), ("ant", 20, 1.0), ("quadruped", 25, 1.0), ("atlas", 10, 2.0)])
+def test_gradient_parity(name, T, scale):
+    """dojo_step_grad (IFT gradients from the retained block-LDU factor, condensed system) vs the oracle's
+    get_maximal_gradients restatement (dense `solmat \\ datamat`, gradients/state.jl:99).
+    Tolerance: relative 1e-5 of the largest entry for >= 90 % of the environments (median typically 1e-10); contact-rich
+    steps are ill-conditioned -- the oracle's own dense-vs-LDU solves differ by up to 1e-6 there -- so a loose 1e-2 bound
+    covers the rest."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(21)
+    B = 12
+    Z = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
+    stepper, oracle = BatchedStepper(mech, B), Oracle(mech)
+    for _ in range(T):
+        Z, _, _ = stepper.step(Z, random_inputs(mech, B, rng, scale))
+    U = random_inputs(mech, B, rng, scale)
+    Zn, Fz, Fu, sg, ig = stepper.step_grad(Z, U)
+    Zf, sf, _ = stepper.step(Z, U)
+    assert np.array_equal(Zn, Zf)  # the gradient kernel takes the same forward step
+    errs = []
+    for e in range(B):
+        zo, Fzo, Fuo, so, io = oracle.step_grad(Z[e], U[e])
+        if so != 0 or sg[e] != 0 or io != ig[e]:
+            continue
+        scale_z, scale_u = max(1.0, np.abs(Fzo).max()), max(1.0, np.abs(Fuo).max())
+        errs.append(max(np.abs(Fz[e] - Fzo).max() / scale_z, np.abs(Fu[e] - Fuo).max() / scale_u))
+    errs = np.array(errs)
+    assert len(errs) >= B // 2
+    assert np.quantile(errs, 0.9) < 1e-5 and errs.max() < 1e-2, errs
