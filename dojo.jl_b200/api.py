@@ -1,0 +1,107 @@
+"""Host-side mirror of the reference interface for the hot path (same names, argument meaning and error behaviour;
+Python has no `!`, so `step!` is `step`):
+
+    reference (Julia)                                              here
+    -------------------------------------------------------------  ------------------------------------------
+    SolverOptions{T}(; rtol, btol, ...)   solver/options.jl:16-26   SolverOptions(rtol=..., btol=..., ...)
+    step!(mechanism, z, u; opts)          simulation/step.jl:11     step(mechanism, z, u, opts=None)
+    simulate!(mechanism, steps, storage, control!; opts)            simulate(mechanism, steps, control=None, record=False, opts=None)
+                                          simulation/simulate.jl:16
+    get_maximal_gradients!(mechanism, z, u; opts)                   get_maximal_gradients(mechanism, z, u, opts=None)
+                                          gradients/state.jl:69
+    mehrotra!(mechanism; opts) -> :success / :failed                status codes returned next to the states (STATUS)
+
+NEW relative to the reference: every function also accepts a batch -- z of shape [B, 13 Nb], u of shape [B, nu] --
+and then returns batched results.  All compute happens in libdojo_b200.so on the GPU (solver.BatchedStepper).
+
+Deviations (documented switches):
+  * step returns the TRUE next state (x3, v25, q3, w25) -- the mechanism's internal state after step! -- unless
+    literal_q1=True (the reference's return value advances the configuration twice, Q1);
+  * gradients are the consistent IFT gradients at the solution (Q2);
+  * "Excessive angular velocity" (solver/line_search.jl:18-20) raises RuntimeError for a single environment, as the
+    reference's error(); in a batch it is reported per environment in `status` (code 2).
+"""
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import capi
+from .mechanism import Mechanism
+from .solver import DOJO_FLAG_Q1_LITERAL_RETURN, STATUS, BatchedStepper
+
+SolverOptions = capi.solver_options
+
+_steppers = {}
+
+
+def _stepper(mech: Mechanism, B: int, device: int = 0) -> BatchedStepper:
+    key = (id(mech), device)
+    s = _steppers.get(key)
+    if s is None or s.max_batch < B:
+        if s is not None:
+            s.close()
+        s = BatchedStepper(mech, max(B, 64), device)
+        _steppers[key] = s
+    return s
+
+
+def _check_single(status):
+    if int(status[0]) == 2:
+        raise RuntimeError("Excessive angular velocity.")  # reference: error(...) in line_search!
+
+
+def step(mechanism: Mechanism, z, u, opts=None, literal_q1: bool = False, device: int = 0):
+    """step!(mechanism, z, u; opts).  z: [13Nb] or [B, 13Nb]; u: [nu] or [B, nu].  Returns z_next (same shape); for a batch
+    also (status, iters)."""
+    z = np.asarray(z, dtype=float)
+    single = z.ndim == 1
+    Z = np.atleast_2d(z)
+    U = np.atleast_2d(np.asarray(u, dtype=float))
+    s = _stepper(mechanism, Z.shape[0], device)
+    Zn, status, iters = s.step(Z, U, opts, flags=DOJO_FLAG_Q1_LITERAL_RETURN if literal_q1 else 0)
+    if single:
+        _check_single(status)
+        return Zn[0]
+    return Zn, status, iters
+
+
+def simulate(mechanism: Mechanism, steps: int, z0=None, control: Optional[Callable] = None, record: bool = False, opts=None, device: int = 0):
+    """simulate!(mechanism, steps, storage, control!): `control(k)` returns the input(s) of step k ([nu] or [B, nu]; None = 0).
+    Returns the final state(s) and, with record=True, the trajectory [steps, B, 13Nb] (the reference's Storage)."""
+    z0 = mechanism.z0 if z0 is None else z0
+    z0 = np.asarray(z0, dtype=float)
+    single = z0.ndim == 1
+    Z = np.atleast_2d(z0)
+    B = Z.shape[0]
+    s = _stepper(mechanism, B, device)
+    U = None
+    if control is not None:
+        U = np.zeros((steps, B, mechanism.nu))
+        for k in range(steps):
+            uk = control(k)
+            if uk is not None:
+                U[k] = np.asarray(uk, dtype=float)
+    out = s.rollout(Z, U, steps, opts, record=record)
+    Zf, traj = out[0], (out[2] if record else None)
+    if single:
+        return (Zf[0], traj[:, 0]) if record else Zf[0]
+    return (Zf, traj) if record else Zf
+
+
+def get_maximal_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0):
+    """get_maximal_gradients!(mechanism, z, u; opts) -> (jacobian_state [12Nb x 12Nb], jacobian_control [12Nb x nu]);
+    batched inputs give [B, 12Nb, 12Nb] and [B, 12Nb, nu]."""
+    z = np.asarray(z, dtype=float)
+    single = z.ndim == 1
+    Z = np.atleast_2d(z)
+    U = np.atleast_2d(np.asarray(u, dtype=float))
+    s = _stepper(mechanism, Z.shape[0], device)
+    _, Fz, Fu, status, _ = s.step_grad(Z, U, opts)
+    if single:
+        _check_single(status)
+        return Fz[0], Fu[0]
+    return Fz, Fu
+
+
+def status_name(code: int) -> str:
+    return STATUS.get(int(code), "unknown")

@@ -1,0 +1,140 @@
+# DojoB200.jl -- Julia binding of libdojo_b200.so for Dojo.jl v0.7.6 (NOT runnable in the build image: no Julia there).
+#
+# It flattens a live `Dojo.Mechanism` into the C descriptor of include/dojo_b200.h and adds batched methods to the
+# functions that enter / leave the per-timestep hot path, keeping their signatures:
+#
+#   Dojo.step!(mechanism, Z::Matrix, U::Matrix; opts)                 -> Z_next   (new batched method, 13Nb x B)
+#   Dojo.get_maximal_gradients!(mechanism, Z::Matrix, U::Matrix; opts) -> (Fz, Fu) (12Nb x 12Nb x B, 12Nb x nu x B)
+#   DojoB200.mehrotra_gpu!(mechanism; opts)                            -> :success / :failed  (B = 1 drop-in for mehrotra!)
+#
+# Node order = Julia ids (joints 1..Ne, bodies Ne+1..Ne+Nb, contacts after), exactly what the library assumes.
+module DojoB200
+
+using Dojo
+using Dojo: Mechanism, JointConstraint, ContactConstraint, NonlinearContact, SolverOptions, vector
+
+const LIB = get(ENV, "DOJO_B200_LIB", joinpath(@__DIR__, "..", "dojo.jl_b200", "libdojo_b200.so"))
+
+struct BodyDesc
+    mass::Float64
+    inertia::NTuple{9,Float64}          # row-major
+end
+struct ElementDesc
+    nlambda::Int32; nlimits::Int32
+    axis_mask::NTuple{9,Float64}        # rows V1, V2, V3
+    spring::Float64; damper::Float64
+    spring_offset::NTuple{3,Float64}; limit_lo::NTuple{3,Float64}; limit_hi::NTuple{3,Float64}
+end
+struct JointDesc
+    parent_body::Int32; child_body::Int32          # 0-based body index, -1 = origin
+    vertex_parent::NTuple{3,Float64}; vertex_child::NTuple{3,Float64}
+    orientation_offset::NTuple{4,Float64}
+    tra::ElementDesc; rot::ElementDesc
+end
+struct ContactDesc
+    type::Int32; parent_body::Int32
+    friction_coefficient::Float64
+    tangent::NTuple{6,Float64}; normal::NTuple{3,Float64}; origin::NTuple{3,Float64}
+    radius::Float64; offset::NTuple{3,Float64}
+end
+struct MechanismDesc
+    num_bodies::Int32; num_joints::Int32; num_contacts::Int32
+    timestep::Float64; input_scaling::Float64; gravity::NTuple{3,Float64}
+    bodies::Ptr{BodyDesc}; joints::Ptr{JointDesc}; contacts::Ptr{ContactDesc}
+end
+struct COptions
+    rtol::Float64; btol::Float64; ls_scale::Float64
+    max_iter::Int32; max_ls::Int32
+    undercut::Float64; no_progress_max::Int32; no_progress_undercut::Float64; verbose::Int32
+end
+COptions(o::SolverOptions) = COptions(o.rtol, o.btol, o.ls_scale, o.max_iter, o.max_ls, o.undercut, o.no_progress_max,
+                                      o.no_progress_undercut, o.verbose)
+
+pad3(v) = ntuple(i -> i <= length(v) ? Float64(v[i]) : 0.0, 3)
+rowmajor(M) = ntuple(k -> Float64(M[div(k - 1, 3) + 1, mod(k - 1, 3) + 1]), 9)
+
+function element(el)
+    Nλ = Dojo.joint_length(el); Nb½ = div(Dojo.limits_length(el), 2)
+    mask = (vec(el.axis_mask1')..., vec(el.axis_mask2')..., vec(el.axis_mask3')...)
+    lo = Nb½ > 0 ? el.joint_limits[1] : Float64[]; hi = Nb½ > 0 ? el.joint_limits[2] : Float64[]
+    ElementDesc(Nλ, Nb½, Float64.(mask), el.spring, el.damper, pad3(el.spring_offset), pad3(lo), pad3(hi))
+end
+
+function flatten(mech::Mechanism{T,Nn,Ne,Nb,Ni}) where {T,Nn,Ne,Nb,Ni}
+    bodies = [BodyDesc(b.mass, rowmajor(b.inertia)) for b in mech.bodies]
+    bidx(id) = id == 0 ? Int32(-1) : Int32(id - Ne - 1)
+    joints = [JointDesc(bidx(j.parent_id), bidx(j.child_id), Tuple(j.translational.vertices[1]), Tuple(j.translational.vertices[2]),
+                        Tuple(vector(j.rotational.orientation_offset)), element(j.translational), element(j.rotational)) for j in mech.joints]
+    contacts = map(mech.contacts) do c
+        c.model isa NonlinearContact || error("DojoB200: only NonlinearContact is implemented")
+        col = c.model.collision
+        ContactDesc(2, bidx(c.parent_id), c.model.friction_coefficient, Tuple(vec(col.contact_tangent')), Tuple(vec(col.contact_normal')),
+                    Tuple(col.contact_origin), col.contact_radius, Tuple(col.contact_offset))
+    end
+    return bodies, joints, contacts
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    nz::Int; nu::Int; ng::Int
+end
+
+function Handle(mech::Mechanism; device = 0, max_batch = 65536)
+    bodies, joints, contacts = flatten(mech)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve bodies joints contacts begin
+        desc = MechanismDesc(length(bodies), length(joints), length(contacts), mech.timestep, mech.input_scaling, Tuple(mech.gravity),
+                             pointer(bodies), pointer(joints), pointer(contacts))
+        rc = ccall((:dojo_create, LIB), Cint, (Ref{MechanismDesc}, Cint, Cint, Ref{Ptr{Cvoid}}), desc, device, max_batch, h)
+        rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+    hd = Handle(h[], 13 * length(bodies), Dojo.input_dimension(mech), 12 * length(bodies))
+    finalizer(x -> ccall((:dojo_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), hd)
+    return hd
+end
+
+const HANDLES = IdDict{Mechanism,Handle}()
+handle(mech) = get!(() -> Handle(mech), HANDLES, mech)
+
+"batched step!: Z is 13Nb x B, U is nu x B (column = environment)"
+function Dojo.step!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}(), literal_q1 = false)
+    h = handle(mech); B = size(Z, 2)
+    Zn = similar(Z); status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_step, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32),
+               h.ptr, COptions(opts), B, Z, U, C_NULL, Zn, C_NULL, status, iters, literal_q1 ? 1 : 0)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    B == 1 && status[1] == 2 && error("Excessive angular velocity.")   # reference behaviour: line_search.jl:18-20
+    return Zn
+end
+
+"batched get_maximal_gradients!"
+function Dojo.get_maximal_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(Z, 2)
+    Zn = similar(Z); Fz = zeros(h.ng, h.ng, B); Fu = zeros(h.ng, h.nu, B)
+    status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_step_grad, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32),
+               h.ptr, COptions(opts), B, Z, U, C_NULL, Zn, Fz, Fu, status, iters, 0)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Fz, Fu
+end
+
+"B = 1 drop-in for mehrotra!(mechanism; opts): runs the step on the GPU and writes vsol / wsol back into the Mechanism"
+function mehrotra_gpu!(mech::Mechanism; opts = SolverOptions{Float64}())
+    h = handle(mech)
+    z = Dojo.get_maximal_state(mech)
+    # inputs were already turned into JF2 / Jτ2 by set_input!; they are passed as external impulses: Fext = J / timestep
+    Fext = vcat([[b.state.Fext + b.state.JF2 / mech.timestep; b.state.τext + b.state.Jτ2 / mech.timestep] for b in mech.bodies]...)
+    zn = zeros(h.nz); status = zeros(Int32, 1); iters = zeros(Int32, 1)
+    ccall((:dojo_step, LIB), Cint,
+          (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32),
+          h.ptr, COptions(opts), 1, z, C_NULL, Fext, zn, C_NULL, status, iters, 0)
+    for (i, b) in enumerate(mech.bodies)
+        b.state.vsol[2] = zn[13 * (i - 1) .+ (4:6)]; b.state.ωsol[2] = zn[13 * (i - 1) .+ (11:13)]
+    end
+    status[1] == 2 && error("Excessive angular velocity.")
+    return status[1] == 0 ? :success : :failed
+end
+
+end # module

@@ -1,0 +1,33 @@
+# export_fixtures.jl -- deferred true-parity hook (SURVEY.md §8c).  Pure Julia; NOT runnable in the build image.
+# On a machine with Julia + Dojo 0.7.6 + DojoEnvironments:   julia --project tools/export_fixtures.jl out_dir
+# Dumps, for pendulum / ant / quadruped / atlas: the flattened mechanism (same fields as include/dojo_b200.h, with explicit
+# name -> index maps because the body order is Dict-hash order), N random (z, u), and the reference results
+# z_next (true and Q1-literal), the solution vector, iteration counts, full_matrix(system) and get_maximal_gradients.
+using Dojo, DojoEnvironments, JSON, Random, LinearAlgebra
+include(joinpath(@__DIR__, "..", "ext", "DojoB200.jl"))
+out = length(ARGS) > 0 ? ARGS[1] : "fixtures"; mkpath(out)
+Random.seed!(100)
+for name in (:pendulum, :ant, :quadruped, :atlas)
+    mech = get_mechanism(name)
+    bodies, joints, contacts = DojoB200.flatten(mech)
+    z = get_maximal_state(mech); nu = input_dimension(mech)
+    cases = []
+    for k in 1:20
+        u = name == :pendulum ? 0.2 .* randn(nu) : [zeros(6); 0.5 .* randn(nu - 6)]
+        m1 = deepcopy(mech)
+        set_maximal_state!(m1, z); set_input!(m1, u)
+        status = Dojo.mehrotra!(m1, opts = SolverOptions())
+        sol = Dojo.get_solution(m1)
+        znext_true = Dojo.get_next_state(m1)
+        solmat = Dojo.full_matrix(m1.system)
+        Fz, Fu = Dojo.get_maximal_gradients(m1)
+        znext_q1 = step!(deepcopy(mech), z, u)
+        push!(cases, Dict("z" => z, "u" => u, "status" => String(status), "sol" => sol, "z_next" => znext_true, "z_next_q1" => znext_q1,
+                          "solmat" => vec(solmat), "Fz" => vec(Fz), "Fu" => vec(Fu)))
+        z = znext_true
+    end
+    open(joinpath(out, "$(name).json"), "w") do io
+        JSON.print(io, Dict("body_names" => [String(b.name) for b in mech.bodies], "joint_names" => [String(j.name) for j in mech.joints],
+                            "contact_names" => [String(c.name) for c in mech.contacts], "timestep" => mech.timestep, "cases" => cases))
+    end
+end
