@@ -111,24 +111,14 @@ class ClockSampler:
 
 
 def cpu_port_throughput(mech, Z, U, opts, threads):
-    """env-steps/s of the CPU oracle (oracle/, a port of the reference algorithm) on `threads` host threads:
-    each thread owns one mechanism instance and steps a contiguous slice of the batch once."""
-    from oracle.oracle import Oracle  # test infrastructure: only used as the timed CPU baseline
-    B = Z.shape[0]
-    threads = max(1, min(threads, B))
-    oracles = [Oracle(mech, opts) for _ in range(threads)]
-    bounds = np.linspace(0, B, threads + 1).astype(int)
-    out = [None] * threads
-
-    def work(i):
-        out[i] = oracles[i].step_batch(Z[bounds[i]:bounds[i + 1]], U[bounds[i]:bounds[i + 1]])
-
+    """env-steps/s of the CPU oracle (oracle/, a port of the reference algorithm) on `threads` host threads (C++
+    std::thread pool inside the oracle library: one mechanism instance per thread, contiguous slices of the batch)."""
+    from oracle import oracle as orc  # test infrastructure: only used as the timed CPU baseline
     t0 = time.perf_counter()
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
+    out = orc.step_batch_threads(mech, Z, U, opts, max(1, min(threads, Z.shape[0])))
     dt = time.perf_counter() - t0
-    return B / dt, dt
+    cpu_port_throughput.last = out
+    return Z.shape[0] / dt, dt
 
 
 def peak_hbm():
@@ -342,20 +332,9 @@ def main():
 
 
 def cpu_port_rollin(mech, Z, U, opts, threads):
-    from oracle.oracle import Oracle
-    B = Z.shape[0]
-    threads = max(1, min(threads, B))
-    oracles = [Oracle(mech, opts) for _ in range(threads)]
-    bounds = np.linspace(0, B, threads + 1).astype(int)
-    out = [None] * threads
-
-    def work(i):
-        out[i] = oracles[i].step_batch(Z[bounds[i]:bounds[i + 1]], U[bounds[i]:bounds[i + 1]])
-
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    return np.concatenate([o[0] for o in out]), None, None
+    from oracle import oracle as orc
+    Zn, st, it = orc.step_batch_threads(mech, Z, U, opts, max(1, min(threads, Z.shape[0])))
+    return Zn, st, it
 
 
 if __name__ == "__main__":

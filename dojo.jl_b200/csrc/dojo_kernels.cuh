@@ -361,35 +361,45 @@ DJ_DEV void eval_body(Ctx& c, int idx, double f, double* res) {
 // Closed-form solve of the contact diagonal block  D_c y = t  (contacts/nonlinear.jl:78-97), y = [ds(4); dgamma(4)]:
 //   rows 0-3 (complementarity): g1' ys1 + s1' yg1 = t0 ;  Arw(g') [ys2 ys3 ys4] + Arw(s') [yg2 yg3 yg4] = t1..t3
 //   rows 4-7 (constraint)     : -ys1 = t4 ; mu yg1 - yg2 = t5 ; -ys3 = t6 ; -ys4 = t7
-// with the REG-shifted s' = s + REG (1,1,0,0), g' likewise.  Three pivots: s1', s2' and p = g2' - (s3 g3 + s4 g4)/s2',
-// all positive while the iterate is strictly inside the cones (the fraction-to-boundary rule keeps it there).
+// with the REG-shifted s' = s + REG (1,1,0,0), g' likewise (non-singular while the iterate is strictly inside the cones,
+// which the fraction-to-boundary rule maintains).
 // This is the elimination of the contact node that the reference's LDU performs first (contacts are the leaves of the
 // elimination tree), done per lane in closed form instead of a pivoted 8 x 8 inverse.
 struct ContactBlock {
   double s1, s2, s3, s4, g1, g2, g3, g4, mu;  // shifted values
-  double r_s1, r_s2, r_p;                      // reciprocals of the pivots
+  double r_s1;                                 // 1 / s1'
+  double Mi[3][3];                             // inverse of the second-order-cone 3x3 block (adjugate / determinant)
 };
+// After the trivial rows (ys1 = -t4, ys3 = -t6, ys4 = -t7, yg2 = mu yg1 - t5) and yg1 = (t0 - g1' ys1)/s1', the three
+// cone rows read  M [ys2 yg3 yg4]' = b  with  M = [g2' s3 s4; g3 s2' 0; g4 0 s2'].  M is inverted through its adjugate
+// (one division by det = s2' (g2' s2' - s3 g3 - s4 g4)): no intermediate growth when s2' is tiny (sticking contact)
+// or when g2' is tiny (open contact), which a fixed pivot order would suffer from at tight tolerances.
 DJ_DEV ContactBlock contact_block(const double* s, const double* g, double mu) {
   ContactBlock b;
   b.s1 = s[0] + kReg; b.s2 = s[1] + kReg; b.s3 = s[2]; b.s4 = s[3];
   b.g1 = g[0] + kReg; b.g2 = g[1] + kReg; b.g3 = g[2]; b.g4 = g[3];
   b.mu = mu;
   b.r_s1 = 1.0 / b.s1;
-  b.r_s2 = 1.0 / b.s2;
-  b.r_p = 1.0 / (b.g2 - (b.s3 * b.g3 + b.s4 * b.g4) * b.r_s2);
+  const double det = b.s2 * (b.g2 * b.s2 - b.s3 * b.g3 - b.s4 * b.g4);
+  const double rd = 1.0 / det;
+  // adj(M) for M = [a b c; d e 0; f 0 e], a = g2', b = s3, c = s4, d = g3, f = g4, e = s2'
+  b.Mi[0][0] = (b.s2 * b.s2) * rd;            b.Mi[0][1] = (-b.s3 * b.s2) * rd;                    b.Mi[0][2] = (-b.s4 * b.s2) * rd;
+  b.Mi[1][0] = (-b.g3 * b.s2) * rd;           b.Mi[1][1] = (b.g2 * b.s2 - b.s4 * b.g4) * rd;       b.Mi[1][2] = (b.s4 * b.g3) * rd;
+  b.Mi[2][0] = (-b.g4 * b.s2) * rd;           b.Mi[2][1] = (b.s3 * b.g4) * rd;                     b.Mi[2][2] = (b.g2 * b.s2 - b.s3 * b.g3) * rd;
   return b;
 }
 DJ_DEV void contact_solve(const ContactBlock& b, const double* t, double* y) {
   const double ys1 = -t[4], ys3 = -t[6], ys4 = -t[7];
   const double yg1 = (t[0] - b.g1 * ys1) * b.r_s1;
   const double yg2 = b.mu * yg1 - t[5];
-  const double a3 = t[2] - b.g2 * ys3 - b.s3 * yg2;
-  const double a4 = t[3] - b.g2 * ys4 - b.s4 * yg2;
-  const double ys2 = (t[1] - b.g3 * ys3 - b.g4 * ys4 - b.s2 * yg2 - (b.s3 * a3 + b.s4 * a4) * b.r_s2) * b.r_p;
-  y[0] = ys1; y[1] = ys2; y[2] = ys3; y[3] = ys4;
+  const double b1 = t[1] - b.g3 * ys3 - b.g4 * ys4 - b.s2 * yg2;
+  const double b2 = t[2] - b.g2 * ys3 - b.s3 * yg2;
+  const double b3 = t[3] - b.g2 * ys4 - b.s4 * yg2;
+  y[0] = ys1; y[2] = ys3; y[3] = ys4;
   y[4] = yg1; y[5] = yg2;
-  y[6] = (a3 - b.g3 * ys2) * b.r_s2;
-  y[7] = (a4 - b.g4 * ys2) * b.r_s2;
+  y[1] = b.Mi[0][0] * b1 + b.Mi[0][1] * b2 + b.Mi[0][2] * b3;
+  y[6] = b.Mi[1][0] * b1 + b.Mi[1][1] * b2 + b.Mi[1][2] * b3;
+  y[7] = b.Mi[2][0] * b1 + b.Mi[2][1] * b2 + b.Mi[2][2] * b3;
 }
 
 // contacts (contacts/nonlinear.jl:50-97, contacts/contact.jl:37-155, collisions/sphere_halfspace.jl)

@@ -155,6 +155,17 @@ DJ_DEV bool block_inverse_pad16(double* A, int n, int ld, int lane) {
 // Runtime-size fallback: the augmented matrix lives in registers of a 16-column template; only used for block
 // sizes outside the specialised set below.
 DJ_DEV bool block_inverse(double* A, int n, int ld, int lane) {
+#ifdef DJ_PIVOT
+  switch (n) {
+    case 1: return block_inverse_t<1>(A, ld, lane);
+    case 2: return block_inverse_t<2>(A, ld, lane);
+    case 3: return block_inverse_t<3>(A, ld, lane);
+    case 4: return block_inverse_t<4>(A, ld, lane);
+    case 5: return block_inverse_t<5>(A, ld, lane);
+    case 6: return block_inverse_t<6>(A, ld, lane);
+    default: return false;
+  }
+#endif
   switch (n) {
     case 1: return block_inverse_nopivot_t<1>(A, ld, lane);
     case 2: return block_inverse_nopivot_t<2>(A, ld, lane);

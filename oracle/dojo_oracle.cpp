@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/dojo_b200.h"
@@ -548,6 +549,7 @@ struct Oracle {
   std::vector<int> node_dim, node_off;               // nodes: joints | bodies | contacts
   std::vector<int> elim_order;                       // leaves -> root
   std::vector<std::vector<int>> elim_nbrs;           // later-eliminated neighbours (incl. symbolic fill)
+  std::vector<std::pair<int, int>> pattern;          // structurally non-zero (node, node) blocks incl. fill
   bool tree_ok = true;
   int solver_mode = 0;  // 0 block LDU (reference-like), 1 dense partial-pivot LU
   std::vector<double> F;  // factor storage (copy of A)
@@ -681,6 +683,8 @@ struct Oracle {
       for (int a : nb) for (int b : nb) if (a != b) adj[a][b] = 1;
       elim_nbrs[k] = nb;
     }
+    pattern.clear();
+    for (int a = 0; a < N; ++a) for (int b = 0; b < N; ++b) if (a == b || adj[a][b]) pattern.push_back({a, b});
   }
 
   // ---------------------------------------------------------------- state in / out
@@ -981,8 +985,15 @@ struct Oracle {
   }
 
   // ---------------------------------------------------------------- assembly: set_entries! (solver/linear_system.jl:1-17)
+  void zero_pattern(std::vector<double>& M) {
+    const int n = nres;
+    for (auto& pb : pattern) {
+      int oa = node_off[pb.first], da = node_dim[pb.first], ob = node_off[pb.second], db = node_dim[pb.second];
+      for (int r = 0; r < da; ++r) std::memset(&M[(size_t)(oa + r) * n + ob], 0, sizeof(double) * db);
+    }
+  }
   void set_entries() {
-    std::fill(A.begin(), A.end(), 0.0);
+    zero_pattern(A);  // only the structurally non-zero blocks are ever touched
     const int n = nres;
     // bodies: integrators/constraint.jl:82-85
     for (int b = 0; b < Nb; ++b) {
@@ -1104,9 +1115,13 @@ struct Oracle {
   // ---------------------------------------------------------------- linear algebra
   // GraphBasedSystems.ldu_factorization! restated on dense storage with known block structure
   bool factorize() {
-    F = A;
     const int n = nres;
     if (solver_mode == 1) return true;
+    if (F.size() != A.size()) F.assign(A.size(), 0.0);
+    for (auto& pb : pattern) {  // copy the structural blocks only
+      int oa = node_off[pb.first], da = node_dim[pb.first], ob = node_off[pb.second], db = node_dim[pb.second];
+      for (int r = 0; r < da; ++r) std::memcpy(&F[(size_t)(oa + r) * n + ob], &A[(size_t)(oa + r) * n + ob], sizeof(double) * db);
+    }
     for (int k : elim_order) {
       int dk = node_dim[k], ok = node_off[k];
       if (dk == 0) continue;
@@ -1688,6 +1703,27 @@ void oracle_step_batch(void* h, const DojoSolverOptions* opts, int B, const doub
     if (status) status[e] = st;
     if (iters) iters[e] = it;
   }
+}
+// multi-threaded batch: `nthreads` independent mechanism instances (the reference is single-threaded per Mechanism), each
+// stepping a contiguous slice of the batch; returns nothing but the outputs.  Used by bench.py as the CPU baseline.
+void oracle_step_batch_threads(const DojoMechanismDesc* d, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Zn,
+                               int32_t* status, int32_t* iters, int nthreads) {
+  nthreads = std::max(1, std::min(nthreads, B));
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t) {
+    pool.emplace_back([=]() {
+      Oracle o(*d);
+      int lo = (int)((long long)B * t / nthreads), hi = (int)((long long)B * (t + 1) / nthreads);
+      int nz = 13 * o.Nb;
+      for (int e = lo; e < hi; ++e) {
+        int it = 0;
+        int st = o.step(*opts, Z + (size_t)e * nz, U + (size_t)e * o.nu, nullptr, Zn + (size_t)e * nz, nullptr, &it, 0);
+        if (status) status[e] = st;
+        if (iters) iters[e] = it;
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
 }
 int oracle_step_grad(void* h, const DojoSolverOptions* opts, const double* z, const double* u, const double* fext, double* z_next,
                      double* Fz, double* Fu, int32_t* iters, uint32_t flags, int use_factor) {

@@ -47,6 +47,7 @@ def lib():
         L.oracle_step.argtypes = [vp, op, dp, dp, dp, dp, dp, ip, C.c_uint32]
         L.oracle_step.restype = C.c_int
         L.oracle_step_batch.argtypes = [vp, op, C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_uint32]
+        L.oracle_step_batch_threads.argtypes = [C.POINTER(capi.DojoMechanismDesc), op, C.c_int, dp, dp, dp, ip, ip, C.c_int]
         L.oracle_step_grad.argtypes = [vp, op, dp, dp, dp, dp, dp, dp, ip, C.c_uint32, C.c_int]
         L.oracle_step_grad.restype = C.c_int
         L.oracle_set_state.argtypes = [vp, dp, dp, dp]
@@ -188,3 +189,18 @@ class Oracle:
         out = np.empty(6)
         self.L.oracle_momentum(self.h, _d(out))
         return out
+
+
+def step_batch_threads(mech, Z, U, opts=None, nthreads=1):
+    """Step a batch on `nthreads` C++ threads (one mechanism instance each).  Returns (Zn, status, iters)."""
+    L = lib()
+    desc, keep = capi.flatten(mech)
+    Z = np.ascontiguousarray(Z, dtype=float)
+    U = np.ascontiguousarray(U, dtype=float)
+    B = Z.shape[0]
+    Zn = np.empty_like(Z)
+    st = np.zeros(B, dtype=np.int32)
+    it = np.zeros(B, dtype=np.int32)
+    o = opts if opts is not None else capi.solver_options()
+    L.oracle_step_batch_threads(C.byref(desc), C.byref(o), B, _d(Z), _d(U), _d(Zn), capi.iptr(st), capi.iptr(it), int(nthreads))
+    return Zn, st, it
