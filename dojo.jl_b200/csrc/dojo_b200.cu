@@ -34,6 +34,9 @@ struct StepArgs {
   double* Fu;
   uint32_t flags;
   int* counter;  // dynamic work queue over environments
+  int slot_stride;      // doubles between the arenas of two slots of a CTA
+  int T;                // time steps fused in this launch (rollouts: every environment is advanced T steps by one CTA)
+  double* traj;         // nullable [T][B][nz]: state after every step
   unsigned long long* prof;  // DJ_PROFILE builds: cycle counters [eval_jac, eval_ls, factorize, solve, misc]
 };
 
@@ -55,40 +58,73 @@ DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
   }
 }
 
+// register budget: 65536 / (DJ_LB_THREADS * DJ_LB_BLOCKS) registers per thread
+#ifndef DJ_LB_THREADS
+#define DJ_LB_THREADS 256
+#define DJ_LB_BLOCKS 1
+#endif
+#ifdef DJ_PROFILE
+__device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { return *((volatile unsigned long long*)(prof + 14)); }
+#endif
 template <bool GRAD>
-__global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(const StepArgs a) {
   extern __shared__ double arena[];
-  __shared__ int s_env;
+  __shared__ int s_env[8];
+  // a CTA hosts a.slots environments at a time; slot k is served by threads [k * 32 nw, (k + 1) * 32 nw)
+  const int slot_threads = 32 * a.plan.nw;
+  const int slot = threadIdx.x / slot_threads;
   Ctx c;
-  c.A = arena;
+  c.A = arena + (size_t)slot * a.slot_stride;
   c.P = &a.plan;
-  c.tid = threadIdx.x;
-  c.nthreads = blockDim.x;
-  c.warp = threadIdx.x >> 5;
-  c.lane = threadIdx.x & 31;
+  c.tid = threadIdx.x - slot * slot_threads;
+  c.nthreads = slot_threads;
+  c.warp = c.tid >> 5;
+  c.lane = c.tid & 31;
+  c.bar = 1 + slot;
   c.mu = 0.0;
 #ifdef DJ_PROFILE
   c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = 0; c.t_last = clock64();
   c.f_fold = c.f_inv = c.f_rm = c.f_schur = c.f_bar = 0;
+  long long k_c0 = clock64(); unsigned long long k_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
+  int k_envs = 0;
+  if (c.tid == 0 && a.prof) atomicMin(a.prof + 14, k_t0);
 #endif
   const Plan& P = a.plan;
   for (;;) {
-    if (c.tid == 0) s_env = atomicAdd(a.counter, 1);  // dynamic work queue: iteration counts differ between environments
-    __syncthreads();
-    const int e = s_env;
-    __syncthreads();
+    if (c.tid == 0) {  // dynamic work queue: iteration counts differ between environments
+      int q = atomicAdd(a.counter, 1);
+      s_env[slot] = q;
+    }
+    slot_sync(c);
+    const int e = s_env[slot];
+    slot_sync(c);
     if (e >= a.B) break;
     DJ_TICK(c, t_misc)
+#ifdef DJ_PROFILE
+    k_envs++;
+    unsigned long long e_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t0));
+#endif
     const double* z = a.Z + (size_t)e * P.nz;
-    const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
-    const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
-    prologue(c, z, u, fx, GRAD);
-    int iters = 0;
-    int status = mehrotra(c, a.opts, &iters);
-    epilogue(c, a.Zn + (size_t)e * P.nz, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+    int worst = 0, iters = 0, status = 0;
+    for (int t = 0; t < a.T; ++t) {
+      const double* u = a.U ? a.U + ((size_t)t * a.B + e) * P.nu : nullptr;
+      const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
+      prologue(c, z, u, fx, GRAD);
+      status = mehrotra(c, a.opts, &iters);
+      worst = max(worst, status);
+      // state after this step: the trajectory slot if recorded, else the output buffer (re-read by the next step from L2)
+      double* zo = (a.traj ? a.traj + ((size_t)t * a.B + e) * P.nz : a.Zn + (size_t)e * P.nz);
+      epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+      if (t + 1 < a.T) { __threadfence_block(); slot_sync(c); z = zo; }
+    }
+    if (a.traj) {  // final state also goes to Zn
+      slot_sync(c);
+      for (int k = c.tid; k < P.nz; k += c.nthreads) a.Zn[(size_t)e * P.nz + k] = a.traj[((size_t)(a.T - 1) * a.B + e) * P.nz + k];
+    }
+    status = worst;
     if (GRAD) {
       const size_t ng = 12 * (size_t)P.Nb;
-      __syncthreads();
+      slot_sync(c);
       if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu) && status == 0) status = 3;
     }
     if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
@@ -108,9 +144,13 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
     if (c.tid == 0) {
       if (a.status) a.status[e] = status;
       if (a.iters) a.iters[e] = iters;
+#ifdef DJ_PROFILE
+      if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[16 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[17 + 2 * e] = e_t1 - e_t0; }
+#endif
     }
-    __syncthreads();
+    slot_sync(c);
   }
+  while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
 #ifdef DJ_PROFILE
   DJ_TICK(c, t_misc)
   if (c.tid == 0 && a.prof) {
@@ -118,9 +158,13 @@ __global__ void __launch_bounds__(256) dojo_step_kernel(const StepArgs a) {
     atomicAdd(a.prof + 2, (unsigned long long)c.t_fact); atomicAdd(a.prof + 3, (unsigned long long)c.t_solve); atomicAdd(a.prof + 4, (unsigned long long)c.t_misc);
     atomicAdd(a.prof + 5, (unsigned long long)c.f_fold); atomicAdd(a.prof + 6, (unsigned long long)c.f_inv); atomicAdd(a.prof + 7, (unsigned long long)c.f_rm);
     atomicAdd(a.prof + 8, (unsigned long long)c.f_schur); atomicAdd(a.prof + 9, (unsigned long long)c.f_bar);
+    unsigned long long k_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t1));
+    atomicMax(a.prof + 10, (unsigned long long)(clock64() - k_c0)); atomicMax(a.prof + 11, k_t1 - k_t0);
+    atomicMax(a.prof + 12, (unsigned long long)k_envs); atomicAdd(a.prof + 13, (unsigned long long)(clock64() - k_c0));
   }
 #endif
 }
+
 
 // ------------------------------------------------------------------------------------------------------------
 // Host side
@@ -129,7 +173,8 @@ struct DojoHandle {
   int device = 0;
   int max_batch = 0;
   int sm_count = 0;
-  int envs_per_sm = 1;
+  int envs_per_sm = 1;      // CTAs per SM (forward kernel)
+  int slots = 1, slots_grad = 1;  // environments hosted by one CTA
   Plan plan;  // device pointers inside
   int nw = 4;  // warps per environment
   size_t arena_bytes = 0, grad_bytes = 0;
@@ -503,22 +548,32 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
             upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
             upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles) && upload(ucol.data(), sizeof(int) * ucol.size(), (void**)&h->d_ucol);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&h->d_prof, 16 * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_prof, (16 + 2 * (size_t)max_batch) * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
+       cudaMemset(h->d_prof + 14, 0xff, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->arena_bytes) == cudaSuccess;
+  // environments per CTA ("slots"): as many arenas as fit, at most 256 threads (the register file holds 256 threads at 255 registers)
+  auto pick_slots = [&](size_t bytes) {
+    int g = (int)std::min<size_t>((size_t)prop.sharedMemPerBlockOptin / bytes, (size_t)(256 / (32 * nw)));
+    g = std::max(1, std::min(g, 8));
+    if (const char* e = getenv("DOJO_B200_SLOTS")) { int v = atoi(e); if (v >= 1 && v <= g) g = v; }
+    return g;
+  };
+  h->slots = pick_slots(h->arena_bytes);
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->slots * h->arena_bytes)) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   const bool grad_fits = h->grad_bytes <= (size_t)prop.sharedMemPerBlockOptin;
   if (grad_fits) {
-    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->grad_bytes) == cudaSuccess;
+    h->slots_grad = pick_slots(h->grad_bytes);
+    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->slots_grad * h->grad_bytes)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   } else h->grad_bytes = 0;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
   P.bodies = h->d_bodies; P.joints = h->d_joints; P.contacts = h->d_contacts; P.steps = h->d_steps;
   P.sched = h->d_sched; P.ilist = h->d_ilist; P.roles = h->d_roles; P.ucol = h->d_ucol;
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<false>, 32 * h->nw, h->arena_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<false>, 32 * h->nw * h->slots, h->slots * h->arena_bytes);
   h->envs_per_sm = std::max(1, occ);
-  if (h->grad_bytes) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<true>, 32 * h->nw, h->grad_bytes); h->envs_per_sm_grad = std::max(1, occ); }
+  if (h->grad_bytes) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<true>, 32 * h->nw * h->slots_grad, h->slots_grad * h->grad_bytes); h->envs_per_sm_grad = std::max(1, occ); }
   *out = h;
   return DOJO_OK;
 }
@@ -545,8 +600,14 @@ extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->a
 extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
 // debugging aid (DJ_PROFILE builds): cycle counters accumulated by thread 0 of every CTA; out[5]
 extern "C" int dojo_debug_cycles(DojoHandle* h, unsigned long long* out) {
-  cudaMemcpy(out, h->d_prof, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, h->d_prof, 14 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long));
+  cudaMemset(h->d_prof + 14, 0xff, sizeof(unsigned long long));
+  return DOJO_OK;
+}
+// DJ_PROFILE builds: per-environment (start ns since the first CTA of the launch, duration ns) of the last launch
+extern "C" int dojo_debug_env_times(DojoHandle* h, unsigned long long* out, int B) {
+  cudaMemcpy(out, h->d_prof + 16, 2 * (size_t)B * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return DOJO_OK;
 }
 
@@ -567,12 +628,13 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
-  a.Fz = nullptr; a.Fu = nullptr;
+  a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr;
   a.counter = h->d_counter;
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
-  int grid = std::min(B, h->sm_count * h->envs_per_sm);
-  dojo_step_kernel<false><<<grid, 32 * h->nw, h->arena_bytes, s>>>(a);
+  a.slot_stride = (int)(h->arena_bytes / sizeof(double));
+  int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
+  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->slots * h->arena_bytes, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
@@ -646,40 +708,60 @@ extern "C" int dojo_step(DojoHandle* h, const DojoSolverOptions* opts, int B, co
 }
 
 // simulate!: T steps with the state resident on the device (simulation/simulate.jl:16-36)
+static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* dZ0, const double* dU, double* dZf, double* dtraj,
+                          int32_t* dstatus, cudaStream_t s) {
+  StepArgs a;
+  a.plan = h->plan; a.opts = make_options(opts); a.B = B;
+  a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
+  a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj;
+  a.counter = h->d_counter; a.prof = h->d_prof;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  a.slot_stride = (int)(h->arena_bytes / sizeof(double));
+  int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
+  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->slots * h->arena_bytes, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+// simulate!: T steps fused in ONE launch (simulation/simulate.jl:16-36).  Every environment is advanced through all T
+// steps by the CTA that dequeued it, so there is no per-step tail and no per-step launch.  U is [nu x B x T] (step-major).
+// Device-pointer variant for resident data (no synchronisation): all pointers are device pointers.
+extern "C" int dojo_rollout_async(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* dZ0, const double* dU, double* dZ_final,
+                                  double* dZ_traj, int32_t* dstatus_any, void* cuda_stream) {
+  if (!h || B <= 0 || T <= 0 || !dZ0 || !dZ_final) { if (h) h->err = "dojo_rollout_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_rollout(h, opts, B, T, dZ0, dU, dZ_final, dZ_traj, dstatus_any, (cudaStream_t)cuda_stream);
+}
+
 extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0, const double* U, double* Z_final, double* Z_traj,
                             int32_t* status_any) {
   if (!h || B <= 0 || B > h->max_batch || T <= 0 || !Z0 || !Z_final) { if (h) h->err = "dojo_rollout: bad arguments"; return DOJO_EINVAL; }
   CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  if (is_device_ptr(Z0)) {
+    int rc = launch_rollout(h, opts, B, T, Z0, U, Z_final, Z_traj, status_any, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
   int rc = ensure_staging(h);
   if (rc != DOJO_OK) return rc;
   const Plan& P = h->plan;
-  cudaStream_t s = h->stream;
-  const size_t zbytes = (size_t)B * P.nz * sizeof(double), ubytes = (size_t)B * P.nu * sizeof(double);
-  const bool dev_io = is_device_ptr(Z0);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z0, zbytes, cudaMemcpyDefault, s));
-  std::vector<int32_t> worst(B, 0), st(B, 0);
-  double* cur = h->d_Z;
-  double* nxt = h->d_Zn;
-  for (int t = 0; t < T; ++t) {
-    const double* du = nullptr;
-    if (U && P.nu > 0) {
-      if (dev_io) du = U + (size_t)t * B * P.nu;
-      else { CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U + (size_t)t * B * P.nu, ubytes, cudaMemcpyDefault, s)); du = h->d_U; }
-    }
-    rc = dojo_step_async(h, opts, B, cur, du, nullptr, nxt, nullptr, h->d_status, nullptr, 0, s);
-    if (rc != DOJO_OK) return rc;
-    if (Z_traj) CUDA_TRY(h, cudaMemcpyAsync(Z_traj + (size_t)t * B * P.nz, nxt, zbytes, cudaMemcpyDefault, s));
-    if (status_any) {
-      CUDA_TRY(h, cudaMemcpyAsync(st.data(), h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(h, cudaStreamSynchronize(s));
-      for (int e = 0; e < B; ++e) worst[e] = std::max(worst[e], st[e]);
-    }
-    std::swap(cur, nxt);
+  const size_t zbytes = (size_t)B * P.nz * sizeof(double), ubytes = (size_t)B * P.nu * sizeof(double) * T;
+  double *dU = nullptr, *dtraj = nullptr;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z0, zbytes, cudaMemcpyHostToDevice, s));
+  if (U && P.nu > 0) { CUDA_TRY(h, cudaMalloc((void**)&dU, ubytes)); CUDA_TRY(h, cudaMemcpyAsync(dU, U, ubytes, cudaMemcpyHostToDevice, s)); }
+  if (Z_traj) CUDA_TRY(h, cudaMalloc((void**)&dtraj, zbytes * T));
+  rc = launch_rollout(h, opts, B, T, h->d_Z, dU, h->d_Zn, dtraj, h->d_status, s);
+  if (rc == DOJO_OK) {
+    cudaMemcpyAsync(Z_final, h->d_Zn, zbytes, cudaMemcpyDeviceToHost, s);
+    if (Z_traj) cudaMemcpyAsync(Z_traj, dtraj, zbytes * T, cudaMemcpyDeviceToHost, s);
+    if (status_any) cudaMemcpyAsync(status_any, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { h->err = "dojo_rollout: CUDA failure"; rc = DOJO_ECUDA; }
   }
-  CUDA_TRY(h, cudaMemcpyAsync(Z_final, cur, zbytes, cudaMemcpyDefault, s));
-  CUDA_TRY(h, cudaStreamSynchronize(s));
-  if (status_any) std::memcpy(status_any, worst.data(), B * sizeof(int32_t));
-  return DOJO_OK;
+  cudaFree(dU); cudaFree(dtraj);
+  return rc;
 }
 
 // gradients: implemented in dojo_grad.cu
@@ -692,12 +774,13 @@ extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.status = dstatus; a.iters = diters; a.flags = flags;
-  a.Fz = dFz; a.Fu = dFu;
+  a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr;
   a.counter = h->d_counter;
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
-  int grid = std::min(B, h->sm_count * h->envs_per_sm_grad);
-  dojo_step_kernel<true><<<grid, 32 * h->nw, h->grad_bytes, s>>>(a);
+  a.slot_stride = (int)(h->grad_bytes / sizeof(double));
+  int grid = std::min((B + h->slots_grad - 1) / h->slots_grad, h->sm_count * h->envs_per_sm_grad);
+  dojo_step_kernel<true><<<grid, 32 * h->nw * h->slots_grad, h->slots_grad * h->grad_bytes, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;

@@ -393,7 +393,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
         }
       }
     }
-    __syncthreads();
+    slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
@@ -426,7 +426,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
         }
       }
     }
-    __syncthreads();
+    slot_sync(c);
   }
 }
 
@@ -475,7 +475,7 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
   for (int j = c.tid; j < P.Ne; j += c.nthreads)
     if (P.joints[j].gv_off >= 0)
       for (int t = 0; t < 6 * P.ch; ++t) A[P.joints[j].gv_off + t] = 0.0;
-  __syncthreads();
+  slot_sync(c);
   bool ok = factorize(c);
   double* V = A + P.gvec_off;
   for (int c0 = 0; c0 < P.ncol; c0 += P.ch) {
@@ -483,12 +483,12 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
     // are built by warp 0 .. nw-1 in slices of the chunk
     for (int l = c.tid; l < P.ch; l += c.nthreads)
       if (c0 + l < P.ncol) grad_build_rhs(c, V, c0 + l, l);
-    __syncthreads();
+    slot_sync(c);
     const bool active = c.lane < P.ch && c0 + c.lane < P.ncol;
     grad_solve_columns(c, V, active);
     for (int l = c.tid; l < P.ch; l += c.nthreads)
       if (c0 + l < P.ncol) grad_write_column(c, V, c0 + l, l, Fz, Fu);
-    __syncthreads();
+    slot_sync(c);
   }
   return ok;
 }

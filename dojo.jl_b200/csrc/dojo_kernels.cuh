@@ -42,7 +42,8 @@ DJ_DEV Quat ldq(const double* p) { return Quat{p[0], p[1], p[2], p[3]}; }
 struct Ctx {
   double* A;  // this environment's arena
   const Plan* P;
-  int tid, nthreads, warp, lane;
+  int tid, nthreads, warp, lane;  // thread / warp index inside this environment's slot (nthreads = 32 nw)
+  int bar;                        // named barrier of the slot (1 + slot index); barrier 0 is the CTA-wide alignment barrier
   double mu;
 #ifdef DJ_PROFILE
   long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_last;
@@ -57,27 +58,35 @@ struct Ctx {
 #define DJ_FTICK(c, field) {}
 #endif
 
-// CTA-wide reductions (deterministic: per-warp shuffles, then a fixed-order combine of the nw partials)
+// Barrier over the nw warps that own this environment.  A CTA hosts several environments ("slots"), each with its own
+// arena and its own named barrier, so that the slots only meet at the CTA-wide alignment point of the Newton loop.
+DJ_DEV void slot_sync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "r"(c.nthreads) : "memory"); }
+
+// CTA-wide alignment barrier (barrier 0); returns whether any slot of the CTA still has work.  Slots that ran out of
+// environments keep arriving here (with live = false) until every slot is done.
+DJ_DEV bool cta_align(bool live) { return __syncthreads_or(live ? 1 : 0) != 0; }
+
+// slot-wide reductions (deterministic: per-warp shuffles, then a fixed-order combine of the nw partials)
 DJ_DEV void block_nanmax2(const Ctx& c, double& a, double& b) {
   double* red = c.A + c.P->red_off;
   a = warp_nanmax(a);
   b = warp_nanmax(b);
   if (c.P->nw == 1) return;
   if (c.lane == 0) { red[2 * c.warp] = a; red[2 * c.warp + 1] = b; }
-  __syncthreads();
+  slot_sync(c);
   a = red[0]; b = red[1];
   for (int w = 1; w < c.P->nw; ++w) { a = nanmax(a, red[2 * w]); b = nanmax(b, red[2 * w + 1]); }
-  __syncthreads();
+  slot_sync(c);
 }
 DJ_DEV double block_min(const Ctx& c, double a) {
   double* red = c.A + c.P->red_off;
   a = warp_min(a);
   if (c.P->nw == 1) return a;
   if (c.lane == 0) red[c.warp] = a;
-  __syncthreads();
+  slot_sync(c);
   a = red[0];
   for (int w = 1; w < c.P->nw; ++w) a = fmin(a, red[w]);
-  __syncthreads();
+  slot_sync(c);
   return a;
 }
 DJ_DEV void block_sum3(const Ctx& c, double& a, double& b, double& d) {
@@ -85,10 +94,10 @@ DJ_DEV void block_sum3(const Ctx& c, double& a, double& b, double& d) {
   a = warp_sum(a); b = warp_sum(b); d = warp_sum(d);
   if (c.P->nw == 1) return;
   if (c.lane == 0) { red[3 * c.warp] = a; red[3 * c.warp + 1] = b; red[3 * c.warp + 2] = d; }
-  __syncthreads();
+  slot_sync(c);
   a = red[0]; b = red[1]; d = red[2];
   for (int w = 1; w < c.P->nw; ++w) { a += red[3 * w]; b += red[3 * w + 1]; d += red[3 * w + 2]; }
-  __syncthreads();
+  slot_sync(c);
 }
 
 // node index handled by this lane for role pass p (or -1)
@@ -269,7 +278,7 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
   for (int i = 0; i < 2 * jd.nb_r; ++i) so[jd.ne + i] = 1.0;
 }
 
-DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restrict__ u, const double* __restrict__ fext, const bool grad) {
+DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, const double* __restrict__ fext, const bool grad) {
   const Plan& P = *c.P;
   double* A = c.A;
   const WarpRole& role = P.roles[c.warp];
@@ -283,7 +292,7 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
     else if (k < 10) A[bd.st_off + 3 + (k - 6)] = val;
     else A[P.sol_off + bd.sol_off + 3 + (k - 10)] = val;
   }
-  __syncthreads();
+  slot_sync(c);
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
@@ -311,7 +320,7 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
       so[4] = v0; so[5] = v0; so[6] = 0.0; so[7] = 0.0;
     }
   }
-  __syncthreads();
+  slot_sync(c);
   // cst -= [JF2; Jtau2] + spring impulses, gathered per body in a fixed order
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
@@ -324,7 +333,7 @@ DJ_DEV void prologue(Ctx& c, const double* __restrict__ z, const double* __restr
       add3(cst + 3, -ld3(s + 3));
     }
   }
-  __syncthreads();
+  slot_sync(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -780,7 +789,7 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
   double rv = 0.0, bv = 0.0;
   if (JAC) {  // all KKT blocks are rewritten: zero the matrix region cooperatively, then scatter the non-zeros
     for (int t = c.tid; t < P.mat_len; t += c.nthreads) A[P.mat_off + t] = 0.0;
-    __syncthreads();
+    slot_sync(c);
   }
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
@@ -789,7 +798,7 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
     else if (role.type[p] == ROLE_CONTACT) eval_contact<JAC>(c, idx, f, res, rv, bv);
     else eval_joint<JAC>(c, idx, f, res, rv, bv);
   }
-  __syncthreads();
+  slot_sync(c);
   // gather the impulse contributions of the incident joints / contacts into the body rows (fixed order)
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
@@ -819,7 +828,7 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
   block_nanmax2(c, rv, bv);
   rvio = rv;
   bvio = bv;
-  __syncthreads();
+  slot_sync(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -856,10 +865,18 @@ DJ_DEV bool factorize(Ctx& c) {
                        st.nb[j].n, c.lane);
       DJ_FTICK(c, f_schur)
     }
-    __syncthreads();
+    slot_sync(c);
     DJ_FTICK(c, f_bar)
   }
-  return __syncthreads_and(ok ? 1 : 0) != 0;
+  // all warps of the slot agree on the outcome
+  int* flag = (int*)(A + P.red_off);
+  const bool wok = __all_sync(0xffffffffu, ok);
+  if (c.lane == 0) flag[c.warp] = wok ? 1 : 0;
+  slot_sync(c);
+  bool all = true;
+  for (int w = 0; w < P.nw; ++w) all = all && (flag[w] != 0);
+  slot_sync(c);
+  return all;
 }
 
 // x <- KKT^{-1} x for the vector at arena offset vec_off (solution ordering)
@@ -877,7 +894,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     if (role.type[p] == ROLE_CONTACT) condense_contact(c, idx, x);
     else if (role.type[p] == ROLE_JOINT) condense_joint(c, idx, x);
   }
-  __syncthreads();
+  slot_sync(c);
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, lane);
     if (idx < 0 || role.type[p] != ROLE_BODY) continue;
@@ -889,7 +906,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
       add3(xb + 3, ld3(s + 3));
     }
   }
-  __syncthreads();
+  slot_sync(c);
   for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c   (lanes [0,16) serve nb[0], [16,32) nb[1])
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0; s < s0 + sn; ++s) {
@@ -917,7 +934,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
       }
       __syncwarp();
     }
-    __syncthreads();
+    slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
@@ -948,7 +965,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
       if (lane < st.n) xc[lane] = acc;
       __syncwarp();
     }
-    __syncthreads();
+    slot_sync(c);
   }
   // recover the condensed-out steps (ds, dgamma) of the contacts and joint limits
   for (int p = 0; p < role.npass; ++p) {
@@ -957,7 +974,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     if (role.type[p] == ROLE_CONTACT) recover_contact(c, idx, x);
     else if (role.type[p] == ROLE_JOINT) recover_joint(c, idx, x);
   }
-  __syncthreads();
+  slot_sync(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1063,7 +1080,7 @@ DJ_DEV void correction(Ctx& c) {
       }
     }
   }
-  __syncthreads();
+  slot_sync(c);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1090,8 +1107,12 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
   for (;;) {
     double rv, bv;
     DJ_TICK(c, t_misc)
-    if (mode == 0) evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
-    else evaluate<false>(c, fk, P.sav_off, rv, bv);
+    if (mode == 0) {
+      // alignment point: the environments hosted by this CTA start every Newton iteration together, so that their warps run
+      // the same (large, straight-line) code at the same time and share its instruction fetches
+      cta_align(true);
+      evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
+    } else evaluate<false>(c, fk, P.sav_off, rv, bv);
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
     if (mode == 1) {
       // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
@@ -1106,14 +1127,14 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       const double* dl = A + P.rhs_off;
       if (fsel != 0.0) {
         for (int t = c.tid; t < P.nres; t += c.nthreads) sol[t] += fsel * dl[t];
-        __syncthreads();
+        slot_sync(c);
         if (c.tid < P.Nb) {
           double* w = sol + P.bodies[c.tid].sol_off + 3;
           double wmax = 3.9 / (P.h * P.h);
           double wd = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
           if (wd > wmax) { double k = wmax / wd; w[0] *= k; w[1] *= k; w[2] *= k; }
         }
-        __syncthreads();
+        slot_sync(c);
       }
       mode = 0; fk = 0.0;
       continue;  // set_entries! at the new iterate (mu = mutarget)
@@ -1125,7 +1146,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
     if (ndone >= o.max_iter) break;
     ndone += 1;
     for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.sav_off + t] = A[P.rhs_off + t];  // pull_residual!
-    __syncthreads();
+    slot_sync(c);
     DJ_TICK(c, t_misc)
     if (!factorize(c)) { status = 3; break; }
     DJ_TICK(c, t_fact)
@@ -1148,7 +1169,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
         c.mu = mutarget;
         correction(c);
         for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.rhs_off + t] = A[P.sav_off + t];  // push_residual!
-        __syncthreads();
+        slot_sync(c);
       }
     }
     mode = 1; fk = alpha; ls_k = 0;

@@ -20,7 +20,7 @@ STATUS = {0: "success", 1: "failed", 2: "excessive_angular_velocity", 3: "nonfin
 
 EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_error", "dojo_num_state", "dojo_num_input",
            "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env", "dojo_step", "dojo_step_async",
-           "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_launch_count"]
+           "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count"]
 
 _lib = None
 
@@ -57,6 +57,8 @@ def load_library():
     L.dojo_step_grad_async.restype = C.c_int
     L.dojo_rollout.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.dojo_rollout.restype = C.c_int
+    L.dojo_rollout_async.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.dojo_rollout_async.restype = C.c_int
     _lib = L
     return L
 
@@ -173,6 +175,13 @@ class BatchedStepper:
         rc = self.L.dojo_step_async(self.h, C.byref(o), int(B), _p(dZ), _p(dU), _p(dfext), _p(dZn), _p(dsol), _p(dstatus), _p(diters), flags,
                                     C.c_void_p(int(stream)))
         self._check(rc, "dojo_step_async")
+
+    def rollout_device(self, dZ0: int, dU: Optional[int], dZf: int, B: int, T: int, opts=None, dtraj: Optional[int] = None, dstatus: Optional[int] = None,
+                       stream: int = 0):
+        """T steps fused in one launch on resident data (U is [T, B, nu] on the device)."""
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_rollout_async(self.h, C.byref(o), int(B), int(T), _p(dZ0), _p(dU), _p(dZf), _p(dtraj), _p(dstatus), C.c_void_p(int(stream)))
+        self._check(rc, "dojo_rollout_async")
 
     def step_grad_device(self, dZ: int, dU: Optional[int], dZn: int, dFz: int, dFu: int, B: int, opts=None, dstatus=None, diters=None, flags: int = 0,
                          stream: int = 0):

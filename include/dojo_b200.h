@@ -163,9 +163,15 @@ int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, co
 
 /* simulate!: T steps with the state resident on the device.  U is [nu x B x T] (step-major) or
  * NULL (zero input); Z_traj nullable [13Nb x B x T] receives the state after every step
- * (Storage, src/simulation/storage.jl:15-42); Z_final [13Nb x B]; status_any [B] = max status. */
+ * (Storage, src/simulation/storage.jl:15-42); Z_final [13Nb x B]; status_any [B] = max status.
+ * The T steps are fused in ONE kernel launch: the CTA that dequeues an environment advances it through all steps. */
 int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0,
                  const double* U, double* Z_final, double* Z_traj, int32_t* status_any);
+
+/* device-pointer variant of dojo_rollout: one launch, no synchronisation */
+int dojo_rollout_async(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* dZ0,
+                       const double* dU, double* dZ_final, double* dZ_traj, int32_t* dstatus_any,
+                       void* cuda_stream);
 
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t dojo_launch_count(const DojoHandle* h);

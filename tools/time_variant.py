@@ -26,6 +26,17 @@ for t in range(20, 20 + steps):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"{os.path.basename(sys.argv[1]):20s} {name} B={B}: {ms:8.3f} ms/step  {B/ms*1e3:10.0f} env-steps/s  smem/env {s.shared_bytes_per_env}  checksum {float(Za.sum()):.9f}")
+if hasattr(s, "rollout_device") and os.environ.get("DJ_ROLLOUT", "1") != "0":
+    # fused rollout: the same `steps` steps in ONE launch (environment-resident across steps)
+    Zr = Za.clone(); Zf = torch.empty_like(Za)
+    Ur = U[20:20 + steps].contiguous()
+    s.rollout_device(Zr.data_ptr(), Ur.data_ptr(), Zf.data_ptr(), B, steps, stream=st)
+    torch.cuda.synchronize()
+    e0.record()
+    s.rollout_device(Zr.data_ptr(), Ur.data_ptr(), Zf.data_ptr(), B, steps, stream=st)
+    e1.record(); torch.cuda.synchronize()
+    msr = e0.elapsed_time(e1) / steps
+    print(f"{'':20s} fused rollout T={steps}: {msr:8.3f} ms/step  {B/msr*1e3:10.0f} env-steps/s")
 if os.environ.get("DJ_PROF"):
     import ctypes as C
     out = (C.c_ulonglong * 10)()
