@@ -34,6 +34,8 @@ struct StepArgs {
   double* Fu;
   uint32_t flags;
   int* counter;  // dynamic work queue over environments
+  const int* order;     // processing order (longest-expected first), or nullptr
+  int32_t* prev_iters;  // Newton iterations of the previous call per environment (predicts the cost of the next one)
   int slot_stride;      // doubles between the arenas of two slots of a CTA
   int T;                // time steps fused in this launch (rollouts: every environment is advanced T steps by one CTA)
   double* traj;         // nullable [T][B][nz]: state after every step
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   for (;;) {
     if (c.tid == 0) {  // dynamic work queue: iteration counts differ between environments
       int q = atomicAdd(a.counter, 1);
-      s_env[slot] = q;
+      s_env[slot] = (q < a.B && a.order) ? a.order[q] : q;
     }
     slot_sync(c);
     const int e = s_env[slot];
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     if (c.tid == 0) {
       if (a.status) a.status[e] = status;
       if (a.iters) a.iters[e] = iters;
+      if (a.prev_iters) a.prev_iters[e] = iters;
 #ifdef DJ_PROFILE
       if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[16 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[17 + 2 * e] = e_t1 - e_t0; }
 #endif
@@ -163,6 +166,25 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     atomicMax(a.prof + 12, (unsigned long long)k_envs); atomicAdd(a.prof + 13, (unsigned long long)(clock64() - k_c0));
   }
 #endif
+}
+
+
+// Longest-processing-time-first order.  The cost of an environment's step is proportional to its Newton-iteration count
+// (7 .. max_iter, and line-search retries grow with it), which is correlated from one time step to the next; environments
+// that stalled in the previous call are started first so that they do not end up alone at the tail of the launch.
+// Counting sort by decreasing iteration count (one CTA; the order of equal keys is irrelevant to the results).
+__global__ void dojo_order_kernel(const int32_t* __restrict__ prev_iters, int B, int* __restrict__ order) {
+  __shared__ int hist[128], start[128];
+  if (threadIdx.x < 128) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < B; e += blockDim.x) atomicAdd(&hist[min(max(prev_iters[e], 0), 127)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 127; k >= 0; --k) { start[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < B; e += blockDim.x) order[atomicAdd(&start[min(max(prev_iters[e], 0), 127)], 1)] = e;
 }
 
 
@@ -190,6 +212,9 @@ struct DojoHandle {
   int* d_ilist = nullptr;
   WarpRole* d_roles = nullptr;
   int* d_counter = nullptr;
+  int* d_order = nullptr;          // LPT processing order of the next call
+  int32_t* d_prev_iters = nullptr;  // iteration counts of the previous call
+  bool lpt = true;
   unsigned long long* d_prof = nullptr;
   // staging for host-pointer calls
   double *d_Z = nullptr, *d_U = nullptr, *d_F = nullptr, *d_Zn = nullptr, *d_sol = nullptr;
@@ -548,6 +573,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
             upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
             upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles) && upload(ucol.data(), sizeof(int) * ucol.size(), (void**)&h->d_ucol);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_order, sizeof(int) * max_batch) == cudaSuccess && cudaMalloc((void**)&h->d_prev_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
+       cudaMemset(h->d_prev_iters, 0, sizeof(int32_t) * max_batch) == cudaSuccess;
+  if (const char* e = getenv("DOJO_B200_LPT")) h->lpt = atoi(e) != 0;
   ok = ok && cudaMalloc((void**)&h->d_prof, (16 + 2 * (size_t)max_batch) * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMemset(h->d_prof + 14, 0xff, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -630,6 +658,12 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
   a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr;
   a.counter = h->d_counter;
+  // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
+  // simulation loops do; a stale order is harmless -- it is just an order)
+  const bool lpt = h->lpt && B <= h->max_batch && B > h->sm_count * h->envs_per_sm * h->slots;
+  a.order = lpt ? h->d_order : nullptr;
+  a.prev_iters = (h->lpt && B <= h->max_batch) ? h->d_prev_iters : nullptr;
+  if (lpt) { dojo_order_kernel<<<1, 1024, 0, s>>>(h->d_prev_iters, B, h->d_order); h->launches += 1; }
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
@@ -714,7 +748,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
   a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj;
-  a.counter = h->d_counter; a.prof = h->d_prof;
+  a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
   int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
@@ -776,6 +810,12 @@ extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.status = dstatus; a.iters = diters; a.flags = flags;
   a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr;
   a.counter = h->d_counter;
+  // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
+  // simulation loops do; a stale order is harmless -- it is just an order)
+  const bool lpt = h->lpt && B <= h->max_batch && B > h->sm_count * h->envs_per_sm_grad * h->slots_grad;
+  a.order = lpt ? h->d_order : nullptr;
+  a.prev_iters = (h->lpt && B <= h->max_batch) ? h->d_prev_iters : nullptr;
+  if (lpt) { dojo_order_kernel<<<1, 1024, 0, s>>>(h->d_prev_iters, B, h->d_order); h->launches += 1; }
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->grad_bytes / sizeof(double));

@@ -838,31 +838,34 @@ DJ_DEV bool factorize(Ctx& c) {
   const Plan& P = *c.P;
   double* A = c.A;
   bool ok = true;
+  // the two halves of a warp eliminate two steps of the phase at the same time (blocks are at most 6 x 6: 12 lanes busy)
+  const int half = c.lane >> 4, l = c.lane & 15;
+  const unsigned mask = 0xffffu << (16 * half);
 #ifdef DJ_PROFILE
   c.f_last = clock64();
 #endif
   for (int ph = 0; ph < P.nphase; ++ph) {
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0; s < s0 + sn; ++s) {
+    for (int s = s0 + half; s < s0 + sn; s += 2) {
       const ElimStep& st = P.steps[s];
       double* Dc = A + st.d_off;
       if (st.fold_cnt > 0) {  // fold the children's scratch updates into D_c
-        for (int t = c.lane; t < st.n * st.n; t += 32) {
+        for (int t = l; t < st.n * st.n; t += 16) {
           double acc = Dc[t];
           for (int k = 0; k < st.fold_cnt; ++k) acc += A[P.ilist[st.fold_off + k] + t];
           Dc[t] = acc;
         }
-        __syncwarp();
+        __syncwarp(mask);
       }
       DJ_FTICK(c, f_fold)
-      ok = block_inverse(Dc, st.n, st.n, c.lane) && ok;                                                  // D_c <- D_c^-1
+      ok = block_inverse(Dc, st.n, st.n, l, mask) && ok;                                                  // D_c <- D_c^-1
       DJ_FTICK(c, f_inv)
-      for (int i = 0; i < st.nnb; ++i) right_multiply_inplace(A + st.nb[i].L_off, Dc, st.nb[i].n, st.n, c.lane);  // L~_ic = M_ic D_c^-1
+      for (int i = 0; i < st.nnb; ++i) right_multiply_inplace(A + st.nb[i].L_off, Dc, st.nb[i].n, st.n, l, mask);  // L~_ic = M_ic D_c^-1
       DJ_FTICK(c, f_rm)
       for (int i = 0; i < st.nnb; ++i)
         for (int j = 0; j < st.nnb; ++j)                                                                  // M_ij -= L~_ic M_cj
           schur_update(A + st.tgt[i][j], A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
-                       st.nb[j].n, c.lane);
+                       st.nb[j].n, l, mask);
       DJ_FTICK(c, f_schur)
     }
     slot_sync(c);
@@ -885,7 +888,9 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
   double* A = c.A;
   double* x = A + vec_off;
   const int lane = c.lane;
-  const int half = lane >> 4, li = lane & 15;
+  const int half = lane >> 4, l = lane & 15;  // one elimination step per half-warp, as in factorize()
+  const unsigned mask = 0xffffu << (16 * half);
+  const int sub = l >> 3, li = l & 7;         // forward substitution: lanes [0,8) of the group serve nb[0], [8,16) nb[1]
   const WarpRole& role = P.roles[c.warp];
   // condense the right-hand side of the contact / joint-limit rows onto the body rows
   for (int p = 0; p < role.npass; ++p) {
@@ -907,63 +912,64 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     }
   }
   slot_sync(c);
-  for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c   (lanes [0,16) serve nb[0], [16,32) nb[1])
+  for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0; s < s0 + sn; ++s) {
+    for (int s = s0 + half; s < s0 + sn; s += 2) {
       const ElimStep& st = P.steps[s];
       double* xc = x + st.vec_off;
       if (st.fold_cnt > 0) {  // fold (and clear) the children's forward updates of this body
-        if (lane < st.n) {
-          double acc = xc[lane];
+        if (l < st.n) {
+          double acc = xc[l];
           for (int k = 0; k < st.fold_cnt; ++k) {
             double* v = A + P.ilist[st.fold_off + k] + 36;
-            acc += v[lane];
-            v[lane] = 0.0;
+            acc += v[l];
+            v[l] = 0.0;
           }
-          xc[lane] = acc;
+          xc[l] = acc;
         }
-        __syncwarp();
+        __syncwarp(mask);
       }
-      if (half < st.nnb && li < st.nb[half].n) {
-        const ElimNb& nb = st.nb[half];
-        const double* L = A + nb.L_off;
+      if (sub < st.nnb && li < st.nb[sub].n) {
+        const ElimNb& nb = st.nb[sub];
+        const double* L = A + nb.L_off + li * st.n;
         double acc = 0.0;
-        for (int k = 0; k < st.n; ++k) acc += L[li * st.n + k] * xc[k];
+        for (int k = 0; k < st.n; ++k) acc += L[k] * xc[k];
         double* tgt = nb.fwd_abs >= 0 ? A + nb.fwd_abs : x + nb.vec_off;
         tgt[li] -= acc;
       }
-      __syncwarp();
+      __syncwarp(mask);
     }
     slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
     const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0 + sn - 1; s >= s0; --s) {
+    // same pairing as the forward sweep, last pair first (the steps of one phase are independent)
+    for (int s = s0 + half + 2 * ((sn - 1 - half) >> 1); s >= s0 + half && sn > half; s -= 2) {
       const ElimStep& st = P.steps[s];
       const double* Dc = A + st.d_off;
       double* xc = x + st.vec_off;
       if (st.nnb > 0) {
-        if (lane < st.n) {
+        if (l < st.n) {
           double acc = 0.0;
           for (int j = 0; j < st.nnb; ++j) {
             const ElimNb& nb = st.nb[j];
-            int r = lane - nb.U_row;
+            int r = l - nb.U_row;
             if (r >= 0 && r < nb.U_k) {
-              const double* U = A + nb.U_off;
+              const double* U = A + nb.U_off + r * nb.n;
               const double* xj = x + nb.vec_off;
-              for (int k = 0; k < nb.n; ++k) acc += U[r * nb.n + k] * xj[k];
+              for (int k = 0; k < nb.n; ++k) acc += U[k] * xj[k];
             }
           }
-          xc[lane] -= acc;
+          xc[l] -= acc;
         }
-        __syncwarp();
+        __syncwarp(mask);
       }
       double acc = 0.0;
-      if (lane < st.n)
-        for (int k = 0; k < st.n; ++k) acc += Dc[lane * st.n + k] * xc[k];
-      __syncwarp();
-      if (lane < st.n) xc[lane] = acc;
-      __syncwarp();
+      if (l < st.n)
+        for (int k = 0; k < st.n; ++k) acc += Dc[l * st.n + k] * xc[k];
+      __syncwarp(mask);
+      if (l < st.n) xc[l] = acc;
+      __syncwarp(mask);
     }
     slot_sync(c);
   }

@@ -30,7 +30,7 @@ for t in range(30):
     s.L.dojo_debug_env_times(s.h, buf.ctypes.data_as(C.c_void_p), B)
     start, dur = buf[0::2].astype(np.float64) * 1e-6, buf[1::2].astype(np.float64) * 1e-6
     iters, stat = it.cpu().numpy(), stt.cpu().numpy()
-    grid = min(B, 148 * max(1, (227 * 1024) // (s.shared_bytes_per_env + 1024)))
+    grid = min(B, 148 * min(max(1, (227 * 1024) // s.shared_bytes_per_env), 4))  # environments in flight
     print(f"step {t}: wall {e0.elapsed_time(e1):.2f} ms  sum(dur)/grid({grid}) {dur.sum()/grid:.2f} ms  max(start+dur) {np.max(start+dur):.2f}  max dur {dur.max():.2f}  failed {int((stat!=0).sum())}")
     q = np.quantile(dur, [0.5, 0.9, 0.99, 0.999]); print("   dur quantiles 50/90/99/99.9 % (ms):", np.round(q, 2), " iters quantiles:", np.quantile(iters, [0.5, 0.9, 0.99, 0.999]))
     top = np.argsort(-dur)[:8]
