@@ -36,6 +36,9 @@ struct StepArgs {
   int* counter;  // dynamic work queue over environments
   const int* order;     // processing order (longest-expected first), or nullptr
   int32_t* prev_iters;  // Newton iterations of the previous call per environment (predicts the cost of the next one)
+  const char* plan_blob;  // plan tables, one contiguous blob: [bodies | joints | contacts | steps | sched | ilist | roles | ucol]
+  int plan_bytes, plan_off[8];
+  int plan_smem_off;    // >= 0: doubles from the start of dynamic shared memory where the CTA keeps its copy of the blob
   int slot_stride;      // doubles between the arenas of two slots of a CTA
   int T;                // time steps fused in this launch (rollouts: every environment is advanced T steps by one CTA)
   double* traj;         // nullable [T][B][nz]: state after every step
@@ -66,7 +69,7 @@ DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
 #define DJ_LB_BLOCKS 1
 #endif
 #ifdef DJ_PROFILE
-__device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { return *((volatile unsigned long long*)(prof + 14)); }
+__device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { return *((volatile unsigned long long*)(prof + 31)); }
 #endif
 template <bool GRAD>
 __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(const StepArgs a) {
@@ -84,12 +87,30 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   c.lane = c.tid & 31;
   c.bar = 1 + slot;
   c.mu = 0.0;
+  {
+    const char* pb = a.plan_blob;
+    if (a.plan_smem_off >= 0) {  // one copy of the plan tables per CTA, shared by its slots
+      int4* dst = reinterpret_cast<int4*>(arena + a.plan_smem_off);
+      const int4* src = reinterpret_cast<const int4*>(a.plan_blob);
+      for (int i = threadIdx.x; i < a.plan_bytes / 16; i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+      pb = reinterpret_cast<const char*>(dst);
+    }
+    c.bodies = reinterpret_cast<const BodyDev*>(pb + a.plan_off[0]);
+    c.joints = reinterpret_cast<const JointDev*>(pb + a.plan_off[1]);
+    c.contacts = reinterpret_cast<const ContactDev*>(pb + a.plan_off[2]);
+    c.steps = reinterpret_cast<const ElimStep*>(pb + a.plan_off[3]);
+    c.sched = reinterpret_cast<const int*>(pb + a.plan_off[4]);
+    c.ilist = reinterpret_cast<const int*>(pb + a.plan_off[5]);
+    c.roles = reinterpret_cast<const WarpRole*>(pb + a.plan_off[6]);
+    c.ucol = reinterpret_cast<const int*>(pb + a.plan_off[7]);
+  }
 #ifdef DJ_PROFILE
-  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = 0; c.t_last = clock64();
+  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = c.t_align = c.t_cone = c.t_center = 0; c.t_last = clock64();
   c.f_fold = c.f_inv = c.f_rm = c.f_schur = c.f_bar = 0;
   long long k_c0 = clock64(); unsigned long long k_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
   int k_envs = 0;
-  if (c.tid == 0 && a.prof) atomicMin(a.prof + 14, k_t0);
+  if (c.tid == 0 && a.prof) atomicMin(a.prof + 31, k_t0);
 #endif
   const Plan& P = a.plan;
   for (;;) {
@@ -131,11 +152,11 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     }
     if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
       double* so = a.sol + (size_t)e * P.nres;
-      const int first_body = P.bodies[0].sol_off;
+      const int first_body = c.bodies[0].sol_off;
       for (int t = c.tid; t < P.nres; t += c.nthreads)
         if (t >= first_body) so[t] = c.A[P.sol_off + t];
       if (c.tid < P.Ne) {
-        const JointDev& jd = P.joints[c.tid];
+        const JointDev& jd = c.joints[c.tid];
         const double* src = c.A + P.sol_off + jd.sol_off;
         double* dst = so + jd.sol_off;
         for (int i = 0; i < jd.nl_t; ++i) dst[i] = src[i];
@@ -148,7 +169,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
       if (a.iters) a.iters[e] = iters;
       if (a.prev_iters) a.prev_iters[e] = iters;
 #ifdef DJ_PROFILE
-      if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[16 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[17 + 2 * e] = e_t1 - e_t0; }
+      if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[32 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[33 + 2 * e] = e_t1 - e_t0; }
 #endif
     }
     slot_sync(c);
@@ -164,6 +185,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     unsigned long long k_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t1));
     atomicMax(a.prof + 10, (unsigned long long)(clock64() - k_c0)); atomicMax(a.prof + 11, k_t1 - k_t0);
     atomicMax(a.prof + 12, (unsigned long long)k_envs); atomicAdd(a.prof + 13, (unsigned long long)(clock64() - k_c0));
+    atomicAdd(a.prof + 14, (unsigned long long)c.t_align); atomicAdd(a.prof + 15, (unsigned long long)c.t_cone); atomicAdd(a.prof + 16, (unsigned long long)c.t_center);
   }
 #endif
 }
@@ -199,18 +221,14 @@ struct DojoHandle {
   int slots = 1, slots_grad = 1;  // environments hosted by one CTA
   Plan plan;  // device pointers inside
   int nw = 4;  // warps per environment
-  size_t arena_bytes = 0, grad_bytes = 0;
+  size_t arena_bytes = 0, grad_bytes = 0;  // per environment
+  size_t smem_fwd = 0, smem_grad = 0;     // dynamic shared memory per CTA
   int envs_per_sm_grad = 1;
-  int* d_ucol = nullptr;
   double *d_Fz = nullptr, *d_Fu = nullptr;  // staging for host-pointer gradient calls (grad_chunk environments)
   int grad_chunk = 0;
-  BodyDev* d_bodies = nullptr;
-  JointDev* d_joints = nullptr;
-  ContactDev* d_contacts = nullptr;
-  ElimStep* d_steps = nullptr;
-  int* d_sched = nullptr;
-  int* d_ilist = nullptr;
-  WarpRole* d_roles = nullptr;
+  char* d_blob = nullptr;  // plan tables (one contiguous upload)
+  int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
   int* d_counter = nullptr;
   int* d_order = nullptr;          // LPT processing order of the next call
   int32_t* d_prev_iters = nullptr;  // iteration counts of the previous call
@@ -384,7 +402,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   }
   P.mat_len = a - P.mat_off;
   P.arena_len = a;
-  h->arena_bytes = (size_t)a * sizeof(double);
+  h->arena_bytes = (size_t)((a + 1) & ~1) * sizeof(double);  // 16-byte multiples: slots and the plan tables follow each other
 
   // ---- gradient workspace (appended to the arena; only the gradient kernel allocates it)
   std::vector<int> ucol;
@@ -412,7 +430,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
       if ((size_t)g * sizeof(double) <= 113 * 1024) break;
       if (pass >= 1 && (size_t)P.arena_len * sizeof(double) > 100 * 1024 && (size_t)g * sizeof(double) <= 225 * 1024) break;
     }
-    h->grad_bytes = (size_t)P.grad_len * sizeof(double);
+    h->grad_bytes = (size_t)((P.grad_len + 1) & ~1) * sizeof(double);
   }
 
   // ---- gather lists (deterministic accumulation order): contacts of b, its parent joint (child side), its child joints
@@ -568,16 +586,25 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
-  bool ok = upload(bodies.data(), sizeof(BodyDev) * Nb, (void**)&h->d_bodies) && upload(joints.data(), sizeof(JointDev) * Ne, (void**)&h->d_joints) &&
-            upload(contacts.data(), sizeof(ContactDev) * Ni, (void**)&h->d_contacts) && upload(steps.data(), sizeof(ElimStep) * steps.size(), (void**)&h->d_steps) &&
-            upload(sched.data(), sizeof(int) * sched.size(), (void**)&h->d_sched) && upload(ilist.data(), sizeof(int) * ilist.size(), (void**)&h->d_ilist) &&
-            upload(roles.data(), sizeof(WarpRole) * roles.size(), (void**)&h->d_roles) && upload(ucol.data(), sizeof(int) * ucol.size(), (void**)&h->d_ucol);
+  std::vector<char> blob;
+  {
+    const void* src[8] = {bodies.data(), joints.data(), contacts.data(), steps.data(), sched.data(), ilist.data(), roles.data(), ucol.data()};
+    const size_t len[8] = {sizeof(BodyDev) * Nb, sizeof(JointDev) * Ne, sizeof(ContactDev) * Ni, sizeof(ElimStep) * steps.size(), sizeof(int) * sched.size(),
+                           sizeof(int) * ilist.size(), sizeof(WarpRole) * roles.size(), sizeof(int) * ucol.size()};
+    for (int k = 0; k < 8; ++k) {
+      h->blob_off[k] = (int)blob.size();
+      blob.insert(blob.end(), (const char*)src[k], (const char*)src[k] + len[k]);
+      blob.resize((blob.size() + 15) & ~size_t(15), 0);
+    }
+    h->blob_bytes = (int)blob.size();
+  }
+  bool ok = upload(blob.data(), blob.size(), (void**)&h->d_blob);
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&h->d_order, sizeof(int) * max_batch) == cudaSuccess && cudaMalloc((void**)&h->d_prev_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
        cudaMemset(h->d_prev_iters, 0, sizeof(int32_t) * max_batch) == cudaSuccess;
   if (const char* e = getenv("DOJO_B200_LPT")) h->lpt = atoi(e) != 0;
-  ok = ok && cudaMalloc((void**)&h->d_prof, (16 + 2 * (size_t)max_batch) * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)) == cudaSuccess &&
-       cudaMemset(h->d_prof + 14, 0xff, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->d_prof, (32 + 2 * (size_t)max_batch) * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long)) == cudaSuccess &&
+       cudaMemset(h->d_prof + 31, 0xff, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   // environments per CTA ("slots"): as many arenas as fit, at most 256 threads (the register file holds 256 threads at 255 registers)
   auto pick_slots = [&](size_t bytes) {
@@ -587,21 +614,30 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     return g;
   };
   h->slots = pick_slots(h->arena_bytes);
-  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->slots * h->arena_bytes)) == cudaSuccess;
+  // the plan tables ride along in shared memory when they fit behind the arenas
+  const bool smem_plan = !getenv("DOJO_B200_GLOBAL_PLAN");
+  if (smem_plan && h->slots * h->arena_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off = (int)(h->slots * h->arena_bytes / sizeof(double));
+  h->smem_fwd = h->slots * h->arena_bytes + (h->plan_smem_off >= 0 ? h->blob_bytes : 0);
+  ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fwd) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(dojo_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   const bool grad_fits = h->grad_bytes <= (size_t)prop.sharedMemPerBlockOptin;
   if (grad_fits) {
     h->slots_grad = pick_slots(h->grad_bytes);
-    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->slots_grad * h->grad_bytes)) == cudaSuccess;
+    if (smem_plan && h->slots_grad * h->grad_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off_grad = (int)(h->slots_grad * h->grad_bytes / sizeof(double));
+    h->smem_grad = h->slots_grad * h->grad_bytes + (h->plan_smem_off_grad >= 0 ? h->blob_bytes : 0);
+    ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_grad) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(dojo_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   } else h->grad_bytes = 0;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
-  P.bodies = h->d_bodies; P.joints = h->d_joints; P.contacts = h->d_contacts; P.steps = h->d_steps;
-  P.sched = h->d_sched; P.ilist = h->d_ilist; P.roles = h->d_roles; P.ucol = h->d_ucol;
+  // the device code reaches the tables through Ctx (shared-memory copy or this blob); the Plan pointers are kept for debugging
+  P.bodies = (const BodyDev*)(h->d_blob + h->blob_off[0]); P.joints = (const JointDev*)(h->d_blob + h->blob_off[1]);
+  P.contacts = (const ContactDev*)(h->d_blob + h->blob_off[2]); P.steps = (const ElimStep*)(h->d_blob + h->blob_off[3]);
+  P.sched = (const int*)(h->d_blob + h->blob_off[4]); P.ilist = (const int*)(h->d_blob + h->blob_off[5]);
+  P.roles = (const WarpRole*)(h->d_blob + h->blob_off[6]); P.ucol = (const int*)(h->d_blob + h->blob_off[7]);
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<false>, 32 * h->nw * h->slots, h->slots * h->arena_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<false>, 32 * h->nw * h->slots, h->smem_fwd);
   h->envs_per_sm = std::max(1, occ);
-  if (h->grad_bytes) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<true>, 32 * h->nw * h->slots_grad, h->slots_grad * h->grad_bytes); h->envs_per_sm_grad = std::max(1, occ); }
+  if (h->grad_bytes) { occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dojo_step_kernel<true>, 32 * h->nw * h->slots_grad, h->smem_grad); h->envs_per_sm_grad = std::max(1, occ); }
   *out = h;
   return DOJO_OK;
 }
@@ -609,8 +645,8 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_bodies); cudaFree(h->d_joints); cudaFree(h->d_contacts); cudaFree(h->d_steps); cudaFree(h->d_counter);
-  cudaFree(h->d_sched); cudaFree(h->d_ilist); cudaFree(h->d_roles); cudaFree(h->d_ucol); cudaFree(h->d_Fz); cudaFree(h->d_Fu);
+  cudaFree(h->d_blob); cudaFree(h->d_counter);
+  cudaFree(h->d_Fz); cudaFree(h->d_Fu);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
   if (h->p_out) cudaFreeHost(h->p_out);
@@ -628,14 +664,14 @@ extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->a
 extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
 // debugging aid (DJ_PROFILE builds): cycle counters accumulated by thread 0 of every CTA; out[5]
 extern "C" int dojo_debug_cycles(DojoHandle* h, unsigned long long* out) {
-  cudaMemcpy(out, h->d_prof, 14 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long));
-  cudaMemset(h->d_prof + 14, 0xff, sizeof(unsigned long long));
+  cudaMemcpy(out, h->d_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long));
+  cudaMemset(h->d_prof + 31, 0xff, sizeof(unsigned long long));
   return DOJO_OK;
 }
 // DJ_PROFILE builds: per-environment (start ns since the first CTA of the launch, duration ns) of the last launch
 extern "C" int dojo_debug_env_times(DojoHandle* h, unsigned long long* out, int B) {
-  cudaMemcpy(out, h->d_prof + 16, 2 * (size_t)B * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, h->d_prof + 32, 2 * (size_t)B * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   return DOJO_OK;
 }
 
@@ -667,8 +703,10 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off;
+  for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
-  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->slots * h->arena_bytes, s>>>(a);
+  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->smem_fwd, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
@@ -751,8 +789,10 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off;
+  for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
-  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->slots * h->arena_bytes, s>>>(a);
+  dojo_step_kernel<false><<<grid, 32 * h->nw * h->slots, h->smem_fwd, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
@@ -819,8 +859,10 @@ extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->grad_bytes / sizeof(double));
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off_grad;
+  for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots_grad - 1) / h->slots_grad, h->sm_count * h->envs_per_sm_grad);
-  dojo_step_kernel<true><<<grid, 32 * h->nw * h->slots_grad, h->slots_grad * h->grad_bytes, s>>>(a);
+  dojo_step_kernel<true><<<grid, 32 * h->nw * h->slots_grad, h->smem_grad, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;

@@ -45,7 +45,7 @@ DJ_DEV M33 transport(V3 w, double h) { return transpose(rotmat(qmap(w, h))); }  
 DJ_DEV void grad_body(Ctx& c, int idx) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const BodyDev& bd = P.bodies[idx];
+  const BodyDev& bd = c.bodies[idx];
   // the v15 / w15 columns need (x1, q1), i.e. the *initial* velocities: recovered from the constant residual part
   // cst is not invertible for that -> the kernel keeps w15 in the body record (written by the prologue)
   double* rec = A + bd.gb_off;
@@ -65,7 +65,7 @@ DJ_DEV void grad_body(Ctx& c, int idx) {
 DJ_DEV void grad_contact(Ctx& c, int idx) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const ContactDev& cd = P.contacts[idx];
+  const ContactDev& cd = c.contacts[idx];
   const double* so = A + P.sol_off + cd.sol_off;
   Kin k = body_kin(c, cd.body, 0.0);
   V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3), o = ld3(cd.o), off = ld3(cd.off);
@@ -119,7 +119,7 @@ DJ_DEV void grad_contact(Ctx& c, int idx) {
 DJ_DEV void grad_joint(Ctx& c, int idx) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const JointDev& jd = P.joints[idx];
+  const JointDev& jd = c.joints[idx];
   const int ne = jd.ne, nuj = jd.nfree_t + jd.nfree_r;
   double* RJp = A + jd.gj_off;
   double* RJc = RJp + 6 * ne;
@@ -316,7 +316,7 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
   for (int r = 0; r < P.n_red; ++r) V[r * ch + lane] = 0.0;
   if (col < 12 * P.Nb) {
     const int b = col / 12, k = col - 12 * b;
-    const BodyDev& bd = P.bodies[b];
+    const BodyDev& bd = c.bodies[b];
     if (k >= 3 && k < 6) {  // v15 column: m I on the linear rows (gradients/data.jl:30)
       V[(bd.r_off + (k - 3)) * ch + lane] = bd.mass;
     } else if (k >= 9) {    // w15 column
@@ -325,34 +325,34 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
       for (int r = 0; r < 3; ++r) V[(bd.r_off + 3 + r) * ch + lane] = dW[r * 3 + (k - 9)];
     } else {                // x2 (k < 3) or phi2 (6 <= k < 9) column
       const int cc = k < 3 ? k : k - 3;
-      const JointDev& pj = P.joints[bd.pjoint];
+      const JointDev& pj = c.joints[bd.pjoint];
       {  // parent joint: this body is the child
         const double* RJc = A + pj.gj_off + 6 * pj.ne;
         const double* BPc = RJc + 6 * pj.ne + 36;
         const double* BCc = BPc + 72;
         for (int r = 0; r < pj.ne; ++r) V[(pj.r_off + r) * ch + lane] += RJc[r * 6 + cc];
         add_col6(V, ch, lane, bd.r_off, BCc, 6, cc);
-        if (pj.parent >= 0) add_col6(V, ch, lane, P.bodies[pj.parent].r_off, BPc, 6, cc);
+        if (pj.parent >= 0) add_col6(V, ch, lane, c.bodies[pj.parent].r_off, BPc, 6, cc);
       }
       for (int q = 0; q < bd.cj_cnt; ++q) {  // child joints: this body is the parent
-        const JointDev& cj = P.joints[P.ilist[bd.cj_off + q]];
+        const JointDev& cj = c.joints[c.ilist[bd.cj_off + q]];
         const double* RJp = A + cj.gj_off;
         const double* BPp = RJp + 12 * cj.ne;
         const double* BCp = BPp + 72;
         for (int r = 0; r < cj.ne; ++r) V[(cj.r_off + r) * ch + lane] += RJp[r * 6 + cc];
         add_col6(V, ch, lane, bd.r_off, BPp, 6, cc);
-        add_col6(V, ch, lane, P.bodies[cj.child].r_off, BCp, 6, cc);
+        add_col6(V, ch, lane, c.bodies[cj.child].r_off, BCp, 6, cc);
       }
-      for (int q = 0; q < bd.ct_cnt; ++q) add_col6(V, ch, lane, bd.r_off, A + P.contacts[P.ilist[bd.ct_off + q]].gc_off, 6, cc);
+      for (int q = 0; q < bd.ct_cnt; ++q) add_col6(V, ch, lane, bd.r_off, A + c.contacts[c.ilist[bd.ct_off + q]].gc_off, 6, cc);
     }
   } else {  // input column
     const int ui = col - 12 * P.Nb;
-    const JointDev& jd = P.joints[P.ucol[2 * ui]];
-    const int dof = P.ucol[2 * ui + 1], nuj = jd.nfree_t + jd.nfree_r;
+    const JointDev& jd = c.joints[c.ucol[2 * ui]];
+    const int dof = c.ucol[2 * ui + 1], nuj = jd.nfree_t + jd.nfree_r;
     const double* Up = A + jd.gj_off + 12 * jd.ne + 144;
     const double* Uc = Up + 6 * nuj;
-    if (jd.parent >= 0) add_col6(V, ch, lane, P.bodies[jd.parent].r_off, Up, nuj, dof);
-    add_col6(V, ch, lane, P.bodies[jd.child].r_off, Uc, nuj, dof);
+    if (jd.parent >= 0) add_col6(V, ch, lane, c.bodies[jd.parent].r_off, Up, nuj, dof);
+    add_col6(V, ch, lane, c.bodies[jd.child].r_off, Uc, nuj, dof);
   }
 }
 
@@ -362,16 +362,16 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
   double* A = c.A;
   const int ch = P.ch, lane = c.lane;
   for (int ph = 0; ph < P.nphase; ++ph) {
-    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0; s < s0 + sn; ++s) {
-      const ElimStep& st = P.steps[s];
+      const ElimStep& st = c.steps[s];
       if (!active) continue;
       double zc[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) zc[k] = (k < st.n) ? V[(st.r_off + k) * ch + lane] : 0.0;
       if (st.fold_cnt > 0) {
         for (int q = 0; q < st.fold_cnt; ++q) {
-          double* v = A + P.ilist[st.gfold_off + q];
+          double* v = A + c.ilist[st.gfold_off + q];
 #pragma unroll
           for (int k = 0; k < 6; ++k)
             if (k < st.n) { zc[k] += v[k * ch + lane]; v[k * ch + lane] = 0.0; }
@@ -396,9 +396,9 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
     slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {
-    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0 + sn - 1; s >= s0; --s) {
-      const ElimStep& st = P.steps[s];
+      const ElimStep& st = c.steps[s];
       if (!active) continue;
       double t[6];
 #pragma unroll
@@ -437,7 +437,7 @@ DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, double
   const int ch = P.ch, ng = 12 * P.Nb;
   double* out = col < ng ? Fz + (size_t)col * ng : Fu + (size_t)(col - ng) * ng;
   for (int b = 0; b < P.Nb; ++b) {
-    const BodyDev& bd = P.bodies[b];
+    const BodyDev& bd = c.bodies[b];
     const double* rec = A + bd.gb_off;
     V3 dv = v3(V[(bd.r_off + 0) * ch + lane], V[(bd.r_off + 1) * ch + lane], V[(bd.r_off + 2) * ch + lane]);
     V3 dw = v3(V[(bd.r_off + 3) * ch + lane], V[(bd.r_off + 4) * ch + lane], V[(bd.r_off + 5) * ch + lane]);
@@ -463,7 +463,7 @@ DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, double
 DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
@@ -473,8 +473,8 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
   }
   // per-column forward scratch must start from zero
   for (int j = c.tid; j < P.Ne; j += c.nthreads)
-    if (P.joints[j].gv_off >= 0)
-      for (int t = 0; t < 6 * P.ch; ++t) A[P.joints[j].gv_off + t] = 0.0;
+    if (c.joints[j].gv_off >= 0)
+      for (int t = 0; t < 6 * P.ch; ++t) A[c.joints[j].gv_off + t] = 0.0;
   slot_sync(c);
   bool ok = factorize(c);
   double* V = A + P.gvec_off;

@@ -42,11 +42,20 @@ DJ_DEV Quat ldq(const double* p) { return Quat{p[0], p[1], p[2], p[3]}; }
 struct Ctx {
   double* A;  // this environment's arena
   const Plan* P;
+  // plan tables (a copy in shared memory when it fits next to the arenas, else the global-memory originals)
+  const BodyDev* bodies;
+  const JointDev* joints;
+  const ContactDev* contacts;
+  const ElimStep* steps;
+  const int* sched;
+  const int* ilist;
+  const WarpRole* roles;
+  const int* ucol;
   int tid, nthreads, warp, lane;  // thread / warp index inside this environment's slot (nthreads = 32 nw)
   int bar;                        // named barrier of the slot (1 + slot index); barrier 0 is the CTA-wide alignment barrier
   double mu;
 #ifdef DJ_PROFILE
-  long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_last;
+  long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_align, t_cone, t_center, t_last;
   long long f_fold, f_inv, f_rm, f_schur, f_bar, f_last;
 #endif
 };
@@ -120,7 +129,7 @@ DJ_DEV Kin body_kin(const Ctx& c, int b, double f) {
     k.E = m33zero();
     return k;
   }
-  const BodyDev& bd = P.bodies[b];
+  const BodyDev& bd = c.bodies[b];
   const double* st = c.A + bd.st_off;
   const double* so = c.A + P.sol_off + bd.sol_off;
   k.x2 = ld3(st);
@@ -198,7 +207,7 @@ DJ_DEV void write_slot(double* s, V3 f, V3 t, const M33& K) { st3(s, f); st3(s +
 DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const JointDev& jd = P.joints[j];
+  const JointDev& jd = c.joints[j];
   V3 cl_p = v3zero(), ca_p = v3zero(), cl_c = v3zero(), ca_c = v3zero();  // [JF2; Jtau2] + spring impulses
   Kin ka = body_kin(c, jd.parent, 0.0), kb = body_kin(c, jd.child, 0.0);
   M33 Ra = rotmat(ka.q2), Rb = rotmat(kb.q2);
@@ -281,12 +290,12 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
 DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, const double* __restrict__ fext, const bool grad) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   // coalesced read of z: [x2(3) v15(3) q2(4) w15(3)] per body (mechanism/set.jl:10-26)
   for (int t = c.tid; t < P.nz; t += c.nthreads) {
     int b = t / 13, k = t - 13 * b;
     double val = z[t];
-    const BodyDev& bd = P.bodies[b];
+    const BodyDev& bd = c.bodies[b];
     if (k < 3) A[bd.st_off + k] = val;
     else if (k < 6) A[P.sol_off + bd.sol_off + (k - 3)] = val;
     else if (k < 10) A[bd.st_off + 3 + (k - 6)] = val;
@@ -297,7 +306,7 @@ DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, cons
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_BODY) {  // constant part of the discrete Euler-Lagrange residual (integrators/constraint.jl:14-25)
-      const BodyDev& bd = P.bodies[idx];
+      const BodyDev& bd = c.bodies[idx];
       const double* so = A + P.sol_off + bd.sol_off;
       V3 v15 = ld3(so), w15 = ld3(so + 3);
       M33 J = ldm33(bd.J);
@@ -314,7 +323,7 @@ DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, cons
     } else if (role.type[p] == ROLE_JOINT) {
       prologue_joint(c, idx, u);
     } else {  // reset! + initialize! (contacts/constraints.jl:79-86, solver/initialization.jl:7-48)
-      double* so = A + P.sol_off + P.contacts[idx].sol_off;
+      double* so = A + P.sol_off + c.contacts[idx].sol_off;
       const double v0 = 1.0 + 0.5 * 1.0 * 1.0 / (1.0 + 1e-20);  // neutral (1,1,0,0) pushed to 1.5 by the Mehrotra-style start
       so[0] = v0; so[1] = v0; so[2] = 0.0; so[3] = 0.0;
       so[4] = v0; so[5] = v0; so[6] = 0.0; so[7] = 0.0;
@@ -325,10 +334,10 @@ DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, cons
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0 || role.type[p] != ROLE_BODY) continue;
-    const BodyDev& bd = P.bodies[idx];
+    const BodyDev& bd = c.bodies[idx];
     double* cst = A + bd.cst_off;
     for (int g = bd.g_ncontact; g < bd.g_cnt; ++g) {  // joint slots only: contacts carry nothing in the prologue
-      const double* s = A + P.ilist[bd.g_off + g];
+      const double* s = A + c.ilist[bd.g_off + g];
       add3(cst, -ld3(s));
       add3(cst + 3, -ld3(s + 3));
     }
@@ -345,7 +354,7 @@ template <bool JAC>
 DJ_DEV void eval_body(Ctx& c, int idx, double f, double* res) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const BodyDev& bd = P.bodies[idx];
+  const BodyDev& bd = c.bodies[idx];
   Kin k = body_kin(c, idx, f);
   M33 J = ldm33(bd.J);
   const double* cst = A + bd.cst_off;
@@ -418,7 +427,7 @@ DJ_DEV void eval_contact(Ctx& c, int idx, double f, double* res, double& rv, dou
   double* A = c.A;
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
-  const ContactDev& cd = P.contacts[idx];
+  const ContactDev& cd = c.contacts[idx];
   Kin k = body_kin(c, cd.body, f);
   double s[4], g[4];
 #pragma unroll
@@ -520,7 +529,7 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
   double* A = c.A;
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
-  const JointDev& jd = P.joints[idx];
+  const JointDev& jd = c.joints[idx];
   V3 fl_p = v3zero(), fa_p = v3zero(), fl_c = v3zero(), fa_c = v3zero();  // G * eta (+ damper impulses)
   M33 Kaa = m33zero(), Kcc = m33zero();                                     // D_parent -= Kaa, D_child -= Kcc (angular blocks)
   M33 Bpc = m33zero(), Bcp = m33zero();                                     // (parent,child) / (child,parent) angular blocks
@@ -697,7 +706,7 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
 DJ_DEV void condense_contact(Ctx& c, int idx, const double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const ContactDev& cd = P.contacts[idx];
+  const ContactDev& cd = c.contacts[idx];
   const double* so = A + P.sol_off + cd.sol_off;
   ContactBlock cb = contact_block(so, so + 4, cd.mu);
   double y[8];
@@ -713,11 +722,11 @@ DJ_DEV void condense_contact(Ctx& c, int idx, const double* x) {
 DJ_DEV void recover_contact(Ctx& c, int idx, double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const ContactDev& cd = P.contacts[idx];
+  const ContactDev& cd = c.contacts[idx];
   const double* so = A + P.sol_off + cd.sol_off;
   ContactBlock cb = contact_block(so, so + 4, cd.mu);
   const double* J = A + cd.J_off;
-  const double* dv = x + P.bodies[cd.body].sol_off;
+  const double* dv = x + c.bodies[cd.body].sol_off;
   double t[8], y[8];
 #pragma unroll
   for (int r = 0; r < 4; ++r) t[r] = x[cd.sol_off + r];
@@ -735,7 +744,7 @@ DJ_DEV void recover_contact(Ctx& c, int idx, double* x) {
 DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const JointDev& jd = P.joints[idx];
+  const JointDev& jd = c.joints[idx];
   V3 tp = v3zero(), tc = v3zero();
   const double* so = A + P.sol_off + jd.sol_off;
   const double* xr = x + jd.sol_off;
@@ -757,12 +766,12 @@ DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
 DJ_DEV void recover_joint(Ctx& c, int idx, double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const JointDev& jd = P.joints[idx];
+  const JointDev& jd = c.joints[idx];
   if (jd.nb2_r == 0) return;
   const double* so = A + P.sol_off + jd.sol_off;
   double* xr = x + jd.sol_off;
-  V3 wp = (jd.parent >= 0) ? ld3(x + P.bodies[jd.parent].sol_off + 3) : v3zero();
-  V3 wc = ld3(x + P.bodies[jd.child].sol_off + 3);
+  V3 wp = (jd.parent >= 0) ? ld3(x + c.bodies[jd.parent].sol_off + 3) : v3zero();
+  V3 wc = ld3(x + c.bodies[jd.child].sol_off + 3);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nb2_r) {
@@ -785,7 +794,7 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
   const Plan& P = *c.P;
   double* A = c.A;
   double* res = A + res_off;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   double rv = 0.0, bv = 0.0;
   if (JAC) {  // all KKT blocks are rewritten: zero the matrix region cooperatively, then scatter the non-zeros
     for (int t = c.tid; t < P.mat_len; t += c.nthreads) A[P.mat_off + t] = 0.0;
@@ -803,11 +812,11 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0 || role.type[p] != ROLE_BODY) continue;
-    const BodyDev& bd = P.bodies[idx];
+    const BodyDev& bd = c.bodies[idx];
     double* rb = res + bd.sol_off;
     double* D = A + bd.D_off;
     for (int g = 0; g < bd.g_cnt; ++g) {
-      const double* s = A + P.ilist[bd.g_off + g];
+      const double* s = A + c.ilist[bd.g_off + g];
       add3(rb, ld3(s));
       add3(rb + 3, ld3(s + 3));
       if (JAC) {
@@ -845,14 +854,14 @@ DJ_DEV bool factorize(Ctx& c) {
   c.f_last = clock64();
 #endif
   for (int ph = 0; ph < P.nphase; ++ph) {
-    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0 + half; s < s0 + sn; s += 2) {
-      const ElimStep& st = P.steps[s];
+      const ElimStep& st = c.steps[s];
       double* Dc = A + st.d_off;
       if (st.fold_cnt > 0) {  // fold the children's scratch updates into D_c
         for (int t = l; t < st.n * st.n; t += 16) {
           double acc = Dc[t];
-          for (int k = 0; k < st.fold_cnt; ++k) acc += A[P.ilist[st.fold_off + k] + t];
+          for (int k = 0; k < st.fold_cnt; ++k) acc += A[c.ilist[st.fold_off + k] + t];
           Dc[t] = acc;
         }
         __syncwarp(mask);
@@ -891,7 +900,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
   const int half = lane >> 4, l = lane & 15;  // one elimination step per half-warp, as in factorize()
   const unsigned mask = 0xffffu << (16 * half);
   const int sub = l >> 3, li = l & 7;         // forward substitution: lanes [0,8) of the group serve nb[0], [8,16) nb[1]
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   // condense the right-hand side of the contact / joint-limit rows onto the body rows
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, lane);
@@ -903,25 +912,25 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, lane);
     if (idx < 0 || role.type[p] != ROLE_BODY) continue;
-    const BodyDev& bd = P.bodies[idx];
+    const BodyDev& bd = c.bodies[idx];
     double* xb = x + bd.sol_off;
     for (int g = 0; g < bd.g_cnt; ++g) {
-      const double* s = A + P.ilist[bd.g_off + g];
+      const double* s = A + c.ilist[bd.g_off + g];
       add3(xb, ld3(s));
       add3(xb + 3, ld3(s + 3));
     }
   }
   slot_sync(c);
   for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c
-    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     for (int s = s0 + half; s < s0 + sn; s += 2) {
-      const ElimStep& st = P.steps[s];
+      const ElimStep& st = c.steps[s];
       double* xc = x + st.vec_off;
       if (st.fold_cnt > 0) {  // fold (and clear) the children's forward updates of this body
         if (l < st.n) {
           double acc = xc[l];
           for (int k = 0; k < st.fold_cnt; ++k) {
-            double* v = A + P.ilist[st.fold_off + k] + 36;
+            double* v = A + c.ilist[st.fold_off + k] + 36;
             acc += v[l];
             v[l] = 0.0;
           }
@@ -942,10 +951,10 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
-    const int s0 = P.sched[2 * (ph * P.nw + c.warp)], sn = P.sched[2 * (ph * P.nw + c.warp) + 1];
+    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     // same pairing as the forward sweep, last pair first (the steps of one phase are independent)
     for (int s = s0 + half + 2 * ((sn - 1 - half) >> 1); s >= s0 + half && sn > half; s -= 2) {
-      const ElimStep& st = P.steps[s];
+      const ElimStep& st = c.steps[s];
       const double* Dc = A + st.d_off;
       double* xc = x + st.vec_off;
       if (st.nnb > 0) {
@@ -1003,13 +1012,13 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
   const Plan& P = *c.P;
   const double* sol = c.A + P.sol_off;
   const double* dl = c.A + P.rhs_off;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   double a = 1.0;
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_CONTACT) {
-      const ContactDev& cd = P.contacts[idx];
+      const ContactDev& cd = c.contacts[idx];
       const double* s = sol + cd.sol_off;
       const double* g = s + 4;
       const double* ds = dl + cd.sol_off;
@@ -1019,7 +1028,7 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
       a = fmin(a, soc_step(s[1], s[2], s[3], ds[1], ds[2], ds[3], tau_soc));
       a = fmin(a, soc_step(g[1], g[2], g[3], dg[1], dg[2], dg[3], tau_soc));
     } else if (role.type[p] == ROLE_JOINT) {
-      const JointDev& jd = P.joints[idx];
+      const JointDev& jd = c.joints[idx];
       for (int i = 0; i < 2 * jd.nb_r; ++i) a = fmin(a, ort_step(sol[jd.sol_off + jd.ne + i], dl[jd.sol_off + jd.ne + i], tau_ort));
     }
   }
@@ -1031,13 +1040,13 @@ DJ_DEV void centering(Ctx& c, double aaff, double& nu, double& nuaff) {
   const Plan& P = *c.P;
   const double* sol = c.A + P.sol_off;
   const double* dl = c.A + P.rhs_off;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   double sn = 0.0, sa = 0.0, cnt = 0.0;
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_CONTACT) {
-      const ContactDev& cd = P.contacts[idx];
+      const ContactDev& cd = c.contacts[idx];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double s = sol[cd.sol_off + i], g = sol[cd.sol_off + 4 + i];
@@ -1046,7 +1055,7 @@ DJ_DEV void centering(Ctx& c, double aaff, double& nu, double& nuaff) {
       }
       cnt += 2.0;  // cone_degree(NonlinearContact) (contacts/nonlinear.jl:101)
     } else if (role.type[p] == ROLE_JOINT) {
-      const JointDev& jd = P.joints[idx];
+      const JointDev& jd = c.joints[idx];
       for (int i = 0; i < jd.nb_r; ++i) {
         int is = jd.sol_off + jd.ne + i, ig = is + jd.nb_r;
         sn += sol[is] * sol[ig];
@@ -1065,12 +1074,12 @@ DJ_DEV void correction(Ctx& c) {
   const Plan& P = *c.P;
   const double* dl = c.A + P.rhs_off;
   double* sav = c.A + P.sav_off;
-  const WarpRole& role = P.roles[c.warp];
+  const WarpRole& role = c.roles[c.warp];
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_CONTACT) {
-      const ContactDev& cd = P.contacts[idx];
+      const ContactDev& cd = c.contacts[idx];
       const double* ds = dl + cd.sol_off;
       const double* dg = ds + 4;
       double* r = sav + cd.sol_off;
@@ -1079,7 +1088,7 @@ DJ_DEV void correction(Ctx& c) {
       r[2] += -(ds[1] * dg[2] + dg[1] * ds[2]);
       r[3] += -(ds[1] * dg[3] + dg[1] * ds[3]);
     } else if (role.type[p] == ROLE_JOINT) {
-      const JointDev& jd = P.joints[idx];
+      const JointDev& jd = c.joints[idx];
       for (int i = 0; i < jd.nb_r; ++i) {
         int is = jd.sol_off + jd.ne + i;
         sav[is] += -dl[is] * dl[is + jd.nb_r] + c.mu;
@@ -1116,7 +1125,9 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
     if (mode == 0) {
       // alignment point: the environments hosted by this CTA start every Newton iteration together, so that their warps run
       // the same (large, straight-line) code at the same time and share its instruction fetches
+      DJ_TICK(c, t_misc)
       cta_align(true);
+      DJ_TICK(c, t_align)
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
     } else evaluate<false>(c, fk, P.sav_off, rv, bv);
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
@@ -1135,7 +1146,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
         for (int t = c.tid; t < P.nres; t += c.nthreads) sol[t] += fsel * dl[t];
         slot_sync(c);
         if (c.tid < P.Nb) {
-          double* w = sol + P.bodies[c.tid].sol_off + 3;
+          double* w = sol + c.bodies[c.tid].sol_off + 3;
           double wmax = 3.9 / (P.h * P.h);
           double wd = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
           if (wd > wmax) { double k = wmax / wd; w[0] *= k; w[1] *= k; w[2] *= k; }
@@ -1163,7 +1174,9 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       DJ_TICK(c, t_solve)
       double mx = fmax(rvio, bvio);
       double tau = (pass == 0) ? 0.95 : fmax(0.95, 1.0 - mx * mx);
+      DJ_TICK(c, t_misc)
       alpha = cone_line_search(c, tau, fmin(tau, 0.95));
+      DJ_TICK(c, t_cone)
       if (pass == 0) {
         double nu, nuaff;
         centering(c, alpha, nu, nuaff);
@@ -1176,6 +1189,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
         correction(c);
         for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.rhs_off + t] = A[P.sav_off + t];  // push_residual!
         slot_sync(c);
+        DJ_TICK(c, t_center)
       }
     }
     mode = 1; fk = alpha; ls_k = 0;

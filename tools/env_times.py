@@ -16,7 +16,7 @@ s = BatchedStepper(mech, B)
 Za = torch.from_numpy(Z0).cuda(); Zb = torch.empty_like(Za)
 it = torch.zeros(B, dtype=torch.int32, device="cuda"); stt = torch.zeros(B, dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 32)()
 s.L.dojo_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]
 s.L.dojo_debug_env_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 for t in range(30):

@@ -39,8 +39,8 @@ if hasattr(s, "rollout_device") and os.environ.get("DJ_ROLLOUT", "1") != "0":
     print(f"{'':20s} fused rollout T={steps}: {msr:8.3f} ms/step  {B/msr*1e3:10.0f} env-steps/s")
 if os.environ.get("DJ_PROF"):
     import ctypes as C
-    out = (C.c_ulonglong * 16)()
+    out = (C.c_ulonglong * 32)()
     s.L.dojo_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]
     s.L.dojo_debug_cycles(s.h, out)
     tot = sum(out)
-    print("   cycles/env-step: " + "  ".join(f"{n}={v/ (B*(20+steps)):.0f}" for n, v in zip(("eval_jac","eval_ls","fact","solve","misc","f_fold","f_inv","f_rm","f_schur","f_bar"), out)))
+    print("   cycles/env-step: " + "  ".join(f"{n}={v/ (B*(20+steps)):.0f}" for n, v in zip(("eval_jac","eval_ls","fact","solve","misc","f_fold","f_inv","f_rm","f_schur","f_bar","-","-","-","-","align","cone","center"), out) if n != "-"))
