@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     c.ucol = reinterpret_cast<const int*>(pb + a.plan_off[7]);
   }
 #ifdef DJ_PROFILE
-  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = c.t_align = c.t_cone = c.t_center = 0; c.t_last = clock64();
+  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = c.t_align = c.t_cone = c.t_center = c.t_rolewait = 0; c.t_last = clock64();
   c.f_fold = c.f_inv = c.f_rm = c.f_schur = c.f_bar = 0;
   long long k_c0 = clock64(); unsigned long long k_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
   int k_envs = 0;
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
 #ifdef DJ_PROFILE
   DJ_TICK(c, t_misc)
+  if (c.lane == 0 && a.prof) atomicAdd(a.prof + 17 + c.warp, (unsigned long long)c.t_rolewait);
   if (c.tid == 0 && a.prof) {
     atomicAdd(a.prof + 0, (unsigned long long)c.t_eval_jac); atomicAdd(a.prof + 1, (unsigned long long)c.t_eval_ls);
     atomicAdd(a.prof + 2, (unsigned long long)c.t_fact); atomicAdd(a.prof + 3, (unsigned long long)c.t_solve); atomicAdd(a.prof + 4, (unsigned long long)c.t_misc);

@@ -55,7 +55,7 @@ struct Ctx {
   int bar;                        // named barrier of the slot (1 + slot index); barrier 0 is the CTA-wide alignment barrier
   double mu;
 #ifdef DJ_PROFILE
-  long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_align, t_cone, t_center, t_last;
+  long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_align, t_cone, t_center, t_rolewait, t_last;
   long long f_fold, f_inv, f_rm, f_schur, f_bar, f_last;
 #endif
 };
@@ -807,7 +807,13 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
     else if (role.type[p] == ROLE_CONTACT) eval_contact<JAC>(c, idx, f, res, rv, bv);
     else eval_joint<JAC>(c, idx, f, res, rv, bv);
   }
+#ifdef DJ_PROFILE
+  long long _rw0 = clock64();
+#endif
   slot_sync(c);
+#ifdef DJ_PROFILE
+  c.t_rolewait += clock64() - _rw0;
+#endif
   // gather the impulse contributions of the incident joints / contacts into the body rows (fixed order)
   for (int p = 0; p < role.npass; ++p) {
     const int idx = role_item(role, p, c.lane);
@@ -891,6 +897,18 @@ DJ_DEV bool factorize(Ctx& c) {
   return all;
 }
 
+// dot product of length n <= 6 (blocks of the condensed system are at most 6 wide): unrolled and predicated, so that the
+// twelve shared-memory loads are issued back to back instead of one dependent loop iteration at a time
+DJ_DEV double dot6(const double* a, const double* b, int n) {
+  double e = 0.0, o = 0.0;  // two interleaved FMA chains
+#pragma unroll
+  for (int k = 0; k < 6; k += 2) {
+    if (k < n) e = fma(a[k], b[k], e);
+    if (k + 1 < n) o = fma(a[k + 1], b[k + 1], o);
+  }
+  return e + o;
+}
+
 // x <- KKT^{-1} x for the vector at arena offset vec_off (solution ordering)
 DJ_DEV void solve(Ctx& c, int vec_off) {
   const Plan& P = *c.P;
@@ -941,8 +959,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
       if (sub < st.nnb && li < st.nb[sub].n) {
         const ElimNb& nb = st.nb[sub];
         const double* L = A + nb.L_off + li * st.n;
-        double acc = 0.0;
-        for (int k = 0; k < st.n; ++k) acc += L[k] * xc[k];
+        const double acc = dot6(L, xc, st.n);
         double* tgt = nb.fwd_abs >= 0 ? A + nb.fwd_abs : x + nb.vec_off;
         tgt[li] -= acc;
       }
@@ -964,9 +981,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
             const ElimNb& nb = st.nb[j];
             int r = l - nb.U_row;
             if (r >= 0 && r < nb.U_k) {
-              const double* U = A + nb.U_off + r * nb.n;
-              const double* xj = x + nb.vec_off;
-              for (int k = 0; k < nb.n; ++k) acc += U[k] * xj[k];
+              acc += dot6(A + nb.U_off + r * nb.n, x + nb.vec_off, nb.n);
             }
           }
           xc[l] -= acc;
@@ -974,8 +989,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
         __syncwarp(mask);
       }
       double acc = 0.0;
-      if (l < st.n)
-        for (int k = 0; k < st.n; ++k) acc += Dc[l * st.n + k] * xc[k];
+      if (l < st.n) acc = dot6(Dc + l * st.n, xc, st.n);
       __syncwarp(mask);
       if (l < st.n) xc[l] = acc;
       __syncwarp(mask);
