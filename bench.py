@@ -273,6 +273,24 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
+    # ---- fused rollout (dojo_rollout_async): the same K steps of the same batch in ONE launch, every environment advanced
+    #      through all steps by the CTA slot that picked it up (no per-step launch / tail).  Reported beside the headline.
+    rollout = None
+    if args.mode == "fwd" and world == 1:
+        Zr, Zf = Z_timed_start.clone(), torch.empty_like(Z_timed_start)
+        Ur = U[Uoff + args.warmup: Uoff + T].contiguous()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stepper.rollout_device(Zr.data_ptr(), Ur.data_ptr(), Zf.data_ptr(), B, args.steps, opts, stream=stream.cuda_stream)  # warm
+        torch.cuda.synchronize()
+        flush.fill_(1)
+        r0.record(stream)
+        stepper.rollout_device(Zr.data_ptr(), Ur.data_ptr(), Zf.data_ptr(), B, args.steps, opts, stream=stream.cuda_stream)
+        r1.record(stream)
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / args.steps
+        rollout = {"value": B / (rms * 1e-3), "unit": "env-steps/s", "ms_per_step": rms, "steps_fused": args.steps, "launches": 1,
+                   "final_state_matches_stepwise": bool(torch.equal(Zf, Za))}
+
     # ---- e2e through the public host API (pinned staging + H2D + kernel + D2H), same workload, N = 1 path per rank
     Zh = Z_timed_start.cpu().numpy()
     Uh = U_host[Uoff + args.warmup: Uoff + T]
@@ -306,7 +324,7 @@ def main():
     achieved = algo / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.mech, args.mode),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "kernel_ms": kernel_ms,
-                "note": "the KKT system lives in shared memory: the kernel is FP64-issue / shared-memory-latency bound, not HBM bound (DESIGN.md)"}
+                "note": "the KKT system lives in shared memory: the kernel is latency bound (dependent fp64 block algebra, 8 warps/SM), not HBM bound (DESIGN.md)"}
     # ---- CPU baseline (oracle port) on a bounded sample
     cpu = None
     try:
@@ -324,7 +342,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "mean_newton_iters": it_sum / args.steps, "failed_env_steps": fails,
+            "rollout": rollout, "mean_newton_iters": it_sum / args.steps, "failed_env_steps": fails,
             "shared_bytes_per_env": stepper.shared_bytes_per_env}
     print(json.dumps(line))
     if world > 1:
