@@ -356,14 +356,17 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
   }
 }
 
-// forward / backward substitution of the block LDU for one column per lane
-DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
+// forward / backward substitution of the block LDU, one column per lane.  A chunk has ch <= 32 columns: the warp is split
+// in 32 / ch lane groups that take different (independent) elimination steps of the phase for the same ch columns.
+DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int ch = P.ch, lane = c.lane;
+  const int ch = P.ch;
+  const int groups = 32 / ch, grp = c.lane / ch, lane = c.lane - grp * ch;  // `lane` = column of the chunk
+  const bool active = c0 + lane < P.ncol;
   for (int ph = 0; ph < P.nphase; ++ph) {
     const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0; s < s0 + sn; ++s) {
+    for (int s = s0 + grp; s < s0 + sn; s += groups) {
       const ElimStep& st = c.steps[s];
       if (!active) continue;
       double zc[6];
@@ -397,7 +400,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {
     const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0 + sn - 1; s >= s0; --s) {
+    for (int s = s0 + grp; s < s0 + sn; s += groups) {
       const ElimStep& st = c.steps[s];
       if (!active) continue;
       double t[6];
@@ -431,12 +434,13 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, bool active) {
 }
 
 // chain rule to (x3, v25, phi3, w25) and write the column (gradients/state.jl:104-123)
-DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, double* __restrict__ Fz, double* __restrict__ Fu) {
+// (bodies b0, b0 + bstride, ... of the column: the threads of the slot share a column's bodies)
+DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, int b0, int bstride, double* __restrict__ Fz, double* __restrict__ Fu) {
   const Plan& P = *c.P;
   const double* A = c.A;
   const int ch = P.ch, ng = 12 * P.Nb;
   double* out = col < ng ? Fz + (size_t)col * ng : Fu + (size_t)(col - ng) * ng;
-  for (int b = 0; b < P.Nb; ++b) {
+  for (int b = b0; b < P.Nb; b += bstride) {
     const BodyDev& bd = c.bodies[b];
     const double* rec = A + bd.gb_off;
     V3 dv = v3(V[(bd.r_off + 0) * ch + lane], V[(bd.r_off + 1) * ch + lane], V[(bd.r_off + 2) * ch + lane]);
@@ -484,10 +488,11 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
     for (int l = c.tid; l < P.ch; l += c.nthreads)
       if (c0 + l < P.ncol) grad_build_rhs(c, V, c0 + l, l);
     slot_sync(c);
-    const bool active = c.lane < P.ch && c0 + c.lane < P.ncol;
-    grad_solve_columns(c, V, active);
-    for (int l = c.tid; l < P.ch; l += c.nthreads)
-      if (c0 + l < P.ncol) grad_write_column(c, V, c0 + l, l, Fz, Fu);
+    grad_solve_columns(c, V, c0);
+    {
+      const int parts = c.nthreads / P.ch, part = c.tid / P.ch, l = c.tid - part * P.ch;
+      if (c0 + l < P.ncol) grad_write_column(c, V, c0 + l, l, part, parts, Fz, Fu);
+    }
     slot_sync(c);
   }
   return ok;
