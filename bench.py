@@ -292,19 +292,27 @@ def main():
                    "final_state_matches_stepwise": bool(torch.equal(Zf, Za))}
 
     # ---- e2e through the public host API (pinned staging + H2D + kernel + D2H), same workload, N = 1 path per rank
-    Zh = Z_timed_start.cpu().numpy()
-    Uh = U_host[Uoff + args.warmup: Uoff + T]
+    # Host buffers are page-locked (torch pin_memory), as the contract asks: the library DMAs straight from / to them.
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+    Zh, Zh2 = pinned((B, mech.nz), torch.float64), pinned((B, mech.nz), torch.float64)
+    Zh[:] = Z_timed_start.cpu().numpy()
+    Uh = pinned((args.steps, B, mech.nu), torch.float64)
+    Uh[:] = U_host[Uoff + args.warmup: Uoff + T]
+    sth, ith = pinned((B,), torch.int32), pinned((B,), torch.int32)
     e2e_t = []
     if world > 1:
         dist.barrier()
     for k in range(min(args.steps, 10)):
         t0 = time.perf_counter()
         if args.mode == "fwd":
-            Zh2, _, _ = stepper.step(Zh, Uh[k], opts)
+            stepper.step(Zh, Uh[k], opts, out=(Zh2, sth, ith))
+            loss = float(Zh2[0, 2])  # the result is on the host
         else:
-            Zh2, _, _, _, _ = stepper.step_grad(Zh, Uh[k], opts)
+            Zg, _, _, _, _ = stepper.step_grad(Zh, Uh[k], opts)
+            Zh2[:] = Zg
         e2e_t.append(time.perf_counter() - t0)
-        Zh = Zh2
+        Zh, Zh2 = Zh2, Zh
     e2e_ms = 1e3 * float(np.mean(e2e_t))
     if world > 1:
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)

@@ -720,6 +720,14 @@ static bool is_device_ptr(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory): DMA goes straight from / to the caller's buffer
+static bool is_pinned_host_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int ensure_staging(DojoHandle* h) {
   if (h->d_Z) return DOJO_OK;
   const Plan& P = h->plan;
@@ -732,7 +740,7 @@ static int ensure_staging(DojoHandle* h) {
   CUDA_TRY(h, cudaMalloc((void**)&h->d_status, B * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc((void**)&h->d_iters, B * sizeof(int32_t)));
   CUDA_TRY(h, cudaMallocHost((void**)&h->p_in, B * (P.nz + P.nu + 6 * P.Nb) * sizeof(double)));
-  CUDA_TRY(h, cudaMallocHost((void**)&h->p_out, B * (P.nz + P.nres + 1) * sizeof(double)));
+  CUDA_TRY(h, cudaMallocHost((void**)&h->p_out, B * (P.nz + P.nres + 2) * sizeof(double)));
   return DOJO_OK;
 }
 
@@ -751,32 +759,36 @@ extern "C" int dojo_step(DojoHandle* h, const DojoSolverOptions* opts, int B, co
   int rc = ensure_staging(h);
   if (rc != DOJO_OK) return rc;
   cudaStream_t s = h->stream;
+  // inputs: pageable buffers are staged through the handle's pinned buffer, pinned ones are copied from directly
+  auto h2d = [&](double* dst, const double* src, double* stage, size_t n) -> cudaError_t {
+    if (!is_pinned_host_ptr(src)) { std::memcpy(stage, src, n * sizeof(double)); src = stage; }
+    return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, s);
+  };
   double* pz = h->p_in;
   double* pu = pz + (size_t)B * P.nz;
   double* pf = pu + (size_t)B * P.nu;
-  std::memcpy(pz, Z, (size_t)B * P.nz * sizeof(double));
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, pz, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (U && P.nu > 0) {
-    std::memcpy(pu, U, (size_t)B * P.nu * sizeof(double));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_U, pu, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
-  }
-  if (Fext) {
-    std::memcpy(pf, Fext, (size_t)B * 6 * P.Nb * sizeof(double));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_F, pf, (size_t)B * 6 * P.Nb * sizeof(double), cudaMemcpyHostToDevice, s));
-  }
+  CUDA_TRY(h, h2d(h->d_Z, Z, pz, (size_t)B * P.nz));
+  if (U && P.nu > 0) CUDA_TRY(h, h2d(h->d_U, U, pu, (size_t)B * P.nu));
+  if (Fext) CUDA_TRY(h, h2d(h->d_F, Fext, pf, (size_t)B * 6 * P.Nb));
   rc = dojo_step_async(h, opts, B, h->d_Z, (U && P.nu > 0) ? h->d_U : nullptr, Fext ? h->d_F : nullptr, h->d_Zn, sol ? h->d_sol : nullptr, h->d_status,
                        h->d_iters, flags, s);
   if (rc != DOJO_OK) return rc;
+  // outputs: one stream synchronisation; pageable destinations receive a host copy out of the pinned staging buffer
   double* po = h->p_out;
   double* ps = po + (size_t)B * P.nz;
-  int32_t* pi = (int32_t*)(ps + (size_t)B * P.nres);
-  CUDA_TRY(h, cudaMemcpyAsync(po, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (sol) CUDA_TRY(h, cudaMemcpyAsync(ps, h->d_sol, (size_t)B * P.nres * sizeof(double), cudaMemcpyDeviceToHost, s));
+  int32_t* pst = (int32_t*)(ps + (size_t)B * P.nres);
+  int32_t* pit = pst + B;
+  const bool zn_pin = is_pinned_host_ptr(Zn), sol_pin = sol && is_pinned_host_ptr(sol);
+  const bool st_pin = status && is_pinned_host_ptr(status), it_pin = iters && is_pinned_host_ptr(iters);
+  CUDA_TRY(h, cudaMemcpyAsync(zn_pin ? Zn : po, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (sol) CUDA_TRY(h, cudaMemcpyAsync(sol_pin ? sol : ps, h->d_sol, (size_t)B * P.nres * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(h, cudaMemcpyAsync(st_pin ? status : pst, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(it_pin ? iters : pit, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
-  std::memcpy(Zn, po, (size_t)B * P.nz * sizeof(double));
-  if (sol) std::memcpy(sol, ps, (size_t)B * P.nres * sizeof(double));
-  if (status) { CUDA_TRY(h, cudaMemcpy(pi, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost)); std::memcpy(status, pi, B * sizeof(int32_t)); }
-  if (iters) { CUDA_TRY(h, cudaMemcpy(pi, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost)); std::memcpy(iters, pi, B * sizeof(int32_t)); }
+  if (!zn_pin) std::memcpy(Zn, po, (size_t)B * P.nz * sizeof(double));
+  if (sol && !sol_pin) std::memcpy(sol, ps, (size_t)B * P.nres * sizeof(double));
+  if (status && !st_pin) std::memcpy(status, pst, B * sizeof(int32_t));
+  if (iters && !it_pin) std::memcpy(iters, pit, B * sizeof(int32_t));
   return DOJO_OK;
 }
 

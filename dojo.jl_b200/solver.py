@@ -122,7 +122,10 @@ class BatchedStepper:
         return int(self.L.dojo_launch_count(self.h))
 
     # ------------------------------------------------------------------ host buffers
-    def step(self, Z, U=None, opts: Optional[capi.DojoSolverOptions] = None, fext=None, flags: int = 0, return_sol: bool = False):
+    def step(self, Z, U=None, opts: Optional[capi.DojoSolverOptions] = None, fext=None, flags: int = 0, return_sol: bool = False, out=None):
+        """One step! of every environment.  Host arrays in, host arrays out; page-locked arrays (e.g. views of torch pinned
+        tensors) are copied from / to directly, pageable ones go through the library's pinned staging buffers.
+        out = (Z_next, status, iters) reuses caller-provided result arrays."""
         Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
         B = Z.shape[0]
         assert Z.shape[1] == self.nz
@@ -130,9 +133,14 @@ class BatchedStepper:
         assert U.shape == (B, self.nu)
         if fext is not None:
             fext = np.ascontiguousarray(fext, dtype=np.float64).reshape(B, 6 * self.mech.Nb)
-        Zn = np.empty_like(Z)
-        status = np.zeros(B, dtype=np.int32)
-        iters = np.zeros(B, dtype=np.int32)
+        if out is not None:
+            Zn, status, iters = out
+            assert Zn.shape == Z.shape and Zn.dtype == np.float64 and Zn.flags.c_contiguous
+            assert status.shape == (B,) and status.dtype == np.int32 and iters.shape == (B,) and iters.dtype == np.int32
+        else:
+            Zn = np.empty_like(Z)
+            status = np.zeros(B, dtype=np.int32)
+            iters = np.zeros(B, dtype=np.int32)
         sol = np.empty((B, self.nres)) if return_sol else None
         o = opts if opts is not None else capi.solver_options()
         rc = self.L.dojo_step(self.h, C.byref(o), B, _p(Z), _p(U), _p(fext), _p(Zn), _p(sol), _p(status), _p(iters), flags)

@@ -187,3 +187,59 @@ def test_gradient_parity(name, T, scale):
     errs = np.array(errs)
     assert len(errs) >= B // 2
     assert np.median(errs) < 1e-7 and np.quantile(errs, 0.9) < 1e-4 and errs.max() < 1e-2, errs
+
+
+def test_batch_size_independence():
+    """An environment's result does not depend on the batch it is stepped in (slot / CTA assignment, queue order):
+    odd batch sizes (not a multiple of the four slots of a CTA, fewer environments than slots) reproduce the rows of a
+    large batch bit for bit."""
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(17)
+    B = 601
+    Z = jittered_states(mech, 32, rng)[rng.integers(0, 32, B)]
+    U = random_inputs(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Zf, sf, itf = stepper.step(Z, U)
+    for b in (1, 3, 5, 149):
+        Zb, sb, itb = stepper.step(Z[:b], U[:b])
+        assert np.array_equal(Zb, Zf[:b]) and np.array_equal(itb, itf[:b]) and np.array_equal(sb, sf[:b])
+
+
+def test_pinned_host_buffers():
+    """Page-locked caller buffers are copied from / to directly; same results as the staged (pageable) path."""
+    import torch
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("quadruped")
+    rng = np.random.default_rng(19)
+    B = 64
+    Z = jittered_states(mech, B, rng)
+    U = random_inputs(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Zn, st, it = stepper.step(Z, U)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    Zp, Up, Znp = pin(Z.shape, torch.float64), pin(U.shape, torch.float64), pin(Z.shape, torch.float64)
+    stp, itp = pin((B,), torch.int32), pin((B,), torch.int32)
+    Zp[:], Up[:] = Z, U
+    stepper.step(Zp, Up, out=(Znp, stp, itp))
+    assert np.array_equal(Znp, Zn) and np.array_equal(stp, st) and np.array_equal(itp, it)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quadruped"])
+def test_rollout_trajectory(name):
+    """dojo_rollout (all steps fused in one launch) records the same trajectory as T single steps."""
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(23)
+    B, T = 7, 9
+    Z0 = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
+    U = np.stack([random_inputs(mech, B, rng) for _ in range(T)])
+    stepper = BatchedStepper(mech, B)
+    Zf, st, traj = stepper.rollout(Z0, U, T, record=True)
+    Zf2, st2 = stepper.rollout(Z0, U, T)
+    Z, worst = Z0, np.zeros(B, np.int32)
+    for t in range(T):
+        Z, s, _ = stepper.step(Z, U[t])
+        worst = np.maximum(worst, s)
+        assert np.array_equal(traj[t], Z)
+    assert np.array_equal(Zf, Z) and np.array_equal(Zf2, Z) and np.array_equal(st, worst) and np.array_equal(st2, worst)
