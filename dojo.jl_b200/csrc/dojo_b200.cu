@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   c.warp = c.tid >> 5;
   c.lane = c.tid & 31;
   c.bar = 1 + slot;
+  c.sd = 0;
   c.mu = 0.0;
   {
     const char* pb = a.plan_blob;
@@ -369,7 +370,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   P.sol_off = a; a += nres;
   P.rhs_off = a; a += nres;
   P.sav_off = a; a += nres;
-  P.red_off = a; a += 3 * nw + 1;
+  P.red_off = a; a += 4 * nw + 2;
   for (int b = 0; b < Nb; ++b) { bodies[b].st_off = a; a += 7; }
   for (int b = 0; b < Nb; ++b) { bodies[b].cst_off = a; a += 6; }
   for (int j = 0; j < Ne; ++j) {  // joint contribution slots (also used by the prologue) and constant (per step) blocks
@@ -403,6 +404,13 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   }
   P.mat_len = a - P.mat_off;
   P.arena_len = a;
+  {  // paired line-search trials: shadow of the slot region + a second residual vector inside the (then dead) matrix region
+    const int first_slot = Ne > 0 ? joints[0].slot_c : P.mat_off;
+    const int span = P.mat_off - first_slot;
+    P.ls_pair = (nw == 2 && Nb <= 16 && Ne <= 16 && Ni <= 16 && span + nres <= P.mat_len && !getenv("DOJO_B200_NO_LS_PAIR")) ? 1 : 0;
+    P.ls_slot_delta = span;
+    P.ls_res2_off = P.mat_off + span;
+  }
   h->arena_bytes = (size_t)((a + 1) & ~1) * sizeof(double);  // 16-byte multiples: slots and the plan tables follow each other
 
   // ---- gradient workspace (appended to the arena; only the gradient kernel allocates it)

@@ -52,6 +52,7 @@ struct Ctx {
   const WarpRole* roles;
   const int* ucol;
   int tid, nthreads, warp, lane;  // thread / warp index inside this environment's slot (nthreads = 32 nw)
+  int sd;                         // offset added to contribution-slot addresses (second trial of a paired line-search pass)
   int bar;                        // named barrier of the slot (1 + slot index); barrier 0 is the CTA-wide alignment barrier
   double mu;
 #ifdef DJ_PROFILE
@@ -457,8 +458,8 @@ DJ_DEV void eval_contact(Ctx& c, int idx, double f, double* res, double& rv, dou
   rr[4] = -r4; rr[5] = -r5; rr[6] = -r6; rr[7] = -r7;
   V3 F = g[0] * n + g[2] * t0 + g[3] * t1;       // X gamma, X = [n' 0 t0' t1']
   V3 tau = tmul(k.R3, cross(rc, F));              // R3' (rc x F)
-  st3(A + cd.slot, F);
-  st3(A + cd.slot + 3, tau);
+  st3(A + cd.slot + c.sd, F);
+  st3(A + cd.slot + c.sd + 3, tau);
   if (JAC) {
     // J (4 x 6): d(constraint rows)/d(v25, w25); rows (phi - s1, mu g1 - g2 [zero], vt1 - s3, vt2 - s4)
     double* Jm = A + cd.J_off;
@@ -696,8 +697,8 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
         Mcp[(3 + i) * 6 + 3 + j2] = Bcp.m[i][j2];
       }
   }
-  write_slot(A + jd.slot_c, fl_c, fa_c, Kcc);
-  if (jd.parent >= 0) write_slot(A + jd.slot_p, fl_p, fa_p, Kaa);
+  write_slot(A + jd.slot_c + c.sd, fl_c, fa_c, Kcc);
+  if (jd.parent >= 0) write_slot(A + jd.slot_p + c.sd, fl_p, fa_p, Kaa);
 }
 
 // condense_rhs / recover: the per-solve halves of the analytic condensation.  `x` is a right-hand side in solution
@@ -843,6 +844,66 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
   block_nanmax2(c, rv, bv);
   rvio = rv;
   bvio = bv;
+  slot_sync(c);
+}
+
+// Residual-only evaluation for the line search (solver/line_search.jl:1-34) at sol + fk * delta.
+// Mechanisms whose role passes have at most 16 nodes (P.ls_pair) run it on the lower half-warps; with `pair` the upper
+// half-warps evaluate the NEXT trial (fk / 2) at the same time with the same instruction stream: its residual goes to a
+// scratch vector and its contribution slots to a shadow copy, both inside the matrix region, which is dead between the
+// solves and the next assembly.  An environment that stalls (ten trials per iteration) needs six passes instead of ten.
+DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, double& rvB, double& bvB) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const WarpRole& role = c.roles[c.warp];
+  const bool pl = P.ls_pair != 0;
+  const int half = pl ? (c.lane >> 4) : 0;
+  const int ln = pl ? (c.lane & 15) : c.lane;
+  const bool on = (half == 0) || pair;
+  const double f = half ? 0.5 * fk : fk;
+  double* res = A + (half ? P.ls_res2_off : P.sav_off);
+  c.sd = half ? P.ls_slot_delta : 0;
+  double rv = 0.0, bv = 0.0;
+  for (int p = 0; p < role.npass; ++p) {
+    const int idx = on ? role_item(role, p, ln) : -1;
+    if (idx < 0) continue;
+    if (role.type[p] == ROLE_BODY) eval_body<false>(c, idx, f, res);
+    else if (role.type[p] == ROLE_CONTACT) eval_contact<false>(c, idx, f, res, rv, bv);
+    else eval_joint<false>(c, idx, f, res, rv, bv);
+  }
+  slot_sync(c);
+  for (int p = 0; p < role.npass; ++p) {  // gather the impulse contributions into the body rows (fixed order)
+    const int idx = on ? role_item(role, p, ln) : -1;
+    if (idx < 0 || role.type[p] != ROLE_BODY) continue;
+    const BodyDev& bd = c.bodies[idx];
+    double* rb = res + bd.sol_off;
+    for (int g = 0; g < bd.g_cnt; ++g) {
+      const double* s = A + c.ilist[bd.g_off + g] + c.sd;
+      add3(rb, ld3(s));
+      add3(rb + 3, ld3(s + 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rv = nanmax(rv, fabs(rb[i]));
+  }
+  c.sd = 0;
+  // violations per trial: reduce inside the 16-lane halves, then over the warps
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    rv = nanmax(rv, __shfl_xor_sync(0xffffffffu, rv, o));
+    bv = nanmax(bv, __shfl_xor_sync(0xffffffffu, bv, o));
+  }
+  if (!pl) {
+    rv = nanmax(rv, __shfl_xor_sync(0xffffffffu, rv, 16));
+    bv = nanmax(bv, __shfl_xor_sync(0xffffffffu, bv, 16));
+  }
+  double* red = A + P.red_off;
+  if ((c.lane & 15) == 0) { red[4 * c.warp + 2 * (c.lane >> 4)] = rv; red[4 * c.warp + 2 * (c.lane >> 4) + 1] = bv; }
+  slot_sync(c);
+  rvA = red[0]; bvA = red[1]; rvB = red[2]; bvB = red[3];
+  for (int w = 1; w < P.nw; ++w) {
+    rvA = nanmax(rvA, red[4 * w]); bvA = nanmax(bvA, red[4 * w + 1]);
+    rvB = nanmax(rvB, red[4 * w + 2]); bvB = nanmax(bvB, red[4 * w + 3]);
+  }
   slot_sync(c);
 }
 
@@ -1134,7 +1195,8 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
   int ls_k = 0;
   bool first = true;
   for (;;) {
-    double rv, bv;
+    double rv, bv, rv2 = 0.0, bv2 = 0.0;
+    bool pair = false;
     DJ_TICK(c, t_misc)
     if (mode == 0) {
       // alignment point: the environments hosted by this CTA start every Newton iteration together, so that their warps run
@@ -1143,12 +1205,21 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       cta_align(true);
       DJ_TICK(c, t_align)
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
-    } else evaluate<false>(c, fk, P.sav_off, rv, bv);
+    } else {
+      // after a rejected first trial the trials are evaluated two at a time (k at fk, k + 1 at fk / 2)
+      pair = (P.ls_pair != 0) && (ls_k >= 1) && (ls_k + 1 < o.max_ls);
+      evaluate_ls(c, fk, pair, rv, bv, rv2, bv2);
+    }
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
     if (mode == 1) {
       // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
+      if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) {
+        fk *= 0.5; ls_k += 1;
+        if (!pair) continue;
+        rv = rv2; bv = bv2;  // trial k + 1 was evaluated in the same pass
+        if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) { fk *= 0.5; ls_k += 1; continue; }
+      }
       fsel = fk;
-      if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) { fk *= 0.5; ls_k += 1; continue; }
       bool made = (!(rv < o.rtol) && (rv < 0.8 * rvio)) || (!(bv < o.btol) && (bv < 0.8 * bvio));
       no_progress = made ? max(no_progress - 1, 0) : no_progress + 1;
       rvio = rv; bvio = bv;
