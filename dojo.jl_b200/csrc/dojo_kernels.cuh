@@ -851,7 +851,8 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
 // Mechanisms whose role passes have at most 16 nodes (P.ls_pair) run it on the lower half-warps; with `pair` the upper
 // half-warps evaluate the NEXT trial (fk / 2) at the same time with the same instruction stream: its residual goes to a
 // scratch vector and its contribution slots to a shadow copy, both inside the matrix region, which is dead between the
-// solves and the next assembly.  An environment that stalls (ten trials per iteration) needs six passes instead of ten.
+// solves and the next assembly.  A pass with both halves busy costs about the same as a single trial; an environment that stalls (ten trials per
+// iteration) needs five passes instead of ten, one rejection costs no extra pass.
 DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, double& rvB, double& bvB) {
   const Plan& P = *c.P;
   double* A = c.A;
@@ -1206,8 +1207,8 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       DJ_TICK(c, t_align)
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
     } else {
-      // after a rejected first trial the trials are evaluated two at a time (k at fk, k + 1 at fk / 2)
-      pair = (P.ls_pair != 0) && (ls_k >= 1) && (ls_k + 1 < o.max_ls);
+      // trials are evaluated two at a time (k at fk, k + 1 at fk / 2); the second one is used only if the first is rejected
+      pair = (P.ls_pair != 0) && (ls_k + 1 < o.max_ls);
       evaluate_ls(c, fk, pair, rv, bv, rv2, bv2);
     }
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
