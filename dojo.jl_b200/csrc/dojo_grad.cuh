@@ -309,10 +309,9 @@ DJ_DEV void add_col6(double* V, int ch, int lane, int r_off, const double* B, in
   for (int r = 0; r < 6; ++r) V[(r_off + r) * ch + lane] += B[r * ld + col];
 }
 
-DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
+DJ_DEV void grad_build_rhs(Ctx& c, double* V, int ch, int col, int lane) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int ch = P.ch;
   for (int r = 0; r < P.n_red; ++r) V[r * ch + lane] = 0.0;
   if (col < 12 * P.Nb) {
     const int b = col / 12, k = col - 12 * b;
@@ -356,17 +355,18 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int col, int lane) {
   }
 }
 
-// forward / backward substitution of the block LDU, one column per lane.  A chunk has ch <= 32 columns: the warp is split
-// in 32 / ch lane groups that take different (independent) elimination steps of the phase for the same ch columns.
-DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
+// forward / backward substitution of the block LDU, one column per lane.  Every warp owns a chunk of ch <= 32 columns
+// (column vectors V [n_red][ch], per-joint forward scratch at +gvo) and runs ALL elimination steps for it, so the sweeps
+// need no barrier between the warps; the warp is split in 32 / ch lane groups that take different (independent) steps of
+// a phase for the same columns.
+DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0) {
   const Plan& P = *c.P;
   double* A = c.A;
-  const int ch = P.ch;
   const int groups = 32 / ch, grp = c.lane / ch, lane = c.lane - grp * ch;  // `lane` = column of the chunk
   const bool active = c0 + lane < P.ncol;
   for (int ph = 0; ph < P.nphase; ++ph) {
-    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0 + grp; s < s0 + sn; s += groups) {
+    const int s0 = c.sched[2 * (ph * P.nw)], s1 = c.sched[2 * (ph * P.nw + P.nw - 1)] + c.sched[2 * (ph * P.nw + P.nw - 1) + 1];
+    for (int s = s0 + grp; s < s1; s += groups) {
       const ElimStep& st = c.steps[s];
       if (!active) continue;
       double zc[6];
@@ -374,7 +374,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
       for (int k = 0; k < 6; ++k) zc[k] = (k < st.n) ? V[(st.r_off + k) * ch + lane] : 0.0;
       if (st.fold_cnt > 0) {
         for (int q = 0; q < st.fold_cnt; ++q) {
-          double* v = A + c.ilist[st.gfold_off + q];
+          double* v = A + c.ilist[st.gfold_off + q] + gvo;
 #pragma unroll
           for (int k = 0; k < 6; ++k)
             if (k < st.n) { zc[k] += v[k * ch + lane]; v[k * ch + lane] = 0.0; }
@@ -386,7 +386,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
       for (int j = 0; j < st.nnb; ++j) {
         const ElimNb& nb = st.nb[j];
         const double* L = A + nb.L_off;
-        double* tgt = nb.gv_off >= 0 ? A + nb.gv_off : V + nb.r_off * ch;
+        double* tgt = nb.gv_off >= 0 ? A + nb.gv_off + gvo : V + nb.r_off * ch;
         for (int i = 0; i < nb.n; ++i) {
           double acc = 0.0;
 #pragma unroll
@@ -396,11 +396,11 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
         }
       }
     }
-    slot_sync(c);
+    __syncwarp();
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {
-    const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0 + grp; s < s0 + sn; s += groups) {
+    const int s0 = c.sched[2 * (ph * P.nw)], s1 = c.sched[2 * (ph * P.nw + P.nw - 1)] + c.sched[2 * (ph * P.nw + P.nw - 1) + 1];
+    for (int s = s0 + grp; s < s1; s += groups) {
       const ElimStep& st = c.steps[s];
       if (!active) continue;
       double t[6];
@@ -429,16 +429,16 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int c0) {
         }
       }
     }
-    slot_sync(c);
+    __syncwarp();
   }
 }
 
 // chain rule to (x3, v25, phi3, w25) and write the column (gradients/state.jl:104-123)
 // (bodies b0, b0 + bstride, ... of the column: the threads of the slot share a column's bodies)
-DJ_DEV void grad_write_column(Ctx& c, const double* V, int col, int lane, int b0, int bstride, double* __restrict__ Fz, double* __restrict__ Fu) {
+DJ_DEV void grad_write_column(Ctx& c, const double* V, int ch, int col, int lane, int b0, int bstride, double* __restrict__ Fz, double* __restrict__ Fu) {
   const Plan& P = *c.P;
   const double* A = c.A;
-  const int ch = P.ch, ng = 12 * P.Nb;
+  const int ng = 12 * P.Nb;
   double* out = col < ng ? Fz + (size_t)col * ng : Fu + (size_t)(col - ng) * ng;
   for (int b = b0; b < P.Nb; b += bstride) {
     const BodyDev& bd = c.bodies[b];
@@ -481,20 +481,19 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
       for (int t = 0; t < 6 * P.ch; ++t) A[c.joints[j].gv_off + t] = 0.0;
   slot_sync(c);
   bool ok = factorize(c);
-  double* V = A + P.gvec_off;
-  for (int c0 = 0; c0 < P.ncol; c0 += P.ch) {
-    // every warp works on the same chunk (the elimination phases are spread over the warps); the right-hand sides
-    // are built by warp 0 .. nw-1 in slices of the chunk
-    for (int l = c.tid; l < P.ch; l += c.nthreads)
-      if (c0 + l < P.ncol) grad_build_rhs(c, V, c0 + l, l);
-    slot_sync(c);
-    grad_solve_columns(c, V, c0);
-    {
-      const int parts = c.nthreads / P.ch, part = c.tid / P.ch, l = c.tid - part * P.ch;
-      if (c0 + l < P.ncol) grad_write_column(c, V, c0 + l, l, part, parts, Fz, Fu);
-    }
-    slot_sync(c);
+  // every warp takes its own chunks of chw = ch / nw columns (workspace slice [n_red][chw], forward scratch slice at +gvo)
+  const int chw = P.ch / P.nw;
+  double* V = A + P.gvec_off + c.warp * P.n_red * chw;
+  const int gvo = c.warp * 6 * chw;
+  const int parts = 32 / chw, part = c.lane / chw, l = c.lane - part * chw;
+  for (int c0 = c.warp * chw; c0 < P.ncol; c0 += P.ch) {
+    if (part == 0 && c0 + l < P.ncol) grad_build_rhs(c, V, chw, c0 + l, l);
+    __syncwarp();
+    grad_solve_columns(c, V, chw, gvo, c0);
+    if (c0 + l < P.ncol) grad_write_column(c, V, chw, c0 + l, l, part, parts, Fz, Fu);
+    __syncwarp();
   }
+  slot_sync(c);
   return ok;
 }
 
