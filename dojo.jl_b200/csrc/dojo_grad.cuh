@@ -383,6 +383,12 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0) {
         for (int k = 0; k < 6; ++k)
           if (k < st.n) V[(st.r_off + k) * ch + lane] = zc[k];
       }
+      // the right-hand sides are sparse (a column touches one body and its neighbours): nodes outside the paths from
+      // those to the root still hold exact zeros in the forward sweep and have nothing to propagate
+      bool nz = false;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) nz = nz || (zc[k] != 0.0);
+      if (!nz) continue;
       for (int j = 0; j < st.nnb; ++j) {
         const ElimNb& nb = st.nb[j];
         const double* L = A + nb.L_off;
