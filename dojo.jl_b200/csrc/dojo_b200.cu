@@ -30,6 +30,7 @@ struct StepArgs {
   double* sol;
   int32_t* status;
   int32_t* iters;
+  double* sol_raw;  // nullable [nres x B]: final solution in DEVICE ordering (written by the forward kernel, read by the gradient kernel)
   double* Fz;  // gradients (GRAD kernels): [12Nb x 12Nb x B], [12Nb x nu x B], column-major per environment
   double* Fu;
   uint32_t flags;
@@ -130,25 +131,38 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
 #endif
     const double* z = a.Z + (size_t)e * P.nz;
     int worst = 0, iters = 0, status = 0;
-    for (int t = 0; t < a.T; ++t) {
-      const double* u = a.U ? a.U + ((size_t)t * a.B + e) * P.nu : nullptr;
+    if (!GRAD) {
+      for (int t = 0; t < a.T; ++t) {
+        const double* u = a.U ? a.U + ((size_t)t * a.B + e) * P.nu : nullptr;
+        const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
+        prologue(c, z, u, fx, false);
+        status = mehrotra(c, a.opts, &iters);
+        worst = max(worst, status);
+        // state after this step: the trajectory slot if recorded, else the output buffer (re-read by the next step from L2)
+        double* zo = (a.traj ? a.traj + ((size_t)t * a.B + e) * P.nz : a.Zn + (size_t)e * P.nz);
+        epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+        if (t + 1 < a.T) { __threadfence_block(); slot_sync(c); z = zo; }
+      }
+      if (a.traj) {  // final state also goes to Zn
+        slot_sync(c);
+        for (int k = c.tid; k < P.nz; k += c.nthreads) a.Zn[(size_t)e * P.nz + k] = a.traj[((size_t)(a.T - 1) * a.B + e) * P.nz + k];
+      }
+      status = worst;
+      if (a.sol_raw)
+        for (int t = c.tid; t < P.nres; t += c.nthreads) a.sol_raw[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
+    } else {
+      // gradient pass (get_maximal_gradients!, gradients/state.jl:69-126) at the solution the forward launch left in
+      // sol_raw: rebuild the step constants and the KKT blocks of the final iterate, then solve for the columns
+      const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
       const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
-      prologue(c, z, u, fx, GRAD);
-      status = mehrotra(c, a.opts, &iters);
-      worst = max(worst, status);
-      // state after this step: the trajectory slot if recorded, else the output buffer (re-read by the next step from L2)
-      double* zo = (a.traj ? a.traj + ((size_t)t * a.B + e) * P.nz : a.Zn + (size_t)e * P.nz);
-      epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
-      if (t + 1 < a.T) { __threadfence_block(); slot_sync(c); z = zo; }
-    }
-    if (a.traj) {  // final state also goes to Zn
+      prologue(c, z, u, fx, true);
+      for (int t = c.tid; t < P.nres; t += c.nthreads) c.A[P.sol_off + t] = a.sol_raw[(size_t)e * P.nres + t];
       slot_sync(c);
-      for (int k = c.tid; k < P.nz; k += c.nthreads) a.Zn[(size_t)e * P.nz + k] = a.traj[((size_t)(a.T - 1) * a.B + e) * P.nz + k];
-    }
-    status = worst;
-    if (GRAD) {
+      double rv, bv;
+      c.mu = 0.0;
+      evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
+      status = a.status ? a.status[e] : 0;
       const size_t ng = 12 * (size_t)P.Nb;
-      slot_sync(c);
       if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu) && status == 0) status = 3;
     }
     if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
@@ -167,8 +181,10 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     }
     if (c.tid == 0) {
       if (a.status) a.status[e] = status;
-      if (a.iters) a.iters[e] = iters;
-      if (a.prev_iters) a.prev_iters[e] = iters;
+      if (!GRAD) {
+        if (a.iters) a.iters[e] = iters;
+        if (a.prev_iters) a.prev_iters[e] = iters;
+      }
 #ifdef DJ_PROFILE
       if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[32 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[33 + 2 * e] = e_t1 - e_t0; }
 #endif
@@ -232,6 +248,8 @@ struct DojoHandle {
   int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
   int* d_counter = nullptr;
+  double* d_gsol = nullptr;        // final solutions handed from the forward to the gradient launch [nres x max_batch]
+  int32_t* d_gstatus = nullptr;
   int* d_order = nullptr;          // LPT processing order of the next call
   int32_t* d_prev_iters = nullptr;  // iteration counts of the previous call
   bool lpt = true;
@@ -654,7 +672,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_gsol); cudaFree(h->d_gstatus);
   cudaFree(h->d_Fz); cudaFree(h->d_Fu);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
@@ -693,14 +711,11 @@ static Options make_options(const DojoSolverOptions* o) {
   return r;
 }
 
-extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
-                               double* dZn, double* dsol, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
-  if (!h || B <= 0 || !dZ || !dZn) { if (h) h->err = "dojo_step_async: bad arguments"; return DOJO_EINVAL; }
-  cudaStream_t s = (cudaStream_t)cuda_stream;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn, double* dsol,
+                          double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s) {
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
-  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.status = dstatus; a.iters = diters; a.flags = flags;
+  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.sol_raw = dsol_raw; a.status = dstatus; a.iters = diters; a.flags = flags;
   a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr;
   a.counter = h->d_counter;
   // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
@@ -719,6 +734,13 @@ extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
+}
+
+extern "C" int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
+                               double* dZn, double* dsol, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+  if (!h || B <= 0 || !dZ || !dZn) { if (h) h->err = "dojo_step_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_forward(h, opts, B, dZ, dU, dFext, dZn, dsol, nullptr, dstatus, diters, flags, (cudaStream_t)cuda_stream);
 }
 
 static bool is_device_ptr(const void* p) {
@@ -805,7 +827,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
                           int32_t* dstatus, cudaStream_t s) {
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
-  a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
+  a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.sol_raw = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
   a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj;
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
@@ -860,23 +882,28 @@ extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B,
 }
 
 // gradients: implemented in dojo_grad.cu
+// step! + gradients = two launches on the stream: the forward kernel in its own (four slots per CTA) configuration, leaving
+// the final solution of every environment in a device buffer, then the gradient kernel (prologue + assembly at that
+// solution + IFT solves) in the larger-arena configuration.  Running the Newton loop inside the gradient configuration
+// (two slots per CTA) made it twice as slow.  dZn must not alias dZ (the gradient kernel re-reads the input state).
 extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
                                     double* dZn, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
-  if (!h || B <= 0 || !dZ || !dZn || !dFz || !dFu) { if (h) h->err = "dojo_step_grad_async: bad arguments"; return DOJO_EINVAL; }
+  if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dFz || !dFu || dZ == dZn) { if (h) h->err = "dojo_step_grad_async: bad arguments (B <= max_batch, dZn != dZ)"; return DOJO_EINVAL; }
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->d_gsol) {
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_gsol, (size_t)h->max_batch * h->plan.nres * sizeof(double)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_gstatus, (size_t)h->max_batch * sizeof(int32_t)));
+  }
+  int32_t* st = dstatus ? dstatus : h->d_gstatus;
+  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, h->d_gsol, st, diters, flags, s);
+  if (rc != DOJO_OK) return rc;
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
-  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.status = dstatus; a.iters = diters; a.flags = flags;
+  a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.sol_raw = h->d_gsol; a.status = st; a.iters = nullptr; a.flags = flags;
   a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr;
-  a.counter = h->d_counter;
-  // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
-  // simulation loops do; a stale order is harmless -- it is just an order)
-  const bool lpt = h->lpt && B <= h->max_batch && B > h->sm_count * h->envs_per_sm_grad * h->slots_grad;
-  a.order = lpt ? h->d_order : nullptr;
-  a.prev_iters = (h->lpt && B <= h->max_batch) ? h->d_prev_iters : nullptr;
-  if (lpt) { dojo_order_kernel<<<1, 1024, 0, s>>>(h->d_prev_iters, B, h->d_order); h->launches += 1; }
+  a.counter = h->d_counter; a.order = nullptr; a.prev_iters = nullptr;
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->grad_bytes / sizeof(double));
