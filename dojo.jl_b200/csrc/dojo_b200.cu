@@ -30,6 +30,8 @@ struct StepArgs {
   double* sol;
   int32_t* status;
   int32_t* iters;
+  int* done_count;  // forward kernel: environments finished so far; done_list[k] = k-th finished environment (-1 = not yet).
+  int* done_list;   // gradient kernel: consumes done_list in order while the forward kernel is still running (nullable: all ready)
   double* sol_raw;  // nullable [nres x B]: final solution in DEVICE ordering (written by the forward kernel, read by the gradient kernel)
   double* Fz;  // gradients (GRAD kernels): [12Nb x 12Nb x B], [12Nb x nu x B], column-major per environment
   double* Fu;
@@ -114,11 +116,19 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   int k_envs = 0;
   if (c.tid == 0 && a.prof) atomicMin(a.prof + 31, k_t0);
 #endif
+  // let a programmatically dependent launch (the gradient kernel of dojo_step_grad) start as soon as every CTA of this
+  // grid is running; it synchronises per environment through done_list, not through grid completion
+  if (!GRAD) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const Plan& P = a.plan;
   for (;;) {
     if (c.tid == 0) {  // dynamic work queue: iteration counts differ between environments
       int q = atomicAdd(a.counter, 1);
-      s_env[slot] = (q < a.B && a.order) ? a.order[q] : q;
+      int env = (q < a.B && a.order) ? a.order[q] : q;
+      if (GRAD && a.done_list && q < a.B) {  // wait for the q-th environment the forward kernel finishes
+        while ((env = ((volatile int*)a.done_list)[q]) < 0) __nanosleep(256);
+        __threadfence();
+      }
+      s_env[slot] = env;
     }
     slot_sync(c);
     const int e = s_env[slot];
@@ -189,9 +199,20 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
       if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[32 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[33 + 2 * e] = e_t1 - e_t0; }
 #endif
     }
+    if (!GRAD && a.done_list) {  // publish: results of this environment are visible before its index appears in the list
+      __threadfence();
+      slot_sync(c);
+      if (c.tid == 0) {
+        const int pos = atomicAdd(a.done_count, 1);
+        __threadfence();
+        ((volatile int*)a.done_list)[pos] = e;
+      }
+    }
     slot_sync(c);
   }
   while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
+  // a gradient grid that started early (programmatic dependent launch) does not complete before the forward grid has
+  if (GRAD) asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef DJ_PROFILE
   DJ_TICK(c, t_misc)
   if (c.lane == 0 && a.prof) atomicAdd(a.prof + 17 + c.warp, (unsigned long long)c.t_rolewait);
@@ -248,6 +269,8 @@ struct DojoHandle {
   int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
   int* d_counter = nullptr;
+  int* d_done = nullptr;           // [0] finished count, [1] gradient work queue, [2..] completion-ordered environment list
+  bool overlap_grad = true;
   double* d_gsol = nullptr;        // final solutions handed from the forward to the gradient launch [nres x max_batch]
   int32_t* d_gstatus = nullptr;
   int* d_order = nullptr;          // LPT processing order of the next call
@@ -672,7 +695,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_gsol); cudaFree(h->d_gstatus);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   cudaFree(h->d_Fz); cudaFree(h->d_Fu);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
@@ -712,11 +735,11 @@ static Options make_options(const DojoSolverOptions* o) {
 }
 
 static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn, double* dsol,
-                          double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s) {
+                          double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s, int* done_count = nullptr, int* done_list = nullptr) {
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.sol_raw = dsol_raw; a.status = dstatus; a.iters = diters; a.flags = flags;
-  a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr;
+  a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr; a.done_count = done_count; a.done_list = done_list;
   a.counter = h->d_counter;
   // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
   // simulation loops do; a stale order is harmless -- it is just an order)
@@ -828,7 +851,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.sol_raw = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
-  a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj;
+  a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj; a.done_count = nullptr; a.done_list = nullptr;
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
@@ -895,22 +918,44 @@ extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts
   if (!h->d_gsol) {
     CUDA_TRY(h, cudaMalloc((void**)&h->d_gsol, (size_t)h->max_batch * h->plan.nres * sizeof(double)));
     CUDA_TRY(h, cudaMalloc((void**)&h->d_gstatus, (size_t)h->max_batch * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_done, ((size_t)h->max_batch + 2) * sizeof(int)));
+    if (getenv("DOJO_B200_NO_GRAD_OVERLAP")) h->overlap_grad = false;
   }
   int32_t* st = dstatus ? dstatus : h->d_gstatus;
-  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, h->d_gsol, st, diters, flags, s);
+  // The gradient kernel is launched programmatically dependent on the forward kernel (same stream): its CTAs start on the
+  // SMs the forward kernel's tail leaves idle and consume environments in the order the forward kernel finishes them
+  // (done_list), instead of waiting for the whole forward grid.
+  const bool overlap = h->overlap_grad;
+  int* done_count = overlap ? h->d_done : nullptr;
+  int* done_list = overlap ? h->d_done + 2 : nullptr;
+  if (overlap) {
+    CUDA_TRY(h, cudaMemsetAsync(h->d_done, 0, 2 * sizeof(int), s));                 // [0] finished count, [1] gradient work queue
+    CUDA_TRY(h, cudaMemsetAsync(h->d_done + 2, 0xff, (size_t)B * sizeof(int), s));  // -1 = not finished yet
+  }
+  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, h->d_gsol, st, diters, flags, s, done_count, done_list);
   if (rc != DOJO_OK) return rc;
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.sol_raw = h->d_gsol; a.status = st; a.iters = nullptr; a.flags = flags;
-  a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr;
-  a.counter = h->d_counter; a.order = nullptr; a.prev_iters = nullptr;
+  a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr; a.done_count = nullptr; a.done_list = done_list;
+  a.counter = overlap ? h->d_done + 1 : h->d_counter; a.order = nullptr; a.prev_iters = nullptr;
   a.prof = h->d_prof;
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  if (!overlap) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->grad_bytes / sizeof(double));
   a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off_grad;
   for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots_grad - 1) / h->slots_grad, h->sm_count * h->envs_per_sm_grad);
-  dojo_step_kernel<true><<<grid, 32 * h->nw * h->slots_grad, h->smem_grad, s>>>(a);
+  if (overlap) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * h->nw * h->slots_grad); cfg.dynamicSmemBytes = h->smem_grad; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(h, cudaLaunchKernelEx(&cfg, dojo_step_kernel<true>, a));
+  } else {
+    dojo_step_kernel<true><<<grid, 32 * h->nw * h->slots_grad, h->smem_grad, s>>>(a);
+  }
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DOJO_OK;
