@@ -152,7 +152,10 @@ int dojo_step_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const d
                     int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
 
 /* step! + consistent IFT gradients at the solution (get_maximal_gradients evaluated
- * right after mehrotra!, before update_state!).  dFz [12Nb x 12Nb x B], dFu [12Nb x nu x B]. */
+ * right after mehrotra!, before update_state!).  dFz [12Nb x 12Nb x B], dFu [12Nb x nu x B].
+ * Two launches on the stream: the forward kernel, then the gradient kernel, which starts on the SMs the
+ * forward kernel's tail leaves idle and consumes environments in completion order.  B <= max_batch;
+ * the output state buffer must not alias the input state (the gradient kernel re-reads Z). */
 int dojo_step_grad(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z,
                    const double* U, const double* Fext, double* Z_next, double* Fz, double* Fu,
                    int32_t* status, int32_t* iters, uint32_t flags);
