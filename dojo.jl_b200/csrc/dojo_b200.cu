@@ -263,7 +263,9 @@ struct DojoHandle {
   size_t arena_bytes = 0, grad_bytes = 0;  // per environment
   size_t smem_fwd = 0, smem_grad = 0;     // dynamic shared memory per CTA
   int envs_per_sm_grad = 1;
-  double *d_Fz = nullptr, *d_Fu = nullptr;  // staging for host-pointer gradient calls (grad_chunk environments)
+  double *d_Fz[2] = {nullptr, nullptr}, *d_Fu[2] = {nullptr, nullptr};  // staging for host-pointer gradient calls (grad_chunk environments, double buffered)
+  cudaEvent_t ev_kernel[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
   int grad_chunk = 0;
   char* d_blob = nullptr;  // plan tables (one contiguous upload)
   int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -696,7 +698,8 @@ extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
-  cudaFree(h->d_Fz); cudaFree(h->d_Fu);
+  for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
   if (h->p_in) cudaFreeHost(h->p_in);
   if (h->p_out) cudaFreeHost(h->p_out);
@@ -976,26 +979,39 @@ extern "C" int dojo_step_grad(DojoHandle* h, const DojoSolverOptions* opts, int 
   int rc = ensure_staging(h);
   if (rc != DOJO_OK) return rc;
   const size_t ng = 12 * (size_t)P.Nb, fz = ng * ng, fu = ng * P.nu;
-  if (!h->d_Fz) {
-    h->grad_chunk = (int)std::max<size_t>(1, std::min<size_t>(h->max_batch, (size_t(256) << 20) / ((fz + fu) * sizeof(double))));
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_Fz, (size_t)h->grad_chunk * fz * sizeof(double)));
-    CUDA_TRY(h, cudaMalloc((void**)&h->d_Fu, std::max<size_t>(1, (size_t)h->grad_chunk * fu) * sizeof(double)));
+  if (!h->d_Fz[0]) {  // two chunk buffers: the kernels of chunk i + 1 run while the gradients of chunk i travel to the host
+    h->grad_chunk = (int)std::max<size_t>(1, std::min<size_t>(h->max_batch, (size_t(128) << 20) / ((fz + fu) * sizeof(double))));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(h, cudaMalloc((void**)&h->d_Fz[k], (size_t)h->grad_chunk * fz * sizeof(double)));
+      CUDA_TRY(h, cudaMalloc((void**)&h->d_Fu[k], std::max<size_t>(1, (size_t)h->grad_chunk * fu) * sizeof(double)));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   }
-  cudaStream_t s = h->stream;
-  for (int e0 = 0; e0 < B; e0 += h->grad_chunk) {
+  cudaStream_t s = h->stream, cs = h->copy_stream;
+  // whole-batch inputs first (small), per-chunk kernels, gradient copies on the second stream
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (U && P.nu > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (Fext) CUDA_TRY(h, cudaMemcpyAsync(h->d_F, Fext, (size_t)B * 6 * P.Nb * sizeof(double), cudaMemcpyHostToDevice, s));
+  int k = 0;
+  for (int e0 = 0; e0 < B; e0 += h->grad_chunk, k ^= 1) {
     const int nb = std::min(h->grad_chunk, B - e0);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z + (size_t)e0 * P.nz, (size_t)nb * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (U && P.nu > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U + (size_t)e0 * P.nu, (size_t)nb * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (Fext) CUDA_TRY(h, cudaMemcpyAsync(h->d_F, Fext + (size_t)e0 * 6 * P.Nb, (size_t)nb * 6 * P.Nb * sizeof(double), cudaMemcpyHostToDevice, s));
-    rc = dojo_step_grad_async(h, opts, nb, h->d_Z, (U && P.nu > 0) ? h->d_U : nullptr, Fext ? h->d_F : nullptr, h->d_Zn, h->d_Fz, h->d_Fu, h->d_status, h->d_iters,
-                              flags, s);
+    if (e0 >= 2 * h->grad_chunk) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[k], 0));  // buffer k has been drained
+    rc = dojo_step_grad_async(h, opts, nb, h->d_Z + (size_t)e0 * P.nz, (U && P.nu > 0) ? h->d_U + (size_t)e0 * P.nu : nullptr,
+                              Fext ? h->d_F + (size_t)e0 * 6 * P.Nb : nullptr, h->d_Zn + (size_t)e0 * P.nz, h->d_Fz[k], h->d_Fu[k], h->d_status + e0,
+                              h->d_iters + e0, flags, s);
     if (rc != DOJO_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(Zn + (size_t)e0 * P.nz, h->d_Zn, (size_t)nb * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaMemcpyAsync(Fz + (size_t)e0 * fz, h->d_Fz, (size_t)nb * fz * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (fu) CUDA_TRY(h, cudaMemcpyAsync(Fu + (size_t)e0 * fu, h->d_Fu, (size_t)nb * fu * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (status) CUDA_TRY(h, cudaMemcpyAsync(status + e0, h->d_status, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + e0, h->d_iters, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaEventRecord(h->ev_kernel[k], s));
+    CUDA_TRY(h, cudaStreamWaitEvent(cs, h->ev_kernel[k], 0));
+    CUDA_TRY(h, cudaMemcpyAsync(Fz + (size_t)e0 * fz, h->d_Fz[k], (size_t)nb * fz * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (fu) CUDA_TRY(h, cudaMemcpyAsync(Fu + (size_t)e0 * fu, h->d_Fu[k], (size_t)nb * fu * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(h, cudaEventRecord(h->ev_copy[k], cs));
   }
+  CUDA_TRY(h, cudaMemcpyAsync(Zn, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  CUDA_TRY(h, cudaStreamSynchronize(cs));
   return DOJO_OK;
 }

@@ -147,16 +147,24 @@ class BatchedStepper:
         self._check(rc, "dojo_step")
         return (Zn, status, iters, sol) if return_sol else (Zn, status, iters)
 
-    def step_grad(self, Z, U=None, opts=None, flags: int = 0):
+    def step_grad(self, Z, U=None, opts=None, flags: int = 0, out=None):
+        """step! + IFT gradients.  Returns (Z_next, Fz [B, 12Nb, 12Nb], Fu [B, 12Nb, nu], status, iters) with Fz[e] = dz'/dz.
+        out = (Z_next, Fz_raw [B, 12Nb, 12Nb], Fu_raw [B, nu, 12Nb], status, iters) reuses caller buffers (e.g. page-locked
+        ones); the raw arrays hold each environment's Jacobian column-major, the returned Fz / Fu are transposed views."""
         Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
         B = Z.shape[0]
         U = np.zeros((B, self.nu)) if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
-        Zn = np.empty_like(Z)
         ng = self.ngrad
-        Fz = np.empty((B, ng, ng))   # per env column-major [ng x ng]  ==  Fz[e].T is the Jacobian
-        Fu = np.empty((B, self.nu, ng))
-        status = np.zeros(B, dtype=np.int32)
-        iters = np.zeros(B, dtype=np.int32)
+        if out is not None:
+            Zn, Fz, Fu, status, iters = out
+            assert Zn.shape == Z.shape and Fz.shape == (B, ng, ng) and Fu.shape == (B, self.nu, ng)
+            assert all(a.flags.c_contiguous for a in (Zn, Fz, Fu, status, iters)) and status.dtype == np.int32 and iters.dtype == np.int32
+        else:
+            Zn = np.empty_like(Z)
+            Fz = np.empty((B, ng, ng))   # per env column-major [ng x ng]  ==  Fz[e].T is the Jacobian
+            Fu = np.empty((B, self.nu, ng))
+            status = np.zeros(B, dtype=np.int32)
+            iters = np.zeros(B, dtype=np.int32)
         o = opts if opts is not None else capi.solver_options()
         rc = self.L.dojo_step_grad(self.h, C.byref(o), B, _p(Z), _p(U), None, _p(Zn), _p(Fz), _p(Fu), _p(status), _p(iters), flags)
         self._check(rc, "dojo_step_grad")
