@@ -10,6 +10,10 @@ Python has no `!`, so `step!` is `step`):
     get_maximal_gradients!(mechanism, z, u; opts)                   get_maximal_gradients(mechanism, z, u, opts=None)
                                           gradients/state.jl:69
     mehrotra!(mechanism; opts) -> :success / :failed                status codes returned next to the states (STATUS)
+    minimal_to_maximal(mechanism, x)      mechanism/state.jl:9      minimal_to_maximal(mechanism, x)
+    maximal_to_minimal(mechanism, z)      mechanism/state.jl:44     maximal_to_minimal(mechanism, z)
+    step_minimal_coordinates!(mechanism, x, u; opts)                step_minimal_coordinates(mechanism, x, u, opts=None)
+                                          simulation/step.jl:42
 
 NEW relative to the reference: every function also accepts a batch -- z of shape [B, 13 Nb], u of shape [B, nu] --
 and then returns batched results.  All compute happens in libdojo_b200.so on the GPU (solver.BatchedStepper).
@@ -101,6 +105,36 @@ def get_maximal_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0
         _check_single(status)
         return Fz[0], Fu[0]
     return Fz, Fu
+
+
+def minimal_to_maximal(mechanism: Mechanism, x, device: int = 0):
+    """minimal_to_maximal(mechanism, x): x [2 nu] or [B, 2 nu] (per joint [c_tra; c_rot; v_tra; v_rot]) -> z [13 Nb] / [B, 13 Nb]."""
+    x = np.asarray(x, dtype=float)
+    X = np.atleast_2d(x)
+    Z = _stepper(mechanism, X.shape[0], device).minimal_to_maximal(X)
+    return Z[0] if x.ndim == 1 else Z
+
+
+def maximal_to_minimal(mechanism: Mechanism, z, device: int = 0):
+    """maximal_to_minimal(mechanism, z): z [13 Nb] or [B, 13 Nb] -> x [2 nu] / [B, 2 nu]."""
+    z = np.asarray(z, dtype=float)
+    Z = np.atleast_2d(z)
+    X = _stepper(mechanism, Z.shape[0], device).maximal_to_minimal(Z)
+    return X[0] if z.ndim == 1 else X
+
+
+def step_minimal_coordinates(mechanism: Mechanism, x, u, opts=None, device: int = 0):
+    """step_minimal_coordinates!(mechanism, x, u; opts) -> x_next (what DojoEnvironments.step! calls); for a batch also
+    (status, iters).  The maximal states stay on the device between the three launches."""
+    x = np.asarray(x, dtype=float)
+    single = x.ndim == 1
+    X = np.atleast_2d(x)
+    U = np.atleast_2d(np.asarray(u, dtype=float))
+    Xn, status, iters = _stepper(mechanism, X.shape[0], device).step_minimal(X, U, opts)
+    if single:
+        _check_single(status)
+        return Xn[0]
+    return Xn, status, iters
 
 
 def status_name(code: int) -> str:

@@ -13,6 +13,7 @@
 
 #include "../../include/dojo_b200.h"
 #include "dojo_grad.cuh"
+#include "dojo_kin.cuh"
 
 using namespace dj;
 
@@ -271,6 +272,8 @@ struct DojoHandle {
   int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
   int* d_counter = nullptr;
+  int* d_kin_order = nullptr;      // joints root -> leaves (minimal -> maximal map)
+  double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
   int* d_done = nullptr;           // [0] finished count, [1] gradient work queue, [2..] completion-ordered environment list
   bool overlap_grad = true;
   double* d_gsol = nullptr;        // final solutions handed from the forward to the gradient launch [nres x max_batch]
@@ -651,6 +654,16 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     h->blob_bytes = (int)blob.size();
   }
   bool ok = upload(blob.data(), blob.size(), (void**)&h->d_blob);
+  {  // joints root -> leaves: a joint is placed once its parent body has been placed (mechanism.root_to_leaves restricted to joints)
+    std::vector<int> order;
+    std::vector<char> placed(Nb, 0), used(Ne, 0);
+    for (bool progress = true; progress && (int)order.size() < Ne;) {
+      progress = false;
+      for (int j = 0; j < Ne; ++j)
+        if (!used[j] && (joints[j].parent < 0 || placed[joints[j].parent])) { order.push_back(j); used[j] = 1; placed[joints[j].child] = 1; progress = true; }
+    }
+    ok = ok && (int)order.size() == Ne && upload(order.data(), sizeof(int) * Ne, (void**)&h->d_kin_order);
+  }
   ok = ok && cudaMalloc((void**)&h->d_counter, sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&h->d_order, sizeof(int) * max_batch) == cudaSuccess && cudaMalloc((void**)&h->d_prev_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
        cudaMemset(h->d_prev_iters, 0, sizeof(int32_t) * max_batch) == cudaSuccess;
@@ -697,7 +710,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -795,6 +808,8 @@ static int ensure_staging(DojoHandle* h) {
   CUDA_TRY(h, cudaMalloc((void**)&h->d_sol, B * P.nres * sizeof(double)));
   CUDA_TRY(h, cudaMalloc((void**)&h->d_status, B * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc((void**)&h->d_iters, B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_X, std::max<size_t>(1, B * 2 * P.nu) * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_Xn, std::max<size_t>(1, B * 2 * P.nu) * sizeof(double)));
   CUDA_TRY(h, cudaMallocHost((void**)&h->p_in, B * (P.nz + P.nu + 6 * P.Nb) * sizeof(double)));
   CUDA_TRY(h, cudaMallocHost((void**)&h->p_out, B * (P.nz + P.nres + 2) * sizeof(double)));
   return DOJO_OK;
@@ -1013,5 +1028,94 @@ extern "C" int dojo_step_grad(DojoHandle* h, const DojoSolverOptions* opts, int 
   if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   CUDA_TRY(h, cudaStreamSynchronize(cs));
+  return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// minimal <-> maximal coordinate maps and step_minimal_coordinates!
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int dojo_num_minimal(const DojoHandle* h) { return 2 * h->plan.nu; }
+
+static int launch_kin(DojoHandle* h, bool to_maximal, int B, const double* din, double* dout, cudaStream_t s) {
+  KinArgs a;
+  a.joints = h->plan.joints; a.order = h->d_kin_order;
+  a.Ne = h->plan.Ne; a.Nb = h->plan.Nb; a.nu = h->plan.nu; a.B = B; a.h = h->plan.h;
+  a.in = din; a.out = dout;
+  const int threads = 128, grid = (B + threads - 1) / threads;
+  if (to_maximal) dojo_min_to_max_kernel<<<grid, threads, 0, s>>>(a);
+  else dojo_max_to_min_kernel<<<grid, threads, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+extern "C" int dojo_minimal_to_maximal_async(DojoHandle* h, int B, const double* dX, double* dZ, void* cuda_stream) {
+  if (!h || B <= 0 || !dX || !dZ) { if (h) h->err = "dojo_minimal_to_maximal_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_kin(h, true, B, dX, dZ, (cudaStream_t)cuda_stream);
+}
+extern "C" int dojo_maximal_to_minimal_async(DojoHandle* h, int B, const double* dZ, double* dX, void* cuda_stream) {
+  if (!h || B <= 0 || !dX || !dZ) { if (h) h->err = "dojo_maximal_to_minimal_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_kin(h, false, B, dZ, dX, (cudaStream_t)cuda_stream);
+}
+
+// host or device pointers (both arguments of the same kind)
+static int kin_sync(DojoHandle* h, bool to_maximal, int B, const double* in, double* out, const char* who) {
+  if (!h || B <= 0 || B > h->max_batch || !in || !out) { if (h) h->err = std::string(who) + ": bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  const size_t nx = (size_t)B * 2 * P.nu * sizeof(double), nzb = (size_t)B * P.nz * sizeof(double);
+  if (is_device_ptr(in)) {
+    int rc = launch_kin(h, to_maximal, B, in, out, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  double* din = to_maximal ? h->d_X : h->d_Z;
+  double* dout = to_maximal ? h->d_Z : h->d_X;
+  CUDA_TRY(h, cudaMemcpyAsync(din, in, to_maximal ? nx : nzb, cudaMemcpyHostToDevice, s));
+  rc = launch_kin(h, to_maximal, B, din, dout, s);
+  if (rc != DOJO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(out, dout, to_maximal ? nzb : nx, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+extern "C" int dojo_minimal_to_maximal(DojoHandle* h, int B, const double* X, double* Z) { return kin_sync(h, true, B, X, Z, "dojo_minimal_to_maximal"); }
+extern "C" int dojo_maximal_to_minimal(DojoHandle* h, int B, const double* Z, double* X) { return kin_sync(h, false, B, Z, X, "dojo_maximal_to_minimal"); }
+
+// step_minimal_coordinates! (simulation/step.jl:42-61): minimal -> maximal, step!, maximal -> minimal; three launches on one
+// stream, the maximal states never leave the device.  X, U, X_next: host or device pointers (all of the same kind).
+extern "C" int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U, double* X_next, int32_t* status,
+                                 int32_t* iters) {
+  if (!h || B <= 0 || B > h->max_batch || !X || !X_next) { if (h) h->err = "dojo_step_minimal: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  const bool dev = is_device_ptr(X);
+  const size_t nx = (size_t)B * 2 * P.nu * sizeof(double);
+  const double* dX = X;
+  const double* dU = U;
+  double* dXn = X_next;
+  if (!dev) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_X, X, nx, cudaMemcpyHostToDevice, s));
+    if (U && P.nu > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+    dX = h->d_X; dU = (U && P.nu > 0) ? h->d_U : nullptr; dXn = h->d_Xn;
+  }
+  rc = launch_kin(h, true, B, dX, h->d_Z, s);
+  if (rc == DOJO_OK) rc = launch_forward(h, opts, B, h->d_Z, dU, nullptr, h->d_Zn, nullptr, nullptr, dev ? status : h->d_status, dev ? iters : h->d_iters, 0, s);
+  if (rc == DOJO_OK) rc = launch_kin(h, false, B, h->d_Zn, dXn, s);
+  if (rc != DOJO_OK) return rc;
+  if (!dev) {
+    CUDA_TRY(h, cudaMemcpyAsync(X_next, h->d_Xn, nx, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

@@ -20,7 +20,9 @@ STATUS = {0: "success", 1: "failed", 2: "excessive_angular_velocity", 3: "nonfin
 
 EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_error", "dojo_num_state", "dojo_num_input",
            "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env", "dojo_step", "dojo_step_async",
-           "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count"]
+           "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count",
+           "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
+           "dojo_maximal_to_minimal_async", "dojo_step_minimal"]
 
 _lib = None
 
@@ -59,6 +61,15 @@ def load_library():
     L.dojo_rollout.restype = C.c_int
     L.dojo_rollout_async.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     L.dojo_rollout_async.restype = C.c_int
+    L.dojo_num_minimal.argtypes = [vp]
+    L.dojo_num_minimal.restype = C.c_int
+    for name in ("dojo_minimal_to_maximal", "dojo_maximal_to_minimal"):
+        getattr(L, name).argtypes = [vp, C.c_int, vp, vp]
+        getattr(L, name).restype = C.c_int
+        getattr(L, name + "_async").argtypes = [vp, C.c_int, vp, vp, vp]
+        getattr(L, name + "_async").restype = C.c_int
+    L.dojo_step_minimal.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp]
+    L.dojo_step_minimal.restype = C.c_int
     _lib = L
     return L
 
@@ -183,6 +194,38 @@ class BatchedStepper:
         rc = self.L.dojo_rollout(self.h, C.byref(o), B, int(T), _p(Z0), _p(U), _p(Zf), _p(traj), _p(st))
         self._check(rc, "dojo_rollout")
         return (Zf, st, traj) if record else (Zf, st)
+
+    # ------------------------------------------------------------------ minimal coordinates
+    @property
+    def nmin(self) -> int:
+        return self.L.dojo_num_minimal(self.h)
+
+    def minimal_to_maximal(self, X):
+        """minimal_to_maximal (mechanism/state.jl:9-22), batched: X [B, 2 nu] -> Z [B, 13 Nb]."""
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        assert X.shape[1] == self.nmin
+        Z = np.empty((X.shape[0], self.nz))
+        self._check(self.L.dojo_minimal_to_maximal(self.h, X.shape[0], _p(X), _p(Z)), "dojo_minimal_to_maximal")
+        return Z
+
+    def maximal_to_minimal(self, Z):
+        """maximal_to_minimal (mechanism/state.jl:44-66), batched: Z [B, 13 Nb] -> X [B, 2 nu]."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        assert Z.shape[1] == self.nz
+        X = np.empty((Z.shape[0], self.nmin))
+        self._check(self.L.dojo_maximal_to_minimal(self.h, Z.shape[0], _p(Z), _p(X)), "dojo_maximal_to_minimal")
+        return X
+
+    def step_minimal(self, X, U=None, opts=None):
+        """step_minimal_coordinates! (simulation/step.jl:42-61), batched.  Returns (X_next, status, iters)."""
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        B = X.shape[0]
+        U = None if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        Xn = np.empty_like(X)
+        status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        self._check(self.L.dojo_step_minimal(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(status), _p(iters)), "dojo_step_minimal")
+        return Xn, status, iters
 
     # ------------------------------------------------------------------ device buffers (resident data)
     def step_device(self, dZ: int, dU: Optional[int], dZn: int, B: int, opts=None, dstatus: Optional[int] = None, diters: Optional[int] = None,

@@ -20,6 +20,11 @@
  *   dojo_rollout                 <- simulate!(mechanism, steps, storage, control!)
  *                                                                  src/simulation/simulate.jl:16-36
  *   DojoSolverOptions            <- SolverOptions{T}               src/solver/options.jl:16-26
+ *   dojo_minimal_to_maximal      <- minimal_to_maximal(mechanism, x) src/mechanism/state.jl:9-22
+ *                                   (set_minimal_coordinates_velocities!, src/joints/minimal.jl:148-203)
+ *   dojo_maximal_to_minimal      <- maximal_to_minimal(mechanism, z) src/mechanism/state.jl:44-66
+ *   dojo_step_minimal            <- step_minimal_coordinates!(mechanism, x, u; opts)
+ *                                                                  src/simulation/step.jl:42-61
  *
  * All arrays are fp64.  Batched arrays are column-major [feature x B] exactly as a Julia
  * Matrix{Float64}(feature, B) is laid out, i.e. environment e owns the contiguous slice
@@ -175,6 +180,21 @@ int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, con
 int dojo_rollout_async(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* dZ0,
                        const double* dU, double* dZ_final, double* dZ_traj, int32_t* dstatus_any,
                        void* cuda_stream);
+
+/* Minimal <-> maximal coordinate maps (the step either side of step! for every DojoEnvironments call).
+ * Minimal state x = per joint, in joint order, [c_tra; c_rot; v_tra; v_rot] (2 * input_dimension(joint) entries:
+ * coordinates along the free translational / rotational axes and their finite-difference velocities);
+ * X is [2 nu x B].  Host or device pointers (both of the same kind); *_async: device pointers, no synchronisation. */
+int dojo_num_minimal(const DojoHandle* h); /* 2 nu */
+int dojo_minimal_to_maximal(DojoHandle* h, int B, const double* X, double* Z);
+int dojo_maximal_to_minimal(DojoHandle* h, int B, const double* Z, double* X);
+int dojo_minimal_to_maximal_async(DojoHandle* h, int B, const double* dX, double* dZ, void* cuda_stream);
+int dojo_maximal_to_minimal_async(DojoHandle* h, int B, const double* dZ, double* dX, void* cuda_stream);
+
+/* step_minimal_coordinates!: minimal -> maximal, step!, maximal -> minimal in three launches on one stream; the maximal
+ * states never leave the device.  X [2 nu x B], U [nu x B] (nullable), X_next [2 nu x B]; host or device pointers. */
+int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
+                      double* X_next, int32_t* status, int32_t* iters);
 
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t dojo_launch_count(const DojoHandle* h);

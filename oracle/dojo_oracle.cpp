@@ -689,6 +689,92 @@ struct Oracle {
 
   // ---------------------------------------------------------------- state in / out
   // mechanism/set.jl:10-26 (set_maximal_state!), bodies/set.jl:1-20
+  // ----------------------------------------------------------------------------------------
+  // minimal <-> maximal coordinate maps: mechanism/state.jl:9-22 (minimal_to_maximal), :44-66
+  // (maximal_to_minimal), joints/minimal.jl:148-203 (set_minimal_coordinates_velocities!).  Minimal state per joint, in
+  // joint order: [c_tra; c_rot; v_tra; v_rot]  (2 * input_dimension(joint) entries).
+  // ----------------------------------------------------------------------------------------
+  std::vector<int> root_to_leaves_joints() const {  // mechanism.root_to_leaves restricted to joints: parents before children
+    std::vector<int> order;
+    std::vector<char> placed(Nb, 0);
+    bool progress = true;
+    while ((int)order.size() < Ne && progress) {
+      progress = false;
+      for (int j = 0; j < Ne; ++j) {
+        const JointS& jt = joints[j];
+        bool done = false;
+        for (int k : order) done = done || (k == j);
+        if (done) continue;
+        if (jt.parent < 0 || placed[jt.parent]) { order.push_back(j); placed[jt.child] = 1; progress = true; }
+      }
+    }
+    return order;
+  }
+  static Quat axis_angle_to_quaternion(const V3& x) {  // orientation/axis_angle.jl:1-11
+    double th = std::sqrt(dot(x, x));
+    if (th > 0.0) { double s = std::sin(0.5 * th) / th; return Quat(std::cos(0.5 * th), s * x[0], s * x[1], s * x[2]); }
+    return Quat(1.0, 0.0, 0.0, 0.0);
+  }
+  static V3 angular_velocity(const Quat& q1, const Quat& q2, double h) {  // integrators/integrator.jl:22-24
+    return (VLtmat(q1) * vector(q2)) * (2.0 / h);
+  }
+  void minimal_to_maximal(const double* xmin, double* z) const {
+    std::vector<Cfg> st(Nb);
+    for (int j : root_to_leaves_joints()) {
+      const JointS& jt = joints[j];
+      const int nt = jt.el[0].nfree, nr = jt.el[1].nfree, nuj = nt + nr;
+      const double* xm = xmin + 2 * jt.u_off;
+      Cfg a;
+      if (jt.parent >= 0) a = st[jt.parent];
+      else { a.x = V3(); a.v = V3(); a.w = V3(); a.q = Quat(1.0, 0.0, 0.0, 0.0); }
+      V3 dx, dth, dv, dw;  // A' * coordinates
+      for (int i = 0; i < nt; ++i) for (int c = 0; c < 3; ++c) { dx[c] += jt.el[0].A[i][c] * xm[i]; dv[c] += jt.el[0].A[i][c] * xm[nuj + i]; }
+      for (int i = 0; i < nr; ++i) for (int c = 0; c < 3; ++c) { dth[c] += jt.el[1].A[i][c] * xm[nt + i]; dw[c] += jt.el[1].A[i][c] * xm[nuj + nt + i]; }
+      // positions
+      Quat dq = axis_angle_to_quaternion(dth);
+      Quat qb = a.q * jt.qoff * dq;
+      V3 xb = a.x + vector_rotate(jt.pa + dx, a.q) - vector_rotate(jt.pb, qb);
+      // previous configuration
+      V3 xa1 = next_position(a.x, -a.v, h);
+      Quat qa1 = next_orientation(a.q, -a.w, h);
+      // finite-difference configuration
+      V3 dx1 = dx - dv * h;
+      Quat dq1 = dq * inv(axis_angle_to_quaternion(dw * h));
+      Quat qb1 = qa1 * jt.qoff * dq1;
+      V3 xb1 = xa1 + vector_rotate(jt.pa + dx1, qa1) - vector_rotate(jt.pb, qb1);
+      Cfg b;
+      b.x = xb; b.q = qb;
+      b.v = (xb - xb1) / h;
+      b.w = angular_velocity(qb1, qb, h);
+      st[jt.child] = b;
+    }
+    for (int b = 0; b < Nb; ++b) {
+      double* zb = z + 13 * b;
+      for (int i = 0; i < 3; ++i) { zb[i] = st[b].x[i]; zb[3 + i] = st[b].v[i]; zb[10 + i] = st[b].w[i]; }
+      zb[6] = st[b].q.s; zb[7] = st[b].q.v1; zb[8] = st[b].q.v2; zb[9] = st[b].q.v3;
+    }
+  }
+  void maximal_to_minimal(const double* z, double* xmin) const {
+    auto unpack = [&](int b) {
+      Cfg c;
+      if (b < 0) { c.x = V3(); c.v = V3(); c.w = V3(); c.q = Quat(1.0, 0.0, 0.0, 0.0); return c; }
+      const double* zb = z + 13 * b;
+      for (int i = 0; i < 3; ++i) { c.x[i] = zb[i]; c.v[i] = zb[3 + i]; c.w[i] = zb[10 + i]; }
+      c.q = Quat(zb[6], zb[7], zb[8], zb[9]);
+      return c;
+    };
+    for (int j = 0; j < Ne; ++j) {
+      const JointS& jt = joints[j];
+      const int nt = jt.el[0].nfree, nr = jt.el[1].nfree, nuj = nt + nr;
+      double* xm = xmin + 2 * jt.u_off;
+      Cfg a = unpack(jt.parent), b = unpack(jt.child);
+      minimal_coordinates(jt, 0, a.x, a.q, b.x, b.q, xm);
+      minimal_coordinates(jt, 1, a.x, a.q, b.x, b.q, xm + nt);
+      minimal_velocities(jt, 0, a, b, h, xm + nuj);
+      minimal_velocities(jt, 1, a, b, h, xm + nuj + nt);
+    }
+  }
+
   void set_maximal_state(const double* z) {
     for (int b = 0; b < Nb; ++b) {
       BodyS& s = bodies[b];
@@ -1780,5 +1866,8 @@ int oracle_trace(void* h, double* out, int cap) {  // rows of (rvio, bvio, alpha
   std::memcpy(out, o->trace.data(), sizeof(double) * n);
   return (int)o->trace.size() / 4;
 }
+int oracle_num_minimal(void* h) { return 2 * static_cast<Oracle*>(h)->nu; }
+void oracle_minimal_to_maximal(void* h, const double* x, double* z) { static_cast<Oracle*>(h)->minimal_to_maximal(x, z); }
+void oracle_maximal_to_minimal(void* h, const double* z, double* x) { static_cast<Oracle*>(h)->maximal_to_minimal(z, x); }
 void oracle_momentum(void* h, double* out6) { static_cast<Oracle*>(h)->momentum(out6); }
 }

@@ -63,6 +63,8 @@ def lib():
         L.oracle_trace.argtypes = [vp, dp, C.c_int]
         L.oracle_trace.restype = C.c_int
         L.oracle_momentum.argtypes = [vp, dp]
+        L.oracle_minimal_to_maximal.argtypes = [vp, dp, dp]
+        L.oracle_maximal_to_minimal.argtypes = [vp, dp, dp]
         _lib = L
     return _lib
 
@@ -152,6 +154,23 @@ class Oracle:
         out = np.empty(self.nres)
         self.L.oracle_evaluate_rhs(self.h, _d(sol), float(mu), _d(out))
         return out
+
+    # minimal <-> maximal coordinate maps (mechanism/state.jl:9-66)
+    @property
+    def nmin(self):
+        return 2 * self.nu
+
+    def minimal_to_maximal(self, x):
+        x = np.ascontiguousarray(x, dtype=float)
+        z = np.empty(13 * self.mech.Nb)
+        self.L.oracle_minimal_to_maximal(self.h, _d(x), _d(z))
+        return z
+
+    def maximal_to_minimal(self, z):
+        z = np.ascontiguousarray(z, dtype=float)
+        x = np.empty(self.nmin)
+        self.L.oracle_maximal_to_minimal(self.h, _d(z), _d(x))
+        return x
 
     def violations(self):
         r, b = C.c_double(), C.c_double()

@@ -243,3 +243,64 @@ def test_rollout_trajectory(name):
         worst = np.maximum(worst, s)
         assert np.array_equal(traj[t], Z)
     assert np.array_equal(Zf, Z) and np.array_equal(Zf2, Z) and np.array_equal(st, worst) and np.array_equal(st2, worst)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# minimal <-> maximal coordinate maps and step_minimal_coordinates!
+# ----------------------------------------------------------------------------------------------------------------
+def _random_minimal_batch(mech, B, rng):
+    X = np.zeros((B, 2 * mech.nu))
+    off = 0
+    for j in mech.joints:
+        n = j.input_dimension
+        X[:, 2 * off:2 * off + n] = rng.uniform(-0.3, 0.3, (B, n))
+        X[:, 2 * off + n:2 * off + 2 * n] = rng.normal(0.0, 0.5, (B, n))
+        off += n
+    return X
+
+
+@pytest.mark.parametrize("name", ["pendulum", "ant", "quadruped", "atlas"])
+def test_minimal_maximal_maps(name):
+    """dojo_minimal_to_maximal / dojo_maximal_to_minimal vs the oracle's restatement of mechanism/state.jl:9-66, and the
+    round trip on the device."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(31)
+    B = 37
+    X = _random_minimal_batch(mech, B, rng)
+    stepper, o = BatchedStepper(mech, B), Oracle(mech)
+    assert stepper.nmin == 2 * mech.nu
+    Z = stepper.minimal_to_maximal(X)
+    Zo = np.stack([o.minimal_to_maximal(X[e]) for e in range(B)])
+    assert np.abs(Z - Zo).max() < 1e-11
+    Xr = stepper.maximal_to_minimal(Z)
+    Xo = np.stack([o.maximal_to_minimal(Zo[e]) for e in range(B)])
+    assert np.abs(Xr - Xo).max() < 1e-9 and np.abs(Xr - X).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["ant", "quadruped"])
+def test_step_minimal_coordinates(name):
+    """dojo_step_minimal == maximal_to_minimal(step!(minimal_to_maximal(x), u)) (simulation/step.jl:42-61): bit-identical to the
+    composition of the three device calls, and equal to the oracle's composition where the iteration counts agree."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(37)
+    B = 24
+    X = _random_minimal_batch(mech, B, rng)
+    off = 0
+    for j in mech.joints:  # lift the floating base so that the feet start near the ground, not inside it
+        if j.nimpulses == 0:
+            X[:, 2 * off + 2] += 0.6
+        off += j.input_dimension
+    U = random_inputs(mech, B, rng)
+    stepper, o = BatchedStepper(mech, B), Oracle(mech)
+    Xn, st, it = stepper.step_minimal(X, U)
+    Z = stepper.minimal_to_maximal(X)
+    Zn, st2, it2 = stepper.step(Z, U)
+    assert np.array_equal(Xn, stepper.maximal_to_minimal(Zn)) and np.array_equal(st, st2) and np.array_equal(it, it2)
+    for e in range(B):
+        zo, so, io = o.step(o.minimal_to_maximal(X[e]), U[e])
+        if so == 0 and st[e] == 0 and io == it[e]:
+            assert np.abs(Xn[e] - o.maximal_to_minimal(zo)).max() < 1e-6

@@ -225,3 +225,39 @@ def test_ift_gradients_match_finite_difference(name, steps):
         assert np.abs(col - Fu[:, i]).max() < 1e-5 * max(1.0, np.abs(Fu).max())
         checked += 1
     assert checked >= 8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# minimal <-> maximal coordinate maps (reference test/minimal.jl: the maps are mutual inverses)
+# ----------------------------------------------------------------------------------------------------------------
+def _random_minimal(mech, rng, scale_c=0.3, scale_v=0.5):
+    x = np.zeros(2 * mech.nu)
+    off = 0
+    for j in mech.joints:
+        n = j.input_dimension
+        x[2 * off:2 * off + n] = rng.uniform(-scale_c, scale_c, n)
+        x[2 * off + n:2 * off + 2 * n] = rng.normal(0.0, scale_v, n)
+        off += n
+    return x
+
+
+@pytest.mark.parametrize("name", ["pendulum", "ant", "quadruped", "atlas"])
+def test_minimal_maximal_round_trip(name):
+    """maximal_to_minimal(minimal_to_maximal(x)) == x (test/minimal.jl) -- coordinates and finite-difference velocities --
+    and the configuration agrees with the independently written host forward kinematics (set_minimal_coordinates!)."""
+    mech = dj.get_mechanism(name)
+    o = Oracle(mech)
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        x = _random_minimal(mech, rng)
+        z = o.minimal_to_maximal(x)
+        assert np.abs(o.maximal_to_minimal(z) - x).max() < 1e-10
+        coords, off = {}, 0
+        for j in mech.joints:
+            coords[j.name] = x[2 * off:2 * off + j.input_dimension]
+            off += j.input_dimension
+        zk = mech.forward_kinematics(coords).reshape(mech.Nb, 13)
+        zz = z.reshape(mech.Nb, 13)
+        assert np.abs(zz[:, 0:3] - zk[:, 0:3]).max() < 1e-10 and np.abs(zz[:, 6:10] - zk[:, 6:10]).max() < 1e-10
+        q = zz[:, 6:10]
+        assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-12
