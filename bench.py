@@ -291,6 +291,30 @@ def main():
         rollout = {"value": B / (rms * 1e-3), "unit": "env-steps/s", "ms_per_step": rms, "steps_fused": args.steps, "launches": 1,
                    "final_state_matches_stepwise": bool(torch.equal(Zf, Za))}
 
+    # ---- minimal-coordinate path: the maps either side of step! and step_minimal_coordinates! = map + step + map
+    minimal = None
+    if args.mode == "fwd" and world == 1 and mech.nu > 0:
+        Xd = torch.empty((B, 2 * mech.nu), dtype=torch.float64, device=dev)
+        Zd = torch.empty_like(Z_timed_start)
+        m0, m1, m2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        stepper.maximal_to_minimal_device(Z_timed_start.data_ptr(), Xd.data_ptr(), B, stream=stream.cuda_stream)  # warm
+        stepper.minimal_to_maximal_device(Xd.data_ptr(), Zd.data_ptr(), B, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        flush.fill_(2)
+        m0.record(stream)
+        stepper.maximal_to_minimal_device(Z_timed_start.data_ptr(), Xd.data_ptr(), B, stream=stream.cuda_stream)
+        m1.record(stream)
+        stepper.minimal_to_maximal_device(Xd.data_ptr(), Zd.data_ptr(), B, stream=stream.cuda_stream)
+        m2.record(stream)
+        torch.cuda.synchronize()
+        bytes_map = 8 * B * (2 * mech.nu + mech.nz)
+        t_mm, t_mM = m0.elapsed_time(m1), m1.elapsed_time(m2)
+        minimal = {"maximal_to_minimal_us": 1e3 * t_mm, "minimal_to_maximal_us": 1e3 * t_mM,
+                   "maximal_to_minimal_GBps": bytes_map / (t_mm * 1e-3) / 1e9, "minimal_to_maximal_GBps": bytes_map / (t_mM * 1e-3) / 1e9,
+                   "round_trip_max_abs_err": float((Zd - Z_timed_start).abs().max().item()),
+                   "step_minimal_ms": ms_per_step + t_mm + t_mM,
+                   "step_minimal_value": B / ((ms_per_step + t_mm + t_mM) * 1e-3), "unit": "env-steps/s"}
+
     # ---- e2e through the public host API (pinned staging + H2D + kernel + D2H), same workload, N = 1 path per rank
     # Host buffers are page-locked (torch pin_memory), as the contract asks: the library DMAs straight from / to them.
     def pinned(shape, dtype):
@@ -352,7 +376,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "rollout": rollout, "mean_newton_iters": it_sum / args.steps, "failed_env_steps": fails,
+            "rollout": rollout, "minimal_coordinates": minimal, "mean_newton_iters": it_sum / args.steps, "failed_env_steps": fails,
             "shared_bytes_per_env": stepper.shared_bytes_per_env}
     print(json.dumps(line))
     if world > 1:

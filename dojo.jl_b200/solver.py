@@ -235,6 +235,12 @@ class BatchedStepper:
                                     C.c_void_p(int(stream)))
         self._check(rc, "dojo_step_async")
 
+    def minimal_to_maximal_device(self, dX: int, dZ: int, B: int, stream: int = 0):
+        self._check(self.L.dojo_minimal_to_maximal_async(self.h, int(B), _p(dX), _p(dZ), C.c_void_p(int(stream))), "dojo_minimal_to_maximal_async")
+
+    def maximal_to_minimal_device(self, dZ: int, dX: int, B: int, stream: int = 0):
+        self._check(self.L.dojo_maximal_to_minimal_async(self.h, int(B), _p(dZ), _p(dX), C.c_void_p(int(stream))), "dojo_maximal_to_minimal_async")
+
     def rollout_device(self, dZ0: int, dU: Optional[int], dZf: int, B: int, T: int, opts=None, dtraj: Optional[int] = None, dstatus: Optional[int] = None,
                        stream: int = 0):
         """T steps fused in one launch on resident data (U is [T, B, nu] on the device)."""
