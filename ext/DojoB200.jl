@@ -120,6 +120,42 @@ function Dojo.get_maximal_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Mat
     return Fz, Fu
 end
 
+"batched minimal_to_maximal / maximal_to_minimal: X is 2nu x B (per joint [c_tra; c_rot; v_tra; v_rot]), Z is 13Nb x B"
+function Dojo.minimal_to_maximal(mech::Mechanism, X::Matrix{Float64})
+    h = handle(mech); B = size(X, 2); Z = zeros(h.nz, B)
+    rc = ccall((:dojo_minimal_to_maximal, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, B, X, Z)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Z
+end
+function Dojo.maximal_to_minimal(mech::Mechanism, Z::Matrix{Float64})
+    h = handle(mech); B = size(Z, 2); X = zeros(2 * h.nu, B)
+    rc = ccall((:dojo_maximal_to_minimal, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, B, Z, X)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return X
+end
+
+"batched step_minimal_coordinates! (simulation/step.jl:42-61): what DojoEnvironments.step! calls"
+function Dojo.step_minimal_coordinates!(mech::Mechanism, X::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(X, 2)
+    Xn = similar(X); status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_step_minimal, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+               h.ptr, COptions(opts), B, X, U, Xn, status, iters)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Xn
+end
+
+"open-loop batched simulate!: all T steps in one launch; U is nu x B x T, returns (Z_final, Z_traj 13Nb x B x T)"
+function rollout(mech::Mechanism, Z0::Matrix{Float64}, U::Array{Float64,3}; opts = SolverOptions{Float64}(), record = true)
+    h = handle(mech); B = size(Z0, 2); T = size(U, 3)
+    Zf = similar(Z0); traj = record ? zeros(h.nz, B, T) : nothing; status = zeros(Int32, B)
+    rc = ccall((:dojo_rollout, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+               h.ptr, COptions(opts), B, T, Z0, U, Zf, record ? traj : C_NULL, status)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Zf, traj
+end
+
 "B = 1 drop-in for mehrotra!(mechanism; opts): runs the step on the GPU and writes vsol / wsol back into the Mechanism"
 function mehrotra_gpu!(mech::Mechanism; opts = SolverOptions{Float64}())
     h = handle(mech)
