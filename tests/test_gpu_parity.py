@@ -304,3 +304,29 @@ def test_step_minimal_coordinates(name):
         zo, so, io = o.step(o.minimal_to_maximal(X[e]), U[e])
         if so == 0 and st[e] == 0 and io == it[e]:
             assert np.abs(Xn[e] - o.maximal_to_minimal(zo)).max() < 1e-6
+
+
+def test_full_size_invariants_quadruped():
+    """BASELINE config C2 size (quadruped, B = 8192, forward + gradients): size-independent properties -- unit quaternions,
+    determinism, permutation equivariance of states AND gradients, gradient launch leaves the forward result untouched."""
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("quadruped")
+    rng = np.random.default_rng(41)
+    B = 8192
+    Z = jittered_states(mech, 64, rng)[rng.integers(0, 64, B)]
+    Z[:, 2] += rng.uniform(0.0, 0.1, B)
+    U = random_inputs(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Z1, s1, i1 = stepper.step(Z, U)
+    Z2, s2, i2 = stepper.step(Z, U)
+    assert np.array_equal(Z1, Z2) and np.array_equal(i1, i2) and np.isfinite(Z1).all()
+    q = Z1.reshape(B, mech.Nb, 13)[:, :, 6:10]
+    assert np.abs(np.linalg.norm(q, axis=2) - 1).max() < 1e-12
+    n = 512  # gradients on a slice (215 KB per environment)
+    perm = rng.permutation(n)
+    Zg, Fz, Fu, sg, ig = stepper.step_grad(Z[:n], U[:n])
+    Zp, Fzp, Fup, _, _ = stepper.step_grad(Z[:n][perm], U[:n][perm])
+    assert np.array_equal(Zg, Z1[:n]) and np.array_equal(ig, i1[:n])
+    ok = sg == 0
+    assert np.isfinite(Fz[ok]).all() and np.isfinite(Fu[ok]).all()
+    assert np.array_equal(Zp, Zg[perm]) and np.array_equal(Fzp, Fz[perm]) and np.array_equal(Fup, Fu[perm])
