@@ -1,8 +1,8 @@
 // dojo_kernels.cuh -- the per-timestep hot path as one persistent sm_100a kernel.
 //
-// One CTA (nw warps) owns one environment.  The environment's whole interior-point problem (solution vector,
-// residuals, block-sparse KKT matrix) lives in the CTA's shared-memory arena for the duration of the step; HBM is
-// touched only to read z, u (and Fext) at the start and to write z_next (and status / iters / sol / gradients) at the end.
+// A CTA hosts up to four environments ("slots"), each owned by nw warps.  An environment's whole interior-point problem
+// (solution vector, residuals, block-sparse KKT matrix) lives in its slot's shared-memory arena for the duration of the step;
+// HBM is touched only to read z, u (and Fext) at the start and to write z_next (and status / iters / sol / gradients) at the end.
 //
 // Reference call stack restated here (file:line relative to the reference's src/):
 //   step!                 simulation/step.jl:11-30      -> dojo_step_kernel
@@ -10,7 +10,7 @@
 //   set_input!            mechanism/set.jl:40-53        -> prologue() (input / spring impulses, impulse maps)
 //   mehrotra!             solver/mehrotra.jl:9-73       -> mehrotra()
 //   set_entries!          solver/linear_system.jl:1-17  -> evaluate<true>()   (residual + KKT blocks)
-//   residual_violation / bilinear_violation  solver/violations.jl -> evaluate<false>() (line search)
+//   residual_violation / bilinear_violation  solver/violations.jl -> evaluate_ls() (line search, two trials per pass)
 //   ldu_factorization! / ldu_backsubstitution! (GraphBasedSystems) -> factorize() / solve()
 //   cone_line_search! / centering! / correction! / line_search!   -> same names below
 //   update_state! + get_next_state  bodies/set.jl:22-36, mechanism/get.jl:126-134 -> epilogue()

@@ -2,13 +2,13 @@
 // Built once on the host in dojo_create() from the DojoMechanismDesc (include/dojo_b200.h), read-only on
 // the device.  All *_off fields are offsets (in doubles) into the per-environment shared-memory arena.
 //
-// Execution model: one CTA (nw warps) owns one environment.
+// Execution model: nw warps own one environment (a CTA hosts several environments, each in its own arena).
 //   * assembly / residual evaluation: warps take ROLES (bodies, contacts, joints), one lane per node; per-node
 //     contributions to body rows go through 15-double "slots" that the body lanes gather in a fixed order
 //     (deterministic floating-point summation order, no atomics);
 //   * block LDU: elimination steps are grouped in PHASES by height in the elimination tree; the steps of one
 //     phase are independent (updates of a parent body go to a per-joint scratch record that the parent folds in
-//     when its own turn comes) and are spread over the warps; one CTA barrier separates phases.
+//     when its own turn comes) and are spread over the half-warps; one slot barrier separates phases.
 #pragma once
 #include <stdint.h>
 
