@@ -1,0 +1,22 @@
+"""Small invocation of every C-ABI entry point (for compute-sanitizer): python tools/sanity.py [mech]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import dojo_jl_b200 as dj
+from dojo_jl_b200.solver import BatchedStepper
+from conftest import jittered_states, random_inputs
+name = sys.argv[1] if len(sys.argv) > 1 else "ant"
+mech = dj.get_mechanism(name)
+rng = np.random.default_rng(0)
+B, T = 11, 3
+Z = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
+U = random_inputs(mech, B, rng)
+s = BatchedStepper(mech, 16)
+Zn, st, it = s.step(Z, U)
+Zg, Fz, Fu, sg, ig = s.step_grad(Z, U)
+Zf, sr, traj = s.rollout(Z, np.stack([U] * T), T, record=True)
+X = s.maximal_to_minimal(Zn)
+Z2 = s.minimal_to_maximal(X)
+Xn, _, _ = s.step_minimal(X, U)
+print("sanity ok", name, float(np.abs(Zn).max()), float(np.abs(Fz).max()), float(np.abs(traj).max()), float(np.abs(Xn).max()), it.tolist())
