@@ -14,6 +14,10 @@ Python has no `!`, so `step!` is `step`):
     maximal_to_minimal(mechanism, z)      mechanism/state.jl:44     maximal_to_minimal(mechanism, z)
     step_minimal_coordinates!(mechanism, x, u; opts)                step_minimal_coordinates(mechanism, x, u, opts=None)
                                           simulation/step.jl:42
+    maximal_to_minimal_jacobian(mechanism, z)  gradients/state.jl:9   maximal_to_minimal_jacobian(mechanism, z)
+    minimal_to_maximal_jacobian(mechanism, x)  gradients/state.jl:136 minimal_to_maximal_jacobian(mechanism, x)
+    get_minimal_gradients!(mechanism, x, u; opts)                   get_minimal_gradients(mechanism, x, u, opts=None)
+                                          gradients/state.jl:182
 
 NEW relative to the reference: every function also accepts a batch -- z of shape [B, 13 Nb], u of shape [B, nu] --
 and then returns batched results.  All compute happens in libdojo_b200.so on the GPU (solver.BatchedStepper).
@@ -135,6 +139,41 @@ def step_minimal_coordinates(mechanism: Mechanism, x, u, opts=None, device: int 
         _check_single(status)
         return Xn[0]
     return Xn, status, iters
+
+
+def maximal_to_minimal_jacobian(mechanism: Mechanism, z, device: int = 0):
+    """maximal_to_minimal_jacobian(mechanism, z) -> [2 nu x 12 Nb] (columns: attitude-reduced [x, v, phi, w] per body);
+    batched z gives [B, 2 nu, 12 Nb]."""
+    z = np.asarray(z, dtype=float)
+    Z = np.atleast_2d(z)
+    J = _stepper(mechanism, Z.shape[0], device).maximal_to_minimal_jacobian(Z)
+    return J[0] if z.ndim == 1 else J
+
+
+def minimal_to_maximal_jacobian(mechanism: Mechanism, x, device: int = 0):
+    """minimal_to_maximal_jacobian(mechanism, x) -> [12 Nb x 2 nu], the derivative of minimal_to_maximal at x (the
+    reference reads the mechanism's stored state, which its callers set to minimal_to_maximal(x) first; it chains the
+    partials in mechanism.bodies order, identical to the root -> leaves order used here when parents precede children)."""
+    x = np.asarray(x, dtype=float)
+    X = np.atleast_2d(x)
+    s = _stepper(mechanism, X.shape[0], device)
+    J = s.minimal_to_maximal_jacobian(s.minimal_to_maximal(X))
+    return J[0] if x.ndim == 1 else J
+
+
+def get_minimal_gradients(mechanism: Mechanism, x, u, opts=None, device: int = 0):
+    """get_minimal_gradients!(mechanism, x, u; opts) -> (minimal_jacobian_state [2nu x 2nu], minimal_jacobian_control
+    [2nu x nu]); batched inputs give [B, 2nu, 2nu] and [B, 2nu, nu].  Consistent variant: the map Jacobians are
+    taken at z = minimal_to_maximal(x) and at the true next state."""
+    x = np.asarray(x, dtype=float)
+    single = x.ndim == 1
+    X = np.atleast_2d(x)
+    U = np.atleast_2d(np.asarray(u, dtype=float))
+    _, Gx, Gu, status, _ = _stepper(mechanism, X.shape[0], device).minimal_gradients(X, U, opts)
+    if single:
+        _check_single(status)
+        return Gx[0], Gu[0]
+    return Gx, Gu
 
 
 def status_name(code: int) -> str:

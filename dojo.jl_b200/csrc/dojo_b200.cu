@@ -14,6 +14,7 @@
 #include "../../include/dojo_b200.h"
 #include "dojo_grad.cuh"
 #include "dojo_kin.cuh"
+#include "dojo_kinjac.cuh"
 
 using namespace dj;
 
@@ -274,6 +275,10 @@ struct DojoHandle {
   int* d_counter = nullptr;
   int* d_kin_order = nullptr;      // joints root -> leaves (minimal -> maximal map)
   double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
+  double* d_kjws = nullptr;        // workspace of the map-Jacobian kernel (one slice per CTA)
+  int kj_grid = 0;
+  double *d_kjout = nullptr;       // staging of map Jacobians / minimal gradients for host-pointer calls
+  size_t kjout_doubles = 0;
   int* d_done = nullptr;           // [0] finished count, [1] gradient work queue, [2..] completion-ordered environment list
   bool overlap_grad = true;
   double* d_gsol = nullptr;        // final solutions handed from the forward to the gradient launch [nres x max_batch]
@@ -710,7 +715,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -1113,6 +1118,141 @@ extern "C" int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, i
   if (rc != DOJO_OK) return rc;
   if (!dev) {
     CUDA_TRY(h, cudaMemcpyAsync(X_next, h->d_Xn, nx, cudaMemcpyDeviceToHost, s));
+    if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Jacobians of the coordinate maps and get_minimal_gradients! (dojo_kinjac.cuh)
+// ------------------------------------------------------------------------------------------------------------
+static int ensure_kinjac(DojoHandle* h) {
+  if (h->d_kjws) return DOJO_OK;
+  h->kj_grid = std::max(1, std::min(h->max_batch, h->sm_count * 8));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_kjws, (size_t)h->kj_grid * kinjac_ws_doubles(h->plan.Nb, h->plan.nu) * sizeof(double)));
+  return DOJO_OK;
+}
+static int ensure_kjout(DojoHandle* h, size_t doubles) {
+  if (h->kjout_doubles >= doubles) return DOJO_OK;
+  if (h->d_kjout) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); cudaFree(h->d_kjout); h->d_kjout = nullptr; h->kjout_doubles = 0; }
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_kjout, doubles * sizeof(double)));
+  h->kjout_doubles = doubles;
+  return DOJO_OK;
+}
+
+// mode 0: M(Z) -> out   1: N(Z) -> out   2: (Z, Zn, Fz, Fu) -> (Gx, Gu)
+static int launch_kinjac(DojoHandle* h, int mode, int B, const double* dZ, const double* dZn, const double* dFz, const double* dFu, double* out0,
+                         double* out1, cudaStream_t s) {
+  int rc = ensure_kinjac(h);
+  if (rc != DOJO_OK) return rc;
+  const Plan& P = h->plan;
+  KinJacArgs a;
+  a.joints = P.joints; a.order = h->d_kin_order;
+  a.Ne = P.Ne; a.Nb = P.Nb; a.nu = P.nu; a.B = B; a.h = P.h;
+  a.Z = dZ; a.Zm = dZn ? dZn : dZ; a.Fz = dFz; a.Fu = dFu;
+  a.outM = mode == 0 ? out0 : nullptr; a.outN = mode == 1 ? out0 : nullptr;
+  a.Gx = mode == 2 ? out0 : nullptr; a.Gu = mode == 2 ? out1 : nullptr;
+  a.ws = h->d_kjws; a.mode = mode;
+  if (mode == 0) CUDA_TRY(h, cudaMemsetAsync(out0, 0, (size_t)B * 2 * P.nu * 12 * P.Nb * sizeof(double), s));
+  dojo_kinjac_kernel<<<std::min(B, h->kj_grid), 128, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+extern "C" int dojo_maximal_to_minimal_jacobian_async(DojoHandle* h, int B, const double* dZ, double* dJ, void* cuda_stream) {
+  if (!h || B <= 0 || B > h->max_batch || !dZ || !dJ) { if (h) h->err = "dojo_maximal_to_minimal_jacobian_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_kinjac(h, 0, B, dZ, nullptr, nullptr, nullptr, dJ, nullptr, (cudaStream_t)cuda_stream);
+}
+extern "C" int dojo_minimal_to_maximal_jacobian_async(DojoHandle* h, int B, const double* dZ, double* dJ, void* cuda_stream) {
+  if (!h || B <= 0 || B > h->max_batch || !dZ || !dJ) { if (h) h->err = "dojo_minimal_to_maximal_jacobian_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return launch_kinjac(h, 1, B, dZ, nullptr, nullptr, nullptr, dJ, nullptr, (cudaStream_t)cuda_stream);
+}
+
+static int kinjac_sync(DojoHandle* h, int mode, int B, const double* Z, double* J, const char* who) {
+  if (!h || B <= 0 || B > h->max_batch || !Z || !J) { if (h) h->err = std::string(who) + ": bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  if (is_device_ptr(Z)) {
+    int rc = launch_kinjac(h, mode, B, Z, nullptr, nullptr, nullptr, J, nullptr, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const size_t per_env = (size_t)2 * P.nu * 12 * P.Nb;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(B, (size_t(256) << 20) / std::max<size_t>(1, per_env * sizeof(double))));
+  rc = ensure_kjout(h, (size_t)chunk * per_env);
+  if (rc != DOJO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  for (int e0 = 0; e0 < B; e0 += chunk) {
+    const int nb = std::min(chunk, B - e0);
+    rc = launch_kinjac(h, mode, nb, h->d_Z + (size_t)e0 * P.nz, nullptr, nullptr, nullptr, h->d_kjout, nullptr, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(J + (size_t)e0 * per_env, h->d_kjout, (size_t)nb * per_env * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+extern "C" int dojo_maximal_to_minimal_jacobian(DojoHandle* h, int B, const double* Z, double* J) { return kinjac_sync(h, 0, B, Z, J, "dojo_maximal_to_minimal_jacobian"); }
+extern "C" int dojo_minimal_to_maximal_jacobian(DojoHandle* h, int B, const double* Z, double* J) { return kinjac_sync(h, 1, B, Z, J, "dojo_minimal_to_maximal_jacobian"); }
+
+// get_minimal_gradients! (gradients/state.jl:182-217).  Per chunk of environments, on one stream: minimal -> maximal,
+// forward + gradient kernels (dojo_step_grad_async), the map-Jacobian kernel in mode 2, maximal -> minimal of the next state.
+extern "C" int dojo_minimal_gradients(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U, double* X_next, double* Gx,
+                                      double* Gu, int32_t* status, int32_t* iters) {
+  if (!h || B <= 0 || B > h->max_batch || !X || !X_next || !Gx || !Gu) { if (h) h->err = "dojo_minimal_gradients: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  const bool dev = is_device_ptr(X);
+  const size_t ng = 12 * (size_t)P.Nb, fz = ng * ng, fu = ng * P.nu, nm = 2 * (size_t)P.nu, gx = nm * nm, gu = nm * P.nu;
+  if (!h->d_Fz[0]) {  // same chunk buffers as the host-pointer path of dojo_step_grad
+    h->grad_chunk = (int)std::max<size_t>(1, std::min<size_t>(h->max_batch, (size_t(128) << 20) / ((fz + fu) * sizeof(double))));
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(h, cudaMalloc((void**)&h->d_Fz[k], (size_t)h->grad_chunk * fz * sizeof(double)));
+      CUDA_TRY(h, cudaMalloc((void**)&h->d_Fu[k], std::max<size_t>(1, (size_t)h->grad_chunk * fu) * sizeof(double)));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  }
+  const double* dX = X;
+  const double* dU = (U && P.nu > 0) ? U : nullptr;
+  double *dXn = X_next, *dGx = Gx, *dGu = Gu;
+  int32_t *dst = status, *dit = iters;
+  if (!dev) {
+    rc = ensure_kjout(h, (size_t)B * (gx + gu));
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_X, X, (size_t)B * nm * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (dU) { CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s)); dU = h->d_U; }
+    dX = h->d_X; dXn = h->d_Xn; dGx = h->d_kjout; dGu = h->d_kjout + (size_t)B * gx; dst = h->d_status; dit = h->d_iters;
+  }
+  rc = launch_kin(h, true, B, dX, h->d_Z, s);
+  if (rc != DOJO_OK) return rc;
+  for (int e0 = 0; e0 < B; e0 += h->grad_chunk) {
+    const int nb = std::min(h->grad_chunk, B - e0);
+    rc = dojo_step_grad_async(h, opts, nb, h->d_Z + (size_t)e0 * P.nz, dU ? dU + (size_t)e0 * P.nu : nullptr, nullptr, h->d_Zn + (size_t)e0 * P.nz,
+                              h->d_Fz[0], h->d_Fu[0], dst ? dst + e0 : nullptr, dit ? dit + e0 : nullptr, 0, s);
+    if (rc == DOJO_OK)
+      rc = launch_kinjac(h, 2, nb, h->d_Z + (size_t)e0 * P.nz, h->d_Zn + (size_t)e0 * P.nz, h->d_Fz[0], h->d_Fu[0], dGx + (size_t)e0 * gx,
+                         dGu + (size_t)e0 * gu, s);
+    if (rc != DOJO_OK) return rc;
+  }
+  rc = launch_kin(h, false, B, h->d_Zn, dXn, s);
+  if (rc != DOJO_OK) return rc;
+  if (!dev) {
+    CUDA_TRY(h, cudaMemcpyAsync(X_next, h->d_Xn, (size_t)B * nm * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(Gx, dGx, (size_t)B * gx * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (gu) CUDA_TRY(h, cudaMemcpyAsync(Gu, dGu, (size_t)B * gu * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   }

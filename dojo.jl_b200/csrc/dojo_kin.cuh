@@ -46,9 +46,8 @@ DJ_DEV V3 masked_sum(const double* A, int n, const double* c) {                 
   return r;
 }
 
-__global__ void dojo_min_to_max_kernel(const KinArgs a) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.B) return;
+// one environment: minimal -> maximal (called by one thread)
+DJ_DEV void min_to_max_env(const KinArgs& a, int e) {
   const double* x = a.in + (size_t)e * 2 * a.nu;
   double* z = a.out + (size_t)e * 13 * a.Nb;
   const double h = a.h;
@@ -87,9 +86,7 @@ DJ_DEV V3 tra_displacement(const JointDev& jd, V3 xa, Quat qa, V3 xb, Quat qb) {
   return tmul(rotmat(qa), d);
 }
 
-__global__ void dojo_max_to_min_kernel(const KinArgs a) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.B) return;
+DJ_DEV void max_to_min_env(const KinArgs& a, int e) {
   const double* z = a.in + (size_t)e * 13 * a.Nb;
   double* x = a.out + (size_t)e * 2 * a.nu;
   const double h = a.h;
@@ -122,5 +119,16 @@ __global__ void dojo_max_to_min_kernel(const KinArgs a) {
     }
   }
 }
+
+#ifdef __CUDACC__
+__global__ void dojo_min_to_max_kernel(const KinArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.B) min_to_max_env(a, e);
+}
+__global__ void dojo_max_to_min_kernel(const KinArgs a) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.B) max_to_min_env(a, e);
+}
+#endif
 
 }  // namespace dj

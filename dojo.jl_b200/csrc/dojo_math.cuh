@@ -6,10 +6,16 @@
 // 4x4 / 3x4 matrix forms (L, R, T, V ...) the kernels use closed forms written directly in terms of
 // rotation matrices and the *attitude* (body-frame) perturbation q (x) (1, d): see DESIGN.md §"Closed forms".
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
-
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
 #define DJ_DEV __device__ __forceinline__
+#else
+// host compilation of the lane-independent helpers: tests/hostcheck builds the per-environment kinematics code
+// (dojo_kin.cuh, dojo_kinjac.cuh) with g++ so that its arithmetic can be checked on a machine without a GPU.  The product
+// library is always built by nvcc; nothing in it runs on the CPU.
+#define DJ_DEV inline
+#endif
 
 namespace dj {
 
@@ -193,6 +199,7 @@ DJ_DEV M34 drotation_vector_dq(Quat q) {
   return r;
 }
 
+#ifdef __CUDACC__
 // warp reductions
 DJ_DEV double warp_max(double v) {
 #pragma unroll
@@ -216,5 +223,6 @@ DJ_DEV double warp_nanmax(double v) {
   for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+#endif  // __CUDACC__
 
 }  // namespace dj

@@ -22,7 +22,8 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env", "dojo_step", "dojo_step_async",
            "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count",
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
-           "dojo_maximal_to_minimal_async", "dojo_step_minimal"]
+           "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
+           "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients"]
 
 _lib = None
 
@@ -70,6 +71,13 @@ def load_library():
         getattr(L, name + "_async").restype = C.c_int
     L.dojo_step_minimal.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp]
     L.dojo_step_minimal.restype = C.c_int
+    for name in ("dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian"):
+        getattr(L, name).argtypes = [vp, C.c_int, vp, vp]
+        getattr(L, name).restype = C.c_int
+        getattr(L, name + "_async").argtypes = [vp, C.c_int, vp, vp, vp]
+        getattr(L, name + "_async").restype = C.c_int
+    L.dojo_minimal_gradients.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_minimal_gradients.restype = C.c_int
     _lib = L
     return L
 
@@ -227,6 +235,39 @@ class BatchedStepper:
         self._check(self.L.dojo_step_minimal(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(status), _p(iters)), "dojo_step_minimal")
         return Xn, status, iters
 
+    def maximal_to_minimal_jacobian(self, Z):
+        """maximal_to_minimal_jacobian (gradients/state.jl:9-56), batched: Z [B, 13 Nb] -> M [B, 2 nu, 12 Nb]."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        assert Z.shape[1] == self.nz
+        J = np.empty((Z.shape[0], self.ngrad, self.nmin))  # column-major [2 nu x 12 Nb] per environment
+        self._check(self.L.dojo_maximal_to_minimal_jacobian(self.h, Z.shape[0], _p(Z), _p(J)), "dojo_maximal_to_minimal_jacobian")
+        return np.transpose(J, (0, 2, 1))
+
+    def minimal_to_maximal_jacobian(self, Z):
+        """minimal_to_maximal_jacobian (gradients/state.jl:136-179) evaluated at the maximal states Z [B, 13 Nb]
+        (= minimal_to_maximal(X)): N [B, 12 Nb, 2 nu]."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        assert Z.shape[1] == self.nz
+        J = np.empty((Z.shape[0], self.nmin, self.ngrad))  # column-major [12 Nb x 2 nu] per environment
+        self._check(self.L.dojo_minimal_to_maximal_jacobian(self.h, Z.shape[0], _p(Z), _p(J)), "dojo_minimal_to_maximal_jacobian")
+        return np.transpose(J, (0, 2, 1))
+
+    def minimal_gradients(self, X, U=None, opts=None):
+        """get_minimal_gradients! (gradients/state.jl:182-217), batched.
+        Returns (X_next [B, 2nu], dx'/dx [B, 2nu, 2nu], dx'/du [B, 2nu, nu], status, iters)."""
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        B = X.shape[0]
+        assert X.shape[1] == self.nmin
+        U = None if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        Xn = np.empty_like(X)
+        Gx = np.empty((B, self.nmin, self.nmin))
+        Gu = np.empty((B, self.nu, self.nmin))
+        status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_minimal_gradients(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(Gx), _p(Gu), _p(status), _p(iters))
+        self._check(rc, "dojo_minimal_gradients")
+        return Xn, np.transpose(Gx, (0, 2, 1)), np.transpose(Gu, (0, 2, 1)), status, iters
+
     # ------------------------------------------------------------------ device buffers (resident data)
     def step_device(self, dZ: int, dU: Optional[int], dZn: int, B: int, opts=None, dstatus: Optional[int] = None, diters: Optional[int] = None,
                     dsol: Optional[int] = None, dfext: Optional[int] = None, flags: int = 0, stream: int = 0):
@@ -240,6 +281,18 @@ class BatchedStepper:
 
     def maximal_to_minimal_device(self, dZ: int, dX: int, B: int, stream: int = 0):
         self._check(self.L.dojo_maximal_to_minimal_async(self.h, int(B), _p(dZ), _p(dX), C.c_void_p(int(stream))), "dojo_maximal_to_minimal_async")
+
+    def maximal_to_minimal_jacobian_device(self, dZ: int, dJ: int, B: int, stream: int = 0):
+        self._check(self.L.dojo_maximal_to_minimal_jacobian_async(self.h, int(B), _p(dZ), _p(dJ), C.c_void_p(int(stream))), "dojo_maximal_to_minimal_jacobian_async")
+
+    def minimal_to_maximal_jacobian_device(self, dZ: int, dJ: int, B: int, stream: int = 0):
+        self._check(self.L.dojo_minimal_to_maximal_jacobian_async(self.h, int(B), _p(dZ), _p(dJ), C.c_void_p(int(stream))), "dojo_minimal_to_maximal_jacobian_async")
+
+    def minimal_gradients_device(self, dX: int, dU: Optional[int], dXn: int, dGx: int, dGu: int, B: int, opts=None, dstatus=None, diters=None):
+        """device-resident get_minimal_gradients! (synchronises the handle's stream before returning)"""
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_minimal_gradients(self.h, C.byref(o), int(B), _p(dX), _p(dU), _p(dXn), _p(dGx), _p(dGu), _p(dstatus), _p(diters))
+        self._check(rc, "dojo_minimal_gradients")
 
     def rollout_device(self, dZ0: int, dU: Optional[int], dZf: int, B: int, T: int, opts=None, dtraj: Optional[int] = None, dstatus: Optional[int] = None,
                        stream: int = 0):

@@ -196,6 +196,28 @@ int dojo_maximal_to_minimal_async(DojoHandle* h, int B, const double* dZ, double
 int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
                       double* X_next, int32_t* status, int32_t* iters);
 
+/* Jacobians of the coordinate maps in attitude-reduced maximal coordinates ([x, v, phi, w] per body, 12 Nb):
+ *   dojo_maximal_to_minimal_jacobian   maximal_to_minimal_jacobian(mechanism, z)   src/gradients/state.jl:9-56
+ *       J [2 nu x 12 Nb x B] column-major per environment, evaluated at Z [13 Nb x B];
+ *   dojo_minimal_to_maximal_jacobian   minimal_to_maximal_jacobian(mechanism, x)   src/gradients/state.jl:136-179
+ *       J [12 Nb x 2 nu x B], evaluated at the MAXIMAL state Z (the reference reads the mechanism's stored state; pass
+ *       Z = minimal_to_maximal(X)).  The partials are chained root -> leaves, i.e. J is the derivative of
+ *       minimal_to_maximal; the reference chains in mechanism.bodies order, which is the same thing whenever parents
+ *       precede their children in that list.
+ * Host or device pointers (both of the same kind); *_async: device pointers, no synchronisation. */
+int dojo_maximal_to_minimal_jacobian(DojoHandle* h, int B, const double* Z, double* J);
+int dojo_minimal_to_maximal_jacobian(DojoHandle* h, int B, const double* Z, double* J);
+int dojo_maximal_to_minimal_jacobian_async(DojoHandle* h, int B, const double* dZ, double* dJ, void* cuda_stream);
+int dojo_minimal_to_maximal_jacobian_async(DojoHandle* h, int B, const double* dZ, double* dJ, void* cuda_stream);
+
+/* get_minimal_gradients!(mechanism, x, u; opts)  src/gradients/state.jl:182-217: step_minimal_coordinates! and
+ *   Gx = M(z') Fz N(z) [2 nu x 2 nu x B],  Gu = M(z') Fu [2 nu x nu x B]   (column-major per environment),
+ * with z = minimal_to_maximal(x), (z', Fz, Fu) = dojo_step_grad(z, u) (consistent IFT), M / N the two map
+ * Jacobians above.  The maximal states and the 12Nb x 12Nb Jacobians never leave the device (processed in chunks).
+ * X [2 nu x B], U [nu x B] (nullable), X_next [2 nu x B]; status / iters nullable; host or device pointers. */
+int dojo_minimal_gradients(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
+                           double* X_next, double* Gx, double* Gu, int32_t* status, int32_t* iters);
+
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t dojo_launch_count(const DojoHandle* h);
 

@@ -775,6 +775,190 @@ struct Oracle {
     }
   }
 
+  // ---------------------------------------------------------------- Jacobians of the coordinate maps
+  static M43 daxis_angle_to_quaternion_dx(const V3& x) {  // orientation/axis_angle.jl:13-40
+    M43 r;
+    double th = std::sqrt(dot(x, x));
+    if (th > 0.0) {
+      double s = std::sin(0.5 * th), c = std::cos(0.5 * th);
+      for (int k = 0; k < 3; ++k) r(0, k) = -0.5 * s * x[k] / th;
+      for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k)
+          r(1 + i, k) = 0.5 * c * x[k] / th * (x[i] / th) + (i == k ? s / th : 0.0) - s * x[i] / (th * th) * x[k] / th;
+    } else {
+      for (int i = 0; i < 3; ++i) r(1 + i, i) = 0.5;
+    }
+    return r;
+  }
+  static M34 dangular_velocity_dq1(const Quat& q1, const Quat& q2, double h) { return (2.0 / h) * (Vmat() * Rmat(q2) * Tmat()); }  // integrator.jl:26-28
+  static M34 dangular_velocity_dq2(const Quat& q1, const Quat& q2, double h) { return (2.0 / h) * (Vmat() * Ltmat(q1)); }         // :30-32
+  static Cfg unpack_cfg(const double* z, int b) {  // mechanism/state.jl:68-75; the origin: bodies/origin.jl
+    Cfg c;
+    if (b < 0) { c.x = V3(); c.v = V3(); c.w = V3(); c.q = Quat(1.0, 0.0, 0.0, 0.0); return c; }
+    const double* zb = z + 13 * b;
+    for (int i = 0; i < 3; ++i) { c.x[i] = zb[i]; c.v[i] = zb[3 + i]; c.w[i] = zb[10 + i]; }
+    c.q = Quat(zb[6], zb[7], zb[8], zb[9]);
+    return c;
+  }
+  static Mat<3, 3> nullspace_t(const Elem& e) {  // zerodimstaticadjoint(nullspace_mask(joint)): 3 x nfree, unused columns zero
+    Mat<3, 3> A;
+    for (int i = 0; i < e.nfree; ++i) for (int c = 0; c < 3; ++c) A(c, i) = e.A[i][c];
+    return A;
+  }
+
+  // maximal_to_minimal_jacobian, gradients/state.jl:9-56.  J is (2 nu) x (12 Nb), COLUMN-major; columns per body
+  // [x, v, phi, w] (attitude-reduced), rows per joint [c_tra; c_rot; v_tra; v_rot].
+  void maximal_to_minimal_jacobian(const double* z, double* J) const {
+    const int nr_ = 2 * nu, nc_ = 12 * Nb;
+    std::fill(J, J + (size_t)nr_ * nc_, 0.0);
+    auto at = [&](int r, int c) -> double& { return J[(size_t)c * nr_ + r]; };
+    for (int j = 0; j < Ne; ++j) {
+      const JointS& jt = joints[j];
+      const int nuj = jt.el[0].nfree + jt.el[1].nfree;
+      int c_shift = 0, v_shift = nuj;
+      const int row0 = 2 * jt.u_off;
+      const Cfg a = unpack_cfg(z, jt.parent), b = unpack_cfg(z, jt.child);
+      for (int k = 0; k < 2; ++k) {
+        const int ne = jt.el[k].nfree;
+        for (int side = 0; side < 2; ++side) {
+          const bool parent = (side == 0);
+          if (parent && jt.parent < 0) continue;
+          const int body = parent ? jt.parent : jt.child;
+          const Quat& qrel = parent ? a.q : b.q;
+          Mat<3, 7> cj7 = minimal_coordinates_jacobian_configuration(parent, jt, k, a.x, a.q, b.x, b.q);
+          M33 cX = block<3, 3>(cj7, 0, 0);
+          M33 cQ = block<3, 4>(cj7, 0, 3) * LVtmat(qrel);  // attjac = true (joint.jl:149-161, rotational/minimal.jl:76)
+          Mat<3, 6> vc = minimal_velocities_jacobian_configuration(parent, jt, k, a, b, h);
+          Mat<3, 6> vv = minimal_velocities_jacobian_velocity(parent, jt, k, a, b, h);
+          for (int i = 0; i < ne; ++i)
+            for (int c = 0; c < 3; ++c) {
+              at(row0 + c_shift + i, 12 * body + c) = cX(i, c);        // x
+              at(row0 + c_shift + i, 12 * body + 6 + c) = cQ(i, c);    // phi
+              at(row0 + v_shift + i, 12 * body + c) = vc(i, c);        // x
+              at(row0 + v_shift + i, 12 * body + 6 + c) = vc(i, 3 + c);
+              at(row0 + v_shift + i, 12 * body + 3 + c) = vv(i, c);    // v
+              at(row0 + v_shift + i, 12 * body + 9 + c) = vv(i, 3 + c);
+            }
+        }
+        c_shift += ne;
+        v_shift += ne;
+      }
+    }
+  }
+
+  // joints/minimal.jl:206-283 (parent: 13 x 13) and :314-383 (minimal: 13 x 2nu_j in a 13 x 12), rows [xb; vb; qb; wb]
+  struct MinJac { Mat<13, 13> P; Mat<13, 12> M; };
+  MinJac minimal_coordinates_velocities_jacobians(const JointS& jt, const Cfg& a, const double* xm) const {
+    const int nt = jt.el[0].nfree, nr = jt.el[1].nfree, nuj = nt + nr;
+    const Mat<3, 3> Atra = nullspace_t(jt.el[0]), Arot = nullspace_t(jt.el[1]);
+    V3 dx, dth, dv, dw;
+    for (int i = 0; i < nt; ++i) for (int c = 0; c < 3; ++c) { dx[c] += Atra(c, i) * xm[i]; dv[c] += Atra(c, i) * xm[nuj + i]; }
+    for (int i = 0; i < nr; ++i) for (int c = 0; c < 3; ++c) { dth[c] += Arot(c, i) * xm[nt + i]; dw[c] += Arot(c, i) * xm[nuj + nt + i]; }
+    const Quat& qoff = jt.qoff;
+    // positions
+    Quat dq = axis_angle_to_quaternion(dth);
+    Quat qb = a.q * qoff * dq;
+    // step backward in time
+    Quat qa1 = next_orientation(a.q, -a.w, h);
+    V3 dx1 = dx - dv * h;
+    Quat dwq = axis_angle_to_quaternion(dw * h);
+    Quat dq1 = dq * inv(dwq);
+    Quat qb1 = qa1 * qoff * dq1;
+    M44 RIO = rotational_integrator_jacobian_orientation_full(-a.w, h);
+    M43 RIV = rotational_integrator_jacobian_velocity(a.q, -a.w, h);
+    MinJac out;
+    {  // parent, :237-276
+      Mat<13, 13>& P = out.P;
+      M34 dxb_dqa = dvector_rotate_dq(jt.pa + dx, a.q) - dvector_rotate_dq(jt.pb, qb) * Rmat(qoff * dq);
+      M44 dqb_dqa = Rmat(qoff * dq);
+      M34 dvb_dqa = (1.0 / h) * dvector_rotate_dq(jt.pa + dx, a.q);
+      dvb_dqa -= (1.0 / h) * (dvector_rotate_dq(jt.pb, qb) * Rmat(qoff * dq));
+      dvb_dqa += (-1.0 / h) * (dvector_rotate_dq(jt.pa + dx1, qa1) * RIO);
+      dvb_dqa += (1.0 / h) * (dvector_rotate_dq(jt.pb, qb1) * Rmat(qoff * dq1) * RIO);
+      M33 dvb_dwa = (1.0 / h) * (dvector_rotate_dq(jt.pa + dx1, qa1) * RIV);
+      dvb_dwa += (-1.0 / h) * (dvector_rotate_dq(jt.pb, qb1) * Rmat(qoff * dq1) * RIV);
+      M34 dwb_dqa = dangular_velocity_dq1(qb1, qb, h) * Rmat(qoff * dq1) * RIO;
+      dwb_dqa += dangular_velocity_dq2(qb1, qb, h) * Rmat(qoff * dq);
+      M33 dwb_dwa = -1.0 * (dangular_velocity_dq1(qb1, qb, h) * Rmat(qoff * dq1) * RIV);
+      for (int i = 0; i < 3; ++i) { P(i, i) = 1.0; P(3 + i, 3 + i) = 1.0; }
+      set_block(P, 0, 6, dxb_dqa);
+      set_block(P, 3, 6, dvb_dqa);
+      set_block(P, 3, 10, dvb_dwa);
+      set_block(P, 6, 6, dqb_dqa);
+      set_block(P, 10, 6, dwb_dqa);
+      set_block(P, 10, 10, dwb_dwa);
+    }
+    {  // minimal, :346-376
+      Mat<13, 12>& M = out.M;
+      M33 Ra = rotation_matrix(a.q), Ra1 = rotation_matrix(qa1);
+      M43 dth_q = daxis_angle_to_quaternion_dx(dth) * Arot;                 // d(dq)/d(theta)  (4 x nr)
+      M43 dqb_dth = Lmat(a.q * qoff) * dth_q;
+      M43 dqb1_dth = Rmat(inv(dwq)) * Lmat(qa1 * qoff) * dth_q;
+      M43 dqb1_dw = Lmat(qa1 * qoff * dq) * Tmat() * daxis_angle_to_quaternion_dx(dw * h) * Arot;  // per unit (dw h)
+      M33 dxb_dx = Ra * Atra;
+      M33 dxb_dth = -1.0 * (dvector_rotate_dq(jt.pb, qb) * dqb_dth);
+      M33 dvb_dx = (1.0 / h) * (Ra * Atra) + (-1.0 / h) * (Ra1 * Atra);
+      M33 dvb_dth = (-1.0 / h) * (dvector_rotate_dq(jt.pb, qb) * dqb_dth) + (1.0 / h) * (dvector_rotate_dq(jt.pb, qb1) * dqb1_dth);
+      M33 dvb_dv = Ra1 * Atra;
+      M33 dvb_dw = dvector_rotate_dq(jt.pb, qb1) * dqb1_dw;
+      M33 dwb_dth = dangular_velocity_dq1(qb1, qb, h) * dqb1_dth + dangular_velocity_dq2(qb1, qb, h) * dqb_dth;
+      M33 dwb_dw = h * (dangular_velocity_dq1(qb1, qb, h) * dqb1_dw);
+      auto put = [&](int r0, int rows, int c0, int cols, auto& blk) {
+        for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) M(r0 + r, c0 + c) = blk(r, c);
+      };
+      put(0, 3, 0, nt, dxb_dx);          put(0, 3, nt, nr, dxb_dth);
+      put(3, 3, 0, nt, dvb_dx);          put(3, 3, nt, nr, dvb_dth);  put(3, 3, nuj, nt, dvb_dv);  put(3, 3, nuj + nt, nr, dvb_dw);
+      put(6, 4, nt, nr, dqb_dth);
+      put(10, 3, nt, nr, dwb_dth);       put(10, 3, nuj + nt, nr, dwb_dw);
+    }
+    return out;
+  }
+
+  // minimal_to_maximal_jacobian, gradients/state.jl:136-179, evaluated at the maximal state z (the reference reads the
+  // mechanism's stored state; its argument x is unused).  J is (12 Nb) x (2 nu), COLUMN-major.
+  // body_order_literal: chain the partials in mechanism.bodies order exactly like :170-178 (a child listed before its
+  // parent then misses the parent's columns -- the reference's own check is disabled for such models, test/minimal.jl:527,
+  // :560); otherwise root -> leaves, the derivative of minimal_to_maximal.
+  void minimal_to_maximal_jacobian(const double* z, double* J, bool body_order_literal) const {
+    const int nr_ = 12 * Nb, nc_ = 2 * nu;
+    std::fill(J, J + (size_t)nr_ * nc_, 0.0);
+    auto at = [&](int r, int c) -> double& { return J[(size_t)c * nr_ + r]; };
+    std::vector<double> xmin(2 * nu + 1);
+    maximal_to_minimal(z, xmin.data());  // minimal_coordinates_velocities(joint, pnode, cnode), joints/minimal.jl:291,390
+    std::vector<int> pj(Nb, -1);
+    for (int j = 0; j < Ne; ++j) pj[joints[j].child] = j;
+    std::vector<int> order;
+    if (body_order_literal) for (int b = 0; b < Nb; ++b) order.push_back(b);
+    else for (int j : root_to_leaves_joints()) order.push_back(joints[j].child);
+    for (int b : order) {
+      if (pj[b] < 0) continue;
+      const JointS& jt = joints[pj[b]];
+      const int nuj = jt.el[0].nfree + jt.el[1].nfree;
+      const Cfg a = unpack_cfg(z, jt.parent), cb = unpack_cfg(z, b);
+      MinJac mj = minimal_coordinates_velocities_jacobians(jt, a, xmin.data() + 2 * jt.u_off);
+      // attitude reduction: cat(I6, LVᵀ(qb)', I3) * J  and  J * cat(I6, LVᵀ(qa), I3)   (joints/minimal.jl:308-310, 398)
+      Mat<12, 13> Gb;
+      for (int i = 0; i < 6; ++i) Gb(i, i) = 1.0;
+      set_block(Gb, 6, 6, tr(LVtmat(cb.q)));
+      for (int i = 0; i < 3; ++i) Gb(9 + i, 10 + i) = 1.0;
+      Mat<12, 12> Pm = Gb * mj.M;
+      if (nuj > 0)
+        for (int r = 0; r < 12; ++r) for (int c = 0; c < 2 * nuj; ++c) at(12 * b + r, 2 * jt.u_off + c) += Pm(r, c);
+      if (jt.parent < 0) continue;
+      Mat<13, 12> Ga;
+      for (int i = 0; i < 6; ++i) Ga(i, i) = 1.0;
+      set_block(Ga, 6, 6, LVtmat(a.q));
+      for (int i = 0; i < 3; ++i) Ga(10 + i, 9 + i) = 1.0;
+      Mat<12, 12> Pp = Gb * mj.P * Ga;
+      for (int c = 0; c < nc_; ++c)
+        for (int r = 0; r < 12; ++r) {
+          double acc = 0;
+          for (int k = 0; k < 12; ++k) acc += Pp(r, k) * at(12 * jt.parent + k, c);
+          at(12 * b + r, c) += acc;
+        }
+    }
+  }
+
   void set_maximal_state(const double* z) {
     for (int b = 0; b < Nb; ++b) {
       BodyS& s = bodies[b];
@@ -1869,5 +2053,9 @@ int oracle_trace(void* h, double* out, int cap) {  // rows of (rvio, bvio, alpha
 int oracle_num_minimal(void* h) { return 2 * static_cast<Oracle*>(h)->nu; }
 void oracle_minimal_to_maximal(void* h, const double* x, double* z) { static_cast<Oracle*>(h)->minimal_to_maximal(x, z); }
 void oracle_maximal_to_minimal(void* h, const double* z, double* x) { static_cast<Oracle*>(h)->maximal_to_minimal(z, x); }
+void oracle_maximal_to_minimal_jacobian(void* h, const double* z, double* J) { static_cast<Oracle*>(h)->maximal_to_minimal_jacobian(z, J); }
+void oracle_minimal_to_maximal_jacobian(void* h, const double* z, double* J, int body_order_literal) {
+  static_cast<Oracle*>(h)->minimal_to_maximal_jacobian(z, J, body_order_literal != 0);
+}
 void oracle_momentum(void* h, double* out6) { static_cast<Oracle*>(h)->momentum(out6); }
 }

@@ -65,6 +65,8 @@ def lib():
         L.oracle_momentum.argtypes = [vp, dp]
         L.oracle_minimal_to_maximal.argtypes = [vp, dp, dp]
         L.oracle_maximal_to_minimal.argtypes = [vp, dp, dp]
+        L.oracle_maximal_to_minimal_jacobian.argtypes = [vp, dp, dp]
+        L.oracle_minimal_to_maximal_jacobian.argtypes = [vp, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -171,6 +173,31 @@ class Oracle:
         x = np.empty(self.nmin)
         self.L.oracle_maximal_to_minimal(self.h, _d(z), _d(x))
         return x
+
+    # Jacobians of the maps (gradients/state.jl:9-56, :136-179) and the minimal-coordinate gradients (:192-217)
+    def maximal_to_minimal_jacobian(self, z):
+        """(2 nu) x (12 Nb): d(minimal state) / d(maximal state, attitude-reduced [x, v, phi, w] per body)."""
+        z = np.ascontiguousarray(z, dtype=float)
+        J = np.empty((self.nmin, 12 * self.mech.Nb), order="F")
+        self.L.oracle_maximal_to_minimal_jacobian(self.h, _d(z), J.ctypes.data_as(capi.c_double_p))
+        return J
+
+    def minimal_to_maximal_jacobian(self, z, body_order_literal=False):
+        """(12 Nb) x (2 nu) at the maximal state z (the reference evaluates at the mechanism's stored state)."""
+        z = np.ascontiguousarray(z, dtype=float)
+        J = np.empty((12 * self.mech.Nb, self.nmin), order="F")
+        self.L.oracle_minimal_to_maximal_jacobian(self.h, _d(z), J.ctypes.data_as(capi.c_double_p), int(body_order_literal))
+        return J
+
+    def minimal_gradients(self, x, u, opts=None):
+        """get_minimal_gradients! (gradients/state.jl:192-217), consistent variant: the maximal gradients
+        and minimal_to_maximal_jacobian at z = minimal_to_maximal(x), maximal_to_minimal_jacobian at the true next state.
+        Returns (x_next, dx'/dx [2nu x 2nu], dx'/du [2nu x nu], status, iters)."""
+        z = self.minimal_to_maximal(x)
+        zn, Fz, Fu, st, it = self.step_grad(z, u, opts=opts)
+        M = self.maximal_to_minimal_jacobian(zn)
+        N = self.minimal_to_maximal_jacobian(z)
+        return self.maximal_to_minimal(zn), M @ Fz @ N, M @ Fu, st, it
 
     def violations(self):
         r, b = C.c_double(), C.c_double()

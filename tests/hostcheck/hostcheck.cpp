@@ -1,0 +1,97 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Compiles the per-environment kinematics code of the product
+// (dojo.jl_b200/csrc/dojo_kin.cuh, dojo_kinjac.cuh: the exact functions the CUDA kernels call) with g++ and runs it with
+// ONE "thread" (tid = 0, nthr = 1, no-op barrier), so that `pytest -m "not gpu"` can compare the device arithmetic with the
+// oracle on a machine without a GPU.  Nothing in the product library links or loads this file; on the GPU the same
+// functions are exercised through the C-ABI by tests/test_gpu_kinjac.py.
+#include <cstring>
+#include <vector>
+
+#include "../../dojo.jl_b200/csrc/dojo_kinjac.cuh"
+
+using namespace dj;
+
+static void pad_mask(int nlambda, const double* axis_mask, double* A) {  // nullspace_mask rows (joints/joint.jl:61-64)
+  std::memset(A, 0, 9 * sizeof(double));
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (nlambda == 0) std::memcpy(A, I3, sizeof(I3));
+  else if (nlambda == 1) { std::memcpy(A, axis_mask, 3 * sizeof(double)); std::memcpy(A + 3, axis_mask + 3, 3 * sizeof(double)); }
+  else if (nlambda == 2) std::memcpy(A, axis_mask + 6, 3 * sizeof(double));
+}
+
+struct Mech {
+  std::vector<JointDev> joints;
+  std::vector<int> order;
+  int Ne, Nb, nu;
+  double h;
+};
+
+extern "C" {
+
+// jint [Ne][4] = parent, child, nlambda_tra, nlambda_rot ;  jdbl [Ne][28] = pa(3) pb(3) qoff(4) axis_mask_tra(9) axis_mask_rot(9)
+void* hostcheck_create(int Ne, int Nb, double h, const int* jint, const double* jdbl, const int* order) {
+  Mech* m = new Mech;
+  m->Ne = Ne; m->Nb = Nb; m->h = h;
+  m->joints.resize(Ne);
+  int uoff = 0;
+  for (int j = 0; j < Ne; ++j) {
+    JointDev& J = m->joints[j];
+    std::memset(&J, 0, sizeof(J));
+    J.parent = jint[4 * j]; J.child = jint[4 * j + 1];
+    J.nl_t = jint[4 * j + 2]; J.nl_r = jint[4 * j + 3];
+    J.nfree_t = 3 - J.nl_t; J.nfree_r = 3 - J.nl_r;
+    J.u_off = uoff; uoff += J.nfree_t + J.nfree_r;
+    const double* d = jdbl + 28 * j;
+    std::memcpy(J.pa, d, 24); std::memcpy(J.pb, d + 3, 24); std::memcpy(J.qoff, d + 6, 32);
+    pad_mask(J.nl_t, d + 10, J.At);
+    pad_mask(J.nl_r, d + 19, J.Ar);
+  }
+  m->nu = uoff;
+  m->order.assign(order, order + Ne);
+  return m;
+}
+void hostcheck_destroy(void* p) { delete static_cast<Mech*>(p); }
+int hostcheck_num_input(void* p) { return static_cast<Mech*>(p)->nu; }
+
+static KinJacArgs base_args(Mech* m, int B) {
+  KinJacArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.joints = m->joints.data(); a.order = m->order.data();
+  a.Ne = m->Ne; a.Nb = m->Nb; a.nu = m->nu; a.B = B; a.h = m->h;
+  return a;
+}
+static void run(const KinJacArgs& a0) {
+  KinJacArgs a = a0;
+  std::vector<double> ws(kinjac_ws_doubles(a.Nb, a.nu) + 1);
+  a.ws = ws.data();
+  for (int e = 0; e < a.B; ++e) kinjac_env(a, e, a.ws, 0, 1, [] {});
+}
+void hostcheck_minimal_to_maximal(void* p, int B, const double* X, double* Z) {
+  Mech* m = static_cast<Mech*>(p);
+  KinArgs a; a.joints = m->joints.data(); a.order = m->order.data(); a.Ne = m->Ne; a.Nb = m->Nb; a.nu = m->nu; a.B = B; a.h = m->h; a.in = X; a.out = Z;
+  for (int e = 0; e < B; ++e) min_to_max_env(a, e);
+}
+void hostcheck_maximal_to_minimal(void* p, int B, const double* Z, double* X) {
+  Mech* m = static_cast<Mech*>(p);
+  KinArgs a; a.joints = m->joints.data(); a.order = m->order.data(); a.Ne = m->Ne; a.Nb = m->Nb; a.nu = m->nu; a.B = B; a.h = m->h; a.in = Z; a.out = X;
+  for (int e = 0; e < B; ++e) max_to_min_env(a, e);
+}
+void hostcheck_max_to_min_jacobian(void* p, int B, const double* Z, double* J) {  // J zero-filled here
+  Mech* m = static_cast<Mech*>(p);
+  KinJacArgs a = base_args(m, B);
+  std::memset(J, 0, sizeof(double) * (size_t)B * 2 * m->nu * 12 * m->Nb);
+  a.Z = Z; a.Zm = Z; a.outM = J; a.mode = 0;
+  run(a);
+}
+void hostcheck_min_to_max_jacobian(void* p, int B, const double* Z, double* J) {
+  Mech* m = static_cast<Mech*>(p);
+  KinJacArgs a = base_args(m, B);
+  a.Z = Z; a.Zm = Z; a.outN = J; a.mode = 1;
+  run(a);
+}
+void hostcheck_minimal_gradients(void* p, int B, const double* Z, const double* Zn, const double* Fz, const double* Fu, double* Gx, double* Gu) {
+  Mech* m = static_cast<Mech*>(p);
+  KinJacArgs a = base_args(m, B);
+  a.Z = Z; a.Zm = Zn; a.Fz = Fz; a.Fu = Fu; a.Gx = Gx; a.Gu = Gu; a.mode = 2;
+  run(a);
+}
+}

@@ -1,0 +1,122 @@
+"""GPU tests of the map Jacobians and get_minimal_gradients! through the C-ABI:
+dojo_maximal_to_minimal_jacobian / dojo_minimal_to_maximal_jacobian / dojo_minimal_gradients against the oracle's literal
+restatement of gradients/state.jl:9-56, :136-217.  (The file sorts last on purpose: it was written after the round's GPU budget
+was spent, so the long-standing parity tests run first under `pytest -x`.)"""
+import numpy as np
+import pytest
+
+import dojo_jl_b200 as dj
+from conftest import random_inputs
+from test_gpu_parity import _random_minimal_batch
+
+pytestmark = pytest.mark.gpu
+
+MECHS = ["pendulum", "ant", "quadruped", "atlas"]
+
+
+@pytest.mark.parametrize("name", MECHS)
+def test_map_jacobians(name):
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(41)
+    B = 19
+    X = _random_minimal_batch(mech, B, rng)
+    X[-1] = 0.0  # every joint coordinate zero: the theta = 0 branches of axis_angle_to_quaternion / rotation_vector
+    stepper, o = BatchedStepper(mech, B), Oracle(mech)
+    Z = stepper.minimal_to_maximal(X)
+    M = stepper.maximal_to_minimal_jacobian(Z)
+    N = stepper.minimal_to_maximal_jacobian(Z)
+    assert M.shape == (B, 2 * mech.nu, 12 * mech.Nb) and N.shape == (B, 12 * mech.Nb, 2 * mech.nu)
+    for e in range(B):
+        Mo, No = o.maximal_to_minimal_jacobian(Z[e]), o.minimal_to_maximal_jacobian(Z[e])
+        assert np.abs(M[e] - Mo).max() < 1e-9 * max(1.0, np.abs(Mo).max())
+        assert np.abs(N[e] - No).max() < 1e-9 * max(1.0, np.abs(No).max())
+    # size-independent property (test/minimal.jl:430): the two maps are mutual inverses, so M N = I
+    assert np.abs(M @ N - np.eye(2 * mech.nu)).max() < 1e-9
+
+
+def test_map_jacobians_device_pointers_and_chunking():
+    """device-pointer (async) entry points give the same numbers as the host-pointer ones"""
+    import torch
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(43)
+    B = 300
+    X = _random_minimal_batch(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Z = stepper.minimal_to_maximal(X)
+    M = stepper.maximal_to_minimal_jacobian(Z)
+    N = stepper.minimal_to_maximal_jacobian(Z)
+    dZ = torch.from_numpy(Z).cuda()
+    dM = torch.full((B, 12 * mech.Nb, 2 * mech.nu), float("nan"), dtype=torch.float64, device="cuda")
+    dN = torch.full((B, 2 * mech.nu, 12 * mech.Nb), float("nan"), dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    stepper.maximal_to_minimal_jacobian_device(dZ.data_ptr(), dM.data_ptr(), B, stream=s)
+    stepper.minimal_to_maximal_jacobian_device(dZ.data_ptr(), dN.data_ptr(), B, stream=s)
+    torch.cuda.synchronize()
+    assert np.array_equal(dM.cpu().numpy().transpose(0, 2, 1), M)
+    assert np.array_equal(dN.cpu().numpy().transpose(0, 2, 1), N)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "ant", "quadruped"])
+def test_minimal_gradients(name):
+    """dojo_minimal_gradients == M(z') Fz N(z), M(z') Fu with the pieces the library itself returns (tight), and the
+    oracle's get_minimal_gradients! where both paths converged in the same number of iterations (the maximal gradients
+    carry the tolerance documented in test_gradient_parity)."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(47)
+    B = 16
+    X = _random_minimal_batch(mech, B, rng)
+    off = 0
+    for j in mech.joints:
+        if j.nimpulses == 0:
+            X[:, 2 * off + 2] += 0.6
+        off += j.input_dimension
+    U = random_inputs(mech, B, rng)
+    stepper, o = BatchedStepper(mech, B), Oracle(mech)
+    Xn, Gx, Gu, st, it = stepper.minimal_gradients(X, U)
+    # composition of the library's own calls
+    Z = stepper.minimal_to_maximal(X)
+    Zn, Fz, Fu, st2, it2 = stepper.step_grad(Z, U)
+    assert np.array_equal(st, st2) and np.array_equal(it, it2)
+    assert np.array_equal(Xn, stepper.maximal_to_minimal(Zn))
+    M, N = stepper.maximal_to_minimal_jacobian(Zn), stepper.minimal_to_maximal_jacobian(Z)
+    Gx_c, Gu_c = M @ Fz @ N, M @ Fu
+    assert np.abs(Gx - Gx_c).max() < 1e-9 * max(1.0, np.abs(Gx_c).max())
+    assert np.abs(Gu - Gu_c).max() < 1e-9 * max(1.0, np.abs(Gu_c).max())
+    errs = []
+    for e in range(B):
+        xo, Gxo, Guo, so, io = o.minimal_gradients(X[e], U[e])
+        if so != 0 or st[e] != 0 or io != it[e]:
+            continue
+        assert np.abs(Xn[e] - xo).max() < 1e-6
+        errs.append(max(np.abs(Gx[e] - Gxo).max() / max(1.0, np.abs(Gxo).max()), np.abs(Gu[e] - Guo).max() / max(1.0, np.abs(Guo).max())))
+    errs = np.array(errs)
+    assert len(errs) >= B // 2
+    assert np.median(errs) < 1e-7 and np.quantile(errs, 0.9) < 1e-4 and errs.max() < 1e-2, errs
+
+
+def test_minimal_gradients_device_pointers():
+    import torch
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(53)
+    B = 64
+    X = _random_minimal_batch(mech, B, rng)
+    X[:, 2] += 0.6
+    U = random_inputs(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    Xn, Gx, Gu, st, it = stepper.minimal_gradients(X, U)
+    nm, nu = 2 * mech.nu, mech.nu
+    dX, dU = torch.from_numpy(X).cuda(), torch.from_numpy(U).cuda()
+    dXn = torch.empty_like(dX)
+    dGx = torch.empty((B, nm, nm), dtype=torch.float64, device="cuda")
+    dGu = torch.empty((B, nu, nm), dtype=torch.float64, device="cuda")
+    dst = torch.empty(B, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    stepper.minimal_gradients_device(dX.data_ptr(), dU.data_ptr(), dXn.data_ptr(), dGx.data_ptr(), dGu.data_ptr(), B, dstatus=dst.data_ptr())
+    assert np.array_equal(dXn.cpu().numpy(), Xn) and np.array_equal(dst.cpu().numpy(), st)
+    assert np.array_equal(dGx.cpu().numpy().transpose(0, 2, 1), Gx) and np.array_equal(dGu.cpu().numpy().transpose(0, 2, 1), Gu)
