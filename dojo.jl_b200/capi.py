@@ -49,6 +49,19 @@ class DojoSolverOptions(C.Structure):
                 ("no_progress_undercut", C.c_double), ("verbose", C.c_int32)]
 
 
+class DojoEnvSpec(C.Structure):
+    """Environment layer (include/dojo_b200.h: DojoEnvSpec)."""
+    _fields_ = [("n_unactuated", C.c_int32), ("contact_obs", C.c_int32), ("forward_index", C.c_int32), ("healthy_index", C.c_int32),
+                ("bound_index", C.c_int32), ("w_forward", C.c_double), ("w_control", C.c_double), ("w_contact", C.c_double),
+                ("survive_reward", C.c_double), ("healthy_min", C.c_double), ("healthy_max", C.c_double), ("bound_abs", C.c_double)]
+
+
+def env_spec(n_unactuated=0, contact_obs=False, forward_index=-1, healthy_index=-1, bound_index=-1, w_forward=0.0, w_control=0.0,
+             w_contact=0.0, survive_reward=0.0, healthy_min=-float("inf"), healthy_max=float("inf"), bound_abs=float("inf")) -> DojoEnvSpec:
+    return DojoEnvSpec(int(n_unactuated), int(bool(contact_obs)), int(forward_index), int(healthy_index), int(bound_index), float(w_forward),
+                       float(w_control), float(w_contact), float(survive_reward), float(healthy_min), float(healthy_max), float(bound_abs))
+
+
 def solver_options(rtol=1.0e-6, btol=1.0e-4, ls_scale=0.5, max_iter=50, max_ls=10, undercut=float("inf"),
                    no_progress_max=3, no_progress_undercut=10.0, verbose=False) -> DojoSolverOptions:
     return DojoSolverOptions(rtol, btol, ls_scale, max_iter, max_ls, undercut, no_progress_max,

@@ -15,6 +15,7 @@
 #include "dojo_grad.cuh"
 #include "dojo_kin.cuh"
 #include "dojo_kinjac.cuh"
+#include "dojo_envs.cuh"
 
 using namespace dj;
 
@@ -275,6 +276,8 @@ struct DojoHandle {
   int* d_counter = nullptr;
   int* d_kin_order = nullptr;      // joints root -> leaves (minimal -> maximal map)
   double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
+  double *d_envS = nullptr, *d_envSn = nullptr, *d_envA = nullptr, *d_envR = nullptr, *d_envS0 = nullptr;  // environment-layer staging
+  int32_t* d_envDone = nullptr;
   double* d_kjws = nullptr;        // workspace of the map-Jacobian kernel (one slice per CTA)
   int kj_grid = 0;
   double *d_kjout = nullptr;       // staging of map Jacobians / minimal gradients for host-pointer calls
@@ -715,7 +718,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_envS); cudaFree(h->d_envSn); cudaFree(h->d_envA); cudaFree(h->d_envR); cudaFree(h->d_envS0); cudaFree(h->d_envDone); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -1256,6 +1259,112 @@ extern "C" int dojo_minimal_gradients(DojoHandle* h, const DojoSolverOptions* op
     if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   }
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Batched environment layer (dojo_envs.cuh)
+// ------------------------------------------------------------------------------------------------------------
+static bool env_spec_ok(const DojoHandle* h, const DojoEnvSpec* sp) {
+  if (!sp) return false;
+  const int ns = 2 * h->plan.nu + (sp->contact_obs ? h->plan.Ni : 0);
+  return sp->n_unactuated >= 0 && sp->n_unactuated <= h->plan.nu && sp->forward_index < ns && sp->healthy_index < ns && sp->bound_index < ns;
+}
+static EnvSpec to_dev_spec(const DojoEnvSpec* sp) {
+  EnvSpec e;
+  e.n_unactuated = sp->n_unactuated; e.contact_obs = sp->contact_obs; e.forward_index = sp->forward_index; e.healthy_index = sp->healthy_index;
+  e.bound_index = sp->bound_index; e.w_forward = sp->w_forward; e.w_control = sp->w_control; e.w_contact = sp->w_contact;
+  e.survive_reward = sp->survive_reward; e.healthy_min = sp->healthy_min; e.healthy_max = sp->healthy_max; e.bound_abs = sp->bound_abs;
+  return e;
+}
+extern "C" int dojo_env_num_state(const DojoHandle* h, const DojoEnvSpec* spec) { return 2 * h->plan.nu + ((spec && spec->contact_obs) ? h->plan.Ni : 0); }
+extern "C" int dojo_env_num_action(const DojoHandle* h, const DojoEnvSpec* spec) { return h->plan.nu - (spec ? spec->n_unactuated : 0); }
+
+static int ensure_env_staging(DojoHandle* h) {
+  if (h->d_envS) return DOJO_OK;
+  const size_t B = h->max_batch, ns = 2 * (size_t)h->plan.nu + h->plan.Ni;
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envS, B * ns * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envSn, B * ns * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envA, std::max<size_t>(1, B * h->plan.nu) * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envR, B * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envDone, B * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_envS0, ns * sizeof(double)));
+  return DOJO_OK;
+}
+
+extern "C" int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS, const double* dA,
+                                   double* dSn, double* dreward, int32_t* ddone, int32_t* dstatus, int32_t* diters, void* cuda_stream) {
+  if (!h || B <= 0 || B > h->max_batch || !dS || !dSn || dS == dSn || !env_spec_ok(h, spec)) {
+    if (h) h->err = "dojo_env_step_async: bad arguments (B <= max_batch, S_next != S, indices inside the state)";
+    return DOJO_EINVAL;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);  // maximal states, inputs and the solution stay in the handle's device buffers
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const Plan& P = h->plan;
+  EnvArgs a;
+  a.joints = P.joints; a.contacts = P.contacts; a.order = h->d_kin_order;
+  a.Ne = P.Ne; a.Nb = P.Nb; a.Ni = P.Ni; a.nu = P.nu; a.nres = P.nres; a.B = B; a.h = P.h;
+  a.spec = to_dev_spec(spec);
+  a.S = dS; a.A = dA; a.Z = h->d_Z; a.U = h->d_U; a.Zn = h->d_Zn; a.sol = h->d_sol; a.Sn = dSn; a.reward = dreward; a.done = ddone;
+  const int threads = 128, grid = (B + threads - 1) / threads;
+  dojo_env_pre_kernel<<<grid, threads, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  rc = launch_forward(h, opts, B, h->d_Z, P.nu > 0 ? h->d_U : nullptr, nullptr, h->d_Zn, h->d_sol, nullptr, dstatus, diters, 0, s);
+  if (rc != DOJO_OK) return rc;
+  dojo_env_post_kernel<<<grid, threads, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+extern "C" int dojo_env_step(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* S, const double* A, double* Sn,
+                             double* reward, int32_t* done, int32_t* status, int32_t* iters) {
+  if (!h || B <= 0 || B > h->max_batch || !S || !Sn || !env_spec_ok(h, spec)) { if (h) h->err = "dojo_env_step: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  if (is_device_ptr(S)) {
+    int rc = dojo_env_step_async(h, opts, spec, B, S, A, Sn, reward, done, status, iters, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc == DOJO_OK) rc = ensure_env_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const size_t ns = dojo_env_num_state(h, spec), na = dojo_env_num_action(h, spec);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_envS, S, (size_t)B * ns * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (A && na > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_envA, A, (size_t)B * na * sizeof(double), cudaMemcpyHostToDevice, s));
+  rc = dojo_env_step_async(h, opts, spec, B, h->d_envS, (A && na > 0) ? h->d_envA : nullptr, h->d_envSn, h->d_envR, h->d_envDone, h->d_status, h->d_iters, s);
+  if (rc != DOJO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(Sn, h->d_envSn, (size_t)B * ns * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (reward) CUDA_TRY(h, cudaMemcpyAsync(reward, h->d_envR, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (done) CUDA_TRY(h, cudaMemcpyAsync(done, h->d_envDone, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+extern "C" int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, const double* s0, const int32_t* mask, double* S) {
+  if (!h || B <= 0 || B > h->max_batch || !s0 || !S || !spec) { if (h) h->err = "dojo_env_reset: bad arguments"; return DOJO_EINVAL; }
+  const size_t ns = dojo_env_num_state(h, spec);
+  if (!is_device_ptr(S)) {  // host buffers: nothing for the device to do
+    for (int e = 0; e < B; ++e)
+      if (!mask || mask[e]) std::memcpy(S + (size_t)e * ns, s0, ns * sizeof(double));
+    return DOJO_OK;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_env_staging(h);
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_envS0, s0, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+  dojo_env_reset_kernel<<<(B + 127) / 128, 128, 0, s>>>((int)ns, B, h->d_envS0, mask, S);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

@@ -46,13 +46,10 @@ DJ_DEV V3 masked_sum(const double* A, int n, const double* c) {                 
   return r;
 }
 
-// one environment: minimal -> maximal (called by one thread)
-DJ_DEV void min_to_max_env(const KinArgs& a, int e) {
-  const double* x = a.in + (size_t)e * 2 * a.nu;
-  double* z = a.out + (size_t)e * 13 * a.Nb;
-  const double h = a.h;
-  for (int k = 0; k < a.Ne; ++k) {
-    const JointDev& jd = a.joints[a.order[k]];
+// one environment: minimal x [2 nu] -> maximal z [13 Nb] (called by one thread)
+DJ_DEV void min_to_max_one(const JointDev* joints, const int* order, int Ne, double h, const double* x, double* z) {
+  for (int k = 0; k < Ne; ++k) {
+    const JointDev& jd = joints[order[k]];
     const int nt = jd.nfree_t, nr = jd.nfree_r, nuj = nt + nr;
     const double* xm = x + 2 * jd.u_off;
     const BodyState pa = kin_load(z, jd.parent);  // written earlier by this thread (root -> leaves)
@@ -86,12 +83,14 @@ DJ_DEV V3 tra_displacement(const JointDev& jd, V3 xa, Quat qa, V3 xb, Quat qb) {
   return tmul(rotmat(qa), d);
 }
 
-DJ_DEV void max_to_min_env(const KinArgs& a, int e) {
-  const double* z = a.in + (size_t)e * 13 * a.Nb;
-  double* x = a.out + (size_t)e * 2 * a.nu;
-  const double h = a.h;
-  for (int j = 0; j < a.Ne; ++j) {
-    const JointDev& jd = a.joints[j];
+DJ_DEV void min_to_max_env(const KinArgs& a, int e) {
+  min_to_max_one(a.joints, a.order, a.Ne, a.h, a.in + (size_t)e * 2 * a.nu, a.out + (size_t)e * 13 * a.Nb);
+}
+
+// one environment: maximal z [13 Nb] -> minimal x [2 nu]
+DJ_DEV void max_to_min_one(const JointDev* joints, int Ne, double h, const double* z, double* x) {
+  for (int j = 0; j < Ne; ++j) {
+    const JointDev& jd = joints[j];
     const int nt = jd.nfree_t, nr = jd.nfree_r, nuj = nt + nr;
     if (nuj == 0) continue;
     double* xm = x + 2 * jd.u_off;
@@ -118,6 +117,10 @@ DJ_DEV void max_to_min_env(const KinArgs& a, int e) {
       xm[nuj + nt + i] = dot(ai, dth);
     }
   }
+}
+
+DJ_DEV void max_to_min_env(const KinArgs& a, int e) {
+  max_to_min_one(a.joints, a.Ne, a.h, a.in + (size_t)e * 13 * a.Nb, a.out + (size_t)e * 2 * a.nu);
 }
 
 #ifdef __CUDACC__

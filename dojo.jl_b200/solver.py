@@ -23,7 +23,8 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count",
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
-           "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients"]
+           "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
+           "dojo_env_step_async", "dojo_env_reset"]
 
 _lib = None
 
@@ -78,6 +79,16 @@ def load_library():
         getattr(L, name + "_async").restype = C.c_int
     L.dojo_minimal_gradients.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.dojo_minimal_gradients.restype = C.c_int
+    ep = C.POINTER(capi.DojoEnvSpec)
+    for name in ("dojo_env_num_state", "dojo_env_num_action"):
+        getattr(L, name).argtypes = [vp, ep]
+        getattr(L, name).restype = C.c_int
+    L.dojo_env_step.argtypes = [vp, op, ep, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_env_step.restype = C.c_int
+    L.dojo_env_step_async.argtypes = [vp, op, ep, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_env_step_async.restype = C.c_int
+    L.dojo_env_reset.argtypes = [vp, ep, C.c_int, vp, vp, vp]
+    L.dojo_env_reset.restype = C.c_int
     _lib = L
     return L
 
@@ -267,6 +278,48 @@ class BatchedStepper:
         rc = self.L.dojo_minimal_gradients(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(Gx), _p(Gu), _p(status), _p(iters))
         self._check(rc, "dojo_minimal_gradients")
         return Xn, np.transpose(Gx, (0, 2, 1)), np.transpose(Gu, (0, 2, 1)), status, iters
+
+    # ------------------------------------------------------------------ environment layer
+    def env_sizes(self, spec):
+        return self.L.dojo_env_num_state(self.h, C.byref(spec)), self.L.dojo_env_num_action(self.h, C.byref(spec))
+
+    def env_step(self, spec, S, A=None, opts=None):
+        """step!(environment, s, a) + get_state + reward + failure test for a batch (DojoEnvironments/src/environments.jl:77-109,
+        examples/learning/ant_ars.jl:79-116).  S [B, ns], A [B, na] -> (S_next, reward, done, status, iters)."""
+        ns, na = self.env_sizes(spec)
+        S = np.ascontiguousarray(np.atleast_2d(S), dtype=np.float64)
+        B = S.shape[0]
+        assert S.shape[1] == ns
+        if A is not None:
+            A = np.ascontiguousarray(np.atleast_2d(A), dtype=np.float64)
+            assert A.shape == (B, na)
+        Sn = np.empty_like(S)
+        reward = np.empty(B)
+        done, status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_env_step(self.h, C.byref(o), C.byref(spec), B, _p(S), _p(A), _p(Sn), _p(reward), _p(done), _p(status), _p(iters))
+        self._check(rc, "dojo_env_step")
+        return Sn, reward, done, status, iters
+
+    def env_step_device(self, spec, dS: int, dA: Optional[int], dSn: int, B: int, opts=None, dreward=None, ddone=None, dstatus=None, diters=None,
+                        stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_env_step_async(self.h, C.byref(o), C.byref(spec), int(B), _p(dS), _p(dA), _p(dSn), _p(dreward), _p(ddone), _p(dstatus),
+                                        _p(diters), C.c_void_p(int(stream)))
+        self._check(rc, "dojo_env_step_async")
+
+    def env_reset(self, spec, S, s0, mask=None):
+        """S[e] = s0 where mask[e] != 0 (all if mask is None).  S / mask: numpy arrays (in place) or device pointers + B."""
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        if isinstance(S, tuple):  # (device pointer, B)
+            dS, B = S
+            self._check(self.L.dojo_env_reset(self.h, C.byref(spec), int(B), _p(s0), _p(mask), _p(dS)), "dojo_env_reset")
+            return None
+        assert S.flags.c_contiguous and S.dtype == np.float64
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.int32)
+        self._check(self.L.dojo_env_reset(self.h, C.byref(spec), S.shape[0], _p(s0), _p(mask), _p(S)), "dojo_env_reset")
+        return S
 
     # ------------------------------------------------------------------ device buffers (resident data)
     def step_device(self, dZ: int, dU: Optional[int], dZn: int, B: int, opts=None, dstatus: Optional[int] = None, diters: Optional[int] = None,

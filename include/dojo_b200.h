@@ -218,6 +218,36 @@ int dojo_minimal_to_maximal_jacobian_async(DojoHandle* h, int B, const double* d
 int dojo_minimal_gradients(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
                            double* X_next, double* Gx, double* Gu, int32_t* status, int32_t* iters);
 
+/* Batched environment layer (DojoEnvironments/src/environments.jl:77-109 and environments/{ant_ars,quadruped_sampling,
+ * pendulum}.jl): state_map / input_map / step! / get_state plus the reward and failure test of the learning examples
+ * (examples/learning/ant_ars.jl:79-116), fused around the step kernel so that an RL / sampling loop exchanges only
+ * (state, action, reward, done) per step.
+ *   environment state s = [minimal state (2 nu); clamp(gamma_1, -1, 1) per contact if contact_obs]   (ant_ars.jl:72-79)
+ *   state_map(s) = s[1 : 2 nu]; input_map(a) = [zeros(n_unactuated); a]                                (ant_ars.jl:53-61)
+ *   reward = w_forward (s'[forward_index] - s[forward_index]) / timestep - w_control a'a
+ *            - w_contact sum_c clamp(gamma_1,c)^2 + survive_reward                   (forward_index < 0: no forward term)
+ *   done   = !(all finite(s') && healthy_min <= s'[healthy_index] <= healthy_max && |s'[bound_index]| <= bound_abs)
+ *            (an index < 0 disables its test)
+ * AntARS: {6, 1, 0, 2, -1, 100, 0.05/10, 0.5e-3, 0.05, 0.2, 1.0, 0};  QuadrupedSampling: {6, 0, -1, 2, 0, 0,0,0,0, 0, inf, 1000}. */
+typedef struct {
+  int32_t n_unactuated, contact_obs, forward_index, healthy_index, bound_index;
+  double w_forward, w_control, w_contact, survive_reward, healthy_min, healthy_max, bound_abs;
+} DojoEnvSpec;
+int dojo_env_num_state(const DojoHandle* h, const DojoEnvSpec* spec);  /* ns = 2 nu + (contact_obs ? Ni : 0) */
+int dojo_env_num_action(const DojoHandle* h, const DojoEnvSpec* spec); /* na = nu - n_unactuated */
+/* One step!(environment, s, a) for B environments: S [ns x B], A [na x B] (nullable: zero input), S_next [ns x B],
+ * reward [B], done [B], status [B], iters [B] (all four nullable).  Three launches on one stream (pre, step, post); the
+ * maximal states and the solver solution stay on the device.  Host or device pointers (all of the same kind);
+ * _async: device pointers, no synchronisation.  S_next must not alias S. */
+int dojo_env_step(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* S,
+                  const double* A, double* S_next, double* reward, int32_t* done, int32_t* status, int32_t* iters);
+int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS,
+                        const double* dA, double* dS_next, double* dreward, int32_t* ddone, int32_t* dstatus,
+                        int32_t* diters, void* cuda_stream);
+/* reset (initialize!(environment, model), environments.jl:118-120): S[:, e] = s0 for every e with mask[e] != 0 (mask
+ * nullable: all).  s0 [ns] is a HOST vector; S / mask host or device pointers of the same kind. */
+int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, const double* s0, const int32_t* mask, double* S);
+
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t dojo_launch_count(const DojoHandle* h);
 

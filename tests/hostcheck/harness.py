@@ -39,6 +39,8 @@ class HostCheck:
         for n in ("hostcheck_minimal_to_maximal", "hostcheck_maximal_to_minimal", "hostcheck_max_to_min_jacobian", "hostcheck_min_to_max_jacobian"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.hostcheck_minimal_gradients.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.hostcheck_env_pre.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+        L.hostcheck_env_post.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
         self.L, self.mech = L, mech
         jint = np.zeros((mech.Ne, 4), dtype=np.int32)
         jdbl = np.zeros((mech.Ne, 28))
@@ -94,3 +96,34 @@ class HostCheck:
         Gu = np.empty((B, self.mech.nu, self.nm))
         self.L.hostcheck_minimal_gradients(self.h, B, _d(Z), _d(Zn), _d(Fzc), _d(Fuc), _d(Gx), _d(Gu))
         return Gx.transpose(0, 2, 1), Gu.transpose(0, 2, 1)
+
+    # ---- environment layer (dojo_envs.cuh)
+    @staticmethod
+    def _spec_arrays(spec):
+        si = np.array([spec.n_unactuated, spec.contact_obs, spec.forward_index, spec.healthy_index, spec.bound_index], dtype=np.int32)
+        sd = np.array([spec.w_forward, spec.w_control, spec.w_contact, spec.survive_reward, spec.healthy_min, spec.healthy_max, spec.bound_abs])
+        return si, sd
+
+    def env_pre(self, spec, S, A):
+        m = self.mech
+        si, sd = self._spec_arrays(spec)
+        S = np.ascontiguousarray(np.atleast_2d(S), dtype=float)
+        A = None if A is None else np.ascontiguousarray(np.atleast_2d(A), dtype=float)
+        B = S.shape[0]
+        Z, U = np.empty((B, 13 * m.Nb)), np.empty((B, m.nu))
+        self.L.hostcheck_env_pre(self.h, si.ctypes.data_as(_ip), _d(sd), m.Ni, B, _d(S), None if A is None else _d(A), _d(Z), _d(U))
+        return Z, U
+
+    def env_post(self, spec, S, A, Zn, sol):
+        m = self.mech
+        si, sd = self._spec_arrays(spec)
+        S = np.ascontiguousarray(np.atleast_2d(S), dtype=float)
+        A = None if A is None else np.ascontiguousarray(np.atleast_2d(A), dtype=float)
+        Zn = np.ascontiguousarray(np.atleast_2d(Zn), dtype=float)
+        sol = np.ascontiguousarray(np.atleast_2d(sol), dtype=float)
+        B = S.shape[0]
+        offs = np.array([m.contact_sol_offset(c) for c in range(m.Ni)] or [0], dtype=np.int32)
+        Sn, reward, done = np.empty_like(S), np.empty(B), np.zeros(B, dtype=np.int32)
+        self.L.hostcheck_env_post(self.h, si.ctypes.data_as(_ip), _d(sd), m.Ni, m.nres, offs.ctypes.data_as(_ip), B, _d(S),
+                                  None if A is None else _d(A), _d(Zn), _d(sol), _d(Sn), _d(reward), done.ctypes.data_as(_ip))
+        return Sn, reward, done

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../dojo.jl_b200/csrc/dojo_kinjac.cuh"
+#include "../../dojo.jl_b200/csrc/dojo_envs.cuh"
 
 using namespace dj;
 
@@ -93,5 +94,34 @@ void hostcheck_minimal_gradients(void* p, int B, const double* Z, const double* 
   KinJacArgs a = base_args(m, B);
   a.Z = Z; a.Zm = Zn; a.Fz = Fz; a.Fu = Fu; a.Gx = Gx; a.Gu = Gu; a.mode = 2;
   run(a);
+}
+
+// environment layer (dojo_envs.cuh).  spec_i [5] / spec_d [7] = the DojoEnvSpec fields in declaration order.
+static EnvArgs env_args(Mech* m, const int* spec_i, const double* spec_d, int Ni, int nres, const ContactDev* contacts, int B) {
+  EnvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.joints = m->joints.data(); a.contacts = contacts; a.order = m->order.data();
+  a.Ne = m->Ne; a.Nb = m->Nb; a.Ni = Ni; a.nu = m->nu; a.nres = nres; a.B = B; a.h = m->h;
+  a.spec.n_unactuated = spec_i[0]; a.spec.contact_obs = spec_i[1]; a.spec.forward_index = spec_i[2]; a.spec.healthy_index = spec_i[3];
+  a.spec.bound_index = spec_i[4];
+  a.spec.w_forward = spec_d[0]; a.spec.w_control = spec_d[1]; a.spec.w_contact = spec_d[2]; a.spec.survive_reward = spec_d[3];
+  a.spec.healthy_min = spec_d[4]; a.spec.healthy_max = spec_d[5]; a.spec.bound_abs = spec_d[6];
+  return a;
+}
+void hostcheck_env_pre(void* p, const int* spec_i, const double* spec_d, int Ni, int B, const double* S, const double* A, double* Z, double* U) {
+  Mech* m = static_cast<Mech*>(p);
+  EnvArgs a = env_args(m, spec_i, spec_d, Ni, 0, nullptr, B);
+  a.S = S; a.A = A; a.Z = Z; a.U = U;
+  for (int e = 0; e < B; ++e) env_pre(a, e);
+}
+void hostcheck_env_post(void* p, const int* spec_i, const double* spec_d, int Ni, int nres, const int* contact_sol_off, int B, const double* S,
+                        const double* A, const double* Zn, const double* sol, double* Sn, double* reward, int32_t* done) {
+  Mech* m = static_cast<Mech*>(p);
+  std::vector<ContactDev> contacts(Ni > 0 ? Ni : 1);
+  std::memset(contacts.data(), 0, sizeof(ContactDev) * contacts.size());
+  for (int c = 0; c < Ni; ++c) contacts[c].sol_off = contact_sol_off[c];
+  EnvArgs a = env_args(m, spec_i, spec_d, Ni, nres, contacts.data(), B);
+  a.S = S; a.A = A; a.Zn = Zn; a.sol = sol; a.Sn = Sn; a.reward = reward; a.done = done;
+  for (int e = 0; e < B; ++e) env_post(a, e);
 }
 }
