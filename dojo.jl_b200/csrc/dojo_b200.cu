@@ -1133,7 +1133,7 @@ extern "C" int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, i
 // ------------------------------------------------------------------------------------------------------------
 static int ensure_kinjac(DojoHandle* h) {
   if (h->d_kjws) return DOJO_OK;
-  h->kj_grid = std::max(1, std::min(h->max_batch, h->sm_count * 8));
+  h->kj_grid = std::max(1, std::min(h->max_batch, h->sm_count * 4));  // 254 registers x 128 threads: two CTAs resident per SM
   CUDA_TRY(h, cudaMalloc((void**)&h->d_kjws, (size_t)h->kj_grid * kinjac_ws_doubles(h->plan.Nb, h->plan.nu) * sizeof(double)));
   return DOJO_OK;
 }
