@@ -5,6 +5,9 @@
 #
 #   Dojo.step!(mechanism, Z::Matrix, U::Matrix; opts)                 -> Z_next   (new batched method, 13Nb x B)
 #   Dojo.get_maximal_gradients!(mechanism, Z::Matrix, U::Matrix; opts) -> (Fz, Fu) (12Nb x 12Nb x B, 12Nb x nu x B)
+#   Dojo.minimal_to_maximal / maximal_to_minimal / step_minimal_coordinates!(mechanism, X::Matrix, ...)   (2nu x B)
+#   Dojo.maximal_to_minimal_jacobian / minimal_to_maximal_jacobian / get_minimal_gradients!(mechanism, X::Matrix, ...)
+#   DojoB200.env_step(mechanism, spec, S, A)                           -> (S_next, reward, done)  (DojoEnvironments.step! + get_state)
 #   DojoB200.mehrotra_gpu!(mechanism; opts)                            -> :success / :failed  (B = 1 drop-in for mehrotra!)
 #
 # Node order = Julia ids (joints 1..Ne, bodies Ne+1..Ne+Nb, contacts after), exactly what the library assumes.
@@ -143,6 +146,53 @@ function Dojo.step_minimal_coordinates!(mech::Mechanism, X::Matrix{Float64}, U::
                h.ptr, COptions(opts), B, X, U, Xn, status, iters)
     rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
     return Xn
+end
+
+"batched maximal_to_minimal_jacobian (gradients/state.jl:9-56): 2nu x 12Nb x B"
+function Dojo.maximal_to_minimal_jacobian(mech::Mechanism, Z::Matrix{Float64})
+    h = handle(mech); B = size(Z, 2); J = zeros(2 * h.nu, 12 * length(mech.bodies), B)
+    rc = ccall((:dojo_maximal_to_minimal_jacobian, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, B, Z, J)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return J
+end
+"batched minimal_to_maximal_jacobian (gradients/state.jl:136-179) at x: 12Nb x 2nu x B (root -> leaves chain, see INTEGRATION.md)"
+function Dojo.minimal_to_maximal_jacobian(mech::Mechanism, X::Matrix{Float64})
+    h = handle(mech); B = size(X, 2); J = zeros(12 * length(mech.bodies), 2 * h.nu, B)
+    Z = Dojo.minimal_to_maximal(mech, X)
+    rc = ccall((:dojo_minimal_to_maximal_jacobian, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, B, Z, J)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return J
+end
+"batched get_minimal_gradients! (gradients/state.jl:182-217): (2nu x 2nu x B, 2nu x nu x B)"
+function Dojo.get_minimal_gradients!(mech::Mechanism, X::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(X, 2); nm = 2 * h.nu
+    Xn = similar(X); Gx = zeros(nm, nm, B); Gu = zeros(nm, h.nu, B); status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_minimal_gradients, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+               h.ptr, COptions(opts), B, X, U, Xn, Gx, Gu, status, iters)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Gx, Gu
+end
+
+# ---- DojoEnvironments on a batched axis (environments.jl:77-109, environments/ant_ars.jl): the spec carries state_map /
+# input_map / get_state / the reward and failure test of examples/learning/ant_ars.jl:98-112
+struct EnvSpec
+    n_unactuated::Int32; contact_obs::Int32; forward_index::Int32; healthy_index::Int32; bound_index::Int32   # indices 0-based, -1 = off
+    w_forward::Float64; w_control::Float64; w_contact::Float64; survive_reward::Float64
+    healthy_min::Float64; healthy_max::Float64; bound_abs::Float64
+end
+const ANT_ARS = EnvSpec(6, 1, 0, 2, -1, 100.0, 0.05 / 10, 0.5e-3, 0.05, 0.2, 1.0, Inf)
+const QUADRUPED_SAMPLING = EnvSpec(6, 0, -1, 2, 0, 0.0, 0.0, 0.0, 0.0, 0.0, Inf, 1000.0)
+
+"step!(environment, S, A) for B environments: returns (S_next, reward, done); S is ns x B, A is na x B"
+function env_step(mech::Mechanism, spec::EnvSpec, S::Matrix{Float64}, A::Matrix{Float64}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(S, 2)
+    Sn = similar(S); reward = zeros(B); done = zeros(Int32, B); status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_env_step, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Ref{EnvSpec}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+               h.ptr, COptions(opts), spec, B, S, A, Sn, reward, done, status, iters)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Sn, reward, done
 end
 
 "open-loop batched simulate!: all T steps in one launch; U is nu x B x T, returns (Z_final, Z_traj 13Nb x B x T)"
