@@ -18,6 +18,8 @@ Python has no `!`, so `step!` is `step`):
     minimal_to_maximal_jacobian(mechanism, x)  gradients/state.jl:136 minimal_to_maximal_jacobian(mechanism, x)
     get_minimal_gradients!(mechanism, x, u; opts)                   get_minimal_gradients(mechanism, x, u, opts=None)
                                           gradients/state.jl:182
+    simulate!(...; record=true) -> Storage  simulation/simulate.jl:16, storage.jl:15-67      simulate_record(mechanism, steps, ...) -> Storage
+    momentum / kinetic_energy / potential_energy / mechanical_energy(mechanism, storage)   same names (mechanics/{momentum,energy}.jl)
 
 NEW relative to the reference: every function also accepts a batch -- z of shape [B, 13 Nb], u of shape [B, nu] --
 and then returns batched results.  All compute happens in libdojo_b200.so on the GPU (solver.BatchedStepper).
@@ -174,6 +176,59 @@ def get_minimal_gradients(mechanism: Mechanism, x, u, opts=None, device: int = 0
         _check_single(status)
         return Gx[0], Gu[0]
     return Gx, Gu
+
+
+class Storage:
+    """Storage{T,N} (simulation/storage.jl:15-42) for a batch: arrays indexed [step, environment, body, :].
+    x, q, v, ω: the state before every solve; px, pq: body momenta (world frame); vl, ωl: velocities derived from them."""
+
+    def __init__(self, traj, sto, diag):
+        T, B, _ = traj.shape
+        z = traj.reshape(T, B, -1, 13)
+        self.x, self.v, self.q, self.ω = z[..., 0:3], z[..., 3:6], z[..., 6:10], z[..., 10:13]
+        self.px, self.pq, self.vl, self.ωl = sto[..., 0:3], sto[..., 3:6], sto[..., 6:9], sto[..., 9:12]
+        self._diag = diag
+
+    def __len__(self):
+        return self.x.shape[0]
+
+
+def momentum(mechanism: Mechanism, storage: Storage):
+    """momentum(mechanism, storage) (mechanics/momentum.jl:1-15): [steps, B, 6] = linear; angular about the centre of mass"""
+    return storage._diag[..., 0:6]
+
+
+def kinetic_energy(mechanism: Mechanism, storage: Storage):
+    """kinetic_energy(mechanism, storage) (mechanics/energy.jl:17-41): [steps, B]"""
+    return storage._diag[..., 6]
+
+
+def potential_energy(mechanism: Mechanism, storage: Storage):
+    """potential_energy(mechanism, storage) (mechanics/energy.jl:43-93): [steps, B]"""
+    return storage._diag[..., 7]
+
+
+def mechanical_energy(mechanism: Mechanism, storage: Storage):
+    """mechanical_energy(mechanism, storage) (mechanics/energy.jl:1-15)"""
+    return storage._diag[..., 6] + storage._diag[..., 7]
+
+
+def simulate_record(mechanism: Mechanism, steps: int, z0=None, control: Optional[Callable] = None, opts=None, device: int = 0) -> Storage:
+    """simulate!(mechanism, steps, storage, control!; record=true) -> Storage, everything computed on the device
+    (momenta and energies included: save_to_storage!, simulation/storage.jl:50-67)."""
+    z0 = mechanism.z0 if z0 is None else z0
+    Z = np.atleast_2d(np.asarray(z0, dtype=float))
+    B = Z.shape[0]
+    s = _stepper(mechanism, B, device)
+    U = None
+    if control is not None:
+        U = np.zeros((steps, B, mechanism.nu))
+        for k in range(steps):
+            uk = control(k)
+            if uk is not None:
+                U[k] = np.asarray(uk, dtype=float)
+    _, traj, sto, diag, _ = s.simulate_record(Z, U, steps, opts)
+    return Storage(traj, sto, diag)
 
 
 def status_name(code: int) -> str:

@@ -16,6 +16,7 @@
 #include "dojo_kin.cuh"
 #include "dojo_kinjac.cuh"
 #include "dojo_envs.cuh"
+#include "dojo_storage.cuh"
 
 using namespace dj;
 
@@ -278,6 +279,8 @@ struct DojoHandle {
   double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
   double *d_envS = nullptr, *d_envSn = nullptr, *d_envA = nullptr, *d_envR = nullptr, *d_envS0 = nullptr;  // environment-layer staging
   int32_t* d_envDone = nullptr;
+  double *d_recZ[2] = {nullptr, nullptr}, *d_recS = nullptr, *d_recD = nullptr;  // dojo_simulate_record staging
+  int32_t* d_recAny = nullptr;
   double* d_kjws = nullptr;        // workspace of the map-Jacobian kernel (one slice per CTA)
   int kj_grid = 0;
   double *d_kjout = nullptr;       // staging of map Jacobians / minimal gradients for host-pointer calls
@@ -718,7 +721,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_envS); cudaFree(h->d_envSn); cudaFree(h->d_envA); cudaFree(h->d_envR); cudaFree(h->d_envS0); cudaFree(h->d_envDone); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_recZ[0]); cudaFree(h->d_recZ[1]); cudaFree(h->d_recS); cudaFree(h->d_recD); cudaFree(h->d_recAny); cudaFree(h->d_envS); cudaFree(h->d_envSn); cudaFree(h->d_envA); cudaFree(h->d_envR); cudaFree(h->d_envS0); cudaFree(h->d_envDone); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -1365,6 +1368,122 @@ extern "C" int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, con
   dojo_env_reset_kernel<<<(B + 127) / 128, 128, 0, s>>>((int)ns, B, h->d_envS0, mask, S);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Trajectory recording and momentum / energy diagnostics (dojo_storage.cuh)
+// ------------------------------------------------------------------------------------------------------------
+static int launch_storage(DojoHandle* h, int B, const double* dZ, const double* dZn, const double* dU, const double* dsol, double* dstorage, double* ddiag,
+                          cudaStream_t s) {
+  const Plan& P = h->plan;
+  StorageArgs a;
+  a.bodies = P.bodies; a.joints = P.joints;
+  a.Ne = P.Ne; a.Nb = P.Nb; a.nu = P.nu; a.nres = P.nres; a.B = B; a.h = P.h; a.input_scaling = P.input_scaling;
+  for (int i = 0; i < 3; ++i) a.g[i] = P.g[i];
+  a.Z = dZ; a.Zn = dZn; a.U = dU; a.sol = dsol; a.body_out = dstorage; a.diag = ddiag;
+  dojo_storage_kernel<<<(B + 127) / 128, 128, 0, s>>>(a);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DOJO_OK;
+}
+
+__global__ void dojo_status_max_kernel(int B, const int32_t* st, int32_t* any) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < B) any[e] = max(any[e], st[e]);
+}
+
+extern "C" int dojo_step_record_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, double* dZn, double* dstorage,
+                                      double* ddiag, int32_t* dstatus, int32_t* diters, void* cuda_stream) {
+  if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dstorage || !ddiag || dZ == dZn) {
+    if (h) h->err = "dojo_step_record_async: bad arguments (B <= max_batch, Z_next != Z)";
+    return DOJO_EINVAL;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);  // the solver solution stays in the handle's device buffer
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  rc = launch_forward(h, opts, B, dZ, dU, nullptr, dZn, h->d_sol, nullptr, dstatus, diters, 0, s);
+  if (rc != DOJO_OK) return rc;
+  return launch_storage(h, B, dZ, dZn, dU, h->d_sol, dstorage, ddiag, s);
+}
+
+static int ensure_record_staging(DojoHandle* h) {
+  if (h->d_recS) return DOJO_OK;
+  const size_t B = h->max_batch;
+  for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaMalloc((void**)&h->d_recZ[k], B * h->plan.nz * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_recS, B * 12 * h->plan.Nb * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_recD, B * 8 * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->d_recAny, B * sizeof(int32_t)));
+  return DOJO_OK;
+}
+
+extern "C" int dojo_step_record(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Zn, double* storage,
+                                double* diag, int32_t* status, int32_t* iters) {
+  if (!h || B <= 0 || B > h->max_batch || !Z || !Zn || !storage || !diag) { if (h) h->err = "dojo_step_record: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const Plan& P = h->plan;
+  if (is_device_ptr(Z)) {
+    int rc = dojo_step_record_async(h, opts, B, Z, U, Zn, storage, diag, status, iters, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc == DOJO_OK) rc = ensure_record_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const bool hasU = U && P.nu > 0;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (hasU) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+  rc = dojo_step_record_async(h, opts, B, h->d_Z, hasU ? h->d_U : nullptr, h->d_Zn, h->d_recS, h->d_recD, h->d_status, h->d_iters, s);
+  if (rc != DOJO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(Zn, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(storage, h->d_recS, (size_t)B * 12 * P.Nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(diag, h->d_recD, (size_t)B * 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+extern "C" int dojo_simulate_record(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0, const double* U, double* Z_final,
+                                    double* Z_traj, double* storage, double* diag, int32_t* status_any) {
+  if (!h || B <= 0 || B > h->max_batch || T <= 0 || !Z0 || !Z_final) { if (h) h->err = "dojo_simulate_record: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc == DOJO_OK) rc = ensure_record_staging(h);
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = h->stream;
+  const Plan& P = h->plan;
+  const bool dev = is_device_ptr(Z0);
+  const cudaMemcpyKind in = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, out = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t nzb = (size_t)B * P.nz * sizeof(double), nsb = (size_t)B * 12 * P.Nb * sizeof(double), ndb = (size_t)B * 8 * sizeof(double);
+  const bool hasU = U && P.nu > 0;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_recZ[0], Z0, nzb, in, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_recAny, 0, (size_t)B * sizeof(int32_t), s));
+  int cur = 0;
+  for (int k = 0; k < T; ++k, cur ^= 1) {
+    const double* dU = nullptr;
+    if (hasU) {
+      if (dev) dU = U + (size_t)k * B * P.nu;
+      else { CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U + (size_t)k * B * P.nu, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s)); dU = h->d_U; }
+    }
+    // with device pointers the per-step outputs are written in place
+    double* dS = (dev && storage) ? storage + (size_t)k * B * 12 * P.Nb : h->d_recS;
+    double* dD = (dev && diag) ? diag + (size_t)k * B * 8 : h->d_recD;
+    rc = dojo_step_record_async(h, opts, B, h->d_recZ[cur], dU, h->d_recZ[cur ^ 1], dS, dD, h->d_status, nullptr, s);
+    if (rc != DOJO_OK) return rc;
+    dojo_status_max_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, h->d_status, h->d_recAny);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    if (Z_traj) CUDA_TRY(h, cudaMemcpyAsync(Z_traj + (size_t)k * B * P.nz, h->d_recZ[cur], nzb, out, s));
+    if (!dev && storage) CUDA_TRY(h, cudaMemcpyAsync(storage + (size_t)k * B * 12 * P.Nb, h->d_recS, nsb, cudaMemcpyDeviceToHost, s));
+    if (!dev && diag) CUDA_TRY(h, cudaMemcpyAsync(diag + (size_t)k * B * 8, h->d_recD, ndb, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(Z_final, h->d_recZ[cur], nzb, out, s));
+  if (status_any) CUDA_TRY(h, cudaMemcpyAsync(status_any, h->d_recAny, (size_t)B * sizeof(int32_t), out, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

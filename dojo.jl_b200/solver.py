@@ -24,7 +24,7 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
-           "dojo_env_step_async", "dojo_env_reset"]
+           "dojo_env_step_async", "dojo_env_reset", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
 
 _lib = None
 
@@ -89,6 +89,12 @@ def load_library():
     L.dojo_env_step_async.restype = C.c_int
     L.dojo_env_reset.argtypes = [vp, ep, C.c_int, vp, vp, vp]
     L.dojo_env_reset.restype = C.c_int
+    L.dojo_step_record.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_step_record.restype = C.c_int
+    L.dojo_step_record_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_step_record_async.restype = C.c_int
+    L.dojo_simulate_record.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_simulate_record.restype = C.c_int
     _lib = L
     return L
 
@@ -278,6 +284,43 @@ class BatchedStepper:
         rc = self.L.dojo_minimal_gradients(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(Gx), _p(Gu), _p(status), _p(iters))
         self._check(rc, "dojo_minimal_gradients")
         return Xn, np.transpose(Gx, (0, 2, 1)), np.transpose(Gu, (0, 2, 1)), status, iters
+
+    # ------------------------------------------------------------------ trajectory recording / diagnostics
+    def step_record(self, Z, U=None, opts=None):
+        """step! + save_to_storage! (simulation/storage.jl:50-67).  Returns (Z_next, storage [B, Nb, 12] = px pq vl wl per body,
+        diag [B, 8] = linear momentum, angular momentum about the centre of mass, kinetic, potential energy, status, iters)."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        U = None if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        Zn = np.empty_like(Z)
+        sto, diag = np.empty((B, self.mech.Nb, 12)), np.empty((B, 8))
+        status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_record(self.h, C.byref(o), B, _p(Z), _p(U), _p(Zn), _p(sto), _p(diag), _p(status), _p(iters))
+        self._check(rc, "dojo_step_record")
+        return Zn, sto, diag, status, iters
+
+    def simulate_record(self, Z0, U=None, T: int = 1, opts=None):
+        """simulate!(...; record=true) with open-loop inputs U [T, B, nu].  Returns (Z_final, Z_traj [T, B, 13Nb] = the state
+        before every solve (Storage.x, q, v, w), storage [T, B, Nb, 12], diag [T, B, 8], status_any)."""
+        Z0 = np.ascontiguousarray(np.atleast_2d(Z0), dtype=np.float64)
+        B = Z0.shape[0]
+        if U is not None:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+            assert U.shape == (T, B, self.nu)
+        Zf = np.empty_like(Z0)
+        traj, sto, diag = np.empty((T, B, self.nz)), np.empty((T, B, self.mech.Nb, 12)), np.empty((T, B, 8))
+        st = np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_simulate_record(self.h, C.byref(o), B, int(T), _p(Z0), _p(U), _p(Zf), _p(traj), _p(sto), _p(diag), _p(st))
+        self._check(rc, "dojo_simulate_record")
+        return Zf, traj, sto, diag, st
+
+    def step_record_device(self, dZ: int, dU: Optional[int], dZn: int, dstorage: int, ddiag: int, B: int, opts=None, dstatus=None, diters=None, stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_record_async(self.h, C.byref(o), int(B), _p(dZ), _p(dU), _p(dZn), _p(dstorage), _p(ddiag), _p(dstatus), _p(diters),
+                                           C.c_void_p(int(stream)))
+        self._check(rc, "dojo_step_record_async")
 
     # ------------------------------------------------------------------ environment layer (SURVEY 8 f2)
     def env_sizes(self, spec):

@@ -248,6 +248,25 @@ int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const Dojo
  * nullable: all).  s0 [ns] is a HOST vector; S / mask host or device pointers of the same kind. */
 int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, const double* s0, const int32_t* mask, double* S);
 
+/* Trajectory recording (Storage, src/simulation/storage.jl:15-67) and the diagnostics derived from it
+ * (src/mechanics/momentum.jl:17-74, src/mechanics/energy.jl:32-93), computed on the device right after the solve exactly
+ * where simulate! calls save_to_storage! (src/simulation/simulate.jl:16-36: after mehrotra!, before update_state!):
+ *   storage [12 Nb x B]: per body px(3), pq(3) (momenta, world frame), vl(3) = px / m, wl(3) = J \ R(q2)' pq;
+ *   diag    [8 x B]:     total linear momentum(3), angular momentum about the centre of mass(3), kinetic, potential energy.
+ * Storage.x / q / v / w of step k are the state BEFORE the k-th solve, i.e. the input Z itself (x2, v15, q2, w15).
+ * External forces are taken as zero (simulate! clears them before save_to_storage!).  Host or device pointers (all of the
+ * same kind); _async: device pointers, no synchronisation. */
+int dojo_step_record(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Z_next,
+                     double* storage, double* diag, int32_t* status, int32_t* iters);
+int dojo_step_record_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU,
+                           double* dZ_next, double* dstorage, double* ddiag, int32_t* dstatus, int32_t* diters,
+                           void* cuda_stream);
+/* simulate!(mechanism, 1:T, storage, control!; record = true) with open-loop inputs U [nu x B x T] (nullable): per step k
+ * Z_traj[:, :, k] = state before the k-th solve (Storage.x, q, v, w), storage[:, :, k], diag[:, :, k] as above (each
+ * nullable); Z_final [13 Nb x B] = state after the last solve; status_any [B] = max status.  2 T launches. */
+int dojo_simulate_record(DojoHandle* h, const DojoSolverOptions* opts, int B, int T, const double* Z0, const double* U,
+                         double* Z_final, double* Z_traj, double* storage, double* diag, int32_t* status_any);
+
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t dojo_launch_count(const DojoHandle* h);
 

@@ -1931,6 +1931,44 @@ struct Oracle {
       L += pa[bi] + skew(r) * (bodies[bi].mass * (vb - vcom));
     }
     for (int i = 0; i < 3; ++i) { out6[i] = P[i]; out6[3 + i] = L[i]; }
+    last_pl = pl; last_pa = pa;
+  }
+  mutable std::vector<V3> last_pl, last_pa;
+
+  // save_to_storage! (simulation/storage.jl:50-67) right after mehrotra!: per body [px; pq; vl; wl], and the diagnostics
+  // derived from a Storage: momentum (mechanics/momentum.jl:54-74), kinetic_energy (mechanics/energy.jl:32-41),
+  // potential_energy (:60-93).  diag = [p_linear(3); p_angular(3); kinetic; potential].
+  void storage_record(double* body_out, double* diag) const {
+    momentum(diag);
+    double ke = 0, pe = 0;
+    for (int bi = 0; bi < Nb; ++bi) {
+      const BodyS& s = bodies[bi];
+      V3 px = last_pl[bi], pq = last_pa[bi];
+      V3 vl = px / s.mass;
+      V3 rhs = vector_rotate(pq, inv(s.q2));
+      double Jm[9], x[3] = {rhs[0], rhs[1], rhs[2]};
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Jm[3 * r + c] = s.J(r, c);
+      dense_solve(std::vector<double>(Jm, Jm + 9), 3, x, 1);  // inertia \ (...)
+      V3 wl = vec3(x[0], x[1], x[2]);
+      double* o = body_out + 12 * bi;
+      for (int i = 0; i < 3; ++i) { o[i] = px[i]; o[3 + i] = pq[i]; o[6 + i] = vl[i]; o[9 + i] = wl[i]; }
+      ke += 0.5 * s.mass * dot(vl, vl) + 0.5 * dot(wl, s.J * wl);
+      pe -= s.mass * dot(gravity, s.x2);
+    }
+    for (const JointS& j : joints) {
+      if (!j.spring) continue;
+      for (int k = 0; k < 2; ++k) {
+        const Elem& e = j.el[k];
+        if (!(e.spring > 0) || e.nl == 3) continue;
+        Cfg a = cfg_current(j.parent, 1), b = cfg_current(j.child, 1);
+        double th[3], dist[3];
+        minimal_coordinates(j, k, a.x, a.q, b.x, b.q, th);
+        for (int i = 0; i < e.nfree; ++i) dist[i] = e.spring_offset[i] - th[i];
+        V3 force = e.spring * At_times(e, dist);  // |spring_force| (translational/springs.jl:31-52, rotational/springs.jl:40-62)
+        pe += 0.5 * dot(force, force) / e.spring;
+      }
+    }
+    diag[6] = ke; diag[7] = pe;
   }
 };
 
@@ -2058,4 +2096,5 @@ void oracle_minimal_to_maximal_jacobian(void* h, const double* z, double* J, int
   static_cast<Oracle*>(h)->minimal_to_maximal_jacobian(z, J, body_order_literal != 0);
 }
 void oracle_momentum(void* h, double* out6) { static_cast<Oracle*>(h)->momentum(out6); }
+void oracle_storage_record(void* h, double* body_out, double* diag) { static_cast<Oracle*>(h)->storage_record(body_out, diag); }
 }

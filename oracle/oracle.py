@@ -63,6 +63,7 @@ def lib():
         L.oracle_trace.argtypes = [vp, dp, C.c_int]
         L.oracle_trace.restype = C.c_int
         L.oracle_momentum.argtypes = [vp, dp]
+        L.oracle_storage_record.argtypes = [vp, dp, dp]
         L.oracle_minimal_to_maximal.argtypes = [vp, dp, dp]
         L.oracle_maximal_to_minimal.argtypes = [vp, dp, dp]
         L.oracle_maximal_to_minimal_jacobian.argtypes = [vp, dp, dp]
@@ -229,6 +230,14 @@ class Oracle:
 
     def set_solver_mode(self, mode):
         self.L.oracle_set_solver_mode(self.h, mode)
+
+    def storage_record(self):
+        """save_to_storage! after the last step's solve: (per body [px; pq; vl; wl] as [Nb, 12],
+        [p_linear(3); p_angular(3); kinetic; potential])  (simulation/storage.jl:50-67, mechanics/{momentum,energy}.jl)."""
+        body = np.empty((self.mech.Nb, 12))
+        diag = np.empty(8)
+        self.L.oracle_storage_record(self.h, _d(body), _d(diag))
+        return body, diag
 
     def momentum(self):
         """[p_linear; p_angular] right after the last step's solve (mechanics/momentum.jl:17-86)."""

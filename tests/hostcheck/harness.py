@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "dojo.jl_b200", "csrc")
 LIB = os.path.join(HERE, "_build", "libdojo_hostcheck.so")
-_SRCS = [os.path.join(HERE, "hostcheck.cpp")] + [os.path.join(CSRC, f) for f in ("dojo_kinjac.cuh", "dojo_kin.cuh", "dojo_envs.cuh", "dojo_math.cuh", "dojo_plan.h")]
+_SRCS = [os.path.join(HERE, "hostcheck.cpp")] + [os.path.join(CSRC, f) for f in ("dojo_kinjac.cuh", "dojo_kin.cuh", "dojo_envs.cuh", "dojo_storage.cuh", "dojo_math.cuh", "dojo_plan.h")]
 
 
 def build() -> str:
@@ -41,6 +41,7 @@ class HostCheck:
         L.hostcheck_minimal_gradients.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         L.hostcheck_env_pre.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.hostcheck_env_post.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.hostcheck_storage.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         self.L, self.mech = L, mech
         jint = np.zeros((mech.Ne, 4), dtype=np.int32)
         jdbl = np.zeros((mech.Ne, 28))
@@ -127,3 +128,21 @@ class HostCheck:
         self.L.hostcheck_env_post(self.h, si.ctypes.data_as(_ip), _d(sd), m.Ni, m.nres, offs.ctypes.data_as(_ip), B, _d(S),
                                   None if A is None else _d(A), _d(Zn), _d(sol), _d(Sn), _d(reward), done.ctypes.data_as(_ip))
         return Sn, reward, done
+
+    # ---- storage / diagnostics (dojo_storage.cuh)
+    def storage(self, Z, Zn, U, sol):
+        """-> (per body [B, Nb, 12] = px pq vl wl, diag [B, 8] = p_linear p_angular kinetic potential)"""
+        m = self.mech
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=float)
+        Zn = np.ascontiguousarray(np.atleast_2d(Zn), dtype=float)
+        U = np.ascontiguousarray(np.atleast_2d(U), dtype=float)
+        sol = np.ascontiguousarray(np.atleast_2d(sol), dtype=float)
+        B = Z.shape[0]
+        jext = np.array([[j.rot.nlimits, j.rot.spring if j.rot.nlambda < 3 else 0.0, j.rot.damper if j.rot.nlambda < 3 else 0.0]
+                         + list(np.asarray(j.rot.spring_offset, dtype=float).ravel()[:3]) + [0.0] * (3 - min(3, np.size(j.rot.spring_offset)))
+                         for j in m.joints], dtype=float)
+        bdbl = np.array([[b.mass] + list(np.asarray(b.inertia, dtype=float).ravel()) for b in m.bodies], dtype=float)
+        g = np.ascontiguousarray(m.gravity, dtype=float)
+        body, diag = np.empty((B, m.Nb, 12)), np.empty((B, 8))
+        self.L.hostcheck_storage(self.h, _d(jext), _d(bdbl), m.nres, float(m.input_scaling), _d(g), B, _d(Z), _d(Zn), _d(U), _d(sol), _d(body), _d(diag))
+        return body, diag

@@ -8,18 +8,24 @@
 
 #include "../../dojo.jl_b200/csrc/dojo_kinjac.cuh"
 #include "../../dojo.jl_b200/csrc/dojo_envs.cuh"
+#include "../../dojo.jl_b200/csrc/dojo_storage.cuh"
 
 using namespace dj;
 
-static void pad_mask(int nlambda, const double* axis_mask, double* A) {  // nullspace_mask rows (joints/joint.jl:61-64)
+static void pad_mask(int nlambda, const double* axis_mask, double* A, double* Cm = nullptr) {  // nullspace / constraint mask rows (joints/joint.jl:56-64)
+  double dummy[9];
+  double* Cc = Cm ? Cm : dummy;
   std::memset(A, 0, 9 * sizeof(double));
+  std::memset(Cc, 0, 9 * sizeof(double));
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   if (nlambda == 0) std::memcpy(A, I3, sizeof(I3));
-  else if (nlambda == 1) { std::memcpy(A, axis_mask, 3 * sizeof(double)); std::memcpy(A + 3, axis_mask + 3, 3 * sizeof(double)); }
-  else if (nlambda == 2) std::memcpy(A, axis_mask + 6, 3 * sizeof(double));
+  else if (nlambda == 1) { std::memcpy(Cc, axis_mask + 6, 3 * sizeof(double)); std::memcpy(A, axis_mask, 3 * sizeof(double)); std::memcpy(A + 3, axis_mask + 3, 3 * sizeof(double)); }
+  else if (nlambda == 2) { std::memcpy(Cc, axis_mask, 6 * sizeof(double)); std::memcpy(A, axis_mask + 6, 3 * sizeof(double)); }
+  else std::memcpy(Cc, I3, sizeof(I3));
 }
 
 struct Mech {
+  std::vector<BodyDev> bodies;
   std::vector<JointDev> joints;
   std::vector<int> order;
   int Ne, Nb, nu;
@@ -43,8 +49,8 @@ void* hostcheck_create(int Ne, int Nb, double h, const int* jint, const double* 
     J.u_off = uoff; uoff += J.nfree_t + J.nfree_r;
     const double* d = jdbl + 28 * j;
     std::memcpy(J.pa, d, 24); std::memcpy(J.pb, d + 3, 24); std::memcpy(J.qoff, d + 6, 32);
-    pad_mask(J.nl_t, d + 10, J.At);
-    pad_mask(J.nl_r, d + 19, J.Ar);
+    pad_mask(J.nl_t, d + 10, J.At, J.Ct);
+    pad_mask(J.nl_r, d + 19, J.Ar, J.Cr);
   }
   m->nu = uoff;
   m->order.assign(order, order + Ne);
@@ -123,5 +129,36 @@ void hostcheck_env_post(void* p, const int* spec_i, const double* spec_d, int Ni
   EnvArgs a = env_args(m, spec_i, spec_d, Ni, nres, contacts.data(), B);
   a.S = S; a.A = A; a.Zn = Zn; a.sol = sol; a.Sn = Sn; a.reward = reward; a.done = done;
   for (int e = 0; e < B; ++e) env_post(a, e);
+}
+
+// storage / diagnostics (dojo_storage.cuh).  jext [Ne][6] = rot limits (Nb/2), spring_r, damper_r, spring_offset_r(3);
+// bdbl [Nb][10] = mass, inertia (row-major).  Solution offsets follow dojo_create: joints in order, n = nl_t + nl_r + 4 * limits.
+void hostcheck_storage(void* p, const double* jext, const double* bdbl, int nres, double input_scaling, const double* g, int B, const double* Z,
+                       const double* Zn, const double* U, const double* sol, double* body_out, double* diag) {
+  Mech* m = static_cast<Mech*>(p);
+  m->bodies.resize(m->Nb);
+  int off = 0;
+  for (int j = 0; j < m->Ne; ++j) {
+    JointDev& J = m->joints[j];
+    const double* d = jext + 6 * j;
+    J.nb2_r = (int)d[0]; J.nb_r = 2 * J.nb2_r; J.spring_r = d[1]; J.damper_r = d[2];
+    for (int i = 0; i < 3; ++i) J.spring_off_r[i] = d[3 + i];
+    J.ne = J.nl_t + J.nl_r; J.n = J.ne + 2 * J.nb_r;
+    J.sol_off = off; off += J.n;
+  }
+  for (int b = 0; b < m->Nb; ++b) {
+    BodyDev& Bd = m->bodies[b];
+    std::memset(&Bd, 0, sizeof(Bd));
+    Bd.mass = bdbl[10 * b];
+    std::memcpy(Bd.J, bdbl + 10 * b + 1, 9 * sizeof(double));
+    Bd.sol_off = off; off += 6;
+  }
+  StorageArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.bodies = m->bodies.data(); a.joints = m->joints.data();
+  a.Ne = m->Ne; a.Nb = m->Nb; a.nu = m->nu; a.nres = nres; a.B = B; a.h = m->h; a.input_scaling = input_scaling;
+  for (int i = 0; i < 3; ++i) a.g[i] = g[i];
+  a.Z = Z; a.Zn = Zn; a.U = U; a.sol = sol; a.body_out = body_out; a.diag = diag;
+  for (int e = 0; e < B; ++e) storage_env(a, e);
 }
 }
