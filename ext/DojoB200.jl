@@ -195,6 +195,18 @@ function env_step(mech::Mechanism, spec::EnvSpec, S::Matrix{Float64}, A::Matrix{
     return Sn, reward, done
 end
 
+"batched simulate!(...; record = true): returns (Z_traj 13Nb x B x T = Storage.x/q/v/ω, storage 12Nb x B x T = px pq vl ωl per body,
+ diag 8 x B x T = momentum(6), kinetic, potential) -- save_to_storage! and mechanics/{momentum,energy}.jl evaluated on the device"
+function simulate_record(mech::Mechanism, Z0::Matrix{Float64}, U::Array{Float64,3}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(Z0, 2); T = size(U, 3); Nb = length(mech.bodies)
+    Zf = similar(Z0); traj = zeros(h.nz, B, T); sto = zeros(12 * Nb, B, T); diag = zeros(8, B, T); status = zeros(Int32, B)
+    rc = ccall((:dojo_simulate_record, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+               h.ptr, COptions(opts), B, T, Z0, U, Zf, traj, sto, diag, status)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return traj, sto, diag
+end
+
 "open-loop batched simulate!: all T steps in one launch; U is nu x B x T, returns (Z_final, Z_traj 13Nb x B x T)"
 function rollout(mech::Mechanism, Z0::Matrix{Float64}, U::Array{Float64,3}; opts = SolverOptions{Float64}(), record = true)
     h = handle(mech); B = size(Z0, 2); T = size(U, 3)

@@ -19,4 +19,19 @@ Zf, sr, traj = s.rollout(Z, np.stack([U] * T), T, record=True)
 X = s.maximal_to_minimal(Zn)
 Z2 = s.minimal_to_maximal(X)
 Xn, _, _ = s.step_minimal(X, U)
+M = s.maximal_to_minimal_jacobian(Zn)
+N = s.minimal_to_maximal_jacobian(Z2)
+Xg, Gx, Gu, _, _ = s.minimal_gradients(X, U)
+Zr, sto, diag, _, _ = s.step_record(Z, U)
+Zs, trj, sts, dgs, _ = s.simulate_record(Z, np.stack([U] * T), T)
+from dojo_jl_b200 import capi, environments as E
+cls = {"ant": E.AntARS, "quadruped": E.QuadrupedSampling, "pendulum": E.Pendulum}.get(name)
+if cls is not None:
+    spec = capi.env_spec(**cls.spec_kwargs)
+    ns, na = s.env_sizes(spec)
+    S = np.zeros((B, ns))
+    S[:, :2 * mech.nu] = X
+    Sn, rew, done, _, _ = s.env_step(spec, S, rng.uniform(-1, 1, (B, na)))
+    s.env_reset(spec, Sn, S[0], done)
+print("widened ok", float(np.abs(M).max()), float(np.abs(N).max()), float(np.abs(Gx).max()), float(np.abs(sto).max()), float(np.abs(dgs).max()))
 print("sanity ok", name, float(np.abs(Zn).max()), float(np.abs(Fz).max()), float(np.abs(traj).max()), float(np.abs(Xn).max()), it.tolist())
