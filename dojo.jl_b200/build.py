@@ -32,11 +32,12 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     if not force and not needs_build() and out == LIB:
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-maxrregcount=255",
-           "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-o", out] + \
+           "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-o", out + ".tmp"] + \
           [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
+    os.replace(out + ".tmp", out)  # never leave a half-written library in the tree (gpurun snapshots it)
     return out
 
 

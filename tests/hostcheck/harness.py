@@ -17,7 +17,8 @@ def build() -> str:
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
-                               "-Wno-unused-function", "-o", LIB, _SRCS[0]])
+                               "-Wno-unused-function", "-o", LIB + ".tmp", _SRCS[0]])
+        os.replace(LIB + ".tmp", LIB)
     return LIB
 
 
