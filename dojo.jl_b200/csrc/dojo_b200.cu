@@ -1296,8 +1296,14 @@ static int ensure_env_staging(DojoHandle* h) {
   return DOJO_OK;
 }
 
+static int env_step_impl(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS, const double* dA, double* dSn,
+                         double* dreward, int32_t* ddone, int32_t* dstatus, int32_t* diters, double* dret, int32_t* ddead, void* cuda_stream);
 extern "C" int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS, const double* dA,
                                    double* dSn, double* dreward, int32_t* ddone, int32_t* dstatus, int32_t* diters, void* cuda_stream) {
+  return env_step_impl(h, opts, spec, B, dS, dA, dSn, dreward, ddone, dstatus, diters, nullptr, nullptr, cuda_stream);
+}
+static int env_step_impl(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS, const double* dA, double* dSn,
+                         double* dreward, int32_t* ddone, int32_t* dstatus, int32_t* diters, double* dret, int32_t* ddead, void* cuda_stream) {
   if (!h || B <= 0 || B > h->max_batch || !dS || !dSn || dS == dSn || !env_spec_ok(h, spec)) {
     if (h) h->err = "dojo_env_step_async: bad arguments (B <= max_batch, S_next != S, indices inside the state)";
     return DOJO_EINVAL;
@@ -1312,6 +1318,7 @@ extern "C" int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts,
   a.Ne = P.Ne; a.Nb = P.Nb; a.Ni = P.Ni; a.nu = P.nu; a.nres = P.nres; a.B = B; a.h = P.h;
   a.spec = to_dev_spec(spec);
   a.S = dS; a.A = dA; a.Z = h->d_Z; a.U = h->d_U; a.Zn = h->d_Zn; a.sol = h->d_sol; a.Sn = dSn; a.reward = dreward; a.done = ddone;
+  a.ret = dret; a.dead = ddead;
   const int threads = 128, grid = (B + threads - 1) / threads;
   dojo_env_pre_kernel<<<grid, threads, 0, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
@@ -1484,6 +1491,38 @@ extern "C" int dojo_simulate_record(DojoHandle* h, const DojoSolverOptions* opts
   }
   CUDA_TRY(h, cudaMemcpyAsync(Z_final, h->d_recZ[cur], nzb, out, s));
   if (status_any) CUDA_TRY(h, cudaMemcpyAsync(status_any, h->d_recAny, (size_t)B * sizeof(int32_t), out, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+extern "C" int dojo_env_rollout(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, int T, const double* S0, const double* A,
+                                double* S_final, double* ret, int32_t* failed) {
+  if (!h || B <= 0 || B > h->max_batch || T <= 0 || !S0 || !S_final || !env_spec_ok(h, spec)) { if (h) h->err = "dojo_env_rollout: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc == DOJO_OK) rc = ensure_env_staging(h);
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = h->stream;
+  const bool dev = is_device_ptr(S0);
+  const cudaMemcpyKind in = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, out = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t ns = dojo_env_num_state(h, spec), na = dojo_env_num_action(h, spec);
+  double* buf[2] = {h->d_envS, h->d_envSn};
+  CUDA_TRY(h, cudaMemcpyAsync(buf[0], S0, (size_t)B * ns * sizeof(double), in, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_envR, 0, (size_t)B * sizeof(double), s));        // return accumulator
+  CUDA_TRY(h, cudaMemsetAsync(h->d_envDone, 0, (size_t)B * sizeof(int32_t), s));    // failure flags
+  int cur = 0;
+  for (int k = 0; k < T; ++k, cur ^= 1) {
+    const double* dA = nullptr;
+    if (A && na > 0) {
+      if (dev) dA = A + (size_t)k * B * na;
+      else { CUDA_TRY(h, cudaMemcpyAsync(h->d_envA, A + (size_t)k * B * na, (size_t)B * na * sizeof(double), cudaMemcpyHostToDevice, s)); dA = h->d_envA; }
+    }
+    rc = env_step_impl(h, opts, spec, B, buf[cur], dA, buf[cur ^ 1], nullptr, nullptr, h->d_status, nullptr, h->d_envR, h->d_envDone, s);
+    if (rc != DOJO_OK) return rc;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(S_final, buf[cur], (size_t)B * ns * sizeof(double), out, s));
+  if (ret) CUDA_TRY(h, cudaMemcpyAsync(ret, h->d_envR, (size_t)B * sizeof(double), out, s));
+  if (failed) CUDA_TRY(h, cudaMemcpyAsync(failed, h->d_envDone, (size_t)B * sizeof(int32_t), out, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

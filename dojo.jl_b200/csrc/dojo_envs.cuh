@@ -36,6 +36,9 @@ struct EnvArgs {
   double* Sn;            // post: out [ns x B]
   double* reward;        // post: out [B] (nullable)
   int32_t* done;         // post: out [B] (nullable)
+  double* ret;           // post: in/out [B] (nullable) return accumulated over a rollout: += reward while the environment is alive
+  int32_t* dead;         // post: in/out [B] (nullable) set once the failure test fires (the failing step's reward still counts,
+                         //       as in rollout_policy, examples/learning/ant_ars.jl:106-115)
 };
 
 DJ_DEV int env_num_state(int nu, int Ni, const EnvSpec& sp) { return 2 * nu + (sp.contact_obs ? Ni : 0); }
@@ -62,19 +65,22 @@ DJ_DEV void env_post(const EnvArgs& a, int e) {
     if (sp.contact_obs) sn[2 * a.nu + c] = g;
     contact_cost += g * g;
   }
-  if (a.reward) {
+  double r = 0.0;
+  if (a.reward || a.ret) {
     double ctrl = 0.0;
     if (a.A) for (int i = 0; i < na; ++i) { const double v = a.A[(size_t)e * na + i]; ctrl += v * v; }
-    double r = sp.survive_reward - sp.w_control * ctrl - sp.w_contact * contact_cost;
+    r = sp.survive_reward - sp.w_control * ctrl - sp.w_contact * contact_cost;
     if (sp.forward_index >= 0) r += sp.w_forward * (sn[sp.forward_index] - s[sp.forward_index]) / a.h;
-    a.reward[e] = r;
+    if (a.reward) a.reward[e] = r;
+    if (a.ret && !(a.dead && a.dead[e])) a.ret[e] += r;
   }
-  if (a.done) {
+  if (a.done || a.dead) {
     bool ok = true;
     for (int i = 0; i < ns; ++i) ok = ok && (fabs(sn[i]) <= 1.79769313486231570e308);  // all(isfinite.(state_after))
     if (sp.healthy_index >= 0) ok = ok && (sn[sp.healthy_index] >= sp.healthy_min) && (sn[sp.healthy_index] <= sp.healthy_max);
     if (sp.bound_index >= 0) ok = ok && (fabs(sn[sp.bound_index]) <= sp.bound_abs);
-    a.done[e] = ok ? 0 : 1;
+    if (a.done) a.done[e] = ok ? 0 : 1;
+    if (a.dead && !ok) a.dead[e] = 1;
   }
 }
 

@@ -65,6 +65,15 @@ class Environment:
         return reward, done
 
 
+    def rollout(self, actions, state=None, opts=None):
+        """Open-loop rollout from `state` (default: the held state) with actions [T, B, na]: returns (return [B], failed [B]);
+        the held state becomes the final state.  One C call, 3 T launches, nothing crosses the PCIe bus in between."""
+        A = np.asarray(actions, dtype=float)
+        S = self.state if state is None else np.atleast_2d(np.asarray(state, dtype=float))
+        self.state, ret, failed = self.stepper.env_rollout(self.spec, S, A, A.shape[0], opts)
+        return ret, failed
+
+
 class AntARS(Environment):
     """environments/ant_ars.jl: state [minimal state (28); clamped normal contact impulses (9)], 8 actions, the reward of
     examples/learning/ant_ars.jl:98-107 and its failure test :112."""

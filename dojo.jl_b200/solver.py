@@ -24,7 +24,7 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
-           "dojo_env_step_async", "dojo_env_reset", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
+           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
 
 _lib = None
 
@@ -89,6 +89,8 @@ def load_library():
     L.dojo_env_step_async.restype = C.c_int
     L.dojo_env_reset.argtypes = [vp, ep, C.c_int, vp, vp, vp]
     L.dojo_env_reset.restype = C.c_int
+    L.dojo_env_rollout.argtypes = [vp, op, ep, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.dojo_env_rollout.restype = C.c_int
     L.dojo_step_record.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.dojo_step_record.restype = C.c_int
     L.dojo_step_record_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -350,6 +352,21 @@ class BatchedStepper:
         rc = self.L.dojo_env_step_async(self.h, C.byref(o), C.byref(spec), int(B), _p(dS), _p(dA), _p(dSn), _p(dreward), _p(ddone), _p(dstatus),
                                         _p(diters), C.c_void_p(int(stream)))
         self._check(rc, "dojo_env_step_async")
+
+    def env_rollout(self, spec, S0, A=None, T: int = 1, opts=None):
+        """Open-loop rollout of T environment steps on the device (examples/learning/ant_ars.jl:79-116 without the policy):
+        S0 [B, ns], A [T, B, na] -> (S_final, return [B], failed [B])."""
+        ns, na = self.env_sizes(spec)
+        S0 = np.ascontiguousarray(np.atleast_2d(S0), dtype=np.float64)
+        B = S0.shape[0]
+        if A is not None:
+            A = np.ascontiguousarray(A, dtype=np.float64)
+            assert A.shape == (T, B, na)
+        Sf, ret, failed = np.empty_like(S0), np.empty(B), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_env_rollout(self.h, C.byref(o), C.byref(spec), B, int(T), _p(S0), _p(A), _p(Sf), _p(ret), _p(failed))
+        self._check(rc, "dojo_env_rollout")
+        return Sf, ret, failed
 
     def env_reset(self, spec, S, s0, mask=None):
         """S[e] = s0 where mask[e] != 0 (all if mask is None).  S / mask: numpy arrays (in place) or device pointers + B."""

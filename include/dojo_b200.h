@@ -244,6 +244,12 @@ int dojo_env_step(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpe
 int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, const double* dS,
                         const double* dA, double* dS_next, double* dreward, int32_t* ddone, int32_t* dstatus,
                         int32_t* diters, void* cuda_stream);
+/* Open-loop rollout of T environment steps (the inner loop of sampling-based MPC / ARS evaluation, examples/learning/
+ * ant_ars.jl:79-116, quadruped_sampling.jl:66-77) with everything resident on the device: A [na x B x T] (nullable),
+ * S_final [ns x B], ret [B] = sum of the rewards up to and including the step at which the failure test fires,
+ * failed [B] = 1 if it fired (both nullable).  3 T launches, no host round trip.  Host or device pointers. */
+int dojo_env_rollout(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, int T, const double* S0,
+                     const double* A, double* S_final, double* ret, int32_t* failed);
 /* reset (initialize!(environment, model), environments.jl:118-120): S[:, e] = s0 for every e with mask[e] != 0 (mask
  * nullable: all).  s0 [ns] is a HOST vector; S / mask host or device pointers of the same kind. */
 int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, const double* s0, const int32_t* mask, double* S);

@@ -41,7 +41,7 @@ class HostCheck:
             getattr(L, n).argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.hostcheck_minimal_gradients.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         L.hostcheck_env_pre.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
-        L.hostcheck_env_post.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.hostcheck_env_post.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
         L.hostcheck_storage.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         self.L, self.mech = L, mech
         jint = np.zeros((mech.Ne, 4), dtype=np.int32)
@@ -116,7 +116,7 @@ class HostCheck:
         self.L.hostcheck_env_pre(self.h, si.ctypes.data_as(_ip), _d(sd), m.Ni, B, _d(S), None if A is None else _d(A), _d(Z), _d(U))
         return Z, U
 
-    def env_post(self, spec, S, A, Zn, sol):
+    def env_post(self, spec, S, A, Zn, sol, ret=None, dead=None):
         m = self.mech
         si, sd = self._spec_arrays(spec)
         S = np.ascontiguousarray(np.atleast_2d(S), dtype=float)
@@ -127,7 +127,8 @@ class HostCheck:
         offs = np.array([m.contact_sol_offset(c) for c in range(m.Ni)] or [0], dtype=np.int32)
         Sn, reward, done = np.empty_like(S), np.empty(B), np.zeros(B, dtype=np.int32)
         self.L.hostcheck_env_post(self.h, si.ctypes.data_as(_ip), _d(sd), m.Ni, m.nres, offs.ctypes.data_as(_ip), B, _d(S),
-                                  None if A is None else _d(A), _d(Zn), _d(sol), _d(Sn), _d(reward), done.ctypes.data_as(_ip))
+                                  None if A is None else _d(A), _d(Zn), _d(sol), _d(Sn), _d(reward), done.ctypes.data_as(_ip),
+                                  None if ret is None else _d(ret), None if dead is None else dead.ctypes.data_as(_ip))
         return Sn, reward, done
 
     # ---- storage / diagnostics (dojo_storage.cuh)

@@ -121,13 +121,13 @@ void hostcheck_env_pre(void* p, const int* spec_i, const double* spec_d, int Ni,
   for (int e = 0; e < B; ++e) env_pre(a, e);
 }
 void hostcheck_env_post(void* p, const int* spec_i, const double* spec_d, int Ni, int nres, const int* contact_sol_off, int B, const double* S,
-                        const double* A, const double* Zn, const double* sol, double* Sn, double* reward, int32_t* done) {
+                        const double* A, const double* Zn, const double* sol, double* Sn, double* reward, int32_t* done, double* ret, int32_t* dead) {
   Mech* m = static_cast<Mech*>(p);
   std::vector<ContactDev> contacts(Ni > 0 ? Ni : 1);
   std::memset(contacts.data(), 0, sizeof(ContactDev) * contacts.size());
   for (int c = 0; c < Ni; ++c) contacts[c].sol_off = contact_sol_off[c];
   EnvArgs a = env_args(m, spec_i, spec_d, Ni, nres, contacts.data(), B);
-  a.S = S; a.A = A; a.Zn = Zn; a.sol = sol; a.Sn = Sn; a.reward = reward; a.done = done;
+  a.S = S; a.A = A; a.Zn = Zn; a.sol = sol; a.Sn = Sn; a.reward = reward; a.done = done; a.ret = ret; a.dead = dead;
   for (int e = 0; e < B; ++e) env_post(a, e);
 }
 

@@ -61,3 +61,22 @@ def test_failure_test_flags_nonfinite_and_out_of_range():
     _, reward, done = hc.env_post(spec, S, np.zeros((3, 8)), Zn, sol)
     assert list(done) == [0, 1, 1]
     assert abs(reward[0] - 0.05) < 1e-9  # no motion, no control, no contact: survive reward only
+
+
+def test_rollout_return_accumulation_stops_after_failure():
+    """rollout_policy (examples/learning/ant_ars.jl:106-115): the reward of the step at which the failure test fires still
+    counts, later steps do not."""
+    mech = dj.get_mechanism("ant")
+    spec = _spec(E.AntARS)
+    hc, o = HostCheck(mech), Oracle(mech)
+    x = o.maximal_to_minimal(mech.z0)
+    S = np.tile(np.concatenate([x, np.zeros(mech.Ni)]), (2, 1))
+    sol = np.zeros((2, mech.nres))
+    ret, dead = np.zeros(2), np.zeros(2, dtype=np.int32)
+    A = np.zeros((2, 8))
+    Zok, Zbad = np.tile(mech.z0, (2, 1)), np.tile(mech.z0, (2, 1))
+    Zbad[1, 2] = 1.5  # environment 1 leaves the healthy range at the second step
+    for Zn in (Zok, Zbad, Zok, Zok):
+        hc.env_post(spec, S, A, Zn, sol, ret, dead)
+    assert list(dead) == [0, 1]
+    assert abs(ret[0] - 4 * 0.05) < 1e-12 and abs(ret[1] - (2 * 0.05 + 100 * (Zbad[1, 0] - x[0]) / mech.timestep)) < 1e-9

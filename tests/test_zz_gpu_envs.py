@@ -93,3 +93,26 @@ def test_env_step_device_pointers_and_reset_on_device():
     env.stepper.env_reset(spec, (dSn.data_ptr(), B), env.initial_state(), mask.data_ptr())
     out = dSn.cpu().numpy()
     assert np.array_equal(out[: B // 2], np.tile(env.initial_state(), (B // 2, 1))) and np.array_equal(out[B // 2:], Sn[B // 2:])
+
+
+def test_env_rollout_equals_stepwise_accumulation():
+    """dojo_env_rollout == T calls of dojo_env_step with the return accumulated on the host until the failure test fires"""
+    rng = np.random.default_rng(73)
+    B, T = 48, 12
+    env = E.get_environment("ant_ars", batch=B)
+    spec = env.spec
+    S0 = _batch_states(env, rng)
+    S0[:4, 2] = 0.25  # close to the lower end of the healthy range: some of these fail during the rollout
+    A = rng.uniform(-1, 1, (T, B, env.na))
+    Sf, ret, failed = env.stepper.env_rollout(spec, S0, A, T)
+    S, acc, dead = S0, np.zeros(B), np.zeros(B, dtype=bool)
+    for k in range(T):
+        S, r, d, _, _ = env.stepper.env_step(spec, S, A[k])
+        acc += np.where(dead, 0.0, r)
+        dead |= d.astype(bool)
+    assert np.array_equal(Sf, S) and np.array_equal(failed.astype(bool), dead)
+    assert np.abs(ret - acc).max() < 1e-9 * max(1.0, np.abs(acc).max())
+    env2 = E.get_environment("ant_ars", batch=B)
+    env2.state = S0.copy()
+    ret2, failed2 = env2.rollout(A)
+    assert np.array_equal(ret2, ret) and np.array_equal(env2.get_state(), Sf)
