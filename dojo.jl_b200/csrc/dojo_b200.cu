@@ -1526,3 +1526,30 @@ extern "C" int dojo_env_rollout(DojoHandle* h, const DojoSolverOptions* opts, co
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Parameter update (system identification): rebuild the plan tables for the same topology and swap them in place
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int dojo_update_params(DojoHandle* h, const DojoMechanismDesc* d) {
+  if (!h || !d) { if (h) h->err = "dojo_update_params: bad arguments"; return DOJO_EINVAL; }
+  DojoHandle* t = nullptr;
+  int rc = dojo_create(d, h->device, 1, &t);  // validates the descriptor and builds the tables exactly like a fresh handle
+  if (rc != DOJO_OK) { h->err = std::string("dojo_update_params: ") + g_create_error; return rc; }
+  const Plan &A = h->plan, &B = t->plan;
+  bool same = A.Nb == B.Nb && A.Ne == B.Ne && A.Ni == B.Ni && A.nres == B.nres && A.nu == B.nu && A.nw == B.nw && A.nphase == B.nphase &&
+              A.arena_len == B.arena_len && A.grad_len == B.grad_len && A.n_red == B.n_red && h->blob_bytes == t->blob_bytes &&
+              h->arena_bytes == t->arena_bytes && (h->grad_bytes == t->grad_bytes);
+  for (int k = 0; k < 8; ++k) same = same && h->blob_off[k] == t->blob_off[k];
+  if (!same) { dojo_destroy(t); h->err = "dojo_update_params: the descriptor has a different topology (use dojo_create)"; return DOJO_EINVAL; }
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();  // kernels on caller streams may still read the tables
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, t->d_blob, (size_t)h->blob_bytes, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_kin_order, t->d_kin_order, sizeof(int) * A.Ne, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) { dojo_destroy(t); h->err = std::string("dojo_update_params: ") + cudaGetErrorString(e); return DOJO_ECUDA; }
+  h->plan.h = B.h; h->plan.input_scaling = B.input_scaling;
+  for (int i = 0; i < 3; ++i) h->plan.g[i] = B.g[i];
+  h->plan.ls_pair = B.ls_pair; h->plan.ls_slot_delta = B.ls_slot_delta; h->plan.ls_res2_off = B.ls_res2_off;
+  dojo_destroy(t);
+  return DOJO_OK;
+}

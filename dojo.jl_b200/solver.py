@@ -24,7 +24,7 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
-           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
+           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_update_params", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
 
 _lib = None
 
@@ -91,6 +91,8 @@ def load_library():
     L.dojo_env_reset.restype = C.c_int
     L.dojo_env_rollout.argtypes = [vp, op, ep, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.dojo_env_rollout.restype = C.c_int
+    L.dojo_update_params.argtypes = [vp, C.POINTER(capi.DojoMechanismDesc)]
+    L.dojo_update_params.restype = C.c_int
     L.dojo_step_record.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.dojo_step_record.restype = C.c_int
     L.dojo_step_record_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -150,6 +152,13 @@ class BatchedStepper:
     def _check(self, rc, what):
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {self.L.dojo_last_error(self.h).decode()}")
+
+    def update_params(self, mech: Mechanism):
+        """Swap in the parameters of `mech` (same topology: bodies, joints, joint types, limits, contacts) without re-creating
+        the handle -- the system-identification loop of examples/system_identification/utilities.jl:41-87."""
+        desc, keep = capi.flatten(mech)
+        self._check(self.L.dojo_update_params(self.h, C.byref(desc)), "dojo_update_params")
+        self.mech = mech
 
     @property
     def shared_bytes_per_env(self) -> int:

@@ -138,6 +138,13 @@ int dojo_create(const DojoMechanismDesc* desc, int device, int max_batch, DojoHa
 int dojo_destroy(DojoHandle* h);
 const char* dojo_last_error(const DojoHandle* h); /* h may be NULL: last create error */
 
+/* Parameter update for system identification (examples/system_identification/utilities.jl:41-87 rebuilds the data of a live
+ * Mechanism between solves): same topology (bodies, joints, joint types, limits, contacts), new numbers (masses, inertias,
+ * vertices, offsets, springs, dampers, limit values, friction coefficients, contact radii / origins, timestep, gravity,
+ * input scaling).  The plan tables are rebuilt and swapped in place; device buffers, streams and max_batch are kept.
+ * Returns DOJO_EINVAL if the topology differs.  Synchronises the handle's stream. */
+int dojo_update_params(DojoHandle* h, const DojoMechanismDesc* desc);
+
 /* sizes derived from the descriptor */
 int dojo_num_state(const DojoHandle* h);    /* 13 Nb */
 int dojo_num_input(const DojoHandle* h);    /* nu */
