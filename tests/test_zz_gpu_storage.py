@@ -31,8 +31,10 @@ def test_step_record_matches_oracle(name):
         if so != 0 or st[e] != 0 or io != it[e]:
             continue
         body, d = o.storage_record()
-        assert np.abs(sto[e] - body).max() < 1e-6 * max(1.0, np.abs(body).max())
-        assert np.abs(diag[e] - d).max() < 1e-6 * max(1.0, np.abs(d).max())
+        # joint impulses of ill-conditioned contact steps agree to ~1e-6 between the two factorisation orders (see
+        # test_gradient_parity); the formulas themselves are checked to 1e-11 on the CPU (tests/test_storage_host.py)
+        assert np.abs(sto[e] - body).max() < 1e-5 * max(1.0, np.abs(body).max())
+        assert np.abs(diag[e] - d).max() < 1e-5 * max(1.0, np.abs(d).max())
         compared += 1
     assert compared >= B // 2
 
