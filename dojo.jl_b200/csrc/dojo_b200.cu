@@ -277,6 +277,7 @@ struct DojoHandle {
   int* d_counter = nullptr;
   int* d_kin_order = nullptr;      // joints root -> leaves (minimal -> maximal map)
   double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
+  double *d_envTheta = nullptr, *d_envNorm = nullptr;  // policy rollout: [na x ns x max_batch], [2 ns]
   double *d_envS = nullptr, *d_envSn = nullptr, *d_envA = nullptr, *d_envR = nullptr, *d_envS0 = nullptr;  // environment-layer staging
   int32_t* d_envDone = nullptr;
   double *d_recZ[2] = {nullptr, nullptr}, *d_recS = nullptr, *d_recD = nullptr;  // dojo_simulate_record staging
@@ -721,7 +722,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
 extern "C" int dojo_destroy(DojoHandle* h) {
   if (!h) return DOJO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_recZ[0]); cudaFree(h->d_recZ[1]); cudaFree(h->d_recS); cudaFree(h->d_recD); cudaFree(h->d_recAny); cudaFree(h->d_envS); cudaFree(h->d_envSn); cudaFree(h->d_envA); cudaFree(h->d_envR); cudaFree(h->d_envS0); cudaFree(h->d_envDone); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
+  cudaFree(h->d_blob); cudaFree(h->d_counter); cudaFree(h->d_kin_order); cudaFree(h->d_kjws); cudaFree(h->d_kjout); cudaFree(h->d_recZ[0]); cudaFree(h->d_recZ[1]); cudaFree(h->d_recS); cudaFree(h->d_recD); cudaFree(h->d_recAny); cudaFree(h->d_envTheta); cudaFree(h->d_envNorm); cudaFree(h->d_envS); cudaFree(h->d_envSn); cudaFree(h->d_envA); cudaFree(h->d_envR); cudaFree(h->d_envS0); cudaFree(h->d_envDone); cudaFree(h->d_X); cudaFree(h->d_Xn); cudaFree(h->d_gsol); cudaFree(h->d_gstatus); cudaFree(h->d_done);
   for (int k = 0; k < 2; ++k) { cudaFree(h->d_Fz[k]); cudaFree(h->d_Fu[k]); if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]); if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaFree(h->d_Z); cudaFree(h->d_U); cudaFree(h->d_F); cudaFree(h->d_Zn); cudaFree(h->d_sol); cudaFree(h->d_status); cudaFree(h->d_iters);
@@ -1551,5 +1552,55 @@ extern "C" int dojo_update_params(DojoHandle* h, const DojoMechanismDesc* d) {
   for (int i = 0; i < 3; ++i) h->plan.g[i] = B.g[i];
   h->plan.ls_pair = B.ls_pair; h->plan.ls_slot_delta = B.ls_slot_delta; h->plan.ls_res2_off = B.ls_res2_off;
   dojo_destroy(t);
+  return DOJO_OK;
+}
+
+extern "C" int dojo_env_policy_rollout(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, int T, const double* S0,
+                                       const double* Theta, const double* mean, const double* stdev, double* S_final, double* ret, int32_t* failed,
+                                       double* S_traj) {
+  if (!h || B <= 0 || B > h->max_batch || T <= 0 || !S0 || !Theta || !S_final || !env_spec_ok(h, spec) || ((mean == nullptr) != (stdev == nullptr))) {
+    if (h) h->err = "dojo_env_policy_rollout: bad arguments";
+    return DOJO_EINVAL;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = ensure_staging(h);
+  if (rc == DOJO_OK) rc = ensure_env_staging(h);
+  if (rc != DOJO_OK) return rc;
+  cudaStream_t s = h->stream;
+  const bool dev = is_device_ptr(S0);
+  const cudaMemcpyKind in = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, out = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t ns = dojo_env_num_state(h, spec), na = dojo_env_num_action(h, spec);
+  if (na == 0) { h->err = "dojo_env_policy_rollout: the environment has no actions"; return DOJO_EINVAL; }
+  if (!h->d_envNorm) CUDA_TRY(h, cudaMalloc((void**)&h->d_envNorm, 2 * (2 * (size_t)h->plan.nu + h->plan.Ni) * sizeof(double)));
+  const double* dTheta = Theta;
+  if (!dev) {
+    if (!h->d_envTheta) CUDA_TRY(h, cudaMalloc((void**)&h->d_envTheta, (size_t)h->max_batch * h->plan.nu * (2 * (size_t)h->plan.nu + h->plan.Ni) * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_envTheta, Theta, (size_t)B * ns * na * sizeof(double), cudaMemcpyHostToDevice, s));
+    dTheta = h->d_envTheta;
+  }
+  if (mean) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_envNorm, mean, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_envNorm + ns, stdev, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  double* buf[2] = {h->d_envS, h->d_envSn};
+  CUDA_TRY(h, cudaMemcpyAsync(buf[0], S0, (size_t)B * ns * sizeof(double), in, s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_envR, 0, (size_t)B * sizeof(double), s));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_envDone, 0, (size_t)B * sizeof(int32_t), s));
+  int cur = 0;
+  for (int k = 0; k < T; ++k, cur ^= 1) {
+    PolicyArgs p;
+    p.ns = (int)ns; p.na = (int)na; p.B = B; p.S = buf[cur]; p.Theta = dTheta;
+    p.mean = mean ? h->d_envNorm : nullptr; p.stdev = mean ? h->d_envNorm + ns : nullptr; p.A = h->d_envA;
+    dojo_env_policy_kernel<<<(B + 127) / 128, 128, 0, s>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    if (S_traj) CUDA_TRY(h, cudaMemcpyAsync(S_traj + (size_t)k * B * ns, buf[cur], (size_t)B * ns * sizeof(double), out, s));
+    rc = env_step_impl(h, opts, spec, B, buf[cur], h->d_envA, buf[cur ^ 1], nullptr, nullptr, h->d_status, nullptr, h->d_envR, h->d_envDone, s);
+    if (rc != DOJO_OK) return rc;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(S_final, buf[cur], (size_t)B * ns * sizeof(double), out, s));
+  if (ret) CUDA_TRY(h, cudaMemcpyAsync(ret, h->d_envR, (size_t)B * sizeof(double), out, s));
+  if (failed) CUDA_TRY(h, cudaMemcpyAsync(failed, h->d_envDone, (size_t)B * sizeof(int32_t), out, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

@@ -84,6 +84,28 @@ DJ_DEV void env_post(const EnvArgs& a, int e) {
   }
 }
 
+// linear policy with observation normalisation (examples/learning/ant_ars.jl:47-50 normalize, :88 action = theta * state):
+//   a = Theta_e ((s - mean) ./ std),  Theta [na x ns x B] column-major per environment (ARS evaluates one perturbed policy per
+//   environment), mean / std [ns] shared (nullable: no normalisation)
+struct PolicyArgs {
+  int ns, na, B;
+  const double* S;
+  const double* Theta;
+  const double* mean;
+  const double* stdev;
+  double* A;
+};
+DJ_DEV void env_policy(const PolicyArgs& p, int e) {
+  const double* s = p.S + (size_t)e * p.ns;
+  const double* th = p.Theta + (size_t)e * p.ns * p.na;
+  double* a = p.A + (size_t)e * p.na;
+  for (int k = 0; k < p.na; ++k) a[k] = 0.0;
+  for (int i = 0; i < p.ns; ++i) {
+    const double o = p.mean ? (s[i] - p.mean[i]) / p.stdev[i] : s[i];
+    for (int k = 0; k < p.na; ++k) a[k] += th[(size_t)i * p.na + k] * o;
+  }
+}
+
 // reset: environments with mask != 0 (or all, mask == nullptr) get the initial state s0 [ns]
 DJ_DEV void env_reset(int ns, const double* s0, const int32_t* mask, double* S, int e) {
   if (mask && mask[e] == 0) return;
@@ -98,6 +120,10 @@ __global__ void dojo_env_pre_kernel(const EnvArgs a) {
 __global__ void dojo_env_post_kernel(const EnvArgs a) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < a.B) env_post(a, e);
+}
+__global__ void dojo_env_policy_kernel(const PolicyArgs p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < p.B) env_policy(p, e);
 }
 __global__ void dojo_env_reset_kernel(int ns, int B, const double* s0, const int32_t* mask, double* S) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

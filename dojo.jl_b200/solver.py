@@ -24,7 +24,7 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
-           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_update_params", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
+           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_env_policy_rollout", "dojo_update_params", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
 
 _lib = None
 
@@ -91,6 +91,8 @@ def load_library():
     L.dojo_env_reset.restype = C.c_int
     L.dojo_env_rollout.argtypes = [vp, op, ep, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.dojo_env_rollout.restype = C.c_int
+    L.dojo_env_policy_rollout.argtypes = [vp, op, ep, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_env_policy_rollout.restype = C.c_int
     L.dojo_update_params.argtypes = [vp, C.POINTER(capi.DojoMechanismDesc)]
     L.dojo_update_params.restype = C.c_int
     L.dojo_step_record.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -376,6 +378,25 @@ class BatchedStepper:
         rc = self.L.dojo_env_rollout(self.h, C.byref(o), C.byref(spec), B, int(T), _p(S0), _p(A), _p(Sf), _p(ret), _p(failed))
         self._check(rc, "dojo_env_rollout")
         return Sf, ret, failed
+
+    def env_policy_rollout(self, spec, S0, Theta, T: int, mean=None, std=None, opts=None, record_states: bool = False):
+        """Closed-loop rollout with one linear policy per environment (ARS evaluation): Theta [B, na, ns], a = Theta_e ((s - mean) / std).
+        Returns (S_final, return [B], failed [B]) and, with record_states, the states observed before every step [T, B, ns]."""
+        ns, na = self.env_sizes(spec)
+        S0 = np.ascontiguousarray(np.atleast_2d(S0), dtype=np.float64)
+        B = S0.shape[0]
+        Theta = np.asarray(Theta, dtype=np.float64)
+        assert Theta.shape == (B, na, ns)
+        ThetaC = np.ascontiguousarray(Theta.transpose(0, 2, 1))  # column-major [na x ns] per environment
+        mean = None if mean is None else np.ascontiguousarray(mean, dtype=np.float64)
+        std = None if std is None else np.ascontiguousarray(std, dtype=np.float64)
+        Sf, ret, failed = np.empty_like(S0), np.empty(B), np.zeros(B, dtype=np.int32)
+        traj = np.empty((T, B, ns)) if record_states else None
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_env_policy_rollout(self.h, C.byref(o), C.byref(spec), B, int(T), _p(S0), _p(ThetaC), _p(mean), _p(std), _p(Sf), _p(ret),
+                                            _p(failed), _p(traj))
+        self._check(rc, "dojo_env_policy_rollout")
+        return (Sf, ret, failed, traj) if record_states else (Sf, ret, failed)
 
     def env_reset(self, spec, S, s0, mask=None):
         """S[e] = s0 where mask[e] != 0 (all if mask is None).  S / mask: numpy arrays (in place) or device pointers + B."""

@@ -257,6 +257,14 @@ int dojo_env_step_async(DojoHandle* h, const DojoSolverOptions* opts, const Dojo
  * failed [B] = 1 if it fired (both nullable).  3 T launches, no host round trip.  Host or device pointers. */
 int dojo_env_rollout(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, int T, const double* S0,
                      const double* A, double* S_final, double* ret, int32_t* failed);
+/* Closed-loop rollout with one linear policy per environment (ARS evaluation, examples/learning/ant_ars.jl:79-116):
+ *   a = Theta_e ((s - mean) ./ std)   Theta [na x ns x B] column-major per environment; mean / std [ns] HOST vectors, frozen for
+ *   the call (nullable: no normalisation; the reference updates its Normalizer inside the rollout -- S_traj [ns x B x T],
+ *   nullable, returns the state observed before every step so that the caller can update the statistics afterwards).
+ * 4 T launches (policy, pre, step, post), nothing leaves the device in between.  Host or device pointers. */
+int dojo_env_policy_rollout(DojoHandle* h, const DojoSolverOptions* opts, const DojoEnvSpec* spec, int B, int T,
+                            const double* S0, const double* Theta, const double* mean, const double* std, double* S_final,
+                            double* ret, int32_t* failed, double* S_traj);
 /* reset (initialize!(environment, model), environments.jl:118-120): S[:, e] = s0 for every e with mask[e] != 0 (mask
  * nullable: all).  s0 [ns] is a HOST vector; S / mask host or device pointers of the same kind. */
 int dojo_env_reset(DojoHandle* h, const DojoEnvSpec* spec, int B, const double* s0, const int32_t* mask, double* S);

@@ -42,6 +42,7 @@ class HostCheck:
         L.hostcheck_minimal_gradients.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         L.hostcheck_env_pre.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]
         L.hostcheck_env_post.argtypes = [C.c_void_p, _ip, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
+        L.hostcheck_env_policy.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.hostcheck_storage.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
         self.L, self.mech = L, mech
         jint = np.zeros((mech.Ne, 4), dtype=np.int32)
@@ -148,3 +149,14 @@ class HostCheck:
         body, diag = np.empty((B, m.Nb, 12)), np.empty((B, 8))
         self.L.hostcheck_storage(self.h, _d(jext), _d(bdbl), m.nres, float(m.input_scaling), _d(g), B, _d(Z), _d(Zn), _d(U), _d(sol), _d(body), _d(diag))
         return body, diag
+
+    def env_policy(self, S, Theta, mean=None, std=None):
+        """Theta [B, na, ns] -> actions [B, na]"""
+        S = np.ascontiguousarray(np.atleast_2d(S), dtype=float)
+        B, ns = S.shape
+        na = Theta.shape[1]
+        Tc = np.ascontiguousarray(np.asarray(Theta, dtype=float).transpose(0, 2, 1))
+        A = np.empty((B, na))
+        self.L.hostcheck_env_policy(ns, na, B, _d(S), _d(Tc), None if mean is None else _d(np.ascontiguousarray(mean, dtype=float)),
+                                    None if std is None else _d(np.ascontiguousarray(std, dtype=float)), _d(A))
+        return A

@@ -161,4 +161,10 @@ void hostcheck_storage(void* p, const double* jext, const double* bdbl, int nres
   a.Z = Z; a.Zn = Zn; a.U = U; a.sol = sol; a.body_out = body_out; a.diag = diag;
   for (int e = 0; e < B; ++e) storage_env(a, e);
 }
+
+void hostcheck_env_policy(int ns, int na, int B, const double* S, const double* Theta, const double* mean, const double* stdev, double* A) {
+  PolicyArgs p;
+  p.ns = ns; p.na = na; p.B = B; p.S = S; p.Theta = Theta; p.mean = mean; p.stdev = stdev; p.A = A;
+  for (int e = 0; e < B; ++e) env_policy(p, e);
+}
 }

@@ -80,3 +80,18 @@ def test_rollout_return_accumulation_stops_after_failure():
         hc.env_post(spec, S, A, Zn, sol, ret, dead)
     assert list(dead) == [0, 1]
     assert abs(ret[0] - 4 * 0.05) < 1e-12 and abs(ret[1] - (2 * 0.05 + 100 * (Zbad[1, 0] - x[0]) / mech.timestep)) < 1e-9
+
+
+def test_linear_policy_device_code_on_host():
+    """a = theta * normalize(state)  (examples/learning/ant_ars.jl:47-50, :88)"""
+    mech = dj.get_mechanism("ant")
+    hc = HostCheck(mech)
+    rng = np.random.default_rng(4)
+    B, ns, na = 5, 37, 8
+    S = rng.normal(size=(B, ns))
+    Theta = rng.normal(size=(B, na, ns))
+    mean, var = rng.normal(size=ns), rng.uniform(0.01, 2.0, ns)
+    A = hc.env_policy(S, Theta, mean, np.sqrt(var))
+    ref = np.einsum("bki,bi->bk", Theta, (S - mean) / np.sqrt(var))
+    assert np.abs(A - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    assert np.abs(hc.env_policy(S, Theta) - np.einsum("bki,bi->bk", Theta, S)).max() < 1e-12 * 50

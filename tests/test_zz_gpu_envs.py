@@ -116,3 +116,30 @@ def test_env_rollout_equals_stepwise_accumulation():
     env2.state = S0.copy()
     ret2, failed2 = env2.rollout(A)
     assert np.array_equal(ret2, ret) and np.array_equal(env2.get_state(), Sf)
+
+
+def test_env_policy_rollout_equals_host_policy_loop():
+    """dojo_env_policy_rollout == a host loop that evaluates a = Theta_e ((s - mean) / std) and calls dojo_env_step"""
+    rng = np.random.default_rng(79)
+    B, T = 32, 10
+    env = E.get_environment("ant_ars", batch=B)
+    spec, ns, na = env.spec, env.ns, env.na
+    S0 = np.tile(env.initial_state(), (B, 1))
+    Theta = 0.2 * rng.normal(size=(B, na, ns))
+    mean, std = 0.1 * rng.normal(size=ns), np.sqrt(rng.uniform(0.01, 1.0, ns))
+    Sf, ret, failed, traj = env.stepper.env_policy_rollout(spec, S0, Theta, T, mean, std, record_states=True)
+    S, acc, dead = S0, np.zeros(B), np.zeros(B, dtype=bool)
+    for k in range(T):
+        assert np.abs(traj[k] - S).max() < 1e-9 * max(1.0, np.abs(S).max())
+        A = np.einsum("bki,bi->bk", Theta, (traj[k] - mean) / std)   # same observations as the device (summation order may differ)
+        S, r, d, _, _ = env.stepper.env_step(spec, traj[k], A)
+        acc += np.where(dead, 0.0, r)
+        dead |= d.astype(bool)
+    # the host evaluates the policy with a different summation order: actions agree to rounding; a rounding-level flip of a
+    # line-search comparison (DESIGN.md section 6) may move single environments to solver tolerance
+    scale = max(1.0, np.abs(S).max())
+    err = np.abs(Sf - S).max(axis=1) / scale
+    assert np.quantile(err, 0.9) < 1e-6 and err.max() < 5e-3, err
+    assert (failed.astype(bool) == dead).mean() >= 0.9
+    rerr = np.abs(ret - acc) / max(1.0, np.abs(acc).max())
+    assert np.quantile(rerr, 0.9) < 1e-6, rerr
