@@ -74,6 +74,16 @@ class Environment:
         return ret, failed
 
 
+    def policy_rollout(self, theta, horizon: int, mean=None, std=None, state=None, opts=None, record_states: bool = False):
+        """rollout_policy(θ, env, normalizer, parameters) of examples/learning/ant_ars.jl:79-116 for B policies at once:
+        theta [B, na, ns] (one perturbed policy per environment), action = theta_e * normalize(state) with the normaliser
+        frozen for the call.  Returns (return [B], failed [B]) (+ the observed states [horizon, B, ns] for observe!)."""
+        S = self.state if state is None else np.atleast_2d(np.asarray(state, dtype=float))
+        out = self.stepper.env_policy_rollout(self.spec, S, theta, horizon, mean, std, opts, record_states)
+        self.state = out[0]
+        return out[1:]
+
+
 class AntARS(Environment):
     """environments/ant_ars.jl: state [minimal state (28); clamped normal contact impulses (9)], 8 actions, the reward of
     examples/learning/ant_ars.jl:98-107 and its failure test :112."""
