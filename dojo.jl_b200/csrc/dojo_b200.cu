@@ -23,6 +23,7 @@ using namespace dj;
 // ------------------------------------------------------------------------------------------------------------
 // Kernels
 // ------------------------------------------------------------------------------------------------------------
+// [hostemu:kernel:begin]
 struct StepArgs {
   Plan plan;
   Options opts;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
 #endif
 }
 
+// [hostemu:kernel:end]
 
 // Longest-processing-time-first order.  The cost of an environment's step is proportional to its Newton-iteration count
 // (7 .. max_iter, and line-search retries grow with it), which is correlated from one time step to the next; environments
@@ -256,6 +258,7 @@ __global__ void dojo_order_kernel(const int32_t* __restrict__ prev_iters, int B,
 // ------------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------------
+// [hostemu:handle:begin]
 struct DojoHandle {
   int device = 0;
   int max_batch = 0;
@@ -302,6 +305,7 @@ struct DojoHandle {
   int64_t launches = 0;
   std::string err;
 };
+// [hostemu:handle:end]
 
 static std::string g_create_error;
 
@@ -319,6 +323,7 @@ extern "C" void dojo_default_options(DojoSolverOptions* o) {
   o->undercut = INFINITY; o->no_progress_max = 3; o->no_progress_undercut = 10.0; o->verbose = 0;
 }
 
+// [hostemu:padmask:begin]
 static void pad_mask(const DojoJointElementDesc& e, double* C, double* A) {
   // joints/joint.jl:56-64 (constraint_mask / nullspace_mask), zero-padded to 3 rows
   std::memset(C, 0, 9 * sizeof(double));
@@ -333,6 +338,8 @@ static void pad_mask(const DojoJointElementDesc& e, double* C, double* A) {
   }
 }
 
+// [hostemu:padmask:end]
+
 extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch, DojoHandle** out) {
   g_create_error.clear();
   if (!d || !out || max_batch <= 0) { g_create_error = "dojo_create: bad arguments"; return DOJO_EINVAL; }
@@ -341,6 +348,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     g_create_error = "dojo_create: no usable CUDA device (this library has no CPU fallback)";
     return DOJO_ENODEVICE;
   }
+  // [hostemu:tables:begin]
   const int Nb = d->num_bodies, Ne = d->num_joints, Ni = d->num_contacts;
   auto fail = [&](const char* msg) { g_create_error = std::string("dojo_create: ") + msg; return DOJO_EINVAL; };
   if (Nb < 1 || Nb > 32 || Ne > 32 || Ni > 32) return fail("this build supports up to 32 bodies / 32 joints / 32 contacts per mechanism");
@@ -638,6 +646,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     }
   }
   P.nphase = nphase;
+  // [hostemu:tables:end]
 
   // ---- device resources
   cudaDeviceProp prop;
@@ -653,6 +662,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
   };
+  // [hostemu:blob:begin]
   std::vector<char> blob;
   {
     const void* src[8] = {bodies.data(), joints.data(), contacts.data(), steps.data(), sched.data(), ilist.data(), roles.data(), ucol.data()};
@@ -665,6 +675,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     }
     h->blob_bytes = (int)blob.size();
   }
+  // [hostemu:blob:end]
   bool ok = upload(blob.data(), blob.size(), (void**)&h->d_blob);
   {  // joints root -> leaves: a joint is placed once its parent body has been placed (mechanism.root_to_leaves restricted to joints)
     std::vector<int> order;
@@ -753,6 +764,7 @@ extern "C" int dojo_debug_env_times(DojoHandle* h, unsigned long long* out, int 
   return DOJO_OK;
 }
 
+// [hostemu:options:begin]
 static Options make_options(const DojoSolverOptions* o) {
   DojoSolverOptions d;
   if (!o) { dojo_default_options(&d); o = &d; }
@@ -761,6 +773,7 @@ static Options make_options(const DojoSolverOptions* o) {
   r.max_iter = o->max_iter; r.max_ls = o->max_ls; r.no_progress_max = o->no_progress_max;
   return r;
 }
+// [hostemu:options:end]
 
 static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn, double* dsol,
                           double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s, int* done_count = nullptr, int* done_list = nullptr) {

@@ -70,7 +70,11 @@ struct Ctx {
 
 // Barrier over the nw warps that own this environment.  A CTA hosts several environments ("slots"), each with its own
 // arena and its own named barrier, so that the slots only meet at the CTA-wide alignment point of the Newton loop.
+#ifdef DJ_HOSTEMU  // tests/hostemu runs this code on CPU fibers; the named barrier is provided by its shim
+DJ_DEV void slot_sync(const Ctx& c) { hostemu_bar_sync(c.bar, c.nthreads); }
+#else
 DJ_DEV void slot_sync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "r"(c.nthreads) : "memory"); }
+#endif
 
 // CTA-wide alignment barrier (barrier 0); returns whether any slot of the CTA still has work.  Slots that ran out of
 // environments keep arriving here (with live = false) until every slot is done.

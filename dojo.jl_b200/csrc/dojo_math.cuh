@@ -199,7 +199,7 @@ DJ_DEV M34 drotation_vector_dq(Quat q) {
   return r;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(DJ_HOSTEMU)
 // warp reductions
 DJ_DEV double warp_max(double v) {
 #pragma unroll

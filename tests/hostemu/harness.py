@@ -1,0 +1,74 @@
+"""ctypes wrapper of the host emulation of the step / gradient kernels -- TEST INFRASTRUCTURE (see cuda_shim.h, gen.py)."""
+import ctypes as C
+
+import numpy as np
+
+from dojo_jl_b200 import capi
+from . import gen
+
+_vp, _ip = C.c_void_p, C.c_int
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class HostEmu:
+    """The product's dojo_step_kernel<false/true> run on CPU fibers for one mechanism."""
+
+    def __init__(self, mech):
+        L = C.CDLL(gen.build())
+        L.hostemu_create.restype = _vp
+        L.hostemu_create.argtypes = [C.POINTER(capi.DojoMechanismDesc)]
+        L.hostemu_destroy.argtypes = [_vp]
+        L.hostemu_last_error.restype = C.c_char_p
+        for n in ("hostemu_num_residual", "hostemu_num_input", "hostemu_warps_per_env"):
+            getattr(L, n).argtypes = [_vp]
+        L.hostemu_arena_bytes.argtypes = [_vp, _ip]
+        L.hostemu_arena_bytes.restype = C.c_long
+        op = C.POINTER(capi.DojoSolverOptions)
+        L.hostemu_step.argtypes = [_vp, op, _ip, _ip, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _ip, _ip, _ip, _vp]
+        L.hostemu_step_grad.argtypes = [_vp, op, _ip, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _ip, _ip, _ip]
+        self.L, self.mech = L, mech
+        desc, self._keep = capi.flatten(mech)
+        h = L.hostemu_create(C.byref(desc))
+        if not h:
+            raise RuntimeError("hostemu_create failed: " + L.hostemu_last_error().decode())
+        self.h = C.c_void_p(h)
+        assert L.hostemu_num_residual(self.h) == mech.nres and L.hostemu_num_input(self.h) == mech.nu
+
+    def __del__(self):
+        try:
+            self.L.hostemu_destroy(self.h)
+        except Exception:
+            pass
+
+    def step(self, Z, U=None, opts=None, T=1, fext=None, flags=0, slots=1, smem_plan=True, grid=1, record=False):
+        """dojo_step (T = 1) / dojo_rollout (T > 1, U [T, B, nu]).  Returns (Z_next, status, iters, sol[, traj])."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        if U is not None:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+        Zn = np.empty_like(Z)
+        sol = np.empty((B, self.mech.nres))
+        st, it = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        traj = np.empty((T, B, Z.shape[1])) if record else None
+        o = opts if opts is not None else capi.solver_options()
+        self.L.hostemu_step(self.h, C.byref(o), B, T, _p(Z), _p(U), _p(fext), _p(Zn), _p(sol), _p(st), _p(it), flags, slots, int(smem_plan), grid, _p(traj))
+        return (Zn, st, it, sol, traj) if record else (Zn, st, it, sol)
+
+    def step_grad(self, Z, U=None, opts=None, slots=1, slots_grad=1, smem_plan=True, publish_order=True):
+        """dojo_step_grad.  Returns (Z_next, Fz [B, 12Nb, 12Nb], Fu [B, 12Nb, nu], status, iters)."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        U = np.zeros((B, self.mech.nu)) if U is None else np.ascontiguousarray(U, dtype=np.float64)
+        ng = 12 * self.mech.Nb
+        Zn = np.empty_like(Z)
+        Fz, Fu = np.empty((B, ng, ng)), np.empty((B, self.mech.nu, ng))
+        st, it = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.hostemu_step_grad(self.h, C.byref(o), B, _p(Z), _p(U), _p(Zn), _p(Fz), _p(Fu), _p(st), _p(it), slots, slots_grad, int(smem_plan),
+                                      int(publish_order))
+        if rc != 0:
+            raise RuntimeError("the gradient workspace does not fit for this mechanism")
+        return Zn, Fz.transpose(0, 2, 1), Fu.transpose(0, 2, 1), st, it
