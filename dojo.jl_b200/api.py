@@ -9,6 +9,7 @@ Python has no `!`, so `step!` is `step`):
                                           simulation/simulate.jl:16
     get_maximal_gradients!(mechanism, z, u; opts)                   get_maximal_gradients(mechanism, z, u, opts=None)
                                           gradients/state.jl:69
+    get_contact_gradients(mechanism)      gradients/contact.jl:1    get_contact_gradients(mechanism, z, u, opts=None)
     mehrotra!(mechanism; opts) -> :success / :failed                status codes returned next to the states (STATUS)
     minimal_to_maximal(mechanism, x)      mechanism/state.jl:9      minimal_to_maximal(mechanism, x)
     maximal_to_minimal(mechanism, z)      mechanism/state.jl:44     maximal_to_minimal(mechanism, z)
@@ -111,6 +112,21 @@ def get_maximal_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0
         _check_single(status)
         return Fz[0], Fu[0]
     return Fz, Fu
+
+
+def get_contact_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0):
+    """get_contact_gradients!(mechanism, z, u; opts) (gradients/contact.jl:1-55, the step is taken first as in
+    get_maximal_gradients!) -> (jacobian_state [12Nb x 12Nb], jacobian_contact [12Nb x 5Ni]); per contact the data are
+    [friction_coefficient, contact_radius, contact_origin(3)].  Batched inputs give [B, ...]."""
+    z = np.asarray(z, dtype=float)
+    single = z.ndim == 1
+    Z = np.atleast_2d(z)
+    U = np.atleast_2d(np.asarray(u, dtype=float))
+    _, Fz, _, Fc, status, _ = _stepper(mechanism, Z.shape[0], device).step_grad_contact(Z, U, opts)
+    if single:
+        _check_single(status)
+        return Fz[0], Fc[0]
+    return Fz, Fc
 
 
 def minimal_to_maximal(mechanism: Mechanism, x, device: int = 0):

@@ -40,6 +40,7 @@ struct StepArgs {
   double* sol_raw;  // nullable [nres x B]: final solution in DEVICE ordering (written by the forward kernel, read by the gradient kernel)
   double* Fz;  // gradients (GRAD kernels): [12Nb x 12Nb x B], [12Nb x nu x B], column-major per environment
   double* Fu;
+  double* Fc;  // nullable: contact-data gradients [12Nb x 5Ni x B] (get_contact_gradients)
   uint32_t flags;
   int* counter;  // dynamic work queue over environments
   const int* order;     // processing order (longest-expected first), or nullptr
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
       status = a.status ? a.status[e] : 0;
       const size_t ng = 12 * (size_t)P.Nb;
-      if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu) && status == 0) status = 3;
+      if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu, a.Fc ? a.Fc + (size_t)e * ng * 5 * P.Ni : nullptr) && status == 0) status = 3;
     }
     if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
       double* so = a.sol + (size_t)e * P.nres;
@@ -780,7 +781,7 @@ static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.sol_raw = dsol_raw; a.status = dstatus; a.iters = diters; a.flags = flags;
-  a.Fz = nullptr; a.Fu = nullptr; a.T = 1; a.traj = nullptr; a.done_count = done_count; a.done_list = done_list;
+  a.Fz = nullptr; a.Fu = nullptr; a.Fc = nullptr; a.T = 1; a.traj = nullptr; a.done_count = done_count; a.done_list = done_list;
   a.counter = h->d_counter;
   // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
   // simulation loops do; a stale order is harmless -- it is just an order)
@@ -894,7 +895,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.sol_raw = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
-  a.Fz = nullptr; a.Fu = nullptr; a.T = T; a.traj = dtraj; a.done_count = nullptr; a.done_list = nullptr;
+  a.Fz = nullptr; a.Fu = nullptr; a.Fc = nullptr; a.T = T; a.traj = dtraj; a.done_count = nullptr; a.done_list = nullptr;
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
@@ -952,8 +953,21 @@ extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B,
 // the final solution of every environment in a device buffer, then the gradient kernel (prologue + assembly at that
 // solution + IFT solves) in the larger-arena configuration.  Running the Newton loop inside the gradient configuration
 // (two slots per CTA) made it twice as slow.  dZn must not alias dZ (the gradient kernel re-reads the input state).
+static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn,
+                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
 extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
                                     double* dZn, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+  return step_grad_impl(h, opts, B, dZ, dU, dFext, dZn, dFz, dFu, nullptr, dstatus, diters, flags, cuda_stream);
+}
+// + contact-data gradients (get_contact_gradients, gradients/contact.jl:1-55): dFc [12Nb x 5Ni x B], solved as extra columns
+extern "C" int dojo_step_grad_contact_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
+                                            double* dZn, double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags,
+                                            void* cuda_stream) {
+  if (h && !dFc) { h->err = "dojo_step_grad_contact_async: Fc is required"; return DOJO_EINVAL; }
+  return step_grad_impl(h, opts, B, dZ, dU, dFext, dZn, dFz, dFu, dFc, dstatus, diters, flags, cuda_stream);
+}
+static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn,
+                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
   if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dFz || !dFu || dZ == dZn) { if (h) h->err = "dojo_step_grad_async: bad arguments (B <= max_batch, dZn != dZ)"; return DOJO_EINVAL; }
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -980,7 +994,7 @@ extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.sol_raw = h->d_gsol; a.status = st; a.iters = nullptr; a.flags = flags;
-  a.Fz = dFz; a.Fu = dFu; a.T = 1; a.traj = nullptr; a.done_count = nullptr; a.done_list = done_list;
+  a.Fz = dFz; a.Fu = dFu; a.Fc = dFc; a.T = 1; a.traj = nullptr; a.done_count = nullptr; a.done_list = done_list;
   a.counter = overlap ? h->d_done + 1 : h->d_counter; a.order = nullptr; a.prev_iters = nullptr;
   a.prof = h->d_prof;
   if (!overlap) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
@@ -1614,6 +1628,50 @@ extern "C" int dojo_env_policy_rollout(DojoHandle* h, const DojoSolverOptions* o
   CUDA_TRY(h, cudaMemcpyAsync(S_final, buf[cur], (size_t)B * ns * sizeof(double), out, s));
   if (ret) CUDA_TRY(h, cudaMemcpyAsync(ret, h->d_envR, (size_t)B * sizeof(double), out, s));
   if (failed) CUDA_TRY(h, cudaMemcpyAsync(failed, h->d_envDone, (size_t)B * sizeof(int32_t), out, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// get_contact_gradients (gradients/contact.jl:1-55): host- or device-pointer entry
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int dojo_num_contact_data(const DojoHandle* h) { return 5 * h->plan.Ni; }
+
+extern "C" int dojo_step_grad_contact(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Zn, double* Fz,
+                                      double* Fu, double* Fc, int32_t* status, int32_t* iters) {
+  if (!h || B <= 0 || B > h->max_batch || !Z || !Zn || !Fz || !Fu || !Fc) { if (h) h->err = "dojo_step_grad_contact: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Plan& P = h->plan;
+  cudaStream_t s = h->stream;
+  if (is_device_ptr(Z)) {
+    int rc = dojo_step_grad_contact_async(h, opts, B, Z, U, nullptr, Zn, Fz, Fu, Fc, status, iters, 0, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return DOJO_OK;
+  }
+  int rc = ensure_staging(h);
+  if (rc != DOJO_OK) return rc;
+  const size_t ng = 12 * (size_t)P.Nb, fz = ng * ng, fu = ng * P.nu, fc = ng * 5 * P.Ni;
+  // chunks of environments whose three Jacobians fit 192 MB of device staging
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(B, (size_t(192) << 20) / ((fz + fu + fc) * sizeof(double))));
+  rc = ensure_kjout(h, (size_t)chunk * (fz + fu + fc));
+  if (rc != DOJO_OK) return rc;
+  double *dFz = h->d_kjout, *dFu = dFz + (size_t)chunk * fz, *dFc = dFu + (size_t)chunk * fu;
+  const bool hasU = U && P.nu > 0;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z, (size_t)B * P.nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (hasU) CUDA_TRY(h, cudaMemcpyAsync(h->d_U, U, (size_t)B * P.nu * sizeof(double), cudaMemcpyHostToDevice, s));
+  for (int e0 = 0; e0 < B; e0 += chunk) {
+    const int nb = std::min(chunk, B - e0);
+    rc = dojo_step_grad_contact_async(h, opts, nb, h->d_Z + (size_t)e0 * P.nz, hasU ? h->d_U + (size_t)e0 * P.nu : nullptr, nullptr,
+                                      h->d_Zn + (size_t)e0 * P.nz, dFz, dFu, dFc, h->d_status + e0, h->d_iters + e0, 0, s);
+    if (rc != DOJO_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(Fz + (size_t)e0 * fz, dFz, (size_t)nb * fz * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (fu) CUDA_TRY(h, cudaMemcpyAsync(Fu + (size_t)e0 * fu, dFu, (size_t)nb * fu * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (fc) CUDA_TRY(h, cudaMemcpyAsync(Fc + (size_t)e0 * fc, dFc, (size_t)nb * fc * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(Zn, h->d_Zn, (size_t)B * P.nz * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return DOJO_OK;
 }

@@ -115,6 +115,52 @@ DJ_DEV void grad_contact(Ctx& c, int idx) {
     }
 }
 
+// Contact-data columns (get_contact_gradients, gradients/contact.jl:1-55; data blocks gradients/data.jl:152-192):
+// theta_c = [friction_coefficient; contact_radius; contact_origin(3)].  Column p of contact idx touches only the rows of the
+// contact's body after condensation:  v = Q + G W Z,  Z = the four constraint rows [d - s1; mu g1 - g2; vt - s34] of the
+// data block, Q = its torque rows.  Computed by the lane that owns the column (no storage).
+DJ_DEV void grad_contact_param_rhs(Ctx& c, int idx, int p, double* v) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const ContactDev& cd = c.contacts[idx];
+  const double* so = A + P.sol_off + cd.sol_off;
+  Kin k = body_kin(c, cd.body, 0.0);
+  V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3);
+  V3 ww = k.R3 * k.w;
+  const double* g = so + 4;
+  V3 Fb = tmul(k.R3, g[0] * n + g[2] * t0 + g[3] * t1);  // contact force in the body frame
+  double Z[4] = {0.0, 0.0, 0.0, 0.0};
+  V3 Q = v3zero();
+  if (p == 0) {
+    Z[1] = -g[0];
+  } else if (p == 1) {
+    V3 wn = cross(ww, n);
+    Z[0] = dot(n, n); Z[2] = dot(t0, wn); Z[3] = dot(t1, wn);
+    Q = cross(Fb, tmul(k.R3, n));
+  } else {
+    const int kk = p - 2;
+    V3 ek = v3(kk == 0 ? 1.0 : 0.0, kk == 1 ? 1.0 : 0.0, kk == 2 ? 1.0 : 0.0);
+    V3 rk = k.R3 * ek;            // d(contact point) / d(origin_k)
+    V3 wr = cross(ww, rk);
+    Z[0] = -dot(n, rk); Z[2] = -dot(t0, wr); Z[3] = -dot(t1, wr);
+    Q = -1.0 * cross(Fb, ek);
+  }
+  ContactBlock cb = contact_block(so, g, cd.mu);
+  double WZ[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8];
+    t[4 + kx] = 1.0;
+    contact_solve(cb, t, y);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) WZ[r] += y[4 + r] * Z[kx];
+  }
+  const double* G = A + cd.G_off;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) v[r] = G[r * 4 + 0] * WZ[0] + G[r * 4 + 2] * WZ[2] + G[r * 4 + 3] * WZ[3];
+  v[3] += Q.x; v[4] += Q.y; v[5] += Q.z;
+}
+
 // record layout of a joint (doubles): RJp[ne*6] RJc[ne*6] BPp[36] BPc[36] BCp[36] BCc[36] Up[6*nu] Uc[6*nu]
 DJ_DEV void grad_joint(Ctx& c, int idx) {
   const Plan& P = *c.P;
@@ -344,6 +390,13 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int ch, int col, int lane) {
       }
       for (int q = 0; q < bd.ct_cnt; ++q) add_col6(V, ch, lane, bd.r_off, A + c.contacts[c.ilist[bd.ct_off + q]].gc_off, 6, cc);
     }
+  } else if (col >= P.ncol) {  // contact-data column
+    const int ci = (col - P.ncol) / 5, p = (col - P.ncol) - 5 * ci;
+    double v[6];
+    grad_contact_param_rhs(c, ci, p, v);
+    const BodyDev& bd = c.bodies[c.contacts[ci].body];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) V[(bd.r_off + r) * ch + lane] = v[r];
   } else {  // input column
     const int ui = col - 12 * P.Nb;
     const JointDev& jd = c.joints[c.ucol[2 * ui]];
@@ -359,11 +412,11 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int ch, int col, int lane) {
 // (column vectors V [n_red][ch], per-joint forward scratch at +gvo) and runs ALL elimination steps for it, so the sweeps
 // need no barrier between the warps; the warp is split in 32 / ch lane groups that take different (independent) steps of
 // a phase for the same columns.
-DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0) {
+DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0, int ncol) {
   const Plan& P = *c.P;
   double* A = c.A;
   const int groups = 32 / ch, grp = c.lane / ch, lane = c.lane - grp * ch;  // `lane` = column of the chunk
-  const bool active = c0 + lane < P.ncol;
+  const bool active = c0 + lane < ncol;
   for (int ph = 0; ph < P.nphase; ++ph) {
     const int s0 = c.sched[2 * (ph * P.nw)], s1 = c.sched[2 * (ph * P.nw + P.nw - 1)] + c.sched[2 * (ph * P.nw + P.nw - 1) + 1];
     for (int s = s0 + grp; s < s1; s += groups) {
@@ -441,11 +494,12 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0) {
 
 // chain rule to (x3, v25, phi3, w25) and write the column (gradients/state.jl:104-123)
 // (bodies b0, b0 + bstride, ... of the column: the threads of the slot share a column's bodies)
-DJ_DEV void grad_write_column(Ctx& c, const double* V, int ch, int col, int lane, int b0, int bstride, double* __restrict__ Fz, double* __restrict__ Fu) {
+DJ_DEV void grad_write_column(Ctx& c, const double* V, int ch, int col, int lane, int b0, int bstride, double* __restrict__ Fz, double* __restrict__ Fu,
+                              double* __restrict__ Fc) {
   const Plan& P = *c.P;
   const double* A = c.A;
   const int ng = 12 * P.Nb;
-  double* out = col < ng ? Fz + (size_t)col * ng : Fu + (size_t)(col - ng) * ng;
+  double* out = col < ng ? Fz + (size_t)col * ng : (col < P.ncol ? Fu + (size_t)(col - ng) * ng : Fc + (size_t)(col - P.ncol) * ng);
   for (int b = b0; b < P.Nb; b += bstride) {
     const BodyDev& bd = c.bodies[b];
     const double* rec = A + bd.gb_off;
@@ -470,7 +524,8 @@ DJ_DEV void grad_write_column(Ctx& c, const double* V, int ch, int col, int lane
 }
 
 // the whole gradient pass for one environment; the KKT blocks of the final iterate must be assembled (unfactorised)
-DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) {
+// Fc (nullable): [12 Nb x 5 Ni] contact-data gradients, solved as extra columns against the same factor
+DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu, double* __restrict__ Fc) {
   const Plan& P = *c.P;
   double* A = c.A;
   const WarpRole& role = c.roles[c.warp];
@@ -492,11 +547,12 @@ DJ_DEV bool gradients(Ctx& c, double* __restrict__ Fz, double* __restrict__ Fu) 
   double* V = A + P.gvec_off + c.warp * P.n_red * chw;
   const int gvo = c.warp * 6 * chw;
   const int parts = 32 / chw, part = c.lane / chw, l = c.lane - part * chw;
-  for (int c0 = c.warp * chw; c0 < P.ncol; c0 += P.ch) {
-    if (part == 0 && c0 + l < P.ncol) grad_build_rhs(c, V, chw, c0 + l, l);
+  const int ncol = P.ncol + (Fc ? 5 * P.Ni : 0);
+  for (int c0 = c.warp * chw; c0 < ncol; c0 += P.ch) {
+    if (part == 0 && c0 + l < ncol) grad_build_rhs(c, V, chw, c0 + l, l);
     __syncwarp();
-    grad_solve_columns(c, V, chw, gvo, c0);
-    if (c0 + l < P.ncol) grad_write_column(c, V, chw, c0 + l, l, part, parts, Fz, Fu);
+    grad_solve_columns(c, V, chw, gvo, c0, ncol);
+    if (c0 + l < ncol) grad_write_column(c, V, chw, c0 + l, l, part, parts, Fz, Fu, Fc);
     __syncwarp();
   }
   slot_sync(c);

@@ -24,7 +24,8 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
-           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_env_policy_rollout", "dojo_update_params", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
+           "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_env_policy_rollout", "dojo_update_params", "dojo_num_contact_data", "dojo_step_grad_contact",
+           "dojo_step_grad_contact_async", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
 
 _lib = None
 
@@ -93,6 +94,12 @@ def load_library():
     L.dojo_env_rollout.restype = C.c_int
     L.dojo_env_policy_rollout.argtypes = [vp, op, ep, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.dojo_env_policy_rollout.restype = C.c_int
+    L.dojo_num_contact_data.argtypes = [vp]
+    L.dojo_num_contact_data.restype = C.c_int
+    L.dojo_step_grad_contact.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dojo_step_grad_contact.restype = C.c_int
+    L.dojo_step_grad_contact_async.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.dojo_step_grad_contact_async.restype = C.c_int
     L.dojo_update_params.argtypes = [vp, C.POINTER(capi.DojoMechanismDesc)]
     L.dojo_update_params.restype = C.c_int
     L.dojo_step_record.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -218,6 +225,21 @@ class BatchedStepper:
         rc = self.L.dojo_step_grad(self.h, C.byref(o), B, _p(Z), _p(U), None, _p(Zn), _p(Fz), _p(Fu), _p(status), _p(iters), flags)
         self._check(rc, "dojo_step_grad")
         return Zn, np.transpose(Fz, (0, 2, 1)), np.transpose(Fu, (0, 2, 1)), status, iters
+
+    def step_grad_contact(self, Z, U=None, opts=None):
+        """step! + get_contact_gradients (gradients/contact.jl:1-55).  Returns (Z_next, Fz [B, 12Nb, 12Nb], Fu [B, 12Nb, nu],
+        Fc [B, 12Nb, 5Ni] = dz'/d[friction_coefficient, contact_radius, contact_origin(3)] per contact, status, iters)."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B = Z.shape[0]
+        U = np.zeros((B, self.nu)) if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
+        ng, nc = self.ngrad, self.L.dojo_num_contact_data(self.h)
+        Zn = np.empty_like(Z)
+        Fz, Fu, Fc = np.empty((B, ng, ng)), np.empty((B, self.nu, ng)), np.empty((B, nc, ng))
+        status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_grad_contact(self.h, C.byref(o), B, _p(Z), _p(U), _p(Zn), _p(Fz), _p(Fu), _p(Fc), _p(status), _p(iters))
+        self._check(rc, "dojo_step_grad_contact")
+        return Zn, np.transpose(Fz, (0, 2, 1)), np.transpose(Fu, (0, 2, 1)), np.transpose(Fc, (0, 2, 1)), status, iters
 
     def rollout(self, Z0, U=None, T: int = 1, opts=None, record: bool = False):
         Z0 = np.ascontiguousarray(np.atleast_2d(Z0), dtype=np.float64)

@@ -176,6 +176,19 @@ int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, co
                          double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags,
                          void* cuda_stream);
 
+/* get_contact_gradients(mechanism) (src/gradients/contact.jl:1-55; data blocks src/gradients/data.jl:152-192): step! and the
+ * gradients with respect to the contact data theta_c = [friction_coefficient; contact_radius; contact_origin(3)] of every
+ * contact, next to the state / control gradients (the reference returns jacobian_state with jacobian_contact):
+ *   Fc [12Nb x 5Ni x B] column-major per environment, columns ordered by contact.
+ * The extra 5 Ni columns are solved against the same block-LDU factor in the gradient kernel.  Used with dojo_update_params for
+ * system identification (examples/system_identification/utilities.jl:41-87). */
+int dojo_num_contact_data(const DojoHandle* h); /* 5 Ni */
+int dojo_step_grad_contact(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Z_next,
+                           double* Fz, double* Fu, double* Fc, int32_t* status, int32_t* iters);
+int dojo_step_grad_contact_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU,
+                                 const double* dFext, double* dZ_next, double* dFz, double* dFu, double* dFc,
+                                 int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
+
 /* simulate!: T steps with the state resident on the device.  U is [nu x B x T] (step-major) or
  * NULL (zero input); Z_traj nullable [13Nb x B x T] receives the state after every step
  * (Storage, src/simulation/storage.jl:15-42); Z_final [13Nb x B]; status_any [B] = max status.

@@ -1890,6 +1890,76 @@ struct Oracle {
     return true;
   }
 
+  // Contact data theta_c = [friction_coefficient; contact_radius; contact_origin(3)] (data_dim = 5, contacts/nonlinear.jl):
+  // body rows   body_constraint_jacobian_contact_data     gradients/data.jl:152-171
+  // contact rows contact_constraint_jacobian_contact_data gradients/data.jl:173-192
+  // D is nres x 5 Ni, row-major.
+  void contact_data_jacobian(std::vector<double>& D) const {
+    const int m = 5 * Ni;
+    D.assign((size_t)nres * m, 0.0);
+    for (int ci = 0; ci < Ni; ++ci) {
+      const ContactS& c = contacts[ci];
+      Cfg p = cfg_next(c.body);  // (x3, v25, q3, w25)
+      Mat<4, 1> gam;
+      for (int i = 0; i < 4; ++i) gam[i] = c.gam[1][i];
+      Mat<3, 4> X = force_mapping(c);
+      V3 Fb = (VRmat(p.q) * LtVtmat(p.q)) * (X * gam);
+      M33 dp = -dskew_dp(Fb);                                            // ∇p
+      V3 drad = (-dskew_dp(Fb)) * (-(rotation_matrix(inv(p.q)) * tr(c.nrm)));  // ∇contact_radius
+      const int ob = body_off[c.body], col0 = 5 * ci;
+      for (int r = 0; r < 3; ++r) {  // ∇Q = -[∇friction_coefficient ∇contact_radius ∇p], ∇X = 0
+        D[(size_t)(ob + 3 + r) * m + col0 + 1] = -drad[r];
+        for (int k = 0; k < 3; ++k) D[(size_t)(ob + 3 + r) * m + col0 + 2 + k] = -dp(r, k);
+      }
+      V3 ww = vector_rotate(p.w, p.q);
+      Mat<4, 3> A43;                       // [-cn; 0; -ct skew(ww)]
+      Mat<2, 3> cts = c.t * skew(ww);
+      for (int k = 0; k < 3; ++k) { A43(0, k) = -c.nrm[k]; A43(2, k) = -cts(0, k); A43(3, k) = -cts(1, k); }
+      Mat<4, 1> g_rad = A43 * tr(c.nrm);
+      Mat<4, 3> g_p = (-1.0) * (A43 * rotation_matrix(p.q));   // [cn R; 0; ct skew(ww) R]
+      const int oc = c.sol_off + 4;     // rows of g; the complementarity rows get ∇compμ = 0
+      D[(size_t)(oc + 1) * m + col0 + 0] = -gam[0];            // -∇friction_coefficient = -[0, γ1, 0, 0]
+      for (int r = 0; r < 4; ++r) {
+        D[(size_t)(oc + r) * m + col0 + 1] = -g_rad[r];
+        for (int k = 0; k < 3; ++k) D[(size_t)(oc + r) * m + col0 + 2 + k] = -g_p(r, k);
+      }
+    }
+  }
+
+  // get_contact_gradients, gradients/contact.jl:1-55 (the jacobian_contact part), consistent variant like maximal_gradients.
+  // Fc is 12Nb x 5Ni, COLUMN-major.
+  bool contact_gradients(double* Fc, bool use_factor) {
+    const int m = 5 * Ni, ns = 12 * Nb;
+    std::vector<double> D;
+    contact_data_jacobian(D);
+    bool ok = true;
+    if (m > 0) {
+      if (use_factor) ok = factorize() && solve(D.data(), m);
+      else ok = dense_solve(A, nres, D.data(), m);
+    }
+    if (!ok) return false;
+    std::fill(Fc, Fc + (size_t)ns * m, 0.0);
+    for (int b = 0; b < Nb; ++b) {
+      const BodyS& s = bodies[b];
+      int ob = body_off[b];
+      Quat q3 = next_orientation(s.q2, s.wsol[1], h);
+      M33 Mq = tr(LVtmat(q3)) * rotational_integrator_jacobian_velocity(s.q2, s.wsol[1], h);
+      for (int c = 0; c < m; ++c) {
+        double* o = Fc + (size_t)c * ns + 12 * b;
+        for (int r = 0; r < 3; ++r) {
+          double dv = D[(size_t)(ob + r) * m + c], dw = D[(size_t)(ob + 3 + r) * m + c];
+          o[3 + r] += dv; o[9 + r] += dw; o[r] += h * dv;
+        }
+        for (int r = 0; r < 3; ++r) {
+          double acc = 0;
+          for (int t = 0; t < 3; ++t) acc += Mq(r, t) * D[(size_t)(ob + 3 + t) * m + c];
+          o[6 + r] += acc;
+        }
+      }
+    }
+    return true;
+  }
+
   // ---------------------------------------------------------------- diagnostics (mechanics/momentum.jl:17-86)
   // Momentum of the mechanism evaluated right after mehrotra! (before update_state!), exactly what
   // save_to_storage! records (simulation/storage.jl:50-67).  out6 = [p_linear; p_angular] in the world frame.
@@ -2042,6 +2112,12 @@ int oracle_step_grad(void* h, const DojoSolverOptions* opts, const double* z, co
   if (!o->maximal_gradients(Fz, Fu, use_factor != 0)) return DOJO_STATUS_NONFINITE;
   return st;
 }
+void oracle_contact_data_jacobian(void* h, double* out) {  // nres x 5Ni row-major
+  std::vector<double> D;
+  static_cast<Oracle*>(h)->contact_data_jacobian(D);
+  std::memcpy(out, D.data(), D.size() * sizeof(double));
+}
+int oracle_contact_gradients(void* h, double* Fc, int use_factor) { return static_cast<Oracle*>(h)->contact_gradients(Fc, use_factor != 0) ? 0 : 1; }
 // --- pieces exposed for the property tests -------------------------------------------------
 void oracle_set_state(void* h, const double* z, const double* u, const double* fext) {
   Oracle* o = static_cast<Oracle*>(h);

@@ -64,6 +64,9 @@ def lib():
         L.oracle_trace.restype = C.c_int
         L.oracle_momentum.argtypes = [vp, dp]
         L.oracle_storage_record.argtypes = [vp, dp, dp]
+        L.oracle_contact_data_jacobian.argtypes = [vp, dp]
+        L.oracle_contact_gradients.argtypes = [vp, dp, C.c_int]
+        L.oracle_contact_gradients.restype = C.c_int
         L.oracle_minimal_to_maximal.argtypes = [vp, dp, dp]
         L.oracle_maximal_to_minimal.argtypes = [vp, dp, dp]
         L.oracle_maximal_to_minimal_jacobian.argtypes = [vp, dp, dp]
@@ -127,6 +130,21 @@ class Oracle:
         st = self.L.oracle_step_grad(self.h, C.byref(opts or self.opts), _d(z), _d(u), None, _d(zn),
                                      Fz.ctypes.data_as(capi.c_double_p), Fu.ctypes.data_as(capi.c_double_p), capi.iptr(it), 0, int(use_factor))
         return zn, Fz, Fu, st, int(it[0])
+
+    def contact_data_jacobian(self):
+        """data Jacobian restricted to the contact data columns (gradients/data.jl:152-192): [nres, 5 Ni]"""
+        out = np.empty((self.nres, 5 * self.mech.Ni))
+        self.L.oracle_contact_data_jacobian(self.h, _d(out))
+        return out
+
+    def contact_gradients(self, use_factor=False):
+        """get_contact_gradients (gradients/contact.jl:1-55) at the solution of the last step: d z' / d theta, theta = per contact
+        [friction_coefficient, contact_radius, contact_origin(3)]; [12 Nb, 5 Ni]."""
+        Fc = np.empty((12 * self.mech.Nb, 5 * self.mech.Ni), order="F")
+        rc = self.L.oracle_contact_gradients(self.h, Fc.ctypes.data_as(capi.c_double_p), int(use_factor))
+        if rc != 0:
+            raise np.linalg.LinAlgError("singular KKT matrix")
+        return Fc
 
     # -- pieces for the property tests -----------------------------------------------------
     def set_state(self, z, u=None, fext=None):

@@ -127,3 +127,28 @@ def test_options_flags_and_failure_status():
     for e in range(2):
         zo, so, io = o.step(Z[e], U[e], fext=F[e])
         assert np.abs(Zf[e] - zo).max() < 1e-9
+
+
+def test_contact_gradient_columns_match_oracle():
+    """dojo_step_grad_contact: the 5 Ni contact-data columns are solved against the same factor in the gradient kernel;
+    against get_contact_gradients of the oracle (ant after a roll-in: feet on the ground); the state / control gradients are
+    bit-identical with and without the extra columns"""
+    mech = dj.get_mechanism("ant")
+    em, o = HostEmu(mech), Oracle(mech)
+    rng = np.random.default_rng(31)
+    B = 4
+    Z = jittered_states(mech, B, rng)
+    for _ in range(12):
+        Z = np.stack([o.step(Z[e], random_inputs(mech, 1, rng)[0])[0] for e in range(B)])
+    U = random_inputs(mech, B, rng)
+    Zn, Fz, Fu, Fc, st, it = em.step_grad(Z, U, slots=2, slots_grad=2, contact=True)
+    _, Fz0, Fu0, _, _ = em.step_grad(Z, U, slots=2, slots_grad=2)
+    assert np.array_equal(Fz, Fz0) and np.array_equal(Fu, Fu0) and Fc.shape == (B, 12 * mech.Nb, 5 * mech.Ni)
+    errs = []
+    for e in range(B):
+        _, _, _, so, io = o.step_grad(Z[e], U[e])
+        Fco = o.contact_gradients()
+        assert so == st[e] == 0 and io == it[e]
+        errs.append(np.abs(Fc[e] - Fco).max() / max(1.0, np.abs(Fco).max()))
+        assert np.abs(Fco).max() > 1.0  # contacts are active: the columns are not trivially zero
+    assert np.median(errs) < 1e-7 and max(errs) < 1e-4, errs

@@ -261,3 +261,68 @@ def test_minimal_maximal_round_trip(name):
         assert np.abs(zz[:, 0:3] - zk[:, 0:3]).max() < 1e-10 and np.abs(zz[:, 6:10] - zk[:, 6:10]).max() < 1e-10
         q = zz[:, 6:10]
         assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# contact data (get_contact_gradients, gradients/contact.jl; data blocks gradients/data.jl:152-192)
+# ----------------------------------------------------------------------------------------------------------------
+def _perturbed_contact(mech, ci, p, delta):
+    import copy
+    m2 = copy.deepcopy(mech)
+    c = m2.contacts[ci]
+    if p == 0:
+        c.friction += delta
+    elif p == 1:
+        c.radius += delta
+    else:
+        o = np.array(c.origin, dtype=float)
+        o[p - 2] += delta
+        c.origin = o
+    return m2
+
+
+@pytest.mark.parametrize("name,steps", [("ant", 30), ("quadruped", 40)])
+def test_contact_data_jacobian_matches_finite_difference(name, steps):
+    """test/data.jl for the contact data: the analytic blocks == central differences of the residual with respect to
+    [friction_coefficient, contact_radius, contact_origin] at a fixed solution (contacts active after the roll-in)"""
+    mech = dj.get_mechanism(name)
+    o = Oracle(mech, capi.solver_options(rtol=1e-10, btol=1e-10))
+    u = np.zeros(mech.nu)
+    z = _advance(Oracle(mech), mech, mech.z0.copy(), u, steps)
+    zn, st, _, sol = o.step(z, u, return_sol=True)
+    assert st == 0
+    o.set_state(z, u)
+    o.set_solution(sol, 0.0)
+    D = o.contact_data_jacobian()
+    assert np.abs(D).max() > 0.1
+    eps = 1e-6
+    for ci in range(mech.Ni):
+        for p in range(5):
+            r = []
+            for sgn in (1.0, -1.0):
+                o2 = Oracle(_perturbed_contact(mech, ci, p, sgn * eps))
+                o2.set_state(z, u)
+                o2.set_solution(sol, 0.0)
+                r.append(o2.evaluate_rhs(sol, 0.0))
+            assert np.abs((r[0] - r[1]) / (2 * eps) - D[:, 5 * ci + p]).max() < 1e-7
+
+
+def test_contact_gradients_match_finite_difference_of_the_step():
+    """get_contact_gradients == d z' / d(contact data) by central differences of the step itself (quadruped standing on
+    sticking contacts: a well-conditioned KKT system; at a sliding contact the IFT system of the reference has a condition
+    number ~1e10 and its solution is not a usable reference for finite differences)"""
+    mech = dj.get_mechanism("quadruped")
+    opts = capi.solver_options(rtol=1e-11, btol=1e-11)
+    o = Oracle(mech, opts)
+    u = np.zeros(mech.nu)
+    z = _advance(Oracle(mech), mech, mech.z0.copy(), u, 40)
+    zn, _, _, st, _ = o.step_grad(z, u)
+    Fc = o.contact_gradients()
+    assert st == 0 and np.abs(Fc).max() > 1.0
+    eps = 1e-6
+    for ci in (0, 3):
+        for p in range(5):
+            zp, _, _ = Oracle(_perturbed_contact(mech, ci, p, eps), opts).step(z, u)
+            zm, _, _ = Oracle(_perturbed_contact(mech, ci, p, -eps), opts).step(z, u)
+            fd = (_reduce(zp, zn, mech.Nb) - _reduce(zm, zn, mech.Nb)) / (2 * eps)
+            assert np.abs(fd - Fc[:, 5 * ci + p]).max() < 1e-5 * max(1.0, np.abs(Fc).max())

@@ -49,3 +49,52 @@ def test_update_params_refuses_other_topology():
     stepper = BatchedStepper(dj.get_mechanism("ant"), 4)
     with pytest.raises(RuntimeError, match="topology"):
         stepper.update_params(dj.get_mechanism("quadruped"))
+
+
+def test_contact_gradients_parity_and_sysid_finite_differences():
+    """dojo_step_grad_contact vs the oracle's get_contact_gradients, and -- the system-identification loop itself -- vs central
+    differences of dojo_step through dojo_update_params(contact radius +- eps) on a standing quadruped"""
+    import copy
+    from dojo_jl_b200 import capi
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism("quadruped")
+    opts = capi.solver_options(rtol=1e-9, btol=1e-9)
+    B = 8
+    rng = np.random.default_rng(93)
+    Z = np.tile(mech.z0, (B, 1))
+    Z[:, 2] += rng.uniform(0.0, 0.02, B)
+    stepper = BatchedStepper(mech, B)
+    U = np.zeros((B, mech.nu))
+    for _ in range(40):
+        Z, _, _ = stepper.step(Z, U)
+    Zn, Fz, Fu, Fc, st, it = stepper.step_grad_contact(Z, U, opts)
+    Zn2, Fz2, Fu2, _, _ = stepper.step_grad(Z, U, opts)
+    assert np.array_equal(Zn, Zn2) and np.array_equal(Fz, Fz2) and np.array_equal(Fu, Fu2)
+    o = Oracle(mech, opts)
+    errs = []
+    for e in range(B):
+        _, _, _, so, io = o.step_grad(Z[e], U[e])
+        if so != 0 or st[e] != 0 or io != it[e]:
+            continue
+        Fco = o.contact_gradients()
+        errs.append(np.abs(Fc[e] - Fco).max() / max(1.0, np.abs(Fco).max()))
+    errs = np.array(errs)
+    assert len(errs) >= B // 2 and np.median(errs) < 1e-6 and errs.max() < 1e-2, errs
+    # finite differences through dojo_update_params: radius of contact 0
+    eps = 1e-6
+    out = []
+    for sgn in (1.0, -1.0):
+        m2 = copy.deepcopy(mech)
+        m2.contacts[0].radius += sgn * eps
+        stepper.update_params(m2)
+        out.append(stepper.step(Z, U, opts)[0])
+    stepper.update_params(mech)
+    fd = (out[0] - out[1]) / (2 * eps)
+    zr = fd.reshape(B, mech.Nb, 13)
+    col = Fc[:, :, 1].reshape(B, mech.Nb, 12)
+    # velocities and positions (the attitude rows need the quaternion reduction: compared through x, v, w only)
+    scale = max(1.0, np.abs(col).max())
+    assert np.abs(zr[:, :, 0:3] - col[:, :, 0:3]).max() < 1e-3 * scale
+    assert np.abs(zr[:, :, 3:6] - col[:, :, 3:6]).max() < 1e-3 * scale
+    assert np.abs(zr[:, :, 10:13] - col[:, :, 9:12]).max() < 1e-3 * scale
