@@ -123,6 +123,29 @@ function Dojo.get_maximal_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Mat
     return Fz, Fu
 end
 
+"batched get_contact_gradients (gradients/contact.jl:1-55): (Fz 12Nb x 12Nb x B, Fc 12Nb x 5Ni x B), contact data per contact =
+ [friction_coefficient, contact_radius, contact_origin(3)]"
+function get_contact_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+    h = handle(mech); B = size(Z, 2); ng = 12 * length(mech.bodies); nc = 5 * length(mech.contacts)
+    Zn = similar(Z); Fz = zeros(ng, ng, B); Fu = zeros(ng, h.nu, B); Fc = zeros(ng, nc, B); status = zeros(Int32, B); iters = zeros(Int32, B)
+    rc = ccall((:dojo_step_grad_contact, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+               h.ptr, COptions(opts), B, Z, U, Zn, Fz, Fu, Fc, status, iters)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return Fz, Fc
+end
+"swap the parameters of the live handle after the Mechanism's data changed (system identification): same topology"
+function update_params!(mech::Mechanism)
+    h = handle(mech); bodies, joints, contacts = flatten(mech)
+    GC.@preserve bodies joints contacts begin
+        desc = MechanismDesc(length(bodies), length(joints), length(contacts), mech.timestep, mech.input_scaling, Tuple(mech.gravity),
+                             pointer(bodies), pointer(joints), pointer(contacts))
+        rc = ccall((:dojo_update_params, LIB), Cint, (Ptr{Cvoid}, Ref{MechanismDesc}), h.ptr, desc)
+        rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    end
+    return nothing
+end
+
 "batched minimal_to_maximal / maximal_to_minimal: X is 2nu x B (per joint [c_tra; c_rot; v_tra; v_rot]), Z is 13Nb x B"
 function Dojo.minimal_to_maximal(mech::Mechanism, X::Matrix{Float64})
     h = handle(mech); B = size(X, 2); Z = zeros(h.nz, B)
