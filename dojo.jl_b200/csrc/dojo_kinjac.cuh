@@ -326,7 +326,7 @@ DJ_DEV void kinjac_env(const KinJacArgs& a, int e, double* ws, int tid, int nthr
   }
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(DJ_HOSTEMU)
 // persistent grid: CTA b takes environments b, b + gridDim.x, ...; workspace slice b
 __global__ void __launch_bounds__(128) dojo_kinjac_kernel(const KinJacArgs a) {
   double* ws = a.ws + (size_t)blockIdx.x * kinjac_ws_doubles(a.Nb, a.nu);

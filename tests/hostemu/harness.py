@@ -29,6 +29,7 @@ class HostEmu:
         op = C.POINTER(capi.DojoSolverOptions)
         L.hostemu_step.argtypes = [_vp, op, _ip, _ip, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _ip, _ip, _ip, _vp]
         L.hostemu_step_grad.argtypes = [_vp, op, _ip, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _ip, _ip, _ip, _vp]
+        L.hostemu_kinjac.argtypes = [_vp, _ip, _ip, _ip, _vp, _vp, _vp, _vp, _vp, _vp]
         self.L, self.mech = L, mech
         desc, self._keep = capi.flatten(mech)
         h = L.hostemu_create(C.byref(desc))
@@ -76,3 +77,24 @@ class HostEmu:
         if contact:
             return Zn, Fz.transpose(0, 2, 1), Fu.transpose(0, 2, 1), Fc.transpose(0, 2, 1), st, it
         return Zn, Fz.transpose(0, 2, 1), Fu.transpose(0, 2, 1), st, it
+
+    def kinjac(self, mode, Z, Zn=None, Fz=None, Fu=None, grid=2):
+        """dojo_kinjac_kernel with 128-thread CTAs.  mode 0: M [B, 2nu, 12Nb]; 1: N [B, 12Nb, 2nu]; 2: (Gx, Gu) from Fz / Fu in
+        math layout [B, 12Nb, 12Nb] / [B, 12Nb, nu]."""
+        m = self.mech
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        B, nm, ns = Z.shape[0], 2 * m.nu, 12 * m.Nb
+        if mode == 0:
+            J = np.empty((B, ns, nm))
+            self.L.hostemu_kinjac(self.h, 0, B, grid, _p(Z), None, None, None, _p(J), None)
+            return J.transpose(0, 2, 1)
+        if mode == 1:
+            J = np.empty((B, nm, ns))
+            self.L.hostemu_kinjac(self.h, 1, B, grid, _p(Z), None, None, None, _p(J), None)
+            return J.transpose(0, 2, 1)
+        Zn = np.ascontiguousarray(np.atleast_2d(Zn), dtype=np.float64)
+        Fzc = np.ascontiguousarray(np.asarray(Fz, dtype=np.float64).transpose(0, 2, 1))
+        Fuc = np.ascontiguousarray(np.asarray(Fu, dtype=np.float64).transpose(0, 2, 1))
+        Gx, Gu = np.empty((B, nm, nm)), np.empty((B, m.nu, nm))
+        self.L.hostemu_kinjac(self.h, 2, B, grid, _p(Z), _p(Zn), _p(Fzc), _p(Fuc), _p(Gx), _p(Gu))
+        return Gx.transpose(0, 2, 1), Gu.transpose(0, 2, 1)

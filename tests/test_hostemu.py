@@ -152,3 +152,30 @@ def test_contact_gradient_columns_match_oracle():
         errs.append(np.abs(Fc[e] - Fco).max() / max(1.0, np.abs(Fco).max()))
         assert np.abs(Fco).max() > 1.0  # contacts are active: the columns are not trivially zero
     assert np.median(errs) < 1e-7 and max(errs) < 1e-4, errs
+
+
+@pytest.mark.parametrize("name", ["ant", "atlas"])
+def test_kinjac_kernel_with_real_ctas(name):
+    """dojo_kinjac_kernel as launched on the GPU (128 threads per CTA, persistent grid over the environments, workspace slice
+    per CTA): map Jacobians against the oracle, minimal gradients against M Fz N / M Fu"""
+    from test_oracle_properties import _random_minimal
+    mech = dj.get_mechanism(name)
+    em, o = HostEmu(mech), Oracle(mech)
+    rng = np.random.default_rng(37)
+    B = 5
+    X = np.stack([_random_minimal(mech, rng) for _ in range(B)])
+    Z = np.stack([o.minimal_to_maximal(x) for x in X])
+    M = em.kinjac(0, Z, grid=2)
+    N = em.kinjac(1, Z, grid=3)
+    for e in range(B):
+        Mo, No = o.maximal_to_minimal_jacobian(Z[e]), o.minimal_to_maximal_jacobian(Z[e])
+        assert np.abs(M[e] - Mo).max() < 1e-10 * max(1.0, np.abs(Mo).max())
+        assert np.abs(N[e] - No).max() < 1e-10 * max(1.0, np.abs(No).max())
+    Fz = rng.normal(size=(B, 12 * mech.Nb, 12 * mech.Nb))
+    Fu = rng.normal(size=(B, 12 * mech.Nb, mech.nu))
+    Zn = Z[::-1].copy()
+    Gx, Gu = em.kinjac(2, Z, Zn, Fz, Fu, grid=2)
+    Mn = em.kinjac(0, Zn)
+    ref_x, ref_u = Mn @ Fz @ N, Mn @ Fu
+    assert np.abs(Gx - ref_x).max() < 1e-10 * max(1.0, np.abs(ref_x).max())
+    assert np.abs(Gu - ref_u).max() < 1e-10 * max(1.0, np.abs(ref_u).max())
