@@ -105,7 +105,7 @@ def flatten(mech: Mechanism):
         joints[i].rot = _element(j.rot)
     contacts = (DojoContactDesc * max(mech.Ni, 1))()
     for i, c in enumerate(mech.contacts):
-        contacts[i].type = 2
+        contacts[i].type = int(getattr(c, "type", 2))
         contacts[i].parent_body = int(c.body)
         contacts[i].friction_coefficient = float(c.friction)
         _fill(contacts[i].tangent, c.tangent)

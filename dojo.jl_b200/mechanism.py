@@ -98,9 +98,15 @@ class Joint:
         return self.tra.damper != 0 or self.rot.damper != 0
 
 
+CONTACT_TYPES = {"impact": 0, "linear": 1, "nonlinear": 2}  # DojoContactDesc.type (contacts/constructor.jl:117-128)
+CONTACT_DIMS = {"impact": 2, "linear": 12, "nonlinear": 8}   # N of Contact{T,N}: impact.jl:38, linear.jl:46, nonlinear.jl:47
+
+
 @dataclass
 class Contact:
-    """NonlinearContact + SphereHalfSpaceCollision (contacts/nonlinear.jl:12-48)."""
+    """ContactConstraint{model} + SphereHalfSpaceCollision (contacts/constructor.jl:14-43).
+    model: "nonlinear" (contacts/nonlinear.jl:12-48), "linear" (contacts/linear.jl:10-47: 4-sided friction pyramid) or
+    "impact" (contacts/impact.jl:8-39: no friction) -- the reference's `contact_type` keyword."""
     name: str
     body: int
     friction: float
@@ -109,6 +115,15 @@ class Contact:
     origin: np.ndarray  # 3
     radius: float
     offset: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    model: str = "nonlinear"
+
+    @property
+    def type(self) -> int:
+        return CONTACT_TYPES[self.model]
+
+    @property
+    def dim(self) -> int:
+        return CONTACT_DIMS[self.model]
 
 
 class Mechanism:
@@ -148,7 +163,7 @@ class Mechanism:
     @property
     def node_dims(self) -> List[int]:
         """joints (by id) | bodies | contacts  (mechanism/id.jl:5-13)."""
-        return [j.nimpulses for j in self.joints] + [6] * self.Nb + [8] * self.Ni
+        return [j.nimpulses for j in self.joints] + [6] * self.Nb + [c.dim for c in self.contacts]
 
     @property
     def nres(self) -> int:
@@ -258,7 +273,7 @@ class Mechanism:
                          orientation_offset=j.orientation_offset.tolist()) for j in self.joints],
             contacts=[dict(name=c.name, body=c.body, friction=c.friction, normal=c.normal.tolist(),
                            tangent=c.tangent.tolist(), origin=c.origin.tolist(), radius=c.radius,
-                           offset=c.offset.tolist()) for c in self.contacts],
+                           offset=c.offset.tolist(), **({} if c.model == "nonlinear" else {"model": c.model})) for c in self.contacts],
             z0=None if self.z0 is None else self.z0.tolist(),
         )
 
@@ -278,7 +293,7 @@ class Mechanism:
                    np.array(j["orientation_offset"], dtype=float)) for j in d["joints"]],
             [Contact(c["name"], int(c["body"]), float(c["friction"]), np.array(c["normal"], dtype=float),
                      np.array(c["tangent"], dtype=float), np.array(c["origin"], dtype=float), float(c["radius"]),
-                     np.array(c["offset"], dtype=float)) for c in d["contacts"]],
+                     np.array(c["offset"], dtype=float), c.get("model", "nonlinear")) for c in d["contacts"]],
             timestep=d["timestep"], input_scaling=d["input_scaling"], gravity=d["gravity"])
         if d.get("z0") is not None:
             m.z0 = np.array(d["z0"], dtype=float)
@@ -297,7 +312,8 @@ class Mechanism:
 def get_mechanism(name: str, **overrides) -> Mechanism:
     """Mirror of DojoEnvironments.get_mechanism(:name) for the BASELINE models: loads the
     flattened descriptor generated from the reference's builder (tools/build_mechanisms.py).
-    Overrides: timestep, input_scaling, gravity (mechanism kwargs, constructor.jl:47)."""
+    Overrides: timestep, input_scaling, gravity (mechanism kwargs, constructor.jl:47); contact_type = "nonlinear" | "linear" |
+    "impact" switches the model of every contact as the builders' `contact_type` keyword does (contacts/constructor.jl:117-128)."""
     m = Mechanism.load(os.path.join(MECHANISM_DIR, f"{name}.json"))
     if "timestep" in overrides:
         h = float(overrides.pop("timestep"))
@@ -309,6 +325,12 @@ def get_mechanism(name: str, **overrides) -> Mechanism:
     if "gravity" in overrides:
         g = overrides.pop("gravity")
         m.gravity = np.array([0.0, 0.0, g], dtype=float) if np.isscalar(g) else np.asarray(g, dtype=float)
+    if "contact_type" in overrides:
+        ct = str(overrides.pop("contact_type")).lstrip(":")
+        if ct not in CONTACT_TYPES:
+            raise ValueError(f"unknown contact_type {ct!r}")
+        for c in m.contacts:
+            c.model = ct
     if overrides:
         raise TypeError(f"unknown mechanism options: {sorted(overrides)}")
     return m

@@ -61,14 +61,22 @@ struct JointS {  // joints/constraints.jl:17-86
   std::vector<double> imp[2];
 };
 
-struct ContactS {  // contacts/constructor.jl:14-43 + nonlinear.jl:12-48 + sphere_halfspace.jl:11-24
+struct ContactS {  // contacts/constructor.jl:14-43 + {nonlinear.jl:12-48, linear.jl:10-47, impact.jl:8-39} + sphere_halfspace.jl:11-24
+  int type = 2;    // 0 ImpactContact{T,2}, 1 LinearContact{T,12}, 2 NonlinearContact{T,8}
+  int nh = 4;      // N½: impact 1, nonlinear 4, linear 6; the node's entry is [s(nh); γ(nh)]
   int body = 0, sol_off = 0;
   double mu_f = 0, radius = 0;
   Mat<2, 3> t;
   Mat<1, 3> nrm;
   V3 o, off;
-  double gam[2][4], s[2][4];
+  double gam[2][6], s[2][6];
+  // neutral_vector: nonlinear [1,1,0,0] (nonlinear.jl:99), impact / linear ones(N½) (contact.jl:196)
+  double neutral(int i) const { return type == 2 ? (i < 2 ? 1.0 : 0.0) : 1.0; }
+  // cone_degree: nonlinear 2 (nonlinear.jl:101), impact / linear N½ (contact.jl:197)
+  int cone_degree() const { return type == 2 ? 2 : nh; }
 };
+// friction_parameterization of LinearContact (linear.jl:29-34) / NonlinearContact (identity, nonlinear.jl:40-43)
+static const double kLinearParam[4][2] = {{0.0, 1.0}, {0.0, -1.0}, {1.0, 0.0}, {-1.0, 0.0}};
 
 struct Cfg {  // (x, v, q, w) of a node; the origin is all-zero / identity (bodies/origin.jl)
   V3 x, v, w;
@@ -626,7 +634,8 @@ struct Oracle {
       for (int i = 0; i < 6; ++i) ct.t.a[i] = cd.tangent[i];
       for (int i = 0; i < 3; ++i) ct.nrm.a[i] = cd.normal[i];
       ct.o = vec3(cd.origin); ct.off = vec3(cd.offset);
-      ct.sol_off = off; off += 8;
+      ct.type = cd.type; ct.nh = (cd.type == 0 ? 1 : (cd.type == 1 ? 6 : 4));
+      ct.sol_off = off; off += 2 * ct.nh;
     }
     nres = off;
     A.assign((size_t)nres * nres, 0.0); rhs.assign(nres, 0.0); res_saved.assign(nres, 0.0);
@@ -639,7 +648,7 @@ struct Oracle {
     node_dim.resize(N); node_off.resize(N);
     for (int j = 0; j < Ne; ++j) { node_dim[j] = joints[j].n; node_off[j] = joints[j].sol_off; }
     for (int b = 0; b < Nb; ++b) { node_dim[Ne + b] = 6; node_off[Ne + b] = body_off[b]; }
-    for (int c = 0; c < Ni; ++c) { node_dim[Ne + Nb + c] = 8; node_off[Ne + Nb + c] = contacts[c].sol_off; }
+    for (int c = 0; c < Ni; ++c) { node_dim[Ne + Nb + c] = 2 * contacts[c].nh; node_off[Ne + Nb + c] = contacts[c].sol_off; }
     // adjacency (mechanism/system.jl:15-51): joint-parent, joint-child, parent-child bodies, contact-body
     std::vector<std::vector<char>> adj(N, std::vector<char>(N, 0));
     auto link = [&](int a, int b) { adj[a][b] = adj[b][a] = 1; };
@@ -1027,7 +1036,7 @@ struct Oracle {
   void get_solution(double* sol, int idx = 1) const {
     for (const JointS& j : joints) for (int i = 0; i < j.n; ++i) sol[j.sol_off + i] = j.imp[idx][i];
     for (int b = 0; b < Nb; ++b) for (int i = 0; i < 3; ++i) { sol[body_off[b] + i] = bodies[b].vsol[idx][i]; sol[body_off[b] + 3 + i] = bodies[b].wsol[idx][i]; }
-    for (const ContactS& c : contacts) for (int i = 0; i < 4; ++i) { sol[c.sol_off + i] = c.s[idx][i]; sol[c.sol_off + 4 + i] = c.gam[idx][i]; }
+    for (const ContactS& c : contacts) for (int i = 0; i < c.nh; ++i) { sol[c.sol_off + i] = c.s[idx][i]; sol[c.sol_off + c.nh + i] = c.gam[idx][i]; }
   }
   void set_solution(const double* sol) {
     for (JointS& j : joints) for (int i = 0; i < j.n; ++i) j.imp[0][i] = j.imp[1][i] = sol[j.sol_off + i];
@@ -1035,35 +1044,67 @@ struct Oracle {
       bodies[b].vsol[0][i] = bodies[b].vsol[1][i] = sol[body_off[b] + i];
       bodies[b].wsol[0][i] = bodies[b].wsol[1][i] = sol[body_off[b] + 3 + i];
     }
-    for (ContactS& c : contacts) for (int i = 0; i < 4; ++i) { c.s[0][i] = c.s[1][i] = sol[c.sol_off + i]; c.gam[0][i] = c.gam[1][i] = sol[c.sol_off + 4 + i]; }
+    for (ContactS& c : contacts) for (int i = 0; i < c.nh; ++i) { c.s[0][i] = c.s[1][i] = sol[c.sol_off + i]; c.gam[0][i] = c.gam[1][i] = sol[c.sol_off + c.nh + i]; }
   }
 
   // ---------------------------------------------------------------- contacts
   // sphere_halfspace.jl:34-36 / :55-62, velocity.jl:2-38
   V3 contact_point(const ContactS& c, const Cfg& p) const { return p.x + vector_rotate(c.o, p.q) - c.off - tr(c.nrm) * c.radius; }
   // contacts/nonlinear.jl:50-76: [d - s1; μγ1 - γ2; vt - s(3:4)]
-  Mat<4, 1> contact_constraint(const ContactS& c) const {
+  // contacts/impact.jl:41-56:    [d - s1]
+  // contacts/linear.jl:72-104:   [d - sγ; μ γ - Σβ - sψ; P vt + ψ 1 - sβ],  γ-vector = [γ; ψ; β(4)], s-vector = [sγ; sψ; sβ(4)]
+  // (rows beyond c.nh stay zero)
+  Mat<6, 1> contact_constraint(const ContactS& c) const {
     Cfg p = cfg_next(c.body);
     double d = (c.nrm * (p.x + vector_rotate(c.o, p.q) - c.off))[0] - c.radius;
+    Mat<6, 1> r;
+    r[0] = d - c.s[1][0];
+    if (c.type == 0) return r;
     V3 cp = contact_point(c, p);
     V3 vp = p.v + skew(vector_rotate(p.w, p.q)) * (cp - p.x);
     Mat<2, 1> vt = c.t * vp;  // child = origin: zero velocity
-    Mat<4, 1> r;
-    r[0] = d - c.s[1][0];
-    r[1] = c.mu_f * c.gam[1][0] - c.gam[1][1];
-    r[2] = vt[0] - c.s[1][2];
-    r[3] = vt[1] - c.s[1][3];
+    if (c.type == 2) {
+      r[1] = c.mu_f * c.gam[1][0] - c.gam[1][1];
+      r[2] = vt[0] - c.s[1][2];
+      r[3] = vt[1] - c.s[1][3];
+    } else {
+      r[1] = c.mu_f * c.gam[1][0] - (c.gam[1][2] + c.gam[1][3] + c.gam[1][4] + c.gam[1][5]) - c.s[1][1];
+      for (int i = 0; i < 4; ++i) r[2 + i] = (kLinearParam[i][0] * vt[0] + kLinearParam[i][1] * vt[1]) + c.gam[1][1] - c.s[1][2 + i];
+    }
     return r;
   }
-  // solver/complementarity.jl:16-24: [γ1 s1; cone_product(γ(2:4), s(2:4))]  (contacts/cone.jl:2-8)
-  static void contact_complementarity(const double* g, const double* s, double* out) {
+  // solver/complementarity.jl:16-24: nonlinear [γ1 s1; cone_product(γ(2:4), s(2:4))]  (contacts/cone.jl:2-8); impact / linear γ .* s
+  static void contact_complementarity(const ContactS& c, const double* g, const double* s, double* out) {
+    if (c.type != 2) { for (int i = 0; i < c.nh; ++i) out[i] = g[i] * s[i]; return; }
     out[0] = g[0] * s[0];
     out[1] = g[1] * s[1] + g[2] * s[2] + g[3] * s[3];
     out[2] = g[1] * s[2] + s[1] * g[2];
     out[3] = g[1] * s[3] + s[1] * g[3];
   }
+  // contacts/impact.jl:58-64: [γ s; -1 0];  contacts/linear.jl:49-70: [Diag(γ) Diag(s); -I ∇γ2]   (top-left 2nh x 2nh used)
+  Mat<12, 12> contact_constraint_jacobian_orthant(const ContactS& c) const {
+    const int nh = c.nh;
+    Mat<12, 12> M;
+    for (int i = 0; i < nh; ++i) {
+      M(i, i) = c.gam[1][i] + REG * c.neutral(i);
+      M(i, nh + i) = c.s[1][i] + REG * c.neutral(i);
+      M(nh + i, i) = -1.0;
+    }
+    if (c.type == 1) {
+      M(nh + 1, nh + 0) = c.mu_f;
+      for (int i = 0; i < 4; ++i) { M(nh + 1, nh + 2 + i) = -1.0; M(nh + 2 + i, nh + 1) = 1.0; }
+    }
+    return M;
+  }
   // contacts/nonlinear.jl:78-97
-  Mat<8, 8> contact_constraint_jacobian(const ContactS& c) const {
+  Mat<12, 12> contact_constraint_jacobian(const ContactS& c) const {
+    if (c.type != 2) return contact_constraint_jacobian_orthant(c);
+    Mat<8, 8> M8 = contact_constraint_jacobian_nonlinear(c);
+    Mat<12, 12> M;
+    for (int r = 0; r < 8; ++r) for (int cc = 0; cc < 8; ++cc) M(r, cc) = M8(r, cc);
+    return M;
+  }
+  Mat<8, 8> contact_constraint_jacobian_nonlinear(const ContactS& c) const {
     double g[4], s[4];
     const double neutral[4] = {1, 1, 0, 0};
     for (int i = 0; i < 4; ++i) { g[i] = c.gam[1][i] + REG * neutral[i]; s[i] = c.s[1][i] + REG * neutral[i]; }
@@ -1079,8 +1120,20 @@ struct Oracle {
     M(5, 4) = c.mu_f; M(5, 5) = -1.0;        // ∇γ3
     return M;
   }
+  // Rows of the NonlinearContact pattern [normal; 0; tangent 1; tangent 2] mapped to the model's N½ rows:
+  // impact [normal] (impact.jl:66-101), linear [normal; 0; friction_parameterization * tangents] (contact.jl:22-33, :64-74).
+  template <int C>
+  static Mat<6, C> expand_rows(const ContactS& c, const Mat<4, C>& J4) {
+    Mat<6, C> J;
+    for (int k = 0; k < C; ++k) J(0, k) = J4(0, k);
+    if (c.type == 2) { for (int r = 1; r < 4; ++r) for (int k = 0; k < C; ++k) J(r, k) = J4(r, k); }
+    else if (c.type == 1) { for (int i = 0; i < 4; ++i) for (int k = 0; k < C; ++k) J(2 + i, k) = kLinearParam[i][0] * J4(2, k) + kLinearParam[i][1] * J4(3, k); }
+    return J;
+  }
+  Mat<6, 6> contact_constraint_jacobian_velocity(const ContactS& c) const { return expand_rows(c, contact_constraint_jacobian_velocity4(c)); }
+  Mat<6, 7> contact_constraint_jacobian_configuration(const ContactS& c) const { return expand_rows(c, contact_constraint_jacobian_configuration4(c)); }
   // contacts/contact.jl:37-77 (relative = :parent): 4 x 6
-  Mat<4, 6> contact_constraint_jacobian_velocity(const ContactS& c) const {
+  Mat<4, 6> contact_constraint_jacobian_velocity4(const ContactS& c) const {
     Cfg p = cfg_next(c.body);
     Mat<1, 3> dddx = c.nrm;
     Mat<1, 4> dddq = c.nrm * dvector_rotate_dq(c.o, p.q);
@@ -1106,7 +1159,7 @@ struct Oracle {
     return J;
   }
   // contacts/contact.jl:9-35 (relative = :parent): 4 x 7, used by the data Jacobian
-  Mat<4, 7> contact_constraint_jacobian_configuration(const ContactS& c) const {
+  Mat<4, 7> contact_constraint_jacobian_configuration4(const ContactS& c) const {
     Cfg p = cfg_next(c.body);
     V3 cp = contact_point(c, p);
     M34 dcpv_dq = -skew(cp - p.x) * dvector_rotate_dq(p.w, p.q);
@@ -1120,25 +1173,27 @@ struct Oracle {
     for (int i = 0; i < 4; ++i) { J(0, 3 + i) = dddq[i]; J(2, 3 + i) = dvt_dq(0, i); J(3, 3 + i) = dvt_dq(1, i); }
     return J;
   }
-  // contacts/contact.jl:79-100,141-155: [X; Rot(q3)ᵀ skew(c - x3) X], X = [nᵀ 0 tᵀ]  (6 x 4)
-  Mat<3, 4> force_mapping(const ContactS& c) const {
-    Mat<3, 4> X;
-    for (int i = 0; i < 3; ++i) { X(i, 0) = c.nrm[i]; X(i, 2) = c.t(0, i); X(i, 3) = c.t(1, i); }
+  // contacts/contact.jl:79-100,141-155: [X; Rot(q3)ᵀ skew(c - x3) X], X = [nᵀ 0 tᵀ Pᵀ]  (6 x N½; nonlinear P = I, impact.jl:103-115 X = nᵀ)
+  Mat<3, 6> force_mapping(const ContactS& c) const {
+    Mat<3, 6> X;
+    for (int i = 0; i < 3; ++i) X(i, 0) = c.nrm[i];
+    if (c.type == 2) { for (int i = 0; i < 3; ++i) { X(i, 2) = c.t(0, i); X(i, 3) = c.t(1, i); } }
+    else if (c.type == 1) { for (int k = 0; k < 4; ++k) for (int i = 0; i < 3; ++i) X(i, 2 + k) = c.t(0, i) * kLinearParam[k][0] + c.t(1, i) * kLinearParam[k][1]; }
     return X;
   }
-  Mat<6, 4> contact_impulse_map(const ContactS& c) const {
+  Mat<6, 6> contact_impulse_map(const ContactS& c) const {
     Cfg p = cfg_next(c.body);
-    Mat<3, 4> X = force_mapping(c);
+    Mat<3, 6> X = force_mapping(c);
     V3 r = contact_point(c, p) - p.x;
-    Mat<3, 4> Q = rotation_matrix(inv(p.q)) * skew(r) * X;
+    Mat<3, 6> Q = rotation_matrix(inv(p.q)) * skew(r) * X;
     return vcat(X, Q);
   }
   // contacts/contact.jl:102-138 (relative = jacobian = :parent; normals/tangents constant): 6 x 7
   Mat<6, 7> contact_impulse_map_jacobian(const ContactS& c) const {
     Cfg p = cfg_next(c.body);
-    Mat<3, 4> X = force_mapping(c);
-    Mat<4, 1> lam;
-    for (int i = 0; i < 4; ++i) lam[i] = c.gam[1][i];
+    Mat<3, 6> X = force_mapping(c);
+    Mat<6, 1> lam;
+    for (int i = 0; i < c.nh; ++i) lam[i] = c.gam[1][i];
     V3 r = contact_point(c, p) - p.x;
     V3 Xl = X * lam;
     M33 Qx = -(rotation_matrix(inv(p.q)) * skew(Xl) * (M33::identity() - M33::identity()));
@@ -1222,8 +1277,8 @@ struct Oracle {
     }
     for (const ContactS& c : contacts) {
       if (c.body != bi) continue;
-      Mat<4, 1> lam;
-      for (int i = 0; i < 4; ++i) lam[i] = c.gam[1][i];
+      Mat<6, 1> lam;
+      for (int i = 0; i < c.nh; ++i) lam[i] = c.gam[1][i];
       d -= contact_impulse_map(c) * lam;
     }
     return d;
@@ -1315,21 +1370,21 @@ struct Oracle {
     }
     // contacts: contacts/constraints.jl:60-76
     for (const ContactS& c : contacts) {
-      Mat<8, 8> Dc = contact_constraint_jacobian(c);
-      double comp[4];
-      contact_complementarity(c.gam[1], c.s[1], comp);
-      const double neutral[4] = {1, 1, 0, 0};
-      Mat<4, 1> g = contact_constraint(c);
-      for (int i = 0; i < 4; ++i) { rhs[c.sol_off + i] = -(comp[i] - mu * neutral[i]); rhs[c.sol_off + 4 + i] = -g[i]; }
-      for (int r = 0; r < 8; ++r)
-        for (int cc = 0; cc < 8; ++cc) A[(size_t)(c.sol_off + r) * n + c.sol_off + cc] = Dc(r, cc);
-      Mat<4, 6> Jv = contact_constraint_jacobian_velocity(c);
-      Mat<6, 4> G = contact_impulse_map(c);
+      const int nh = c.nh;
+      Mat<12, 12> Dc = contact_constraint_jacobian(c);
+      double comp[6];
+      contact_complementarity(c, c.gam[1], c.s[1], comp);
+      Mat<6, 1> g = contact_constraint(c);
+      for (int i = 0; i < nh; ++i) { rhs[c.sol_off + i] = -(comp[i] - mu * c.neutral(i)); rhs[c.sol_off + nh + i] = -g[i]; }
+      for (int r = 0; r < 2 * nh; ++r)
+        for (int cc = 0; cc < 2 * nh; ++cc) A[(size_t)(c.sol_off + r) * n + c.sol_off + cc] = Dc(r, cc);
+      Mat<6, 6> Jv = contact_constraint_jacobian_velocity(c);
+      Mat<6, 6> G = contact_impulse_map(c);
       int ob = body_off[c.body];
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < nh; ++r)
         for (int cc = 0; cc < 6; ++cc) {
-          A[(size_t)(c.sol_off + 4 + r) * n + ob + cc] = Jv(r, cc);   // [Z; constraint_jacobian_velocity]
-          A[(size_t)(ob + cc) * n + c.sol_off + 4 + r] = -G(cc, r);   // [Z' -impulse_map]
+          A[(size_t)(c.sol_off + nh + r) * n + ob + cc] = Jv(r, cc);   // [Z; constraint_jacobian_velocity]
+          A[(size_t)(ob + cc) * n + c.sol_off + nh + r] = -G(cc, r);   // [Z' -impulse_map]
         }
     }
   }
@@ -1343,11 +1398,10 @@ struct Oracle {
       for (int i = 0; i < j.n; ++i) out[j.sol_off + i] = -g[i];
     }
     for (const ContactS& c : contacts) {
-      double comp[4];
-      contact_complementarity(c.gam[1], c.s[1], comp);
-      const double neutral[4] = {1, 1, 0, 0};
-      Mat<4, 1> g = contact_constraint(c);
-      for (int i = 0; i < 4; ++i) { out[c.sol_off + i] = -(comp[i] - mu * neutral[i]); out[c.sol_off + 4 + i] = -g[i]; }
+      double comp[6];
+      contact_complementarity(c, c.gam[1], c.s[1], comp);
+      Mat<6, 1> g = contact_constraint(c);
+      for (int i = 0; i < c.nh; ++i) { out[c.sol_off + i] = -(comp[i] - mu * c.neutral(i)); out[c.sol_off + c.nh + i] = -g[i]; }
     }
   }
 
@@ -1363,7 +1417,7 @@ struct Oracle {
       }
     }
     for (int b = 0; b < Nb; ++b) { V6 d = body_constraint(b); for (int r = 0; r < 6; ++r) v = std::max(v, std::fabs(d[r])); }
-    for (const ContactS& c : contacts) { Mat<4, 1> g = contact_constraint(c); for (int r = 0; r < 4; ++r) v = std::max(v, std::fabs(g[r])); }
+    for (const ContactS& c : contacts) { Mat<6, 1> g = contact_constraint(c); for (int r = 0; r < c.nh; ++r) v = std::max(v, std::fabs(g[r])); }
     return v;
   }
   double bilinear_violation() const {
@@ -1375,9 +1429,9 @@ struct Oracle {
         for (int i = 0; i < e.nb; ++i) v = std::max(v, std::fabs(eta[i] * eta[e.nb + i]));
       }
     for (const ContactS& c : contacts) {
-      double comp[4];
-      contact_complementarity(c.gam[1], c.s[1], comp);
-      for (int i = 0; i < 4; ++i) v = std::max(v, std::fabs(comp[i]));
+      double comp[6];
+      contact_complementarity(c, c.gam[1], c.s[1], comp);
+      for (int i = 0; i < c.nh; ++i) v = std::max(v, std::fabs(comp[i]));
     }
     return v;
   }
@@ -1497,7 +1551,11 @@ struct Oracle {
     double a = 1.0;
     for (const ContactS& c : contacts) {
       const double* ds = &rhs[c.sol_off];
-      const double* dg = &rhs[c.sol_off + 4];
+      const double* dg = &rhs[c.sol_off + c.nh];
+      if (c.type != 2) {  // line_search.jl:71-86: impact / linear are orthant-only
+        a = std::min(a, std::min(positive_orthant_step_length(c.s[1], ds, c.nh, tau_ort), positive_orthant_step_length(c.gam[1], dg, c.nh, tau_ort)));
+        continue;
+      }
       double as_ort = positive_orthant_step_length(c.s[1], ds, 1, tau_ort);
       double ag_ort = positive_orthant_step_length(c.gam[1], dg, 1, tau_ort);
       double as_soc = second_order_cone_step_length(c.s[1] + 1, ds + 1, tau_soc);
@@ -1519,9 +1577,9 @@ struct Oracle {
     double sn = 0, sa = 0, cnt = 0;
     for (const ContactS& c : contacts) {
       const double* ds = &rhs[c.sol_off];
-      const double* dg = &rhs[c.sol_off + 4];
-      for (int i = 0; i < 4; ++i) { sn += c.s[1][i] * c.gam[1][i]; sa += (c.s[1][i] + aaff * ds[i]) * (c.gam[1][i] + aaff * dg[i]); }
-      cnt += 2;  // cone_degree(NonlinearContact) = 2 (nonlinear.jl:101)
+      const double* dg = &rhs[c.sol_off + c.nh];
+      for (int i = 0; i < c.nh; ++i) { sn += c.s[1][i] * c.gam[1][i]; sa += (c.s[1][i] + aaff * ds[i]) * (c.gam[1][i] + aaff * dg[i]); }
+      cnt += c.cone_degree();  // cone_degree(NonlinearContact) = 2 (nonlinear.jl:101), N½ otherwise (contact.jl:197)
     }
     for (const JointS& j : joints)
       for (int k = 0; k < 2; ++k) {
@@ -1538,7 +1596,8 @@ struct Oracle {
   void correction() {
     for (const ContactS& c : contacts) {
       const double* ds = &rhs[c.sol_off];
-      const double* dg = &rhs[c.sol_off + 4];
+      const double* dg = &rhs[c.sol_off + c.nh];
+      if (c.type != 2) { for (int i = 0; i < c.nh; ++i) res_saved[c.sol_off + i] += -ds[i] * dg[i] + mu; continue; }  // correction.jl:13-19
       res_saved[c.sol_off + 0] += -ds[0] * dg[0] + mu;
       res_saved[c.sol_off + 1] += -(ds[1] * dg[1] + ds[2] * dg[2] + ds[3] * dg[3]) + mu;
       res_saved[c.sol_off + 2] += -(ds[1] * dg[2] + dg[1] * ds[2]);
@@ -1555,7 +1614,7 @@ struct Oracle {
   void candidate_step(double alpha, int scale) {
     double f = 1.0 / std::pow(2.0, scale) * alpha;
     for (ContactS& c : contacts)
-      for (int i = 0; i < 4; ++i) { c.s[1][i] = c.s[0][i] + f * rhs[c.sol_off + i]; c.gam[1][i] = c.gam[0][i] + f * rhs[c.sol_off + 4 + i]; }
+      for (int i = 0; i < c.nh; ++i) { c.s[1][i] = c.s[0][i] + f * rhs[c.sol_off + i]; c.gam[1][i] = c.gam[0][i] + f * rhs[c.sol_off + c.nh + i]; }
     for (JointS& j : joints)
       for (int i = 0; i < j.n; ++i) j.imp[1][i] = j.imp[0][i] + f * rhs[j.sol_off + i];
     double wmax = 3.9 / (h * h);
@@ -1593,6 +1652,18 @@ struct Oracle {
     double dhs = 0.5 * sh * gh / (gh + eps), dhg = 0.5 * sh * gh / (sh + eps);
     s = sh + dhs; g = gh + dhg;
   }
+  // initialize_positive_orthant! on a vector (initialization.jl:20-33): min / sum over the N½ components
+  static void initialize_positive_orthant_n(double* g, double* s, int n) {
+    const double eps = 1e-20;
+    double smin = s[0], gmin = g[0];
+    for (int i = 1; i < n; ++i) { smin = std::min(smin, s[i]); gmin = std::min(gmin, g[i]); }
+    double ds = std::max(-1.5 * smin, 0.0), dg = std::max(-1.5 * gmin, 0.0);
+    double shg = 0, sums = 0, sumg = 0;
+    for (int i = 0; i < n; ++i) { s[i] += ds; g[i] += dg; }
+    for (int i = 0; i < n; ++i) { shg += s[i] * g[i]; sums += s[i]; sumg += g[i]; }
+    double dhs = 0.5 * shg / (sumg + eps), dhg = 0.5 * shg / (sums + eps);
+    for (int i = 0; i < n; ++i) { s[i] += dhs; g[i] += dhg; }
+  }
   static void initialize_second_order_cone(double* g, double* s) {
     const double eps = 1e-20;
     double ns = std::sqrt(s[1] * s[1] + s[2] * s[2]), ng = std::sqrt(g[1] * g[1] + g[2] * g[2]);
@@ -1606,7 +1677,7 @@ struct Oracle {
   // ---------------------------------------------------------------- mehrotra! (solver/mehrotra.jl:9-73)
   int mehrotra(const DojoSolverOptions& opts, int* iters_out) {
     for (ContactS& c : contacts)  // reset! (contacts/constraints.jl:79-86), neutral = [1,1,0,0]
-      for (int idx = 0; idx < 2; ++idx) { const double nv[4] = {1, 1, 0, 0}; for (int i = 0; i < 4; ++i) { c.gam[idx][i] = nv[i]; c.s[idx][i] = nv[i]; } }
+      for (int idx = 0; idx < 2; ++idx) for (int i = 0; i < c.nh; ++i) { c.gam[idx][i] = c.neutral(i); c.s[idx][i] = c.neutral(i); }
     for (JointS& j : joints)      // reset! (joints/constraints.jl:440-448)
       for (int idx = 0; idx < 2; ++idx)
         for (int k = 0; k < 2; ++k) {
@@ -1621,7 +1692,10 @@ struct Oracle {
     double undercut = opts.undercut;
     double alpha = 1.0;
     for (ContactS& c : contacts)  // initialize! (solver/initialization.jl:7-18)
-      for (int idx = 0; idx < 2; ++idx) { initialize_positive_orthant(c.gam[idx][0], c.s[idx][0]); initialize_second_order_cone(c.gam[idx] + 1, c.s[idx] + 1); }
+      for (int idx = 0; idx < 2; ++idx) {
+        if (c.type == 2) { initialize_positive_orthant(c.gam[idx][0], c.s[idx][0]); initialize_second_order_cone(c.gam[idx] + 1, c.s[idx] + 1); }
+        else initialize_positive_orthant_n(c.gam[idx], c.s[idx], c.nh);  // initialization.jl:1-5
+      }
     set_entries();
     double bvio = bilinear_violation();
     double rvio = residual_violation();
@@ -1659,7 +1733,7 @@ struct Oracle {
       // update! (solver/linear_system.jl:54-69)
       for (BodyS& s : bodies) { s.vsol[0] = s.vsol[1]; s.wsol[0] = s.wsol[1]; }
       for (JointS& j : joints) j.imp[0] = j.imp[1];
-      for (ContactS& c : contacts) for (int i = 0; i < 4; ++i) { c.s[0][i] = c.s[1][i]; c.gam[0][i] = c.gam[1][i]; }
+      for (ContactS& c : contacts) for (int i = 0; i < c.nh; ++i) { c.s[0][i] = c.s[1][i]; c.gam[0][i] = c.gam[1][i]; }
       set_entries();
       if (!(rvio == rvio) || !(bvio == bvio)) { status = DOJO_STATUS_NONFINITE; break; }
     }
@@ -1775,9 +1849,9 @@ struct Oracle {
       int ob = body_off[c.body];
       add(ob, colx(c.body), 6, 3, [&](int r, int cc) { return Zb(r, cc); });
       add(ob, colq(c.body), 6, 3, [&](int r, int cc) { return Zb(r, 3 + cc); });
-      Mat<4, 6> Zc = -(contact_constraint_jacobian_configuration(c) * icj);
-      add(c.sol_off + 4, colx(c.body), 4, 3, [&](int r, int cc) { return Zc(r, cc); });
-      add(c.sol_off + 4, colq(c.body), 4, 3, [&](int r, int cc) { return Zc(r, 3 + cc); });
+      Mat<6, 6> Zc = -(contact_constraint_jacobian_configuration(c) * icj);
+      add(c.sol_off + c.nh, colx(c.body), c.nh, 3, [&](int r, int cc) { return Zc(r, cc); });
+      add(c.sol_off + c.nh, colq(c.body), c.nh, 3, [&](int r, int cc) { return Zc(r, 3 + cc); });
     }
   }
   // translational/springs.jl:44-60, rotational/springs.jl:44-84 (attjac = true): 6 x 6
@@ -1900,9 +1974,10 @@ struct Oracle {
     for (int ci = 0; ci < Ni; ++ci) {
       const ContactS& c = contacts[ci];
       Cfg p = cfg_next(c.body);  // (x3, v25, q3, w25)
-      Mat<4, 1> gam;
+      if (c.type != 2) continue;  // the reference defines the contact-data blocks for NonlinearContact only (gradients/data.jl:152,173)
+      Mat<6, 1> gam;
       for (int i = 0; i < 4; ++i) gam[i] = c.gam[1][i];
-      Mat<3, 4> X = force_mapping(c);
+      Mat<3, 6> X = force_mapping(c);
       V3 Fb = (VRmat(p.q) * LtVtmat(p.q)) * (X * gam);
       M33 dp = -dskew_dp(Fb);                                            // ∇p
       V3 drad = (-dskew_dp(Fb)) * (-(rotation_matrix(inv(p.q)) * tr(c.nrm)));  // ∇contact_radius

@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dojo_jl_b200  # noqa: E402
 from dojo_jl_b200 import quat as Q  # noqa: E402
-from dojo_jl_b200.mechanism import Body, Contact, Joint, JointElement, Mechanism, MECHANISM_DIR  # noqa: E402
+from dojo_jl_b200.mechanism import Body, Contact, Joint, JointElement, Mechanism, MECHANISM_DIR, pack_maximal_state  # noqa: E402
 
 Z_AXIS = np.array([0.0, 0.0, 1.0])
 X_AXIS = np.array([1.0, 0.0, 0.0])
@@ -165,6 +165,35 @@ def build_pendulum():
     return mech
 
 
+def build_sphere():
+    """DojoEnvironments/src/mechanisms/sphere/mechanism.jl:1-67 (defaults): Sphere(0.5, 1) on a Floating joint, one contact of
+    radius 0.5 at the centre; initialize_sphere!: centre at z = 0.5 + r, velocity [1, 0, 0]."""
+    m, r = 1.0, 0.5
+    body = Body("sphere", m, 0.4 * m * r * r * np.eye(3))  # bodies/shapes.jl:247-256
+    j = make_joint("floating", "floating_joint", -1, 0, None, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    mech = Mechanism("sphere", [body], [j], [], timestep=0.01)
+    mech.contacts = [nonlinear_contact(mech, "contact", "sphere", Z_AXIS, 0.8, np.zeros(3), r)]
+    mech.z0 = pack_maximal_state([[0.0, 0.0, 0.5 + r]], [[1.0, 0.0, 0.0]], [[1.0, 0, 0, 0]], [[0.0, 0.0, 0.0]])
+    return mech
+
+
+def build_block():
+    """DojoEnvironments/src/mechanisms/block/mechanism.jl:1-95 (defaults): Box(0.5, 0.5, 0.5, 1) on a Floating joint, 8 corner
+    contacts of radius 0; initialize_block!: centre at z = 1 + 0.25 (angular velocity: the reference draws randn(3); here 0)."""
+    m, a = 1.0, 0.5
+    body = Body("block", m, m / 12.0 * np.diag([2 * a * a, 2 * a * a, 2 * a * a]))  # bodies/shapes.jl:83-92
+    j = make_joint("floating", "joint", -1, 0, None, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    mech = Mechanism("block", [body], [j], [], timestep=0.01)
+    k = 0
+    for sz in (-1, 1):
+        for sx in (1, -1):
+            for sy in (1, -1):
+                k += 1
+                mech.contacts.append(nonlinear_contact(mech, f"contact{k}", "block", Z_AXIS, 0.8, 0.5 * a * np.array([sx, sy, sz], float), 0.0))
+    mech.z0 = pack_maximal_state([[0.0, 0.0, 1.0 + 0.5 * a]], [[0.0, 0.0, 0.0]], [[1.0, 0, 0, 0]], [[0.0, 0.0, 0.0]])
+    return mech
+
+
 def build_ant(ref):
     path = os.path.join(ref, "DojoEnvironments/src/mechanisms/ant/dependencies/ant.urdf")
     mech = mechanism_from_urdf(path, "ant", floating=True, timestep=0.05)
@@ -242,7 +271,7 @@ def main():
     ap.add_argument("--reference", default="/root/reference")
     args = ap.parse_args()
     os.makedirs(MECHANISM_DIR, exist_ok=True)
-    for mech in (build_pendulum(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
+    for mech in (build_pendulum(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
         mech.save(os.path.join(MECHANISM_DIR, f"{mech.name}.json"))
         print(f"{mech.name}: Nb={mech.Nb} Ne={mech.Ne} Ni={mech.Ni} nres={mech.nres} nu={mech.nu}")
 
