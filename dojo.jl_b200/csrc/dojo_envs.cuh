@@ -61,7 +61,7 @@ DJ_DEV void env_post(const EnvArgs& a, int e) {
   max_to_min_one(a.joints, a.Ne, a.h, a.Zn + (size_t)e * 13 * a.Nb, sn);
   double contact_cost = 0.0;
   for (int c = 0; c < a.Ni; ++c) {
-    const double g = clamp_unit(a.sol[(size_t)e * a.nres + a.contacts[c].sol_off + 4]);  // contact.impulses[2][1]
+    const double g = clamp_unit(a.sol[(size_t)e * a.nres + a.contacts[c].sol_off + (a.contacts[c].tn >> 8)]);  // contact.impulses[2][1] (entry = [s(N½); gamma(N½)])
     if (sp.contact_obs) sn[2 * a.nu + c] = g;
     contact_cost += g * g;
   }

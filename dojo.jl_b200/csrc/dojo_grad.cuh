@@ -62,10 +62,61 @@ DJ_DEV void grad_body(Ctx& c, int idx) {
   stm33(rec + 18, k.E);
 }
 
+#ifdef DJ_ANY_CONTACT
+// ImpactContact / LinearContact: the data blocks of the state columns are generic over the contact model (gradients/data.jl:126-135,
+// :194-205 with constraint_jacobian_configuration of impact.jl:66-75 / contact.jl:9-35); condensed like the solver's right-hand sides
+DJ_DEV void grad_contact_orthant(Ctx& c, int idx) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const ContactDev& cd = c.contacts[idx];
+  const int type = contact_type(cd), nh = contact_nh(cd);
+  const double* so = A + P.sol_off + cd.sol_off;
+  Kin k = body_kin(c, cd.body, 0.0);
+  ContactGeom q = contact_geom(cd, k);
+  double s[6], g[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { s[i] = 1.0; g[i] = 1.0; if (i < nh) { s[i] = so[i]; g[i] = so[nh + i]; } }
+  V3 F = orthant_force(type, q, g);
+  V3 tau = tmul(k.R3, cross(q.rc, F));
+  M33 R3so = k.R3 * skew(q.o);
+  M33 Mqq = transport(k.w, P.h);
+  V3 nphi = vtmul((-2.0) * vtmul(q.n, R3so), Mqq);
+  M33 dvc_dd = (2.0 * (skew(q.rc) * (k.R3 * skew(k.w))) - 2.0 * (skew(q.ww) * R3so)) * Mqq;
+  V3 v0 = vtmul(q.t0, dvc_dd), v1 = vtmul(q.t1, dvc_dd);
+  const double Zn[6] = {-q.n.x, -q.n.y, -q.n.z, -nphi.x, -nphi.y, -nphi.z};
+  const double Z0[6] = {0, 0, 0, -v0.x, -v0.y, -v0.z};
+  const double Z1[6] = {0, 0, 0, -v1.x, -v1.y, -v1.z};
+  double Zc[6][6];
+  orthant_expand(type, Zn, Z0, Z1, Zc);
+  const double* G = A + cd.G_off;
+  M33 K = (2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so))) * Mqq;
+  double* CB = A + cd.gc_off;
+#pragma unroll 1
+  for (int cc = 0; cc < 6; ++cc) {
+    double t[12], y[12];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { t[i] = 0.0; t[6 + i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (i < nh) t[nh + i] = Zc[i][cc];
+    orthant_solve(type, s, g, cd.mu, t, y);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double v = 0.0;
+      for (int i = 0; i < nh; ++i) v += G[r * nh + i] * y[nh + i];
+      if (r >= 3 && cc >= 3) v += K.m[r - 3][cc - 3];
+      CB[r * 6 + cc] = v;
+    }
+  }
+}
+#endif
+
 DJ_DEV void grad_contact(Ctx& c, int idx) {
   const Plan& P = *c.P;
   double* A = c.A;
   const ContactDev& cd = c.contacts[idx];
+#ifdef DJ_ANY_CONTACT
+  if (contact_type(cd) != 2) { grad_contact_orthant(c, idx); return; }
+#endif
   const double* so = A + P.sol_off + cd.sol_off;
   Kin k = body_kin(c, cd.body, 0.0);
   V3 n = ld3(cd.n), t0 = ld3(cd.t), t1 = ld3(cd.t + 3), o = ld3(cd.o), off = ld3(cd.off);

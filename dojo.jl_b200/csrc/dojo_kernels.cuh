@@ -20,6 +20,11 @@
 
 namespace dj {
 
+#ifdef DJ_ANY_CONTACT  // contact model of a plan entry (ContactDev::tn), see dojo_contact_orthant.cuh
+DJ_DEV int contact_type(const ContactDev& cd) { return cd.tn & 0xff; }
+DJ_DEV int contact_nh(const ContactDev& cd) { return cd.tn >> 8; }
+#endif
+
 DJ_DEV V3 ld3(const double* p) { return V3{p[0], p[1], p[2]}; }
 DJ_DEV void st3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 DJ_DEV void add3(double* p, V3 v) { p[0] += v.x; p[1] += v.y; p[2] += v.z; }
@@ -330,6 +335,13 @@ DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, cons
     } else {  // reset! + initialize! (contacts/constraints.jl:79-86, solver/initialization.jl:7-48)
       double* so = A + P.sol_off + c.contacts[idx].sol_off;
       const double v0 = 1.0 + 0.5 * 1.0 * 1.0 / (1.0 + 1e-20);  // neutral (1,1,0,0) pushed to 1.5 by the Mehrotra-style start
+#ifdef DJ_ANY_CONTACT
+      if (contact_type(c.contacts[idx]) != 2) {  // impact / linear: neutral = ones(N½), initialize_positive_orthant! (initialization.jl:1-5, :20-33)
+        const int n2 = 2 * contact_nh(c.contacts[idx]);
+        for (int i = 0; i < n2; ++i) so[i] = v0;
+        continue;
+      }
+#endif
       so[0] = v0; so[1] = v0; so[2] = 0.0; so[3] = 0.0;
       so[4] = v0; so[5] = v0; so[6] = 0.0; so[7] = 0.0;
     }
@@ -425,6 +437,10 @@ DJ_DEV void contact_solve(const ContactBlock& b, const double* t, double* y) {
   y[7] = b.Mi[2][0] * b1 + b.Mi[2][1] * b2 + b.Mi[2][2] * b3;
 }
 
+#ifdef DJ_ANY_CONTACT
+#include "dojo_contact_orthant.cuh"  // ImpactContact / LinearContact (only in the translation unit that serves such mechanisms)
+#endif
+
 // contacts (contacts/nonlinear.jl:50-97, contacts/contact.jl:37-155, collisions/sphere_halfspace.jl)
 template <bool JAC>
 DJ_DEV void eval_contact(Ctx& c, int idx, double f, double* res, double& rv, double& bv) {
@@ -433,6 +449,9 @@ DJ_DEV void eval_contact(Ctx& c, int idx, double f, double* res, double& rv, dou
   const double* sol = A + P.sol_off;
   const double* dl = A + P.rhs_off;
   const ContactDev& cd = c.contacts[idx];
+#ifdef DJ_ANY_CONTACT
+  if (contact_type(cd) != 2) { eval_contact_orthant<JAC>(c, idx, f, res, rv, bv); return; }
+#endif
   Kin k = body_kin(c, cd.body, f);
   double s[4], g[4];
 #pragma unroll
@@ -712,6 +731,9 @@ DJ_DEV void condense_contact(Ctx& c, int idx, const double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
   const ContactDev& cd = c.contacts[idx];
+#ifdef DJ_ANY_CONTACT
+  if (contact_type(cd) != 2) { condense_contact_orthant(c, idx, x); return; }
+#endif
   const double* so = A + P.sol_off + cd.sol_off;
   ContactBlock cb = contact_block(so, so + 4, cd.mu);
   double y[8];
@@ -728,6 +750,9 @@ DJ_DEV void recover_contact(Ctx& c, int idx, double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
   const ContactDev& cd = c.contacts[idx];
+#ifdef DJ_ANY_CONTACT
+  if (contact_type(cd) != 2) { recover_contact_orthant(c, idx, x); return; }
+#endif
   const double* so = A + P.sol_off + cd.sol_off;
   ContactBlock cb = contact_block(so, so + 4, cd.mu);
   const double* J = A + cd.J_off;
@@ -1100,6 +1125,13 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
     if (role.type[p] == ROLE_CONTACT) {
       const ContactDev& cd = c.contacts[idx];
       const double* s = sol + cd.sol_off;
+#ifdef DJ_ANY_CONTACT
+      if (contact_type(cd) != 2) {  // impact / linear: positive orthant only (line_search.jl:71-86)
+        const int n2 = 2 * contact_nh(cd);
+        for (int i = 0; i < n2; ++i) a = fmin(a, ort_step(s[i], dl[cd.sol_off + i], tau_ort));
+        continue;
+      }
+#endif
       const double* g = s + 4;
       const double* ds = dl + cd.sol_off;
       const double* dg = ds + 4;
@@ -1127,6 +1159,18 @@ DJ_DEV void centering(Ctx& c, double aaff, double& nu, double& nuaff) {
     if (idx < 0) continue;
     if (role.type[p] == ROLE_CONTACT) {
       const ContactDev& cd = c.contacts[idx];
+#ifdef DJ_ANY_CONTACT
+      if (contact_type(cd) != 2) {  // cone_degree = N½ (contact.jl:197)
+        const int nh = contact_nh(cd);
+        for (int i = 0; i < nh; ++i) {
+          double s = sol[cd.sol_off + i], g = sol[cd.sol_off + nh + i];
+          sn += s * g;
+          sa += (s + aaff * dl[cd.sol_off + i]) * (g + aaff * dl[cd.sol_off + nh + i]);
+        }
+        cnt += (double)nh;
+        continue;
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double s = sol[cd.sol_off + i], g = sol[cd.sol_off + 4 + i];
@@ -1161,6 +1205,13 @@ DJ_DEV void correction(Ctx& c) {
     if (role.type[p] == ROLE_CONTACT) {
       const ContactDev& cd = c.contacts[idx];
       const double* ds = dl + cd.sol_off;
+#ifdef DJ_ANY_CONTACT
+      if (contact_type(cd) != 2) {  // correction.jl:13-19
+        const int nh = contact_nh(cd);
+        for (int i = 0; i < nh; ++i) sav[cd.sol_off + i] += -ds[i] * ds[nh + i] + c.mu;
+        continue;
+      }
+#endif
       const double* dg = ds + 4;
       double* r = sav + cd.sol_off;
       r[0] += -ds[0] * dg[0] + c.mu;

@@ -66,13 +66,17 @@ struct JointDev {
 };
 
 struct ContactDev {
-  int body, sol_off;  // [s(4); gamma(4)] inside the solution vector
+  int body, sol_off;  // [s(N½); gamma(N½)] inside the solution vector (NonlinearContact: N½ = 4)
   double mu, radius;
   double n[3], t[6], o[3], off[3];
   int J_off, G_off, rec_off;  // J = d(constraint)/d(v25,w25) 4x6 ; G = impulse map 6x4 ; 3 reciprocals of the closed-form block solve
   int slot;
   int gc_off;                 // gradient pass: condensed body block CB (6x6)
+  int tn;                     // contact model: type | N½ << 8 (type 0 impact N½ = 1, 1 linear N½ = 6, 2 nonlinear N½ = 4); the entry is
+                              // [s(N½); gamma(N½)], J is N½ x 6, G is 6 x N½.  Occupies what used to be tail padding: the layout the
+                              // NonlinearContact kernels see is unchanged
 };
+static_assert(sizeof(ContactDev) == 168, "ContactDev layout is part of the kernels' addressing");
 
 // One elimination step of the block LDU (GraphBasedSystems ldu_factorization!)
 struct ElimNb {

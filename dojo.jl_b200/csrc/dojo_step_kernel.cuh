@@ -1,0 +1,229 @@
+// dojo_step_kernel.cuh -- kernel entry point of the per-timestep hot path: dojo_step_kernel<GRAD> and its argument block.
+//
+// Compiled twice into libdojo_b200.so:
+//   * dojo_b200.cu     (namespace dj):    NonlinearContact only -- every BASELINE model; this is the benchmarked kernel
+//   * dojo_b200_cm.cu  (namespace dj_cm, DJ_ANY_CONTACT): additionally ImpactContact / LinearContact, selected by
+//     dojo_create for mechanisms that contain such contacts.  The extra model code never enters the first compilation, whose SASS
+//     is bit-identical with and without this split (checked with cuobjdump, profiles/README.md).
+// The `// [hostemu:...]` markers delimit the text that tests/hostemu/gen.py compiles for the CPU emulation of the kernel.
+#pragma once
+#include "../../include/dojo_b200.h"
+#include "dojo_grad.cuh"
+
+namespace dj {
+
+// [hostemu:kernel:begin]
+struct StepArgs {
+  Plan plan;
+  Options opts;
+  int B;
+  const double* Z;
+  const double* U;
+  const double* Fext;
+  double* Zn;
+  double* sol;
+  int32_t* status;
+  int32_t* iters;
+  int* done_count;  // forward kernel: environments finished so far; done_list[k] = k-th finished environment (-1 = not yet).
+  int* done_list;   // gradient kernel: consumes done_list in order while the forward kernel is still running (nullable: all ready)
+  double* sol_raw;  // nullable [nres x B]: final solution in DEVICE ordering (written by the forward kernel, read by the gradient kernel)
+  double* Fz;  // gradients (GRAD kernels): [12Nb x 12Nb x B], [12Nb x nu x B], column-major per environment
+  double* Fu;
+  double* Fc;  // nullable: contact-data gradients [12Nb x 5Ni x B] (get_contact_gradients)
+  uint32_t flags;
+  int* counter;  // dynamic work queue over environments
+  const int* order;     // processing order (longest-expected first), or nullptr
+  int32_t* prev_iters;  // Newton iterations of the previous call per environment (predicts the cost of the next one)
+  const char* plan_blob;  // plan tables, one contiguous blob: [bodies | joints | contacts | steps | sched | ilist | roles | ucol]
+  int plan_bytes, plan_off[8];
+  int plan_smem_off;    // >= 0: doubles from the start of dynamic shared memory where the CTA keeps its copy of the blob
+  int slot_stride;      // doubles between the arenas of two slots of a CTA
+  int T;                // time steps fused in this launch (rollouts: every environment is advanced T steps by one CTA)
+  double* traj;         // nullable [T][B][nz]: state after every step
+  unsigned long long* prof;  // DJ_PROFILE builds: cycle counters [eval_jac, eval_ls, factorize, solve, misc]
+};
+
+// epilogue: update_state! + get_next_state (bodies/set.jl:22-36, mechanism/get.jl:126-134).  The default output is the
+// mechanism's state after the step, (x3, v25, q3, w25); DOJO_FLAG_Q1_LITERAL_RETURN reproduces step!'s literal return
+// value, which advances the configuration a second time.
+DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
+  const Plan& P = *c.P;
+  if (c.tid < P.Nb) {
+    Kin k = body_kin(c, c.tid, 0.0);
+    V3 x3 = k.x3;
+    Quat q3 = k.q3;
+    if (q1_literal) { x3 = x3 + P.h * k.v; q3 = qmul(q3, qmap(k.w, P.h)); }
+    double* o = zn + 13 * c.tid;
+    o[0] = x3.x; o[1] = x3.y; o[2] = x3.z;
+    o[3] = k.v.x; o[4] = k.v.y; o[5] = k.v.z;
+    o[6] = q3.s; o[7] = q3.x; o[8] = q3.y; o[9] = q3.z;
+    o[10] = k.w.x; o[11] = k.w.y; o[12] = k.w.z;
+  }
+}
+
+// register budget: 65536 / (DJ_LB_THREADS * DJ_LB_BLOCKS) registers per thread
+#ifndef DJ_LB_THREADS
+#define DJ_LB_THREADS 256
+#define DJ_LB_BLOCKS 1
+#endif
+#ifdef DJ_PROFILE
+__device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { return *((volatile unsigned long long*)(prof + 31)); }
+#endif
+template <bool GRAD>
+__global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(const StepArgs a) {
+  extern __shared__ double arena[];
+  __shared__ int s_env[8];
+  // a CTA hosts a.slots environments at a time; slot k is served by threads [k * 32 nw, (k + 1) * 32 nw)
+  const int slot_threads = 32 * a.plan.nw;
+  const int slot = threadIdx.x / slot_threads;
+  Ctx c;
+  c.A = arena + (size_t)slot * a.slot_stride;
+  c.P = &a.plan;
+  c.tid = threadIdx.x - slot * slot_threads;
+  c.nthreads = slot_threads;
+  c.warp = c.tid >> 5;
+  c.lane = c.tid & 31;
+  c.bar = 1 + slot;
+  c.sd = 0;
+  c.mu = 0.0;
+  {
+    const char* pb = a.plan_blob;
+    if (a.plan_smem_off >= 0) {  // one copy of the plan tables per CTA, shared by its slots
+      int4* dst = reinterpret_cast<int4*>(arena + a.plan_smem_off);
+      const int4* src = reinterpret_cast<const int4*>(a.plan_blob);
+      for (int i = threadIdx.x; i < a.plan_bytes / 16; i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+      pb = reinterpret_cast<const char*>(dst);
+    }
+    c.bodies = reinterpret_cast<const BodyDev*>(pb + a.plan_off[0]);
+    c.joints = reinterpret_cast<const JointDev*>(pb + a.plan_off[1]);
+    c.contacts = reinterpret_cast<const ContactDev*>(pb + a.plan_off[2]);
+    c.steps = reinterpret_cast<const ElimStep*>(pb + a.plan_off[3]);
+    c.sched = reinterpret_cast<const int*>(pb + a.plan_off[4]);
+    c.ilist = reinterpret_cast<const int*>(pb + a.plan_off[5]);
+    c.roles = reinterpret_cast<const WarpRole*>(pb + a.plan_off[6]);
+    c.ucol = reinterpret_cast<const int*>(pb + a.plan_off[7]);
+  }
+#ifdef DJ_PROFILE
+  c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = c.t_align = c.t_cone = c.t_center = c.t_rolewait = 0; c.t_last = clock64();
+  c.f_fold = c.f_inv = c.f_rm = c.f_schur = c.f_bar = 0;
+  long long k_c0 = clock64(); unsigned long long k_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t0));
+  int k_envs = 0;
+  if (c.tid == 0 && a.prof) atomicMin(a.prof + 31, k_t0);
+#endif
+  // let a programmatically dependent launch (the gradient kernel of dojo_step_grad) start as soon as every CTA of this
+  // grid is running; it synchronises per environment through done_list, not through grid completion
+  if (!GRAD) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const Plan& P = a.plan;
+  for (;;) {
+    if (c.tid == 0) {  // dynamic work queue: iteration counts differ between environments
+      int q = atomicAdd(a.counter, 1);
+      int env = (q < a.B && a.order) ? a.order[q] : q;
+      if (GRAD && a.done_list && q < a.B) {  // wait for the q-th environment the forward kernel finishes
+        while ((env = ((volatile int*)a.done_list)[q]) < 0) __nanosleep(256);
+        __threadfence();
+      }
+      s_env[slot] = env;
+    }
+    slot_sync(c);
+    const int e = s_env[slot];
+    slot_sync(c);
+    if (e >= a.B) break;
+    DJ_TICK(c, t_misc)
+#ifdef DJ_PROFILE
+    k_envs++;
+    unsigned long long e_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t0));
+#endif
+    const double* z = a.Z + (size_t)e * P.nz;
+    int worst = 0, iters = 0, status = 0;
+    if (!GRAD) {
+      for (int t = 0; t < a.T; ++t) {
+        const double* u = a.U ? a.U + ((size_t)t * a.B + e) * P.nu : nullptr;
+        const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
+        prologue(c, z, u, fx, false);
+        status = mehrotra(c, a.opts, &iters);
+        worst = max(worst, status);
+        // state after this step: the trajectory slot if recorded, else the output buffer (re-read by the next step from L2)
+        double* zo = (a.traj ? a.traj + ((size_t)t * a.B + e) * P.nz : a.Zn + (size_t)e * P.nz);
+        epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+        if (t + 1 < a.T) { __threadfence_block(); slot_sync(c); z = zo; }
+      }
+      if (a.traj) {  // final state also goes to Zn
+        slot_sync(c);
+        for (int k = c.tid; k < P.nz; k += c.nthreads) a.Zn[(size_t)e * P.nz + k] = a.traj[((size_t)(a.T - 1) * a.B + e) * P.nz + k];
+      }
+      status = worst;
+      if (a.sol_raw)
+        for (int t = c.tid; t < P.nres; t += c.nthreads) a.sol_raw[(size_t)e * P.nres + t] = c.A[P.sol_off + t];
+    } else {
+      // gradient pass (get_maximal_gradients!, gradients/state.jl:69-126) at the solution the forward launch left in
+      // sol_raw: rebuild the step constants and the KKT blocks of the final iterate, then solve for the columns
+      const double* u = a.U ? a.U + (size_t)e * P.nu : nullptr;
+      const double* fx = a.Fext ? a.Fext + (size_t)e * 6 * P.Nb : nullptr;
+      prologue(c, z, u, fx, true);
+      for (int t = c.tid; t < P.nres; t += c.nthreads) c.A[P.sol_off + t] = a.sol_raw[(size_t)e * P.nres + t];
+      slot_sync(c);
+      double rv, bv;
+      c.mu = 0.0;
+      evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
+      status = a.status ? a.status[e] : 0;
+      const size_t ng = 12 * (size_t)P.Nb;
+      if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu, a.Fc ? a.Fc + (size_t)e * ng * 5 * P.Ni : nullptr) && status == 0) status = 3;
+    }
+    if (a.sol) {  // reference ordering: joints [tra eq | s | gamma | rot eq] | bodies | contacts (device layout keeps eq rows first)
+      double* so = a.sol + (size_t)e * P.nres;
+      const int first_body = c.bodies[0].sol_off;
+      for (int t = c.tid; t < P.nres; t += c.nthreads)
+        if (t >= first_body) so[t] = c.A[P.sol_off + t];
+      if (c.tid < P.Ne) {
+        const JointDev& jd = c.joints[c.tid];
+        const double* src = c.A + P.sol_off + jd.sol_off;
+        double* dst = so + jd.sol_off;
+        for (int i = 0; i < jd.nl_t; ++i) dst[i] = src[i];
+        for (int i = 0; i < 2 * jd.nb_r; ++i) dst[jd.nl_t + i] = src[jd.ne + i];
+        for (int i = 0; i < jd.nl_r; ++i) dst[jd.nl_t + 2 * jd.nb_r + i] = src[jd.nl_t + i];
+      }
+    }
+    if (c.tid == 0) {
+      if (a.status) a.status[e] = status;
+      if (!GRAD) {
+        if (a.iters) a.iters[e] = iters;
+        if (a.prev_iters) a.prev_iters[e] = iters;
+      }
+#ifdef DJ_PROFILE
+      if (a.prof) { unsigned long long e_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e_t1)); a.prof[32 + 2 * e] = e_t0 - k_t0g(a.prof); a.prof[33 + 2 * e] = e_t1 - e_t0; }
+#endif
+    }
+    if (!GRAD && a.done_list) {  // publish: results of this environment are visible before its index appears in the list
+      __threadfence();
+      slot_sync(c);
+      if (c.tid == 0) {
+        const int pos = atomicAdd(a.done_count, 1);
+        __threadfence();
+        ((volatile int*)a.done_list)[pos] = e;
+      }
+    }
+    slot_sync(c);
+  }
+  while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
+  // a gradient grid that started early (programmatic dependent launch) does not complete before the forward grid has
+  if (GRAD) asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef DJ_PROFILE
+  DJ_TICK(c, t_misc)
+  if (c.lane == 0 && a.prof) atomicAdd(a.prof + 17 + c.warp, (unsigned long long)c.t_rolewait);
+  if (c.tid == 0 && a.prof) {
+    atomicAdd(a.prof + 0, (unsigned long long)c.t_eval_jac); atomicAdd(a.prof + 1, (unsigned long long)c.t_eval_ls);
+    atomicAdd(a.prof + 2, (unsigned long long)c.t_fact); atomicAdd(a.prof + 3, (unsigned long long)c.t_solve); atomicAdd(a.prof + 4, (unsigned long long)c.t_misc);
+    atomicAdd(a.prof + 5, (unsigned long long)c.f_fold); atomicAdd(a.prof + 6, (unsigned long long)c.f_inv); atomicAdd(a.prof + 7, (unsigned long long)c.f_rm);
+    atomicAdd(a.prof + 8, (unsigned long long)c.f_schur); atomicAdd(a.prof + 9, (unsigned long long)c.f_bar);
+    unsigned long long k_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k_t1));
+    atomicMax(a.prof + 10, (unsigned long long)(clock64() - k_c0)); atomicMax(a.prof + 11, k_t1 - k_t0);
+    atomicMax(a.prof + 12, (unsigned long long)k_envs); atomicAdd(a.prof + 13, (unsigned long long)(clock64() - k_c0));
+    atomicAdd(a.prof + 14, (unsigned long long)c.t_align); atomicAdd(a.prof + 15, (unsigned long long)c.t_cone); atomicAdd(a.prof + 16, (unsigned long long)c.t_center);
+  }
+#endif
+}
+
+// [hostemu:kernel:end]
+
+}  // namespace dj

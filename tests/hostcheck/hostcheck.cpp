@@ -125,7 +125,7 @@ void hostcheck_env_post(void* p, const int* spec_i, const double* spec_d, int Ni
   Mech* m = static_cast<Mech*>(p);
   std::vector<ContactDev> contacts(Ni > 0 ? Ni : 1);
   std::memset(contacts.data(), 0, sizeof(ContactDev) * contacts.size());
-  for (int c = 0; c < Ni; ++c) contacts[c].sol_off = contact_sol_off[c];
+  for (int c = 0; c < Ni; ++c) { contacts[c].sol_off = contact_sol_off[c]; contacts[c].tn = 2 | (4 << 8); }  // NonlinearContact entries [s(4); gamma(4)]
   EnvArgs a = env_args(m, spec_i, spec_d, Ni, nres, contacts.data(), B);
   a.S = S; a.A = A; a.Zn = Zn; a.sol = sol; a.Sn = Sn; a.reward = reward; a.done = done; a.ret = ret; a.dead = dead;
   for (int e = 0; e < B; ++e) env_post(a, e);
