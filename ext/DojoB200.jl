@@ -69,9 +69,14 @@ function flatten(mech::Mechanism{T,Nn,Ne,Nb,Ni}) where {T,Nn,Ne,Nb,Ni}
     joints = [JointDesc(bidx(j.parent_id), bidx(j.child_id), Tuple(j.translational.vertices[1]), Tuple(j.translational.vertices[2]),
                         Tuple(vector(j.rotational.orientation_offset)), element(j.translational), element(j.rotational)) for j in mech.joints]
     contacts = map(mech.contacts) do c
-        c.model isa NonlinearContact || error("DojoB200: only NonlinearContact is implemented")
+        # contact_type (contacts/constructor.jl:117-128): 0 ImpactContact, 1 LinearContact, 2 NonlinearContact
+        ctype = c.model isa NonlinearContact ? 2 : c.model isa LinearContact ? 1 : c.model isa ImpactContact ? 0 :
+                error("DojoB200: unknown contact model $(typeof(c.model))")
         col = c.model.collision
-        ContactDesc(2, bidx(c.parent_id), c.model.friction_coefficient, Tuple(vec(col.contact_tangent')), Tuple(vec(col.contact_normal')),
+        col isa SphereHalfSpaceCollision || error("DojoB200: only SphereHalfSpaceCollision is implemented")
+        μf = ctype == 0 ? 0.0 : c.model.friction_coefficient                       # ImpactContact has no friction (impact.jl:8-11)
+        tangent = ctype == 0 ? ntuple(_ -> 0.0, 6) : Tuple(vec(col.contact_tangent'))   # ... and a 0 x 3 contact_tangent (impact.jl:34)
+        ContactDesc(ctype, bidx(c.parent_id), μf, tangent, Tuple(vec(col.contact_normal')),
                     Tuple(col.contact_origin), col.contact_radius, Tuple(col.contact_offset))
     end
     return bodies, joints, contacts

@@ -94,10 +94,18 @@ typedef struct {
   DojoJointElementDesc tra, rot;
 } DojoJointDesc;
 
-/* ContactConstraint{NonlinearContact} + SphereHalfSpaceCollision
- * (src/contacts/nonlinear.jl:12-48, src/contacts/collisions/sphere_halfspace.jl:11-24). */
+/* ContactConstraint{model} + SphereHalfSpaceCollision (src/contacts/constructor.jl:14-43,
+ * src/contacts/collisions/sphere_halfspace.jl:11-24); the model is the reference's `contact_type`
+ * (src/contacts/constructor.jl:117-128):
+ *   2 NonlinearContact{T,8}  second-order friction cone        src/contacts/nonlinear.jl:12-97
+ *   1 LinearContact{T,12}    4-sided friction pyramid          src/contacts/linear.jl:10-104
+ *   0 ImpactContact{T,2}     no friction (friction_coefficient, tangent unused)  src/contacts/impact.jl:8-146
+ * The contact's entry in solution / residual vectors is [s(N/2); gamma(N/2)].  Mechanisms whose contacts are all of type 2
+ * (every BASELINE model) run on the benchmarked kernels; any type 0 / 1 contact selects a second compilation of the same
+ * kernels with the two orthant models enabled (csrc/dojo_b200_cm.cu).  dojo_step_grad_contact is defined for type 2 only,
+ * like the reference's contact-data blocks (src/gradients/data.jl:152, :173). */
 typedef struct {
-  int32_t type;        /* 2 = nonlinear (second-order cone); 0 impact / 1 linear are not implemented */
+  int32_t type;        /* 0 impact, 1 linear, 2 nonlinear */
   int32_t parent_body; /* 0-based body index; child is always the origin half-space */
   double friction_coefficient;
   double tangent[6];   /* contact_tangent, row-major 2x3 */
