@@ -98,7 +98,9 @@ struct DojoHandle {
   double *p_in = nullptr, *p_out = nullptr;  // pinned
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
-  bool any_contact = false;                       // some contact is an ImpactContact / LinearContact: DJ_ANY_CONTACT kernels (dojo_b200_cm.cu)
+  bool any_contact = false;                       // the mechanism needs the DJ_ANY_CONTACT kernels (dojo_b200_cm.cu): it has ...
+  bool orthant_contact = false;                   // ... an ImpactContact / LinearContact
+  bool tra_joint = false;                         // ... or translational springs / dampers / limits
   const void *k_fwd = nullptr, *k_grad = nullptr;  // dojo_step_kernel<false> / <true> of the compilation that serves this mechanism
   std::string err;
 };
@@ -156,8 +158,8 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     if (jd.child_body < 0 || jd.child_body >= Nb || jd.parent_body < -1 || jd.parent_body >= Nb) return fail("joint body index out of range");
     if (parent_joint[jd.child_body] >= 0) return fail("loop-closure joints are not supported yet (each body needs exactly one parent joint)");
     parent_joint[jd.child_body] = j;
-    if (jd.tra.nlimits != 0) return fail("translational joint limits are not supported yet");
-    if ((jd.tra.nlambda < 3) && (jd.tra.spring != 0.0 || jd.tra.damper != 0.0)) return fail("translational springs / dampers are not supported yet");
+    if (jd.tra.nlimits != 0 && jd.tra.nlimits != 3 - jd.tra.nlambda) return fail("translational limits must cover every free axis");
+    if (jd.tra.nlimits != 0 && jd.rot.nlimits != 0) return fail("limits on both the translational and the rotational part of one joint are not supported");
     if (jd.rot.nlimits != 0 && jd.rot.nlimits != 3 - jd.rot.nlambda) return fail("rotational limits must cover every free axis");
   }
   for (int b = 0; b < Nb; ++b) if (parent_joint[b] < 0) return fail("every body needs a parent joint (use a Floating joint to the origin)");
@@ -196,6 +198,25 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     J.damper_r = (jd.rot.nlambda < 3) ? jd.rot.damper : 0.0;
     for (int i = 0; i < 3; ++i) { J.spring_off_r[i] = jd.rot.spring_offset[i]; J.lo[i] = jd.rot.limit_lo[i]; J.hi[i] = jd.rot.limit_hi[i]; }
     if (J.nb2_r > 3) { delete h; return fail("too many limited axes"); }
+    // translational springs / dampers / limits (joints/translational/springs.jl, dampers.jl, joints/limits.jl): flags + parameters in
+    // the unused rows of Ct (dojo_plan.h); such mechanisms run on the DJ_ANY_CONTACT compilation of the kernels
+    if (J.nfree_t > 0) {
+      if (jd.tra.spring != 0.0) J.flags |= JF_TRA_SPRING;
+      if (jd.tra.damper != 0.0) J.flags |= JF_TRA_DAMPER | JF_FULL;
+      if (jd.tra.nlimits > 0) {
+        J.flags |= JF_LIM_TRA | JF_FULL;
+        J.nb2_r = jd.tra.nlimits; J.nb_r = 2 * J.nb2_r;
+        J.n = J.ne + 2 * J.nb_r;
+        off += 2 * J.nb_r;  // J.sol_off was assigned above with nb_r = 0
+        for (int i = 0; i < 3; ++i) { J.lo[i] = jd.tra.limit_lo[i]; J.hi[i] = jd.tra.limit_hi[i]; }
+      }
+      if (J.flags & (JF_TRA_SPRING | JF_TRA_DAMPER)) {
+        double* tp = joint_tra_params(J);
+        tp[0] = jd.tra.spring; tp[1] = jd.tra.damper;
+        for (int i = 0; i < J.nfree_t; ++i) tp[2 + i] = jd.tra.spring_offset[i];
+      }
+      if (J.flags) h->any_contact = h->tra_joint = true;
+    }
   }
   const int nu = uoff;
   for (int b = 0; b < Nb; ++b) {
@@ -214,7 +235,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     std::memcpy(C.o, cd.origin, sizeof(C.o)); std::memcpy(C.off, cd.offset, sizeof(C.off));
     const int nh = cd.type == 0 ? 1 : (cd.type == 1 ? 6 : 4);  // N½: impact.jl:38, linear.jl:46, nonlinear.jl:47
     C.tn = cd.type | (nh << 8);
-    if (cd.type != 2) h->any_contact = true;
+    if (cd.type != 2) h->any_contact = h->orthant_contact = true;
     C.sol_off = off; off += 2 * nh;
   }
   const int nres = off;
@@ -241,11 +262,12 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   for (int b = 0; b < Nb; ++b) { bodies[b].cst_off = a; a += 6; }
   for (int j = 0; j < Ne; ++j) {  // joint contribution slots (also used by the prologue) and constant (per step) blocks
     JointDev& J = joints[j];
-    J.slot_c = a; a += kSlot;
-    if (J.parent >= 0) { J.slot_p = a; a += kSlot; } else J.slot_p = -1;
+    const int slot_len = (J.flags & JF_FULL) ? kSlotC : kSlot;  // full joints: force(3) torque(3) K(6x6), like a contact
+    J.slot_c = a; a += slot_len;
+    if (J.parent >= 0) { J.slot_p = a; a += slot_len; } else J.slot_p = -1;
     J.Lc_off = a; a += 6 * J.ne;
     if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.ne; } else J.Gp_off = -1;
-    J.lim_off = a; a += kLim * J.nb2_r;
+    J.lim_off = a; a += ((J.flags & JF_FULL) ? 2 * kLim : kLim) * J.nb2_r;  // full: aP(6) aC(6) tP(6) tC(6) per limited axis
   }
   for (int c = 0; c < Ni; ++c) {  // contact records survive the assembly (used by condense / recover)
     ContactDev& C = contacts[c];
@@ -265,7 +287,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
       J.Up_off = a; a += 6 * J.ne;
       J.Lp_off = a; a += 6 * J.ne;
       // body-body coupling exists with dampers and with (condensed) joint limits
-      if (J.damper_r != 0.0 || J.nb2_r > 0) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
+      if (J.damper_r != 0.0 || J.nb2_r > 0 || (J.flags & JF_TRA_DAMPER)) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
     } else { J.Up_off = J.Lp_off = J.BBpc_off = J.BBcp_off = -1; }
   }
   P.mat_len = a - P.mat_off;
@@ -314,8 +336,10 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     bodies[b].g_off = (int)ilist.size();
     for (int c = 0; c < Ni; ++c) if (contacts[c].body == b) ilist.push_back(contacts[c].slot);
     bodies[b].g_ncontact = (int)ilist.size() - bodies[b].g_off;
-    ilist.push_back(joints[parent_joint[b]].slot_c);
-    for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(joints[j].slot_p);
+    // full joints (6 x 6 slots) are marked with bit 30 of the gather entry; only the DJ_ANY_CONTACT kernels ever see such entries
+    auto slot_entry = [&](const JointDev& J, int slot) { return (J.flags & JF_FULL) ? (slot | (1 << 30)) : slot; };
+    ilist.push_back(slot_entry(joints[parent_joint[b]], joints[parent_joint[b]].slot_c));
+    for (int j = 0; j < Ne; ++j) if (joints[j].parent == b) ilist.push_back(slot_entry(joints[j], joints[j].slot_p));
     bodies[b].g_cnt = (int)ilist.size() - bodies[b].g_off;
   }
 
@@ -765,7 +789,7 @@ extern "C" int dojo_step_grad_contact_async(DojoHandle* h, const DojoSolverOptio
                                             double* dZn, double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags,
                                             void* cuda_stream) {
   if (h && !dFc) { h->err = "dojo_step_grad_contact_async: Fc is required"; return DOJO_EINVAL; }
-  if (h && h->any_contact) {  // the reference defines the contact-data blocks for NonlinearContact only (gradients/data.jl:152, :173)
+  if (h && h->orthant_contact) {  // the reference defines the contact-data blocks for NonlinearContact only (gradients/data.jl:152, :173)
     h->err = "dojo_step_grad_contact: contact-data gradients exist for NonlinearContact only (as in the reference)";
     return DOJO_EINVAL;
   }
@@ -775,6 +799,7 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
                           double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
   if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dFz || !dFu || dZ == dZn) { if (h) h->err = "dojo_step_grad_async: bad arguments (B <= max_batch, dZn != dZ)"; return DOJO_EINVAL; }
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
+  if (h->tra_joint) { h->err = "dojo_step_grad: gradients with translational springs / dampers / limits are not implemented yet"; return DOJO_EINVAL; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (!h->d_gsol) {
@@ -1240,6 +1265,10 @@ extern "C" int dojo_step_record_async(DojoHandle* h, const DojoSolverOptions* op
                                       double* ddiag, int32_t* dstatus, int32_t* diters, void* cuda_stream) {
   if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dstorage || !ddiag || dZ == dZn) {
     if (h) h->err = "dojo_step_record_async: bad arguments (B <= max_batch, Z_next != Z)";
+    return DOJO_EINVAL;
+  }
+  if (h->tra_joint) {  // the storage kernel's momentum knows rotational spring / damper impulses only
+    h->err = "dojo_step_record: recording with translational springs / dampers / limits is not implemented yet";
     return DOJO_EINVAL;
   }
   CUDA_TRY(h, cudaSetDevice(h->device));

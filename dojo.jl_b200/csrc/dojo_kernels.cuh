@@ -20,6 +20,14 @@
 
 namespace dj {
 
+// Gather-list entries (BodyDev::g_off): arena offset of a contribution slot.  In the DJ_ANY_CONTACT compilation bit 30 marks the
+// slot of a "full" joint (JF_FULL: 6 x 6 block like a contact slot); the other compilation never sees such entries.
+#ifdef DJ_ANY_CONTACT
+#define DJ_SLOT_OFF(raw) ((raw) & 0x3fffffff)
+#define DJ_SLOT_FULL(raw) (((raw) >> 30) & 1)
+#else
+#define DJ_SLOT_OFF(raw) (raw)
+#endif
 #ifdef DJ_ANY_CONTACT  // contact model of a plan entry (ContactDev::tn), see dojo_contact_orthant.cuh
 DJ_DEV int contact_type(const ContactDev& cd) { return cd.tn & 0xff; }
 DJ_DEV int contact_nh(const ContactDev& cd) { return cd.tn >> 8; }
@@ -210,6 +218,9 @@ DJ_DEV void rotvec_attitude_jacobians(const JointDev& jd, const JointGeom& g, M3
 }
 
 DJ_DEV void write_slot(double* s, V3 f, V3 t, const M33& K) { st3(s, f); st3(s + 3, t); stm33(s + 6, K); }
+#ifdef DJ_ANY_CONTACT
+#include "dojo_joint_tra.cuh"  // translational springs / dampers / limits (only in the compilation that serves such mechanisms)
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // Prologue: set_maximal_state!, set_input!, explicit spring impulses, joint impulse maps (constant over the solve)
@@ -256,6 +267,9 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
     ca_p += tp;
     ca_c -= Rrel_t * tp;
   }
+#ifdef DJ_ANY_CONTACT
+  if (jd.flags) prologue_joint_tra(c, jd, g, cl_p, ca_p, cl_c, ca_c);
+#endif
   write_slot(A + jd.slot_c, cl_c, ca_c, m33zero());
   if (jd.parent >= 0) write_slot(A + jd.slot_p, cl_p, ca_p, m33zero());
   // impulse maps at the current configuration (joints/joint.jl:67-93, joints/impulses.jl:4-7): 6 x ne for the equality
@@ -285,6 +299,9 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
         G[0 * n + col] = 0.0; G[1 * n + col] = 0.0; G[2 * n + col] = 0.0;
         G[3 * n + col] = sgn * t.x; G[4 * n + col] = sgn * t.y; G[5 * n + col] = sgn * t.z;
       }
+#ifdef DJ_ANY_CONTACT
+      if (jd.flags & JF_LIM_TRA) continue;  // translational limits: 6-vectors, written by prologue_joint_tra
+#endif
       if (i < jd.nb2_r) {  // G[:, gamma_upper_i] = -[0; t], G[:, gamma_lower_i] = +[0; t],  t = 1/2 Qr' A_i
         V3 t = 0.5 * tmul(Qr, ld3(jd.Ar + 3 * i));
         st3(A + jd.lim_off + kLim * i + (par ? 6 : 9), t);
@@ -354,7 +371,7 @@ DJ_DEV void prologue(Ctx& c, const double* z, const double* __restrict__ u, cons
     const BodyDev& bd = c.bodies[idx];
     double* cst = A + bd.cst_off;
     for (int g = bd.g_ncontact; g < bd.g_cnt; ++g) {  // joint slots only: contacts carry nothing in the prologue
-      const double* s = A + c.ilist[bd.g_off + g];
+      const double* s = A + DJ_SLOT_OFF(c.ilist[bd.g_off + g]);
       add3(cst, -ld3(s));
       add3(cst + 3, -ld3(s + 3));
     }
@@ -602,7 +619,11 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
     }
   }
   // rotational limits: rows [s.gamma - mu (Nb); s_u - (hi - theta); s_l - (theta - lo)]   (joints/limits.jl:1-29)
+#ifdef DJ_ANY_CONTACT
+  if (jd.nb2_r > 0 && !(jd.flags & JF_LIM_TRA)) {
+#else
   if (jd.nb2_r > 0) {
+#endif
     V3 rvq = rotation_vector(g.qr);
     M33 Tp, Tc;
     if (JAC) {
@@ -643,6 +664,14 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
       }
     }
   }
+#ifdef DJ_ANY_CONTACT
+  double K6pp[36], K6cc[36], B6pc[36], B6cp[36];  // translational damper / limits: full 6 x 6 blocks (JF_FULL joints only)
+  if (jd.flags & JF_FULL) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) { K6pp[i] = 0.0; K6cc[i] = 0.0; B6pc[i] = 0.0; B6cp[i] = 0.0; }
+    eval_joint_tra<JAC>(c, jd, f, ka, kb, g, rr, so, dd, bv, fl_p, fa_p, fl_c, fa_c, K6pp, K6cc, B6pc, B6cp);
+  }
+#endif
   // impulses of the equality multipliers on the two bodies: G * lambda with the pristine maps (child: Lc = -G_c, parent: Gp)
   {
     const double* Lc = A + jd.Lc_off;
@@ -709,6 +738,32 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
       Bcp = Bcp + Rrt * Ka;                        // (child,parent) = -d tau_b / d w_a = +Rr' Ka
     }
   }
+#ifdef DJ_ANY_CONTACT
+  if (jd.flags & JF_FULL) {  // 6 x 6 slots and body-body blocks: the translational terms plus the angular 3 x 3 terms from above
+    double* sc = A + jd.slot_c + c.sd;
+    st3(sc, fl_c); st3(sc + 3, fa_c);
+    double* sp = (jd.parent >= 0) ? A + jd.slot_p + c.sd : nullptr;
+    if (sp) { st3(sp, fl_p); st3(sp + 3, fa_p); }
+    if (JAC) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j2 = 0; j2 < 3; ++j2) {
+          K6cc[(3 + i) * 6 + 3 + j2] += Kcc.m[i][j2]; K6pp[(3 + i) * 6 + 3 + j2] += Kaa.m[i][j2];
+          B6pc[(3 + i) * 6 + 3 + j2] += Bpc.m[i][j2]; B6cp[(3 + i) * 6 + 3 + j2] += Bcp.m[i][j2];
+        }
+#pragma unroll
+      for (int i = 0; i < 36; ++i) { sc[6 + i] = K6cc[i]; if (sp) sp[6 + i] = K6pp[i]; }
+      if (jd.parent >= 0 && jd.BBpc_off >= 0) {
+        double* Mpc = A + jd.BBpc_off;
+        double* Mcp = A + jd.BBcp_off;
+#pragma unroll
+        for (int i = 0; i < 36; ++i) { Mpc[i] = B6pc[i]; Mcp[i] = B6cp[i]; }
+      }
+    }
+    return;
+  }
+#endif
   if (JAC && coupled && jd.parent >= 0 && jd.BBpc_off >= 0) {
     double* Mpc = A + jd.BBpc_off;
     double* Mcp = A + jd.BBcp_off;
@@ -775,6 +830,9 @@ DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
   const JointDev& jd = c.joints[idx];
+#ifdef DJ_ANY_CONTACT
+  if (jd.flags & JF_LIM_TRA) { condense_joint_tra(c, jd, x); return; }
+#endif
   V3 tp = v3zero(), tc = v3zero();
   const double* so = A + P.sol_off + jd.sol_off;
   const double* xr = x + jd.sol_off;
@@ -798,6 +856,9 @@ DJ_DEV void recover_joint(Ctx& c, int idx, double* x) {
   double* A = c.A;
   const JointDev& jd = c.joints[idx];
   if (jd.nb2_r == 0) return;
+#ifdef DJ_ANY_CONTACT
+  if (jd.flags & JF_LIM_TRA) { recover_joint_tra(c, jd, x); return; }
+#endif
   const double* so = A + P.sol_off + jd.sol_off;
   double* xr = x + jd.sol_off;
   V3 wp = (jd.parent >= 0) ? ld3(x + c.bodies[jd.parent].sol_off + 3) : v3zero();
@@ -852,11 +913,15 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
     double* rb = res + bd.sol_off;
     double* D = A + bd.D_off;
     for (int g = 0; g < bd.g_cnt; ++g) {
-      const double* s = A + c.ilist[bd.g_off + g];
+      const double* s = A + DJ_SLOT_OFF(c.ilist[bd.g_off + g]);
       add3(rb, ld3(s));
       add3(rb + 3, ld3(s + 3));
       if (JAC) {
+#ifdef DJ_ANY_CONTACT
+        if (g < bd.g_ncontact || DJ_SLOT_FULL(c.ilist[bd.g_off + g])) {
+#else
         if (g < bd.g_ncontact) {
+#endif
 #pragma unroll
           for (int i = 0; i < 36; ++i) D[i] -= s[6 + i];
         } else {
@@ -908,7 +973,7 @@ DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, 
     const BodyDev& bd = c.bodies[idx];
     double* rb = res + bd.sol_off;
     for (int g = 0; g < bd.g_cnt; ++g) {
-      const double* s = A + c.ilist[bd.g_off + g] + c.sd;
+      const double* s = A + DJ_SLOT_OFF(c.ilist[bd.g_off + g]) + c.sd;
       add3(rb, ld3(s));
       add3(rb + 3, ld3(s + 3));
     }
@@ -1024,7 +1089,7 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     const BodyDev& bd = c.bodies[idx];
     double* xb = x + bd.sol_off;
     for (int g = 0; g < bd.g_cnt; ++g) {
-      const double* s = A + c.ilist[bd.g_off + g];
+      const double* s = A + DJ_SLOT_OFF(c.ilist[bd.g_off + g]);
       add3(xb, ld3(s));
       add3(xb + 3, ld3(s + 3));
     }

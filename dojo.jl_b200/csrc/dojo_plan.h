@@ -48,6 +48,7 @@ struct JointDev {
   // (the reference orders them [tra eq | s | gamma | rot eq]; the permutation is applied when `sol` is written out)
   int lim_off;        // nb2_r records of kLim doubles
   int nfree_t, nfree_r, u_off;
+  int flags;          // JF_* bits below (occupies what used to be alignment padding: the layout the other fields have is unchanged)
   double pa[3], pb[3], qoff[4];
   double Ct[9], At[9], Cr[9], Ar[9];  // constraint / nullspace masks, zero-padded to 3 rows (joints/joint.jl:56-64)
   double spring_r, damper_r, spring_off_r[3], lo[3], hi[3];
@@ -64,6 +65,25 @@ struct JointDev {
   int gj_off;                   // joint record: RJp(ne x 6) RJc(ne x 6) BPp BPc BCp BCc (6x6 each) Up(6 x nu_j) Uc(6 x nu_j)
   int gv_off;                   // per-column forward scratch v (6 x CH) inside the gradient workspace (-1 for the origin)
 };
+
+// JointDev::flags -- translational springs / dampers / limits (joints/translational/{springs,dampers}.jl, joints/limits.jl); only
+// the DJ_ANY_CONTACT compilation of the kernels (dojo_b200_cm.cu) reads them, dojo_create routes such mechanisms there
+enum JointFlags {
+  JF_TRA_SPRING = 1,  // explicit translational spring impulse (prologue)
+  JF_TRA_DAMPER = 2,  // implicit translational damper: 6 x 6 velocity Jacobians on and between the two bodies
+  JF_LIM_TRA = 4,     // the joint's limits (nb2_r axes, lo / hi) act on the translational coordinates A_t e instead of the rotation vector
+  JF_FULL = 8         // contribution slots carry a full 6 x 6 block (kSlotC) and the limit records 6-vectors (2 kLim per axis)
+};
+// The translational spring / damper parameters [spring, damper, spring_offset(nfree_t)] are kept in the rows nl_t..2 of the
+// zero-padded constraint mask Ct, which no kernel reads (every loop over Ct stops at nl_t): JointDev keeps its size.
+static_assert(sizeof(JointDev) == 568, "JointDev layout is part of the kernels' addressing");
+#if defined(__CUDACC__) || defined(DJ_HOSTEMU)
+#define DJ_PLAN_FN __host__ __device__ inline
+#else
+#define DJ_PLAN_FN inline
+#endif
+DJ_PLAN_FN const double* joint_tra_params(const JointDev& j) { return j.Ct + 3 * j.nl_t; }
+DJ_PLAN_FN double* joint_tra_params(JointDev& j) { return j.Ct + 3 * j.nl_t; }
 
 struct ContactDev {
   int body, sol_off;  // [s(N½); gamma(N½)] inside the solution vector (NonlinearContact: N½ = 4)

@@ -179,9 +179,17 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
         const JointDev& jd = c.joints[c.tid];
         const double* src = c.A + P.sol_off + jd.sol_off;
         double* dst = so + jd.sol_off;
+#ifdef DJ_ANY_CONTACT
+        if (jd.flags & JF_LIM_TRA) {  // translational limits: reference order [tra s | tra gamma | tra eq | rot eq]
+          for (int i = 0; i < 2 * jd.nb_r; ++i) dst[i] = src[jd.ne + i];
+          for (int i = 0; i < jd.ne; ++i) dst[2 * jd.nb_r + i] = src[i];
+        } else
+#endif
+        {
         for (int i = 0; i < jd.nl_t; ++i) dst[i] = src[i];
         for (int i = 0; i < 2 * jd.nb_r; ++i) dst[jd.nl_t + i] = src[jd.ne + i];
         for (int i = 0; i < jd.nl_r; ++i) dst[jd.nl_t + 2 * jd.nb_r + i] = src[jd.nl_t + i];
+        }
       }
     }
     if (c.tid == 0) {

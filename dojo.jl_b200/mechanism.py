@@ -312,7 +312,8 @@ class Mechanism:
 def get_mechanism(name: str, **overrides) -> Mechanism:
     """Mirror of DojoEnvironments.get_mechanism(:name) for the BASELINE models: loads the
     flattened descriptor generated from the reference's builder (tools/build_mechanisms.py).
-    Overrides: timestep, input_scaling, gravity (mechanism kwargs, constructor.jl:47); contact_type = "nonlinear" | "linear" |
+    Overrides: timestep, input_scaling, gravity (mechanism kwargs, constructor.jl:47); springs / dampers (scalar or per joint) and
+    joint_limits = {name: (lo, hi)} as the reference builders apply them (DojoEnvironments/src/utilities.jl:1-59); contact_type = "nonlinear" | "linear" |
     "impact" switches the model of every contact as the builders' `contact_type` keyword does (contacts/constructor.jl:117-128)."""
     m = Mechanism.load(os.path.join(MECHANISM_DIR, f"{name}.json"))
     if "timestep" in overrides:
@@ -325,6 +326,24 @@ def get_mechanism(name: str, **overrides) -> Mechanism:
     if "gravity" in overrides:
         g = overrides.pop("gravity")
         m.gravity = np.array([0.0, 0.0, g], dtype=float) if np.isscalar(g) else np.asarray(g, dtype=float)
+    for key in ("springs", "dampers"):  # set_springs! / set_dampers! (DojoEnvironments/src/utilities.jl:1-39): every joint but a floating base
+        if key in overrides:
+            val = overrides.pop(key)
+            vals = [float(val)] * m.Ne if np.isscalar(val) else [float(v) for v in val]
+            for j, v in zip(m.joints, vals):
+                if v == 0 or j.nimpulses == 0:
+                    continue
+                setattr(j.tra, key[:-1], v)
+                setattr(j.rot, key[:-1], v)
+    if "joint_limits" in overrides:  # set_limits (utilities.jl:41-59): one-dimensional joints only
+        for jname, (lo, hi) in dict(overrides.pop("joint_limits")).items():
+            j = m.joint_by_name(str(jname).lstrip(":"))
+            if j.tra.nfree == 0 and j.rot.nfree == 1:
+                j.rot.limit_lo, j.rot.limit_hi = np.array([lo], float), np.array([hi], float)
+            elif j.tra.nfree == 1 and j.rot.nfree == 0:
+                j.tra.limit_lo, j.tra.limit_hi = np.array([lo], float), np.array([hi], float)
+            else:
+                raise ValueError("joint limits can only be set for one-dimensional joints")
     if "contact_type" in overrides:
         ct = str(overrides.pop("contact_type")).lstrip(":")
         if ct not in CONTACT_TYPES:

@@ -34,6 +34,7 @@ from dojo_jl_b200.mechanism import Body, Contact, Joint, JointElement, Mechanism
 
 Z_AXIS = np.array([0.0, 0.0, 1.0])
 X_AXIS = np.array([1.0, 0.0, 0.0])
+Y_AXIS = np.array([0.0, 1.0, 0.0])
 
 
 def fvec(s, default):
@@ -165,6 +166,29 @@ def build_pendulum():
     return mech
 
 
+def capsule_inertia(r, h, m):
+    """Capsule(r, h, m): bodies/shapes.jl:157-179"""
+    vc, vh = np.pi * h * r ** 2, np.pi * 4.0 / 3.0 * r ** 3 / 2.0
+    mc, mh = m * vc / (vc + 2 * vh), m * vh / (vc + 2 * vh)
+    ixx = mc * (h ** 2 / 12.0 + r ** 2 / 4.0) + 2.0 * (83.0 / 320 * mh * r ** 2 + mh * (3.0 / 8.0 * r + 0.5 * h) ** 2)
+    izz = mc * 0.5 * r ** 2 + 2.0 * (mh * 2.0 / 5.0 * r ** 2 / 2.0)
+    return np.diag([ixx, ixx, izz])
+
+
+def build_cartpole():
+    """DojoEnvironments/src/mechanisms/cartpole/mechanism.jl:1-62 (defaults): cart on a Prismatic joint along y, pole on a Revolute
+    joint about x with child_vertex = -L/2 z; initialize_cartpole!: position 0, orientation pi/4.  Springs / dampers / joint
+    limits are the builder's options (set on the loaded Mechanism: the prismatic joint exercises the translational ones)."""
+    r, L = 0.075, 1.0
+    bodies = [Body("cart", 1.0, capsule_inertia(1.5 * r, 1.0, 1.0)), Body("pole", 1.0, capsule_inertia(r, L, 1.0))]
+    j0 = make_joint("prismatic", "cart_joint", -1, 0, Y_AXIS, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    j1 = make_joint("revolute", "pole_joint", 0, 1, X_AXIS, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    j1.vertex_child = -0.5 * L * Z_AXIS
+    mech = Mechanism("cartpole", bodies, [j0, j1], [], timestep=0.01)
+    mech.z0 = mech.forward_kinematics({"cart_joint": [0.0], "pole_joint": [np.pi / 4]})
+    return mech
+
+
 def build_sphere():
     """DojoEnvironments/src/mechanisms/sphere/mechanism.jl:1-67 (defaults): Sphere(0.5, 1) on a Floating joint, one contact of
     radius 0.5 at the centre; initialize_sphere!: centre at z = 0.5 + r, velocity [1, 0, 0]."""
@@ -271,7 +295,7 @@ def main():
     ap.add_argument("--reference", default="/root/reference")
     args = ap.parse_args()
     os.makedirs(MECHANISM_DIR, exist_ok=True)
-    for mech in (build_pendulum(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
+    for mech in (build_pendulum(), build_cartpole(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
         mech.save(os.path.join(MECHANISM_DIR, f"{mech.name}.json"))
         print(f"{mech.name}: Nb={mech.Nb} Ne={mech.Ne} Ni={mech.Ni} nres={mech.nres} nu={mech.nu}")
 
