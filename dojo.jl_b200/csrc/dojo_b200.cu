@@ -799,7 +799,6 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
                           double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
   if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dFz || !dFu || dZ == dZn) { if (h) h->err = "dojo_step_grad_async: bad arguments (B <= max_batch, dZn != dZ)"; return DOJO_EINVAL; }
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
-  if (h->tra_joint) { h->err = "dojo_step_grad: gradients with translational springs / dampers / limits are not implemented yet"; return DOJO_EINVAL; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (!h->d_gsol) {

@@ -212,6 +212,84 @@ DJ_DEV void grad_contact_param_rhs(Ctx& c, int idx, int p, double* v) {
   v[3] += Q.x; v[4] += Q.y; v[5] += Q.z;
 }
 
+#ifdef DJ_ANY_CONTACT
+// Translational springs / dampers / limits in the data Jacobian (joints/translational/springs.jl:44-76, dampers.jl:40-98,
+// joints/limits.jl with gradients/data.jl:4-14, :67-124).  An impulse h G6(x2, q2) f contributes
+//   d(G6) f  -- covered by the caller's derivative of the translational impulse map once f is added to the projected impulse p_t --
+//   G6 d(f)  -- added here: f depends on the poses through e(x2, q2) and, for the damper, e(x1, q1) with q1 = q2 (x) m(-w25)
+//              (a perturbation d of q2 moves the attitude of q1 by R(m(-w))' d).
+// Returns the force to add to p_t.  Limits: the slack rows move with theta = a.e(x3, q3); condensed like the solver's rows.
+DJ_DEV V3 grad_joint_tra(Ctx& c, const JointDev& jd, const Kin& ka, const Kin& kb, const JointGeom& g2, const JointGeom& g3, const M33& Ma,
+                         const M33& Mb, const double* so, double* BPp, double* BPc, double* BCp, double* BCc) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  V3 extra = v3zero();
+  M33 AtA = m33zero();
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < jd.nfree_t) { V3 a = ld3(jd.At + 3 * i); AtA = AtA + outer(a, a); }
+  const bool par = jd.parent >= 0;
+  if (jd.flags & JF_TRA_SPRING) {
+    const double* tp = joint_tra_params(jd);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < jd.nfree_t) { V3 a = ld3(jd.At + 3 * i); extra += (P.h * tp[0] * (tp[2 + i] - dot(a, g2.et))) * a; }
+    const double k = -P.h * tp[0];
+    M33 Fxa = k * (AtA * g2.Xp), Fqa = k * (AtA * g2.Qtp), Fxb = k * (AtA * g2.Xc), Fqb = k * (AtA * g2.Qtc);
+    g6_accumulate(BCc, g2.Xc, g2.Qtc, Fxb, Fqb, 1.0);
+    if (par) {
+      g6_accumulate(BPp, g2.Xp, g2.Qtp, Fxa, Fqa, 1.0);
+      g6_accumulate(BPc, g2.Xp, g2.Qtp, Fxb, Fqb, 1.0);
+      g6_accumulate(BCp, g2.Xc, g2.Qtc, Fxa, Fqa, 1.0);
+    }
+  }
+  if (jd.flags & JF_TRA_DAMPER) {
+    const double damper = joint_tra_params(jd)[1];
+    V3 xa1 = ka.x2 - P.h * ka.v, xb1 = kb.x2 - P.h * kb.v;
+    Quat qa1 = qmul(ka.q2, qmap(-ka.w, P.h)), qb1 = qmul(kb.q2, qmap(-kb.w, P.h));
+    M33 Ra1 = rotmat(qa1), Rb1 = rotmat(qb1);
+    JointGeom g1 = joint_geom(jd, xa1, qa1, Ra1, xb1, qb1, Rb1);
+    extra += (-damper) * (AtA * (g2.et - g1.et));
+    M33 Fxa = (-damper) * (AtA * (g2.Xp - g1.Xp)), Fqa = (-damper) * (AtA * (g2.Qtp - g1.Qtp * transport(-ka.w, P.h)));
+    M33 Fxb = (-damper) * (AtA * (g2.Xc - g1.Xc)), Fqb = (-damper) * (AtA * (g2.Qtc - g1.Qtc * transport(-kb.w, P.h)));
+    g6_accumulate(BCc, g2.Xc, g2.Qtc, Fxb, Fqb, 1.0);
+    if (par) {
+      g6_accumulate(BPp, g2.Xp, g2.Qtp, Fxa, Fqa, 1.0);
+      g6_accumulate(BPc, g2.Xp, g2.Qtp, Fxb, Fqb, 1.0);
+      g6_accumulate(BCp, g2.Xc, g2.Qtc, Fxa, Fqa, 1.0);
+    }
+  }
+  if (jd.flags & JF_LIM_TRA) {
+    M33 QtpM = g3.Qtp * Ma, QtcM = g3.Qtc * Mb;
+    const int ne = jd.ne;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nb2_r) {
+        V3 ai = ld3(jd.At + 3 * i);
+        const int is_u = ne + i, is_l = ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+        extra += (so[ig_l] - so[ig_u]) * ai;
+        const double kk = (so[ig_u] + kReg) / (so[is_u] + kReg) + (so[ig_l] + kReg) / (so[is_l] + kReg);
+        V3 apx = vtmul(ai, g3.Xp), apq = vtmul(ai, QtpM), acx = vtmul(ai, g3.Xc), acq = vtmul(ai, QtcM);
+        const double ap[6] = {apx.x, apx.y, apx.z, apq.x, apq.y, apq.z}, ac[6] = {acx.x, acx.y, acx.z, acq.x, acq.y, acq.z};
+        const double* lim = A + jd.lim_off + 2 * kLim * i;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            BCc[r * 6 + q] -= kk * lim[18 + r] * ac[q];
+            if (par) {
+              BPp[r * 6 + q] -= kk * lim[12 + r] * ap[q];
+              BPc[r * 6 + q] -= kk * lim[12 + r] * ac[q];
+              BCp[r * 6 + q] -= kk * lim[18 + r] * ap[q];
+            }
+          }
+      }
+    }
+  }
+  return extra;
+}
+#endif
+
 // record layout of a joint (doubles): RJp[ne*6] RJc[ne*6] BPp[36] BPc[36] BCp[36] BCc[36] Up[6*nu] Uc[6*nu]
 DJ_DEV void grad_joint(Ctx& c, int idx) {
   const Plan& P = *c.P;
@@ -262,8 +340,14 @@ DJ_DEV void grad_joint(Ctx& c, int idx) {
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nl_t) pt += so[i] * ld3(jd.Ct + 3 * i);
     if (i < jd.nl_r) pr += so[jd.nl_t + i] * ld3(jd.Cr + 3 * i);
+#ifdef DJ_ANY_CONTACT
+    if (jd.flags & JF_LIM_TRA) continue;  // translational limit duals act through p_t (grad_joint_tra)
+#endif
     if (i < jd.nb2_r) pr += (so[ne + jd.nb_r + jd.nb2_r + i] - so[ne + jd.nb_r + i]) * ld3(jd.Ar + 3 * i);
   }
+#ifdef DJ_ANY_CONTACT
+  if (jd.flags) pt += grad_joint_tra(c, jd, ka, kb, g2, g3, Ma, Mb, so, BPp, BPc, BCp, BCc);
+#endif
   // translational impulses (translational/impulses.jl:9-45):  F_p = -Ra p, F_c = Ra p, tau_p = p x (e + pa), tau_c = pb x (Rb' Ra p)
   {
     V3 pb = ld3(jd.pb);
@@ -352,7 +436,11 @@ DJ_DEV void grad_joint(Ctx& c, int idx) {
     add_block33(BCc, 6, 3, 3, (-1.0) * (Rrt * dta_b) + 2.0 * skew(tb));
   }
   // joint limits, condensed: slack rows -+(A_i Theta Mqq) -> body rows -kk t (abar_p d phi_a + abar_c d phi_b)
+#ifdef DJ_ANY_CONTACT
+  if (jd.nb2_r > 0 && !(jd.flags & JF_LIM_TRA)) {
+#else
   if (jd.nb2_r > 0) {
+#endif
     M33 Tp, Tc;
     rotvec_attitude_jacobians(jd, g3, Tp, Tc);
     Tp = Tp * Ma;

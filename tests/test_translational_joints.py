@@ -1,0 +1,190 @@
+"""Translational springs, dampers and limits (reference src/joints/translational/{springs,dampers}.jl,
+src/joints/limits.jl) -- CPU suite.
+
+Oracle pinned by the reference's property tests on a mechanism that exercises them (a floating body, a Prismatic joint with a
+parent BODY and offsets, a Revolute joint; the reference runs test/jacobian.jl and test/data.jl with springs = dampers = 1 on
+mechanisms with Prismatic / Planar joints such as :slider, :nslider, :cartpole):
+  full_matrix == -d(rhs)/d(solution), jacobian_data! == finite differences, IFT gradients == finite differences of the step.
+Device code (dojo_joint_tra.cuh in the DJ_ANY_CONTACT compilation of the kernels) against the oracle through tests/hostemu.
+"""
+import numpy as np
+import pytest
+
+import dojo_jl_b200 as dj
+from dojo_jl_b200 import capi, quat as Q
+from dojo_jl_b200.mechanism import Body, Joint, JointElement, Mechanism
+from oracle.oracle import Oracle
+
+from test_oracle_properties import _perturb_state, _reduce
+
+
+def _element(nlambda, axis=None, damper=0.0, spring=0.0, limits=None, offset=None):
+    V1, V2, V3 = Q.orthogonal_rows(np.zeros(3) if axis is None else np.asarray(axis, float))
+    e = JointElement(nlambda=nlambda, axis_mask=np.stack([V1, V2, V3]), spring=spring, damper=damper,
+                     spring_offset=np.zeros(3 - nlambda) if offset is None else np.asarray(offset, float))
+    if limits is not None:
+        e.limit_lo, e.limit_hi = np.atleast_1d(limits[0]).astype(float), np.atleast_1d(limits[1]).astype(float)
+    return e
+
+
+def chain(kt=0.0, dt=0.0, kr=0.0, dr=0.0, lim=None, planar=False):
+    """origin -Floating- b0 -Prismatic (or Planar) with vertices and an orientation offset- b1 -Revolute- b2"""
+    bodies = [Body(f"b{i}", 1.0 + 0.3 * i, np.diag([0.1, 0.2, 0.15]) * (1 + 0.2 * i)) for i in range(3)]
+    j0 = Joint("float", -1, 0, _element(0), _element(0))
+    tra = _element(1, axis=[0.3, 1.0, 0.2], spring=kt, damper=dt, offset=[0.05, -0.02]) if planar else \
+        _element(2, axis=[0.3, 1.0, 0.2], spring=kt, damper=dt, limits=lim, offset=[0.05])
+    j1 = Joint("slide", 0, 1, tra, _element(3), vertex_parent=np.array([0.1, 0.2, -0.1]), vertex_child=np.array([-0.05, 0.1, 0.2]),
+               orientation_offset=Q.rpy_to_quat([0.2, -0.1, 0.3]))
+    j2 = Joint("rev", 1, 2, _element(3), _element(2, axis=[1.0, 0.2, 0.0], spring=kr, damper=dr), vertex_parent=np.array([0.0, 0.1, -0.3]),
+               vertex_child=np.array([0.0, 0.0, 0.25]))
+    m = Mechanism("chain", bodies, [j0, j1, j2], [], timestep=0.01)
+    m.z0 = m.forward_kinematics({"float": [0.1, 0.2, 1.0, 0.2, -0.1, 0.3], "slide": [0.15, 0.05][:2 if planar else 1], "rev": [0.4]})
+    return m
+
+
+def cartpole():
+    return dj.get_mechanism("cartpole", springs=2.0, dampers=0.3, joint_limits={"cart_joint": (-0.3, 0.25), "pole_joint": (-1.2, 1.4)})
+
+
+CASES = {"spring": dict(kt=30.0, kr=0.5, dr=0.2), "damper": dict(dt=2.0, kr=0.5, dr=0.2), "limits": dict(kr=0.5, lim=([-0.05], [0.2])),
+         "all": dict(kt=30.0, dt=2.0, kr=0.5, dr=0.2, lim=([-0.05], [0.2])), "planar": dict(kt=10.0, dt=1.0, planar=True)}
+
+
+def _state_in_motion(m, steps, seed=3):
+    o = Oracle(m)
+    rng = np.random.default_rng(seed)
+    z, u = m.z0.copy(), 0.5 * rng.normal(size=m.nu)
+    for _ in range(steps):
+        z, st, _ = o.step(z, u)
+        assert st == 0
+    return z, u
+
+
+def test_cartpole_options_mirror_the_reference_builder():
+    m = cartpole()
+    cart, pole = m.joints
+    assert (cart.tra.spring, cart.tra.damper, cart.tra.nlimits, cart.rot.nlimits) == (2.0, 0.3, 1, 0)
+    assert (pole.rot.spring, pole.rot.damper, pole.rot.nlimits, pole.tra.nlimits) == (2.0, 0.3, 1, 0)
+    assert m.nres == 30 and m.nu == 2  # cart: 2 + 3 eq + 4 limit entries, pole: 3 + 2 eq + 4, bodies 12
+    with pytest.raises(ValueError):
+        dj.get_mechanism("sphere", joint_limits={"floating_joint": (0.0, 1.0)})
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_solution_matrix_and_data_jacobian_match_finite_differences(case):
+    """test/jacobian.jl + test/data.jl on a mechanism with translational springs / dampers / limits"""
+    m = chain(**CASES[case])
+    z, u = _state_in_motion(m, 40 if "lim" in CASES[case] else 10)
+    o = Oracle(m, capi.solver_options(rtol=1e-8, btol=1e-8))
+    u0 = np.zeros(m.nu)
+    _, _, _, sol = o.step(z, u0, return_sol=True)
+    mu = o.trace()[-1, 3]
+    mu = 0.0 if mu != mu else mu
+    o.set_state(z, u0)
+    o.set_solution(sol, mu)
+    A, _ = o.assemble(mu)
+    D = o.data_jacobian()
+    d = 1e-6
+    for i in range(m.nres):
+        sp, sm = sol.copy(), sol.copy()
+        sp[i] += d
+        sm[i] -= d
+        assert np.abs((o.evaluate_rhs(sp, mu) - o.evaluate_rhs(sm, mu)) / (2 * d) + A[:, i]).max() < 1e-6
+    ns = 12 * m.Nb
+    for i in range(ns + m.nu):
+        if i < ns:
+            o.set_state(_perturb_state(z, i, d), u0)
+            rp = o.evaluate_rhs(sol, mu)
+            o.set_state(_perturb_state(z, i, -d), u0)
+            rm = o.evaluate_rhs(sol, mu)
+        else:
+            up, um = u0.copy(), u0.copy()
+            up[i - ns] += d
+            um[i - ns] -= d
+            o.set_state(z, up)
+            rp = o.evaluate_rhs(sol, mu)
+            o.set_state(z, um)
+            rm = o.evaluate_rhs(sol, mu)
+        assert np.abs((rp - rm) / (2 * d) - D[:, i]).max() < 2e-6
+
+
+def test_ift_gradients_match_finite_difference():
+    m = chain(**CASES["all"])
+    z, _ = _state_in_motion(m, 40)
+    o = Oracle(m, capi.solver_options(rtol=1e-10, btol=1e-10))
+    u = np.zeros(m.nu)
+    zn, Fz, Fu, st, it0 = o.step_grad(z, u)
+    assert st == 0
+    eps, checked = 1e-6, 0
+    for i in range(12 * m.Nb):
+        zp, _, ip = o.step(_perturb_state(z, i, eps), u)
+        zm, _, im = o.step(_perturb_state(z, i, -eps), u)
+        if ip != it0 or im != it0:
+            continue
+        col = (_reduce(zp, zn, m.Nb) - _reduce(zm, zn, m.Nb)) / (2 * eps)
+        assert np.abs(col - Fz[:, i]).max() < 5e-5 * max(1.0, np.abs(Fz).max())
+        checked += 1
+    assert checked >= 18
+
+
+def test_cart_stops_at_its_limits_and_dampers_dissipate():
+    m = cartpole()
+    o = Oracle(m)
+    for push, bound in ((6.0, 0.25), (-6.0, -0.3)):
+        z = m.z0.copy()
+        for _ in range(200):
+            z, st, _ = o.step(z, np.array([push, 0.0]))
+            assert st == 0
+            assert -0.3 - 1e-4 <= z[1] <= 0.25 + 1e-4  # joints/limits.jl: the slider coordinate stays inside [lo, hi]
+        assert abs(z[1] - bound) < 2e-2
+    free = dj.get_mechanism("cartpole", gravity=0.0)
+    damped = dj.get_mechanism("cartpole", gravity=0.0, dampers=2.0)
+    v = []
+    for mech in (free, damped):
+        oo, z = Oracle(mech), mech.z0.copy()
+        z[4] = 1.0  # cart velocity along y
+        z[13 + 4] = 1.0
+        for _ in range(100):
+            z, _, _ = oo.step(z, np.zeros(2))
+        v.append(z[4])
+    assert abs(v[0] - 1.0) < 1e-6 and abs(v[1] - np.exp(-1.0)) < 1e-2  # m dv/dt = -d v with m = 2, d = 2, t = 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device code through the kernel emulation
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["all", "planar", "cartpole"])
+def test_kernel_emulation_matches_oracle(case):
+    from hostemu.harness import HostEmu
+    m = cartpole() if case == "cartpole" else chain(**CASES[case])
+    o, em = Oracle(m), HostEmu(m)
+    rng = np.random.default_rng(7)
+    B = 3
+    Z = np.tile(m.z0, (B, 1))
+    U = 0.5 * rng.normal(size=(B, m.nu))
+    if case == "cartpole":
+        U[:, 0] = [3.0, -3.0, 6.0]
+    T = 120 if case == "cartpole" else 40
+    gmax = 0.0
+    for t in range(T):
+        Zn, st, it, sol = em.step(Z, U, slots=4 if t % 2 else 2)
+        for e in range(B):
+            zo, so, io, solo = o.step(Z[e], U[e], return_sol=True)
+            assert (st[e], it[e]) == (so, io), (t, e)
+            assert np.abs(Zn[e] - zo).max() < 1e-10 and np.abs(sol[e] - solo).max() < 1e-8
+            if case == "cartpole":
+                gmax = max(gmax, solo[2], solo[3])
+        Z = Zn
+    if case == "cartpole":
+        assert gmax > 0.5  # the limit duals of the slider are active: the condensed limit rows are exercised
+    Zf = em.step(Z, np.tile(U, (6, 1, 1)), T=6, slots=2)[0]
+    Zs = Z
+    for _ in range(6):
+        Zs = em.step(Zs, U, slots=1, smem_plan=False)[0]
+    assert np.array_equal(Zf, Zs)
+    Zn, Fz, Fu, st, it = em.step_grad(Z, U, slots=2, slots_grad=2)
+    for e in range(B):
+        zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
+        assert (st[e], it[e]) == (so, io)
+        assert np.abs(Fz[e] - Fzo).max() < 1e-8 * max(1.0, np.abs(Fzo).max())
+        assert np.abs(Fu[e] - Fuo).max() < 1e-8 * max(1.0, np.abs(Fuo).max())

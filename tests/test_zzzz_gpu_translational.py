@@ -1,0 +1,61 @@
+"""GPU tests of translational springs / dampers / limits through the C-ABI against the oracle; the same
+comparison runs on the CPU through the kernel emulation (tests/test_translational_joints.py)."""
+import numpy as np
+import pytest
+
+from test_translational_joints import CASES, cartpole, chain
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["all", "planar", "cartpole"])
+def test_step_rollout_and_gradient_parity(case):
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    m = cartpole() if case == "cartpole" else chain(**CASES[case])
+    rng = np.random.default_rng(23)
+    B = 32
+    stepper, o = BatchedStepper(m, B), Oracle(m)
+    Z = np.tile(m.z0, (B, 1))
+    U = 0.5 * rng.normal(size=(B, m.nu))
+    if case == "cartpole":
+        U[:, 0] = rng.uniform(-6.0, 6.0, B)
+    T = 100 if case == "cartpole" else 40
+    same = total = 0
+    for t in range(T):
+        Zn, st, it, sol = stepper.step(Z, U, return_sol=True)
+        for e in range(0, B, 4):
+            zo, so, io, solo = o.step(Z[e], U[e], return_sol=True)
+            total += 1
+            assert st[e] == so == 0
+            if it[e] != io:
+                assert np.abs(Zn[e] - zo).max() < 1e-4
+                continue
+            same += 1
+            assert np.abs(Zn[e] - zo).max() < 1e-8 and np.abs(sol[e] - solo).max() < 1e-6
+        Z = Zn
+    assert same >= 0.95 * total
+    if case == "cartpole":
+        assert (Z[:, 1] > -0.3 - 1e-4).all() and (Z[:, 1] < 0.25 + 1e-4).all() and (np.abs(Z[:, 1]) > 0.2).sum() >= B // 4
+    Zf, _ = stepper.rollout(Z, np.tile(U, (5, 1, 1)), T=5)
+    Zs = Z
+    for _ in range(5):
+        Zs, _, _ = stepper.step(Zs, U)
+    assert np.array_equal(Zf, Zs)
+    Zn, Fz, Fu, st, it = stepper.step_grad(Z, U)
+    errs = []
+    for e in range(0, B, 4):
+        zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
+        if so != 0 or st[e] != 0 or io != it[e]:
+            continue
+        errs.append(max(np.abs(Fz[e] - Fzo).max() / max(1.0, np.abs(Fzo).max()), np.abs(Fu[e] - Fuo).max() / max(1.0, np.abs(Fuo).max())))
+    errs = np.array(errs)
+    assert len(errs) >= 6 and np.median(errs) < 1e-8 and errs.max() < 1e-4, errs
+
+
+def test_recording_is_refused_with_translational_dampers():
+    from dojo_jl_b200.solver import BatchedStepper
+    m = cartpole()
+    stepper = BatchedStepper(m, 2)
+    with pytest.raises(RuntimeError, match="translational"):
+        stepper.step_record(np.tile(m.z0, (2, 1)))
