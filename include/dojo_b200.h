@@ -79,7 +79,8 @@ typedef struct {
   int32_t nlambda;         /* N_lambda: number of constrained axes, 0..3 */
   int32_t nlimits;         /* Nb/2: 0, or 3-nlambda when every free axis is limited (joints/limits.jl) */
   double axis_mask[9];     /* rows V1,V2,V3 (joints/orthogonal.jl:1-12); masks per joints/joint.jl:56-64 */
-  double spring, damper;
+  double spring, damper;   /* act on the free axes (src/joints/{translational,rotational}/{springs,dampers}.jl); the reference's
+                            * set_springs! / set_dampers! (DojoEnvironments/src/utilities.jl:1-39) skip a floating base */
   double spring_offset[3]; /* first 3-nlambda entries used */
   double limit_lo[3], limit_hi[3];
 } DojoJointElementDesc;
