@@ -105,7 +105,32 @@ class Pendulum(Environment):
     spec_kwargs = dict()
 
 
-_ENVIRONMENTS = {"ant_ars": AntARS, "quadruped_sampling": QuadrupedSampling, "pendulum": Pendulum}
+class CartpoleDQN(Environment):
+    """environments/cartpole_dqn.jl: state = minimal state [y, ydot, theta, thetadot], ONE action on the cart (input_map: [a; 0]);
+    springs / dampers / joint_limits are the builder's options (cartpole_dqn.jl:5-33).  The unactuated input comes last here, which
+    the fused dojo_env_step kernels (leading unactuated inputs) do not express: step! is the composition the reference itself
+    performs, state_map -> input_map -> step_minimal_coordinates! (three launches); the DQN example's own reward / termination
+    (examples/learning/cartpole_dqn.jl:157-186) stays with the caller."""
+    mechanism_name = "cartpole"
+    spec_kwargs = dict()
+
+    def __init__(self, batch: int = 1, horizon: int = 100, device: int = 0, **mechanism_kwargs):
+        super().__init__(batch, horizon, device, **mechanism_kwargs)
+        self.na = 1
+
+    def input_map(self, action):
+        a = np.asarray(action, dtype=float).reshape(-1, 1)
+        return np.concatenate([a, np.zeros_like(a)], axis=-1)
+
+    def step(self, state=None, action=None, opts=None):
+        S = self.state if state is None else np.atleast_2d(np.asarray(state, dtype=float))
+        U = self.input_map(np.zeros(S.shape[0]) if action is None else action)
+        self.state, self.status, _ = self.stepper.step_minimal(self.state_map(S), U, opts)
+        done = (~np.isfinite(self.state).all(axis=1)).astype(np.int32)
+        return np.zeros(S.shape[0]), done
+
+
+_ENVIRONMENTS = {"ant_ars": AntARS, "quadruped_sampling": QuadrupedSampling, "pendulum": Pendulum, "cartpole_dqn": CartpoleDQN}
 
 
 def get_environment(name: str, **kwargs) -> Environment:

@@ -188,3 +188,55 @@ def test_kernel_emulation_matches_oracle(case):
         assert (st[e], it[e]) == (so, io)
         assert np.abs(Fz[e] - Fzo).max() < 1e-8 * max(1.0, np.abs(Fzo).max())
         assert np.abs(Fu[e] - Fuo).max() < 1e-8 * max(1.0, np.abs(Fuo).max())
+
+
+@pytest.mark.parametrize("case", ["all", "planar", "cartpole"])
+def test_coordinate_maps_with_translational_free_axes(case):
+    """minimal <-> maximal maps and their Jacobians (the lane-independent device headers compiled for the host) on Prismatic / Planar
+    joints between bodies: what step_minimal_coordinates! and get_minimal_gradients! need around the step"""
+    from hostcheck.harness import HostCheck
+    from test_oracle_properties import _random_minimal
+    m = cartpole() if case == "cartpole" else chain(**CASES[case])
+    hc, o = HostCheck(m), Oracle(m)
+    rng = np.random.default_rng(1)
+    X = np.stack([_random_minimal(m, rng) for _ in range(6)])
+    Zo = np.stack([o.minimal_to_maximal(x) for x in X])
+    assert np.abs(hc.minimal_to_maximal(X) - Zo).max() < 1e-12 and np.abs(hc.maximal_to_minimal(Zo) - X).max() < 1e-12
+    Mo = np.stack([o.maximal_to_minimal_jacobian(z) for z in Zo])
+    No = np.stack([o.minimal_to_maximal_jacobian(z) for z in Zo])
+    assert np.abs(hc.maximal_to_minimal_jacobian(Zo) - Mo).max() < 1e-11 and np.abs(hc.minimal_to_maximal_jacobian(Zo) - No).max() < 1e-11
+
+
+def test_cartpole_dqn_mirror_logic(monkeypatch):
+    """environments/cartpole_dqn.jl mirror: input_map(a) = [a; 0], state_map = identity, step! = step_minimal_coordinates!.  The
+    host logic is exercised with a stand-in for the GPU stepper that answers from the oracle (test-only; on the GPU the same calls go
+    to libdojo_b200.so, tests/test_zzzz_gpu_translational.py)."""
+    from dojo_jl_b200 import environments as E
+
+    class StubStepper:
+        def __init__(self, mech, batch, device=0):
+            self.mech, self.o = mech, Oracle(mech)
+
+        def env_sizes(self, spec):
+            return 2 * self.mech.nu, self.mech.nu
+
+        def maximal_to_minimal(self, Z):
+            return np.stack([self.o.maximal_to_minimal(z) for z in np.atleast_2d(Z)])
+
+        def env_reset(self, spec, S, s0, mask=None):
+            S[:] = s0
+            return S
+
+        def step_minimal(self, X, U, opts=None):
+            out = [self.o.minimal_gradients(x, u) for x, u in zip(X, U)]
+            return np.stack([r[0] for r in out]), np.array([r[3] for r in out], dtype=np.int32), np.array([r[4] for r in out], dtype=np.int32)
+
+    monkeypatch.setattr(E, "BatchedStepper", StubStepper)
+    env = E.get_environment("cartpole_dqn", batch=3, dampers=0.5, joint_limits={"cart_joint": (-0.2, 0.2)})
+    assert (env.ns, env.na) == (4, 1) and np.allclose(env.get_state()[:, 2], np.pi / 4)  # per joint [coordinates; velocities]: [y, ydot, theta, thetadot]
+    assert np.array_equal(env.input_map([1.0, -2.0, 0.5]), [[1.0, 0.0], [-2.0, 0.0], [0.5, 0.0]])
+    for _ in range(300):
+        reward, done = env.step(action=[12.0, -12.0, 0.0])
+    S = env.get_state()
+    assert not done.any() and (np.abs(S[:, 0]) < 0.2 + 1e-4).all()  # the slider stays inside its limits ...
+    assert abs(S[0, 0] - 0.2) < 3e-2 and abs(S[1, 0] + 0.2) < 3e-2   # ... and is pushed against them

@@ -59,3 +59,33 @@ def test_recording_is_refused_with_translational_dampers():
     stepper = BatchedStepper(m, 2)
     with pytest.raises(RuntimeError, match="translational"):
         stepper.step_record(np.tile(m.z0, (2, 1)))
+
+
+def test_cartpole_environment_and_minimal_gradients():
+    """cartpole_dqn mirror (state_map, input_map [a; 0], step_minimal_coordinates!) and get_minimal_gradients! on a mechanism with
+    a Prismatic joint, translational spring / damper / limits, against the oracle"""
+    from dojo_jl_b200 import environments as E
+    from oracle.oracle import Oracle
+    B = 16
+    env = E.get_environment("cartpole_dqn", batch=B, springs=2.0, dampers=0.3, joint_limits={"cart_joint": (-0.3, 0.25)})
+    m = env.mechanism
+    o = Oracle(m)
+    rng = np.random.default_rng(29)
+    a = rng.uniform(-4.0, 4.0, B)
+    S = env.get_state()
+    for _ in range(60):
+        env.step(action=a)
+    Sn = env.get_state()
+    assert np.isfinite(Sn).all() and (Sn[:, 0] > -0.3 - 1e-4).all() and (Sn[:, 0] < 0.25 + 1e-4).all()
+    for e in range(0, B, 4):
+        x = S[e]
+        for _ in range(60):
+            x = o.minimal_gradients(x, np.array([a[e], 0.0]))[0]
+        assert np.abs(x - Sn[e]).max() < 1e-6
+    Xn, Gx, Gu, st, it = env.stepper.minimal_gradients(Sn, env.input_map(a))
+    for e in range(0, B, 4):
+        xo, Gxo, Guo, so, io = o.minimal_gradients(Sn[e], np.array([a[e], 0.0]))
+        if so != 0 or st[e] != 0 or io != it[e]:
+            continue
+        assert np.abs(Xn[e] - xo).max() < 1e-8
+        assert np.abs(Gx[e] - Gxo).max() < 1e-6 * max(1.0, np.abs(Gxo).max()) and np.abs(Gu[e] - Guo).max() < 1e-6 * max(1.0, np.abs(Guo).max())
