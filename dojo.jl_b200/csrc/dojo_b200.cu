@@ -1403,6 +1403,9 @@ extern "C" int dojo_update_params(DojoHandle* h, const DojoMechanismDesc* d) {
               A.arena_len == B.arena_len && A.grad_len == B.grad_len && A.n_red == B.n_red && h->blob_bytes == t->blob_bytes &&
               h->arena_bytes == t->arena_bytes && (h->grad_bytes == t->grad_bytes);
   for (int k = 0; k < 8; ++k) same = same && h->blob_off[k] == t->blob_off[k];
+  // the handle keeps the kernels it was created with: a contact model or a translational spring / damper / limit that needs the other
+  // compilation (dojo_b200_cm.cu) cannot be switched on or off by an update
+  same = same && h->any_contact == t->any_contact && h->orthant_contact == t->orthant_contact && h->tra_joint == t->tra_joint;
   if (!same) { dojo_destroy(t); h->err = "dojo_update_params: the descriptor has a different topology (use dojo_create)"; return DOJO_EINVAL; }
   cudaError_t e = cudaSetDevice(h->device);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
