@@ -240,3 +240,38 @@ def test_cartpole_dqn_mirror_logic(monkeypatch):
     S = env.get_state()
     assert not done.any() and (np.abs(S[:, 0]) < 0.2 + 1e-4).all()  # the slider stays inside its limits ...
     assert abs(S[0, 0] - 0.2) < 3e-2 and abs(S[1, 0] + 0.2) < 3e-2   # ... and is pushed against them
+
+
+def _hopper_batch(m, B, rng):
+    Z = np.tile(m.z0, (B, 1))
+    dz = rng.uniform(0.0, 0.3, B)
+    Z[:, 2] += dz
+    Z[:, 13 + 2] += dz
+    U = np.zeros((B, m.nu))
+    U[:, 6] = rng.uniform(-10.0, 20.0, B)  # leg force (the Prismatic joint's input)
+    return Z, U
+
+
+def test_raiberthopper_kernel_emulation_matches_oracle():
+    """get_raiberthopper defaults (raiberthopper/mechanism.jl:1-86): Floating body, Prismatic leg with a translational damper 0.1,
+    foot and body contacts -- the translational damper together with the contact solve"""
+    from hostemu.harness import HostEmu
+    m = dj.get_mechanism("raiberthopper")
+    assert m.joints[1].tra.damper == 0.1 and m.joints[1].tra.nfree == 1 and m.Ni == 2
+    o, em = Oracle(m), HostEmu(m)
+    Z, U = _hopper_batch(m, 4, np.random.default_rng(2))
+    landed = False
+    for t in range(50):
+        Zn, st, it, sol = em.step(Z, U, slots=4)
+        for e in range(4):
+            zo, so, io, solo = o.step(Z[e], U[e], return_sol=True)
+            assert (st[e], it[e]) == (so, io), (t, e)
+            assert np.abs(Zn[e] - zo).max() < 1e-9 and np.abs(sol[e] - solo).max() < 1e-7
+            landed = landed or solo[m.contact_sol_offset(0) + 4] > 1.0  # normal impulse of the foot contact
+        Z = Zn
+    assert landed
+    Zn, Fz, Fu, st, it = em.step_grad(Z, U, slots=2, slots_grad=2)
+    for e in range(4):
+        zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
+        assert (st[e], it[e]) == (so, io)
+        assert np.abs(Fz[e] - Fzo).max() < 1e-7 * max(1.0, np.abs(Fzo).max()) and np.abs(Fu[e] - Fuo).max() < 1e-7 * max(1.0, np.abs(Fuo).max())

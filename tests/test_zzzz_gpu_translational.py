@@ -89,3 +89,43 @@ def test_cartpole_environment_and_minimal_gradients():
             continue
         assert np.abs(Xn[e] - xo).max() < 1e-8
         assert np.abs(Gx[e] - Gxo).max() < 1e-6 * max(1.0, np.abs(Gxo).max()) and np.abs(Gu[e] - Guo).max() < 1e-6 * max(1.0, np.abs(Guo).max())
+
+
+def test_raiberthopper_parity():
+    """get_raiberthopper defaults: translational damper on the Prismatic leg + foot / body contacts"""
+    import dojo_jl_b200 as dj
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
+    from test_translational_joints import _hopper_batch
+    m = dj.get_mechanism("raiberthopper")
+    B = 64
+    stepper, o = BatchedStepper(m, B), Oracle(m)
+    Z, U = _hopper_batch(m, B, np.random.default_rng(31))
+    same = conv = total = status_diff = 0
+    for t in range(40):
+        Zn, st, it, sol = stepper.step(Z, U, return_sol=True)
+        for e in range(0, B, 4):
+            zo, so, io, solo = o.step(Z[e], U[e], return_sol=True)
+            total += 1
+            if st[e] != so:
+                status_diff += 1
+                continue
+            if so != 0:
+                continue
+            conv += 1
+            if it[e] != io:
+                assert np.abs(Zn[e] - zo).max() < 2e-2
+                continue
+            same += 1
+            assert np.abs(Zn[e] - zo).max() < 1e-6 and np.abs(sol[e] - solo).max() < 1e-5
+        Z = Zn
+    assert status_diff <= 0.03 * total and conv >= 0.7 * total and same >= 0.9 * conv, (same, conv, status_diff, total)
+    Zn, Fz, Fu, st, it = stepper.step_grad(Z, U)
+    errs = []
+    for e in range(0, B, 4):
+        zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
+        if so != 0 or st[e] != 0 or io != it[e]:
+            continue
+        errs.append(max(np.abs(Fz[e] - Fzo).max() / max(1.0, np.abs(Fzo).max()), np.abs(Fu[e] - Fuo).max() / max(1.0, np.abs(Fuo).max())))
+    errs = np.array(errs)
+    assert len(errs) >= 8 and np.median(errs) < 1e-7 and np.quantile(errs, 0.9) < 1e-4 and errs.max() < 1e-2, errs

@@ -189,6 +189,21 @@ def build_cartpole():
     return mech
 
 
+def build_raiberthopper():
+    """DojoEnvironments/src/mechanisms/raiberthopper/mechanism.jl:1-86 (defaults): Sphere(0.1, 4.18) body on a Floating joint, Sphere(0.05,
+    0.52) foot on a Prismatic joint along z with damper 0.1 (set_dampers!(joints, [0; 0.1]): a TRANSLATIONAL damper), contacts on the
+    foot and on the body (friction 0.5); initialize_raiberthopper!: leg_length 0.5, body at z = 0.5 + 0.05."""
+    rb, rf = 0.1, 0.05
+    bodies = [Body("body", 4.18, 0.4 * 4.18 * rb * rb * np.eye(3)), Body("foot", 0.52, 0.4 * 0.52 * rf * rf * np.eye(3))]
+    j0 = make_joint("floating", "floating_joint", -1, 0, None, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    j1 = make_joint("prismatic", "prismatic_joint", 0, 1, Z_AXIS, np.zeros(3), [1.0, 0, 0, 0], 0.1)
+    mech = Mechanism("raiberthopper", bodies, [j0, j1], [], timestep=0.05)
+    mech.contacts = [nonlinear_contact(mech, "foot_contact", "foot", Z_AXIS, 0.5, np.zeros(3), rf),
+                     nonlinear_contact(mech, "body_contact", "body", Z_AXIS, 0.5, np.zeros(3), rb)]
+    mech.z0 = mech.forward_kinematics({"floating_joint": [0, 0, 0.5 + rf, 0, 0, 0], "prismatic_joint": [-0.5]})
+    return mech
+
+
 def build_sphere():
     """DojoEnvironments/src/mechanisms/sphere/mechanism.jl:1-67 (defaults): Sphere(0.5, 1) on a Floating joint, one contact of
     radius 0.5 at the centre; initialize_sphere!: centre at z = 0.5 + r, velocity [1, 0, 0]."""
@@ -295,7 +310,7 @@ def main():
     ap.add_argument("--reference", default="/root/reference")
     args = ap.parse_args()
     os.makedirs(MECHANISM_DIR, exist_ok=True)
-    for mech in (build_pendulum(), build_cartpole(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
+    for mech in (build_pendulum(), build_cartpole(), build_raiberthopper(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
         mech.save(os.path.join(MECHANISM_DIR, f"{mech.name}.json"))
         print(f"{mech.name}: Nb={mech.Nb} Ne={mech.Ne} Ni={mech.Ni} nres={mech.nres} nu={mech.nu}")
 
