@@ -2,8 +2,8 @@
 //
 // Compiled twice into libdojo_b200.so:
 //   * dojo_b200.cu     (namespace dj):    NonlinearContact only -- every BASELINE model; this is the benchmarked kernel
-//   * dojo_b200_cm.cu  (namespace dj_cm, DJ_ANY_CONTACT): additionally ImpactContact / LinearContact, selected by
-//     dojo_create for mechanisms that contain such contacts.  The extra model code never enters the first compilation, whose SASS
+//   * dojo_b200_cm.cu  (namespace dj_cm, DJ_ANY_CONTACT): additionally ImpactContact / LinearContact and translational
+//     springs / dampers / limits (8 a4 / a6), selected by dojo_create for mechanisms that contain them.  The extra model code never enters the first compilation, whose SASS
 //     is bit-identical with and without this split (checked with cuobjdump, profiles/README.md).
 // The `// [hostemu:...]` markers delimit the text that tests/hostemu/gen.py compiles for the CPU emulation of the kernel.
 #pragma once
