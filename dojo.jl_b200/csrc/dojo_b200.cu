@@ -1266,10 +1266,6 @@ extern "C" int dojo_step_record_async(DojoHandle* h, const DojoSolverOptions* op
     if (h) h->err = "dojo_step_record_async: bad arguments (B <= max_batch, Z_next != Z)";
     return DOJO_EINVAL;
   }
-  if (h->tra_joint) {  // the storage kernel's momentum knows rotational spring / damper impulses only
-    h->err = "dojo_step_record: recording with translational springs / dampers / limits is not implemented yet";
-    return DOJO_EINVAL;
-  }
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h);  // the solver solution stays in the handle's device buffer
   if (rc != DOJO_OK) return rc;

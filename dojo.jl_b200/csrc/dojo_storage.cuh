@@ -68,7 +68,10 @@ DJ_DEV JointWrench joint_wrench(const StorageArgs& a, const JointDev& jd, bool p
   const V3 pa = v3(jd.pa[0], jd.pa[1], jd.pa[2]), pb = v3(jd.pb[0], jd.pb[1], jd.pb[2]);
   const Quat qoff = Quat{jd.qoff[0], jd.qoff[1], jd.qoff[2], jd.qoff[3]};
   const M33 Ra = rotmat(A.q), Rb = rotmat(Bc.q);
-  const double* lam = sol + jd.sol_off;  // [tra eq (nl_t) | s (nb_r) | gamma (nb_r) | rot eq (nl_r)]
+  // reference ordering of the joint's entry: [tra eq (nl_t) | s (nb_r) | gamma (nb_r) | rot eq (nl_r)] with rotational limits,
+  // [s (nb_r) | gamma (nb_r) | tra eq (nl_t) | rot eq (nl_r)] with translational limits (JF_LIM_TRA: the limits belong to the first half)
+  const bool lim_tra = (jd.flags & JF_LIM_TRA) != 0;
+  const double* lam = sol + jd.sol_off + (lim_tra ? 2 * jd.nb_r : 0);
   // ---- translational element
   {
     V3 f3 = v3zero();  // C' lambda
@@ -76,6 +79,22 @@ DJ_DEV JointWrench joint_wrench(const StorageArgs& a, const JointDev& jd, bool p
     V3 in3 = v3zero();
     if (u) in3 = a.input_scaling * masked_sum(jd.At, jd.nfree_t, u + jd.u_off);
     const V3 e = tra_displacement(jd, A.x, A.q, Bc.x, Bc.q);
+    if (lim_tra) {  // limit duals: A' (gamma_lower - gamma_upper)   (joints/joint.jl impulse_projector)
+      const double* gam = sol + jd.sol_off + jd.nb_r;
+      for (int i = 0; i < jd.nb2_r; ++i) f3 += (gam[jd.nb2_r + i] - gam[i]) * mask_row_s(jd.At, i);
+    }
+    if (jd.flags & (JF_TRA_SPRING | JF_TRA_DAMPER)) {  // translational/springs.jl:5-29, dampers.jl:5-35 (velocities v25, w25)
+      const double* tp = joint_tra_params(jd);
+      V3 fs = v3zero();
+      if (jd.flags & JF_TRA_SPRING)
+        for (int i = 0; i < jd.nfree_t; ++i) fs += (h * tp[0] * (tp[2 + i] - dot(mask_row_s(jd.At, i), e))) * mask_row_s(jd.At, i);
+      if (jd.flags & JF_TRA_DAMPER) {
+        const Quat qa1 = next_orientation(A.q, -A.w, h), qb1 = next_orientation(Bc.q, -Bc.w, h);
+        const V3 e1 = tra_displacement(jd, A.x - h * A.v, qa1, Bc.x - h * Bc.v, qb1);
+        for (int i = 0; i < jd.nfree_t; ++i) fs += (-tp[1] * dot(mask_row_s(jd.At, i), e - e1)) * mask_row_s(jd.At, i);
+      }
+      f3 += fs;
+    }
     if (parent) {
       w.F += -1.0 * (Ra * f3);  w.tau += -1.0 * cross(e + pa, f3);
       w.JF += -1.0 * (Ra * in3); w.Jtau += (-0.5) * cross(e + pa, in3);
@@ -92,8 +111,8 @@ DJ_DEV JointWrench joint_wrench(const StorageArgs& a, const JointDev& jd, bool p
     const M33 Rrel = rotmat(qmul(qmul(qinv(Bc.q), A.q), qoff));  // rotation_matrix(inv(qb) * qa * qoff)
     V3 f3 = v3zero();
     const double* gam = lam + jd.nl_t + jd.nb_r;
-    for (int i = 0; i < jd.nb2_r; ++i) f3 += (gam[jd.nb2_r + i] - gam[i]) * mask_row_s(jd.Ar, i);
-    const double* lr = lam + jd.nl_t + 2 * jd.nb_r;
+    if (!lim_tra) for (int i = 0; i < jd.nb2_r; ++i) f3 += (gam[jd.nb2_r + i] - gam[i]) * mask_row_s(jd.Ar, i);
+    const double* lr = lam + jd.nl_t + (lim_tra ? 0 : 2 * jd.nb_r);
     for (int i = 0; i < jd.nl_r; ++i) f3 += lr[i] * mask_row_s(jd.Cr, i);
     if (parent) w.tau += (-0.5) * (Roff * (sI_plus_s(q.s, qvec(q)) * f3));
     else w.tau += 0.5 * (sI_minus_s(q.s, qvec(q)) * f3);
@@ -173,6 +192,14 @@ DJ_DEV void storage_env(const StorageArgs& a, int e) {
   }
   for (int j = 0; j < a.Ne; ++j) {  // spring potential (energy.jl:69-90): 1/2 |force|^2 / k
     const JointDev& jd = a.joints[j];
+    if ((jd.flags & JF_TRA_SPRING) && joint_tra_params(jd)[0] > 0.0) {
+      const BodyState A = kin_load(z, jd.parent), Bc = kin_load(z, jd.child);
+      const double* tp = joint_tra_params(jd);
+      const V3 e = tra_displacement(jd, A.x, A.q, Bc.x, Bc.q);
+      double d2 = 0.0;
+      for (int i = 0; i < jd.nfree_t; ++i) { const double di = tp[2 + i] - dot(mask_row_s(jd.At, i), e); d2 += di * di; }
+      potential += 0.5 * tp[0] * d2;
+    }
     if (jd.nfree_r == 0 || !(jd.spring_r > 0.0)) continue;
     const BodyState A = kin_load(z, jd.parent), Bc = kin_load(z, jd.child);
     const Quat q = qmul(qmul(qinv(Quat{jd.qoff[0], jd.qoff[1], jd.qoff[2], jd.qoff[3]}), qinv(A.q)), Bc.q);

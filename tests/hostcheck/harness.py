@@ -141,9 +141,10 @@ class HostCheck:
         U = np.ascontiguousarray(np.atleast_2d(U), dtype=float)
         sol = np.ascontiguousarray(np.atleast_2d(sol), dtype=float)
         B = Z.shape[0]
-        jext = np.array([[j.rot.nlimits, j.rot.spring if j.rot.nlambda < 3 else 0.0, j.rot.damper if j.rot.nlambda < 3 else 0.0]
-                         + list(np.asarray(j.rot.spring_offset, dtype=float).ravel()[:3]) + [0.0] * (3 - min(3, np.size(j.rot.spring_offset)))
-                         for j in m.joints], dtype=float)
+        def half(e):
+            off = list(np.asarray(e.spring_offset, dtype=float).ravel()[:3])
+            return [e.nlimits, e.spring if e.nlambda < 3 else 0.0, e.damper if e.nlambda < 3 else 0.0] + off + [0.0] * (3 - len(off))
+        jext = np.array([half(j.rot) + half(j.tra) for j in m.joints], dtype=float)
         bdbl = np.array([[b.mass] + list(np.asarray(b.inertia, dtype=float).ravel()) for b in m.bodies], dtype=float)
         g = np.ascontiguousarray(m.gravity, dtype=float)
         body, diag = np.empty((B, m.Nb, 12)), np.empty((B, 8))

@@ -131,7 +131,7 @@ void hostcheck_env_post(void* p, const int* spec_i, const double* spec_d, int Ni
   for (int e = 0; e < B; ++e) env_post(a, e);
 }
 
-// storage / diagnostics (dojo_storage.cuh).  jext [Ne][6] = rot limits (Nb/2), spring_r, damper_r, spring_offset_r(3);
+// storage / diagnostics (dojo_storage.cuh).  jext [Ne][12] = rot limits (Nb/2), spring_r, damper_r, spring_offset_r(3), then the same for tra;
 // bdbl [Nb][10] = mass, inertia (row-major).  Solution offsets follow dojo_create: joints in order, n = nl_t + nl_r + 4 * limits.
 void hostcheck_storage(void* p, const double* jext, const double* bdbl, int nres, double input_scaling, const double* g, int B, const double* Z,
                        const double* Zn, const double* U, const double* sol, double* body_out, double* diag) {
@@ -140,9 +140,17 @@ void hostcheck_storage(void* p, const double* jext, const double* bdbl, int nres
   int off = 0;
   for (int j = 0; j < m->Ne; ++j) {
     JointDev& J = m->joints[j];
-    const double* d = jext + 6 * j;
+    const double* d = jext + 12 * j;
     J.nb2_r = (int)d[0]; J.nb_r = 2 * J.nb2_r; J.spring_r = d[1]; J.damper_r = d[2];
     for (int i = 0; i < 3; ++i) J.spring_off_r[i] = d[3 + i];
+    // translational half as dojo_create encodes it (JointDev::flags, joint_tra_params)
+    J.flags = 0;
+    if (J.nfree_t > 0) {
+      if (d[7] != 0.0) J.flags |= JF_TRA_SPRING;
+      if (d[8] != 0.0) J.flags |= JF_TRA_DAMPER | JF_FULL;
+      if ((int)d[6] > 0) { J.flags |= JF_LIM_TRA | JF_FULL; J.nb2_r = (int)d[6]; J.nb_r = 2 * J.nb2_r; }
+      if (J.flags & (JF_TRA_SPRING | JF_TRA_DAMPER)) { double* tp = joint_tra_params(J); tp[0] = d[7]; tp[1] = d[8]; for (int i = 0; i < J.nfree_t; ++i) tp[2 + i] = d[9 + i]; }
+    }
     J.ne = J.nl_t + J.nl_r; J.n = J.ne + 2 * J.nb_r;
     J.sol_off = off; off += J.n;
   }

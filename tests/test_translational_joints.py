@@ -275,3 +275,23 @@ def test_raiberthopper_kernel_emulation_matches_oracle():
         zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
         assert (st[e], it[e]) == (so, io)
         assert np.abs(Fz[e] - Fzo).max() < 1e-7 * max(1.0, np.abs(Fzo).max()) and np.abs(Fu[e] - Fuo).max() < 1e-7 * max(1.0, np.abs(Fuo).max())
+
+
+@pytest.mark.parametrize("case", ["all", "planar", "cartpole", "raiberthopper"])
+def test_storage_with_translational_impulses(case):
+    """save_to_storage! / momentum / energies (dojo_storage.cuh compiled for the host) with translational spring, damper and limit
+    impulses, against the oracle's restatement (simulation/storage.jl:50-67, mechanics/momentum.jl:44-52, energy.jl:69-90)"""
+    from hostcheck.harness import HostCheck
+    m = cartpole() if case == "cartpole" else dj.get_mechanism("raiberthopper") if case == "raiberthopper" else chain(**CASES[case])
+    o, hc = Oracle(m), HostCheck(m)
+    rng = np.random.default_rng(5)
+    z, u = m.z0.copy(), 0.5 * rng.normal(size=m.nu)
+    if case == "cartpole":
+        u[0] = 6.0  # against the upper limit of the slider
+    for t in range(120 if case == "cartpole" else 20):
+        zn, st, _, sol = o.step(z, u, return_sol=True)
+        body, diag = o.storage_record()
+        bh, dh = hc.storage(z, zn, u, sol)
+        assert np.abs(bh[0] - body).max() < 1e-11 * max(1.0, np.abs(body).max())
+        assert np.abs(dh[0] - diag).max() < 1e-11 * max(1.0, np.abs(diag).max())
+        z = zn

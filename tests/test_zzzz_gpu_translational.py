@@ -53,12 +53,27 @@ def test_step_rollout_and_gradient_parity(case):
     assert len(errs) >= 6 and np.median(errs) < 1e-8 and errs.max() < 1e-4, errs
 
 
-def test_recording_is_refused_with_translational_dampers():
+def test_recording_with_translational_impulses():
+    """dojo_step_record on the cartpole with springs, dampers and limits: momentum / energies against the oracle"""
     from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import Oracle
     m = cartpole()
-    stepper = BatchedStepper(m, 2)
-    with pytest.raises(RuntimeError, match="translational"):
-        stepper.step_record(np.tile(m.z0, (2, 1)))
+    B = 8
+    stepper, o = BatchedStepper(m, B), Oracle(m)
+    rng = np.random.default_rng(37)
+    Z = np.tile(m.z0, (B, 1))
+    U = np.zeros((B, m.nu))
+    U[:, 0] = rng.uniform(-6.0, 6.0, B)
+    for _ in range(40):
+        Z, _, _ = stepper.step(Z, U)
+    out = stepper.step_record(Z, U)
+    Zn, storage, diag = out[0], out[1], out[2]
+    for e in range(B):
+        zo, so, io = o.step(Z[e], U[e])
+        body, dg = o.storage_record()
+        assert np.abs(Zn[e] - zo).max() < 1e-8
+        assert np.abs(np.asarray(storage[e]).reshape(-1) - body.reshape(-1)).max() < 1e-6 * max(1.0, np.abs(body).max())
+        assert np.abs(np.asarray(diag[e]) - dg).max() < 1e-6 * max(1.0, np.abs(dg).max())
 
 
 def test_cartpole_environment_and_minimal_gradients():
