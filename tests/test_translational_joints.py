@@ -31,7 +31,7 @@ def chain(kt=0.0, dt=0.0, kr=0.0, dr=0.0, lim=None, planar=False):
     """origin -Floating- b0 -Prismatic (or Planar) with vertices and an orientation offset- b1 -Revolute- b2"""
     bodies = [Body(f"b{i}", 1.0 + 0.3 * i, np.diag([0.1, 0.2, 0.15]) * (1 + 0.2 * i)) for i in range(3)]
     j0 = Joint("float", -1, 0, _element(0), _element(0))
-    tra = _element(1, axis=[0.3, 1.0, 0.2], spring=kt, damper=dt, offset=[0.05, -0.02]) if planar else \
+    tra = _element(1, axis=[0.3, 1.0, 0.2], spring=kt, damper=dt, limits=lim, offset=[0.05, -0.02]) if planar else \
         _element(2, axis=[0.3, 1.0, 0.2], spring=kt, damper=dt, limits=lim, offset=[0.05])
     j1 = Joint("slide", 0, 1, tra, _element(3), vertex_parent=np.array([0.1, 0.2, -0.1]), vertex_child=np.array([-0.05, 0.1, 0.2]),
                orientation_offset=Q.rpy_to_quat([0.2, -0.1, 0.3]))
@@ -47,7 +47,8 @@ def cartpole():
 
 
 CASES = {"spring": dict(kt=30.0, kr=0.5, dr=0.2), "damper": dict(dt=2.0, kr=0.5, dr=0.2), "limits": dict(kr=0.5, lim=([-0.05], [0.2])),
-         "all": dict(kt=30.0, dt=2.0, kr=0.5, dr=0.2, lim=([-0.05], [0.2])), "planar": dict(kt=10.0, dt=1.0, planar=True)}
+         "all": dict(kt=30.0, dt=2.0, kr=0.5, dr=0.2, lim=([-0.05], [0.2])), "planar": dict(kt=10.0, dt=1.0, planar=True),
+         "planar_limits": dict(kt=5.0, dt=0.5, planar=True, lim=([-0.05, -0.1], [0.2, 0.12]))}  # two limited translational axes
 
 
 def _state_in_motion(m, steps, seed=3):
@@ -153,7 +154,7 @@ def test_cart_stops_at_its_limits_and_dampers_dissipate():
 # ----------------------------------------------------------------------------------------------------------------
 # device code through the kernel emulation
 # ----------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["all", "planar", "cartpole"])
+@pytest.mark.parametrize("case", ["all", "planar", "planar_limits", "cartpole"])
 def test_kernel_emulation_matches_oracle(case):
     from hostemu.harness import HostEmu
     m = cartpole() if case == "cartpole" else chain(**CASES[case])
@@ -161,10 +162,10 @@ def test_kernel_emulation_matches_oracle(case):
     rng = np.random.default_rng(7)
     B = 3
     Z = np.tile(m.z0, (B, 1))
-    U = 0.5 * rng.normal(size=(B, m.nu))
+    U = (2.0 if case == "planar_limits" else 0.5) * rng.normal(size=(B, m.nu))
     if case == "cartpole":
         U[:, 0] = [3.0, -3.0, 6.0]
-    T = 120 if case == "cartpole" else 40
+    T = 120 if case == "cartpole" else 80 if case == "planar_limits" else 40
     gmax = 0.0
     for t in range(T):
         Zn, st, it, sol = em.step(Z, U, slots=4 if t % 2 else 2)
