@@ -329,3 +329,31 @@ def test_momentum_conservation_with_translational_springs_dampers_limits(case):
     P = np.array(P)
     assert np.abs(P - P[0]).max() < 1e-8
     assert active  # the limit duals were at work during the run
+
+
+def test_slider_known_answers_of_the_reference():
+    """test/energy.jl "Slider 1" (:188-231): a box on a Prismatic joint with a translational spring k = 10 in zero gravity,
+    released 0.5 from the spring's rest position, is a harmonic oscillator -- the reference asserts the ANALYTIC amplitude and
+    peak velocity (z0, z0 sqrt(k / m), both to 1e-4) and a mechanical-energy band of 1e-3 over 5 s.  One of the few known-answer
+    tests of the reference on this path; run here on the oracle and on the device kernels (emulation)."""
+    from hostemu.harness import HostEmu
+    m = dj.get_mechanism("slider", gravity=0.0, springs=10.0)
+    z0, k, mass = 0.5, 10.0, m.bodies[0].mass
+    o, em = Oracle(m, capi.solver_options(rtol=1e-10, btol=1e-10)), HostEmu(m)
+    z = m.forward_kinematics({"joint": [-z0]})  # initialize!(mech, :slider; position = z0) (slider/mechanism.jl:41-53)
+    zd = z.copy()[None]
+    xs, vs, me, xd = [], [], [], []
+    for step in range(500):
+        z, st, _ = o.step(z, np.zeros(1))
+        assert st == 0
+        body, diag = o.storage_record()
+        xs.append(z[2])
+        vs.append(body[0][8])
+        me.append(diag[6] + diag[7])
+        zd = em.step(zd, np.zeros((1, 1)), capi.solver_options(rtol=1e-10, btol=1e-10))[0]
+        xd.append(zd[0, 2])
+    me = np.array(me[100:])
+    assert abs(max(xs) - z0 + 0.5) < 1e-4                      # maximum amplitude (the body centre sits 0.5 below the joint)
+    assert abs(max(vs) - z0 * np.sqrt(k / mass)) < 1e-4        # maximum velocity
+    assert np.abs((me - me[0]) / me.mean()).max() < 1e-3       # no energy drift with the variational integrator
+    assert np.abs(np.array(xd) - np.array(xs)).max() < 1e-10   # the device kernels follow the same trajectory

@@ -189,6 +189,18 @@ def build_cartpole():
     return mech
 
 
+def build_slider():
+    """DojoEnvironments/src/mechanisms/slider/mechanism.jl:1-53 (defaults): Box(0.1, 0.1, 1, 1) on a Prismatic joint along z with
+    child_vertex = z/2; initialize_slider!: position 0 (body centre at z = -1/2).  Springs / dampers are the builder's options."""
+    x, y, z, m = 0.1, 0.1, 1.0, 1.0
+    body = Body("pbody", m, m / 12.0 * np.diag([y ** 2 + z ** 2, x ** 2 + z ** 2, x ** 2 + y ** 2]))
+    j = make_joint("prismatic", "joint", -1, 0, Z_AXIS, np.zeros(3), [1.0, 0, 0, 0], 0.0)
+    j.vertex_child = 0.5 * Z_AXIS
+    mech = Mechanism("slider", [body], [j], [], timestep=0.01)
+    mech.z0 = mech.forward_kinematics({"joint": [0.0]})
+    return mech
+
+
 def build_raiberthopper():
     """DojoEnvironments/src/mechanisms/raiberthopper/mechanism.jl:1-86 (defaults): Sphere(0.1, 4.18) body on a Floating joint, Sphere(0.05,
     0.52) foot on a Prismatic joint along z with damper 0.1 (set_dampers!(joints, [0; 0.1]): a TRANSLATIONAL damper), contacts on the
@@ -310,7 +322,7 @@ def main():
     ap.add_argument("--reference", default="/root/reference")
     args = ap.parse_args()
     os.makedirs(MECHANISM_DIR, exist_ok=True)
-    for mech in (build_pendulum(), build_cartpole(), build_raiberthopper(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
+    for mech in (build_pendulum(), build_cartpole(), build_slider(), build_raiberthopper(), build_sphere(), build_block(), build_ant(args.reference), build_quadruped(args.reference), build_atlas(args.reference)):
         mech.save(os.path.join(MECHANISM_DIR, f"{mech.name}.json"))
         print(f"{mech.name}: Nb={mech.Nb} Ne={mech.Ne} Ni={mech.Ni} nres={mech.nres} nu={mech.nu}")
 
