@@ -357,3 +357,20 @@ def test_slider_known_answers_of_the_reference():
     assert abs(max(vs) - z0 * np.sqrt(k / mass)) < 1e-4        # maximum velocity
     assert np.abs((me - me[0]) / me.mean()).max() < 1e-3       # no energy drift with the variational integrator
     assert np.abs(np.array(xd) - np.array(xs)).max() < 1e-10   # the device kernels follow the same trajectory
+
+
+@pytest.mark.parametrize("gravity,spring,z0,seconds,band", [(-9.81, 0.0, 0.5, 1.5, 1e-6), (-9.81, 1.0, 0.1, 10.0, 1e-3)])
+def test_slider_energy_conservation_of_the_reference(gravity, spring, z0, seconds, band):
+    """test/energy.jl "Slider 2" (:243-277: gravity only, mechanical energy constant to 1e-6) and "Slider 3" (:288-321: gravity and a
+    translational spring, band 1e-3), energies as the reference records them (save_to_storage!, mechanics/energy.jl)"""
+    m = dj.get_mechanism("slider", gravity=gravity, springs=spring)
+    o = Oracle(m, capi.solver_options(rtol=1e-12, btol=1e-12))
+    z = m.forward_kinematics({"joint": [-z0]})
+    me = []
+    for _ in range(int(seconds / m.timestep)):
+        z, st, _ = o.step(z, np.zeros(1))
+        assert st == 0
+        _, diag = o.storage_record()
+        me.append(diag[6] + diag[7])
+    me = np.array(me[100:])
+    assert np.abs((me - me[0]) / me.mean()).max() < band
