@@ -1,0 +1,94 @@
+"""More of the reference's own behaviour / conservation tests restated on the oracle (and, where cheap, on the device kernels through
+the emulation): they have KNOWN ANSWERS (a rest state, an analytic velocity, a conserved quantity), which is what pins an oracle that
+cannot be compared with Julia output in this image.
+
+  test/behaviors.jl:21-40   "Box toss"            a thrown block comes to rest: |v| < 1e-8, z = 0.25 +- 1e-3, for four time steps
+  test/behaviors.jl:42-55   "Box external force"  set_external_force!: v = F t / m, w = tau t / J
+  test/energy.jl:98-130     "Dice"                free rigid body under gravity: mechanical energy constant to 1e-8
+"""
+import numpy as np
+import pytest
+
+import dojo_jl_b200 as dj
+from dojo_jl_b200 import capi, quat as Q
+from oracle.oracle import Oracle
+
+
+def _block(timestep=0.01, gravity=-9.81, friction=0.8, contact=True):
+    m = dj.get_mechanism("block", timestep=timestep, gravity=gravity)
+    if not contact:
+        m.contacts = []
+    for c in m.contacts:
+        c.friction = friction
+    return m
+
+
+def _toss_state(m, h):
+    z = m.z0.copy()
+    z[0:3] = [0.0, 0.0, 0.5 + 0.25]          # initialize_block!: position + z * edge_length / 2 (block/mechanism.jl:76-95)
+    z[3:6] = [1.0, 1.5, 1.0]
+    z[10:13] = np.array([5.0, 4.0, 2.0]) * h
+    return z
+
+
+@pytest.mark.parametrize("h", [0.10, 0.05, 0.01, 0.005])
+def test_box_toss_comes_to_rest(h):
+    m = _block(timestep=h, friction=0.1)
+    o = Oracle(m, capi.solver_options(rtol=1e-6, btol=1e-6))
+    z = _toss_state(m, h)
+    for _ in range(int(round(5.0 / h))):
+        z, st, _ = o.step(z, np.zeros(m.nu))
+        assert st == 0
+    assert np.abs(z[3:6]).max() < 1e-8 and abs(z[2] - 0.25) < 1e-3
+
+
+def test_box_toss_on_the_device_kernels():
+    """the same toss through dojo_step_kernel (emulation), h = 0.05: same rest state, same trajectory as the oracle"""
+    from hostemu.harness import HostEmu
+    h = 0.05
+    m = _block(timestep=h, friction=0.1)
+    opts = capi.solver_options(rtol=1e-6, btol=1e-6)
+    o, em = Oracle(m, opts), HostEmu(m)
+    z = _toss_state(m, h)
+    zd = z.copy()[None]
+    for k in range(100):
+        z, st, it = o.step(z, np.zeros(m.nu))
+        zd, sd, itd, _ = em.step(zd, np.zeros((1, m.nu)), opts)
+        assert (sd[0], itd[0]) == (st, it) and np.abs(zd[0] - z).max() < 1e-9
+    assert np.abs(zd[0, 3:6]).max() < 1e-8 and abs(zd[0, 2] - 0.25) < 1e-3
+
+
+def test_box_external_force_and_torque():
+    m = _block(gravity=0.0, contact=False)
+    m.bodies[0].inertia = np.eye(3)
+    o = Oracle(m)
+    q = Q.rot_z(np.pi / 2)
+    for force, torque, check in (([1.0, 0, 0], [0.0, 0, 0], lambda z: abs(z[4] - 0.5)), ([0.0, 0, 0], [1.0, 0, 0], lambda z: abs(z[10] - 0.5))):
+        z = m.z0.copy()
+        z[0:3] = 0.0
+        z[3:6] = 0.0
+        z[6:10] = q
+        z[10:13] = 0.0
+        for k in range(1, 101):
+            fext = np.zeros(6)
+            if k <= 50:  # set_external_force!(body; force, torque, vertex = [0.5, 0, 0]) (bodies/set.jl:110-115)
+                fext[0:3] = Q.qrot(np.array(force), z[6:10])
+                fext[3:6] = np.array(torque) + np.cross([0.5, 0.0, 0.0], force)
+            z, st, _ = o.step(z, np.zeros(m.nu), fext=fext)
+            assert st == 0
+        assert check(z) < 1e-3
+
+
+def test_dice_energy_conservation():
+    m = _block(gravity=-10.0, contact=False)
+    o = Oracle(m, capi.solver_options(rtol=1e-12, btol=1e-12))
+    z = m.z0.copy()
+    z[3:6] = [1.0, 2.0, 3.0]
+    z[10:13] = [1.0, 1.0, 1.0]
+    me = []
+    for _ in range(500):
+        z, st, _ = o.step(z, np.zeros(m.nu))
+        _, diag = o.storage_record()
+        me.append(diag[6] + diag[7])
+    me = np.array(me[100:])
+    assert np.abs((me - me[0]) / me.mean()).max() < 1e-8
