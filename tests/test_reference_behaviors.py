@@ -92,3 +92,24 @@ def test_dice_energy_conservation():
         me.append(diag[6] + diag[7])
     me = np.array(me[100:])
     assert np.abs((me - me[0]) / me.mean()).max() < 1e-8
+
+
+def test_quadruped_energy_band_with_springs():
+    """test/energy.jl "Quadruped" (:427-463): zero gravity, springs = 1 on every joint (parse_springs = parse_dampers = false: no
+    dampers), no limits, no contacts, released from initialize_quadruped! away from the springs' rest pose: the mechanical energy
+    (kinetic + spring potential, as recorded by save_to_storage!) stays within 1e-2 over 5 s"""
+    m = dj.get_mechanism("quadruped", gravity=0.0, springs=1.0)
+    m.contacts = []
+    for j in m.joints:
+        j.tra.damper = j.rot.damper = 0.0
+        j.rot.limit_lo = j.rot.limit_hi = None
+    o = Oracle(m, capi.solver_options(rtol=1e-12, btol=1e-12))
+    z = m.z0.copy()
+    me = []
+    for _ in range(500):
+        z, st, _ = o.step(z, np.zeros(m.nu))
+        assert st == 0
+        _, diag = o.storage_record()
+        me.append(diag[6] + diag[7])
+    me = np.array(me[100:])
+    assert me.mean() > 1e-3 and np.abs((me - me[0]) / me.mean()).max() < 1e-2
