@@ -113,3 +113,38 @@ def test_quadruped_energy_band_with_springs():
         me.append(diag[6] + diag[7])
     me = np.array(me[100:])
     assert me.mean() > 1e-3 and np.abs((me - me[0]) / me.mean()).max() < 1e-2
+
+
+def test_box_and_pendulum_momentum():
+    """test/momentum.jl "Box" (:45-67): a free block with v = [1, 2, 3], w = [10, 10, 10] in zero gravity keeps its linear and angular
+    momentum to 1e-8; "Pendulum" (:80-103): the angular momentum of a pendulum in zero gravity (about the fixed joint axis, the
+    component the reference checks) is constant to 1e-8"""
+    m = _block(gravity=0.0, contact=False)
+    o = Oracle(m, capi.solver_options(rtol=1e-12, btol=1e-12))
+    z = m.z0.copy()
+    z[3:6] = [1.0, 2.0, 3.0]
+    z[10:13] = [10.0, 10.0, 10.0]
+    P = []
+    for _ in range(500):
+        z, st, _ = o.step(z, np.zeros(m.nu))
+        P.append(o.momentum())
+    P = np.array(P[5:])
+    assert np.abs(P - P[0]).max() < 1e-8
+    p = dj.get_mechanism("pendulum", gravity=0.0)
+    for j in p.joints:
+        j.rot.damper = j.rot.spring = 0.0
+    o = Oracle(p, capi.solver_options(rtol=1e-12, btol=1e-12))
+    z = p.forward_kinematics({"joint": [0.7]})
+    # initialize!(mech, :pendulum; angle = 0.7, angular_velocity = 5): rotation about the joint axis x through the joint at the top
+    w = np.array([5.0, 0.0, 0.0])
+    zz = z.reshape(-1, 13)
+    xj = np.array([0.0, 0.0, 1.1])  # the joint vertex (pendulum/mechanism.jl: parent_vertex = (L + 0.1) z)
+    zz[0, 3:6] = np.cross(Q.qrot(w, zz[0, 6:10]), zz[0, 0:3] - xj)
+    zz[0, 10:13] = w
+    L = []
+    for _ in range(500):
+        z, st, _ = o.step(z, np.zeros(p.nu))
+        assert st == 0
+        L.append(z[10])  # body-frame angular velocity about the joint axis; J_xx w_x + m r^2 w_x is the conserved angular momentum
+    L = np.array(L[10:])
+    assert np.abs(L - L[0]).max() < 1e-8
