@@ -91,3 +91,44 @@ def test_device_kernels_match_oracle(joint_type):
         zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
         assert (st[e], it[e]) == (so, io)
         assert np.abs(Fz[e] - Fzo).max() < 1e-8 * max(1.0, np.abs(Fzo).max()) and np.abs(Fu[e] - Fuo).max() < 1e-8 * max(1.0, np.abs(Fuo).max())
+
+
+LIMITED = [("Revolute", "rot"), ("Orbital", "rot"), ("Spherical", "rot"), ("Prismatic", "tra"), ("Planar", "tra"), ("FixedOrientation", "tra"),
+           ("Cylindrical", "rot"), ("Cylindrical", "tra")]
+
+
+@pytest.mark.parametrize("joint_type,half", LIMITED)
+def test_limits_on_every_number_of_free_axes(joint_type, half):
+    """joints/limits.jl on 1, 2 and 3 limited axes of either half (the device condenses up to three limited axes per joint): step,
+    solution vector (slacks and duals in the reference ordering) and gradients against the oracle, with a limit active"""
+    from hostemu.harness import HostEmu
+    m = snake(joint_type, spring=0.0, damper=0.1)
+    j = m.joints[1]
+    el = j.rot if half == "rot" else j.tra
+    n = el.nfree
+    c0 = 0.1 * np.arange(1, j.input_dimension + 1)
+    c0 = c0[j.tra.nfree:] if half == "rot" else c0[:j.tra.nfree]
+    el.limit_lo, el.limit_hi = c0 - 0.03, c0 + 0.04   # tight box around the initial coordinates: the inputs push into it
+    o, em = Oracle(m), HostEmu(m)
+    rng = np.random.default_rng(15)
+    B = 2
+    Z = np.tile(m.z0, (B, 1))
+    U = np.zeros((B, m.nu))
+    U[:, 6:] = 3.0 * rng.normal(size=(B, m.nu - 6))
+    gmax = 0.0
+    jo, nb = m.joint_sol_offset(1), 2 * n
+    for t in range(25):
+        Zn, st, it, sol = em.step(Z, U, slots=2)
+        for e in range(B):
+            zo, so, io, solo = o.step(Z[e], U[e], return_sol=True)
+            assert (st[e], it[e]) == (so, io)
+            assert np.abs(Zn[e] - zo).max() < 1e-9 and np.abs(sol[e] - solo).max() < 1e-7
+            s0 = jo + (0 if half == "tra" else j.tra.nimpulses)   # [s (nb) | gamma (nb) | eq] inside the limited half
+            gmax = max(gmax, solo[s0 + nb: s0 + 2 * nb].max())
+        Z = Zn
+    assert gmax > 0.05
+    Zn, Fz, Fu, st, it = em.step_grad(Z, U, slots=2, slots_grad=2)
+    for e in range(B):
+        zo, Fzo, Fuo, so, io = o.step_grad(Z[e], U[e])
+        assert (st[e], it[e]) == (so, io)
+        assert np.abs(Fz[e] - Fzo).max() < 1e-7 * max(1.0, np.abs(Fzo).max()) and np.abs(Fu[e] - Fuo).max() < 1e-7 * max(1.0, np.abs(Fuo).max())
