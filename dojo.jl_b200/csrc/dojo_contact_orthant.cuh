@@ -71,7 +71,7 @@ DJ_DEV V3 orthant_force(int type, const ContactGeom& q, const double* g) {
 }
 // rows of J (nh x 6) = d(constraint rows)/d(v25, w25) and columns of G (6 x nh) = impulse map from the three basic rows / columns
 // [normal | tangent 0 | tangent 1]:  impact [normal];  linear [normal; 0; t1; -t1; t0; -t0]  (P = [0 1; 0 -1; 1 0; -1 0])
-DJ_DEV void orthant_expand(int type, const double* bn, const double* b0, const double* b1, double out[6][6]) {
+DJ_DEV void orthant_expand(const double* bn, const double* b0, const double* b1, double out[6][6]) {
 #pragma unroll
   for (int cc = 0; cc < 6; ++cc) {
     out[0][cc] = bn[cc];
@@ -79,7 +79,6 @@ DJ_DEV void orthant_expand(int type, const double* bn, const double* b0, const d
     out[2][cc] = b1[cc]; out[3][cc] = -b1[cc];
     out[4][cc] = b0[cc]; out[5][cc] = -b0[cc];
   }
-  (void)type;
 }
 
 template <bool JAC>
@@ -139,13 +138,13 @@ DJ_DEV void eval_contact_orthant(Ctx& c, int idx, double f, double* res, double&
     const double J0[6] = {q.t0.x, q.t0.y, q.t0.z, r6w.x, r6w.y, r6w.z};
     const double J1[6] = {q.t1.x, q.t1.y, q.t1.z, r7w.x, r7w.y, r7w.z};
     double Jr[6][6];
-    orthant_expand(type, Jn, J0, J1, Jr);
+    orthant_expand(Jn, J0, J1, Jr);
     V3 qn = tmul(k.R3, cross(q.rc, q.n)), q0 = tmul(k.R3, cross(q.rc, q.t0)), q1 = tmul(k.R3, cross(q.rc, q.t1));
     const double Gn[6] = {q.n.x, q.n.y, q.n.z, qn.x, qn.y, qn.z};
     const double G0[6] = {q.t0.x, q.t0.y, q.t0.z, q0.x, q0.y, q0.z};
     const double G1[6] = {q.t1.x, q.t1.y, q.t1.z, q1.x, q1.y, q1.z};
     double Gt[6][6];  // Gt[col][row]: transposed impulse map
-    orthant_expand(type, Gn, G0, G1, Gt);
+    orthant_expand(Gn, G0, G1, Gt);
     double* Jm = A + cd.J_off;
     double* Gm = A + cd.G_off;
 #pragma unroll

@@ -87,7 +87,7 @@ DJ_DEV void grad_contact_orthant(Ctx& c, int idx) {
   const double Z0[6] = {0, 0, 0, -v0.x, -v0.y, -v0.z};
   const double Z1[6] = {0, 0, 0, -v1.x, -v1.y, -v1.z};
   double Zc[6][6];
-  orthant_expand(type, Zn, Z0, Z1, Zc);
+  orthant_expand(Zn, Z0, Z1, Zc);
   const double* G = A + cd.G_off;
   M33 K = (2.0 * skew(tau) + 2.0 * (transpose(k.R3) * (skew(F) * R3so))) * Mqq;
   double* CB = A + cd.gc_off;
