@@ -35,7 +35,7 @@ def test_step_and_gradient_parity(name, ct):
                 continue
             conv += 1
             if it[e] != io:
-                assert np.abs(Zn[e] - zo).max() < 5e-3  # a rounding-level flip of a line-search comparison: solver tolerance
+                assert np.abs(Zn[e] - zo).max() < 2e-2  # a rounding-level flip of a line-search comparison: solver tolerance (test_gpu_parity.TOL_SOLVER)
                 continue
             same += 1
             assert np.abs(Zn[e] - zo).max() < 1e-6 and np.abs(sol[e] - solo).max() < 1e-5
