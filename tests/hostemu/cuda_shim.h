@@ -9,7 +9,8 @@
 //     a thread that arrives early yields until the barrier's generation changes; a full scheduling round without any
 //     progress aborts with a deadlock report;
 //   * shuffles go through a per-warp exchange buffer between two barriers; atomics are plain operations (one OS thread).
-// Scheduling is deterministic, so a missing synchronisation in the kernel shows up as a reproducible wrong answer here.
+// Scheduling is deterministic, so a missing synchronisation in the kernel shows up as a reproducible wrong answer here;
+// HOSTEMU_ORDER=reverse|random changes the order in which the threads of a round run (see run_cta): a race detector.
 // This is not a performance model and not a CPU fallback: nothing in the product library includes it.
 #pragma once
 #include <math.h>
@@ -107,9 +108,21 @@ inline void run_cta(unsigned block, unsigned grid, int nthreads, size_t smem_byt
   int alive = nthreads;
   unsigned long last_progress = s.progress;
   int idle_rounds = 0;
+  // Scheduling order of a round: ascending thread index by default.  HOSTEMU_ORDER=reverse / random runs the threads of every round in
+  // descending / a pseudo-random order instead: between two synchronisation points the result must not depend on which thread
+  // runs first, so a test that passes in one order and fails in another has found a missing barrier (race detection for free).
+  static const int order_mode = [] { const char* e = getenv("HOSTEMU_ORDER"); return !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r') ? 2 : 0; }();
+  static const bool order_announced = [] { if (order_mode) fprintf(stderr, "hostemu: thread order of a round = %s\n", order_mode == 1 ? "reverse" : "random"); return true; }();
+  (void)order_announced;
+  static uint64_t lcg = 0x9E3779B97F4A7C15ull;
+  std::vector<int> order(nthreads);
   while (alive > 0) {
     alive = 0;
-    for (int t = 0; t < nthreads; ++t) {
+    for (int t = 0; t < nthreads; ++t) order[t] = order_mode == 1 ? nthreads - 1 - t : t;
+    if (order_mode == 2)
+      for (int t = nthreads - 1; t > 0; --t) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; std::swap(order[t], order[(lcg >> 33) % (t + 1)]); }
+    for (int k = 0; k < nthreads; ++k) {
+      const int t = order[k];
       if (s.fibers[t].done) continue;
       s.cur = t;
       swapcontext(&s.sched, &s.fibers[t].ctx);
