@@ -53,3 +53,41 @@ def test_kernels_do_not_depend_on_the_thread_order(tmp_path):
         got = _run(order, str(tmp_path / (order + ".npz")))
         for k in ref.files:
             assert np.array_equal(ref[k], got[k]), (order, k)
+
+
+RACY = r"""
+#include "%(shim)s"
+// thread 0 publishes a value, every other thread reads it -- `with_barrier` selects the correct version
+static void kernel(bool with_barrier, double* out) {
+  double* smem = hostemu_smem();
+  const int t = threadIdx.x;
+  if (t == 0) smem[0] = 42.0;
+  if (with_barrier) __syncthreads();
+  out[t] = smem[0];
+}
+extern "C" void run(int with_barrier, double* out) {
+  emu::run_cta(0, 1, 64, 64, [=] { kernel(with_barrier != 0, out); });
+}
+"""
+
+
+def test_thread_order_modes_detect_a_missing_barrier(tmp_path):
+    """negative control of the detector: a kernel without its barrier gives different answers under different thread orders, the
+    same kernel with the barrier does not"""
+    import ctypes
+    src, lib = tmp_path / "racy.cpp", tmp_path / "libracy.so"
+    src.write_text(RACY % {"shim": os.path.join(ROOT, "tests", "hostemu", "cuda_shim.h")})
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(lib), str(src)])
+    prog = ("import ctypes, numpy as np, sys\nL = ctypes.CDLL(sys.argv[1])\nfor wb in (0, 1):\n    o = np.zeros(64)\n"
+            "    L.run(wb, ctypes.c_void_p(o.ctypes.data))\n    print(int((o == 42.0).sum()))\n")
+    res = {}
+    for order in ("", "reverse"):
+        env = dict(os.environ)
+        env.pop("HOSTEMU_ORDER", None)
+        if order:
+            env["HOSTEMU_ORDER"] = order
+        r = subprocess.run([sys.executable, "-c", prog, str(lib)], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        res[order] = [int(x) for x in r.stdout.split()]
+    assert res[""][1] == 64 and res["reverse"][1] == 64      # with the barrier: every thread sees the value, in any order
+    assert res[""][0] == 64 and res["reverse"][0] == 1       # without it: the ascending order hides the race, the reverse order exposes it
