@@ -99,6 +99,18 @@ class QuadrupedSampling(Environment):
     spec_kwargs = dict(n_unactuated=6, contact_obs=False, healthy_index=2, healthy_min=0.0, bound_index=0, bound_abs=1000.0)
 
 
+class QuadrupedWaypoint(QuadrupedSampling):
+    """environments/quadruped_waypoint.jl: the quadruped_sampling maps on the builder's other defaults -- timestep 0.001 and
+    contact_body = false (the four foot contacts only, quadruped_waypoint.jl:8, :25)."""
+
+    def __init__(self, batch: int = 1, horizon: int = 100, device: int = 0, mechanism: Optional[Mechanism] = None, **mechanism_kwargs):
+        if mechanism is None:
+            mechanism_kwargs.setdefault("timestep", 0.001)
+            mechanism = get_mechanism(self.mechanism_name, **mechanism_kwargs)
+            mechanism.contacts = [c for c in mechanism.contacts if c.name.endswith("_calf_contact")]  # contact_feet only
+        super().__init__(batch, horizon, device, mechanism)
+
+
 class Pendulum(Environment):
     """environments/pendulum.jl: identity maps."""
     mechanism_name = "pendulum"
@@ -130,7 +142,8 @@ class CartpoleDQN(Environment):
         return np.zeros(S.shape[0]), done
 
 
-_ENVIRONMENTS = {"ant_ars": AntARS, "quadruped_sampling": QuadrupedSampling, "pendulum": Pendulum, "cartpole_dqn": CartpoleDQN}
+_ENVIRONMENTS = {"ant_ars": AntARS, "quadruped_sampling": QuadrupedSampling, "quadruped_waypoint": QuadrupedWaypoint, "pendulum": Pendulum,
+                 "cartpole_dqn": CartpoleDQN}
 
 
 def get_environment(name: str, **kwargs) -> Environment:

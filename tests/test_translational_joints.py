@@ -233,6 +233,8 @@ def test_cartpole_dqn_mirror_logic(monkeypatch):
             return np.stack([r[0] for r in out]), np.array([r[3] for r in out], dtype=np.int32), np.array([r[4] for r in out], dtype=np.int32)
 
     monkeypatch.setattr(E, "BatchedStepper", StubStepper)
+    wp = E.get_environment("quadruped_waypoint", batch=2)  # quadruped_waypoint.jl:8, :25: timestep 0.001, foot contacts only
+    assert wp.mechanism.timestep == 0.001 and wp.mechanism.input_scaling == 0.001 and wp.mechanism.Ni == 4 and wp.ns == 36
     env = E.get_environment("cartpole_dqn", batch=3, dampers=0.5, joint_limits={"cart_joint": (-0.2, 0.2)})
     assert (env.ns, env.na) == (4, 1) and np.allclose(env.get_state()[:, 2], np.pi / 4)  # per joint [coordinates; velocities]: [y, ydot, theta, thetadot]
     assert np.array_equal(env.input_map([1.0, -2.0, 0.5]), [[1.0, 0.0], [-2.0, 0.0], [0.5, 0.0]])

@@ -149,3 +149,32 @@ def test_raiberthopper_parity():
         errs.append(max(np.abs(Fz[e] - Fzo).max() / max(1.0, np.abs(Fzo).max()), np.abs(Fu[e] - Fuo).max() / max(1.0, np.abs(Fuo).max())))
     errs = np.array(errs)
     assert len(errs) >= 8 and np.median(errs) < 1e-7 and np.quantile(errs, 0.9) < 1e-4 and errs.max() < 1e-2, errs
+
+
+def test_quadruped_waypoint_environment():
+    """environments/quadruped_waypoint.jl (timestep 0.001, foot contacts only) on the fused environment kernels against the oracle"""
+    from dojo_jl_b200 import environments as E
+    from oracle.oracle import Oracle
+    from oracle.oracle_env import env_step
+    from test_gpu_parity import _random_minimal_batch
+    rng = np.random.default_rng(43)
+    B = 16
+    env = E.get_environment("quadruped_waypoint", batch=B)
+    mech, spec = env.mechanism, env.spec
+    assert mech.timestep == 0.001 and mech.Ni == 4
+    o = Oracle(mech)
+    S = np.zeros((B, env.ns))
+    S[:, :2 * mech.nu] = _random_minimal_batch(mech, B, rng)
+    S[:, 2] += rng.uniform(0.3, 0.5, B)
+    A = rng.uniform(-0.2, 0.2, (B, env.na))
+    for _ in range(10):  # a few steps away from the random start (feet inside the ground)
+        S = env.stepper.env_step(spec, S, A)[0]
+    Sn, reward, done, status, iters = env.stepper.env_step(spec, S, A)
+    compared = 0
+    for e in range(B):
+        sn, r, d, so, io = env_step(o, spec, S[e], A[e])
+        if so != 0 or status[e] != 0 or io != iters[e]:
+            continue
+        assert np.abs(Sn[e] - sn).max() < 1e-6 * max(1.0, np.abs(sn).max()) and done[e] == d
+        compared += 1
+    assert compared >= B // 2
