@@ -7,10 +7,18 @@ import dojo_jl_b200 as dj
 from dojo_jl_b200.solver import BatchedStepper
 from conftest import jittered_states, random_inputs
 name = sys.argv[1] if len(sys.argv) > 1 else "ant"
-mech = dj.get_mechanism(name)
+# mech may carry builder options after a colon: "block:linear", "sphere:impact" (contact_type), "cartpole:full" (springs, dampers,
+# joint limits: translational terms), "raiberthopper" -- these run on the second compilation of the kernels (dojo_b200_cm.cu)
+name, _, opt = name.partition(":")
+kw = {}
+if opt in ("linear", "impact", "nonlinear"):
+    kw["contact_type"] = opt
+elif opt == "full" and name == "cartpole":
+    kw = dict(springs=2.0, dampers=0.3, joint_limits={"cart_joint": (-0.3, 0.25), "pole_joint": (-1.2, 1.4)})
+mech = dj.get_mechanism(name, **kw)
 rng = np.random.default_rng(0)
 B, T = 11, 3
-Z = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
+Z = jittered_states(mech, B, rng) if mech.Nb > 2 else np.tile(mech.z0, (B, 1))
 U = random_inputs(mech, B, rng)
 s = BatchedStepper(mech, 16)
 Zn, st, it = s.step(Z, U)
