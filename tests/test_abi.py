@@ -91,3 +91,28 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", "").lower() or f in ("capi.py",), f
+
+
+def test_ctypes_mirrors_match_the_c_header(tmp_path):
+    """every struct of include/dojo_b200.h: size and the offset of each field as the C compiler lays them out == the ctypes mirror in
+    dojo.jl_b200/capi.py (what the Python host, the tests and the bench pass through the C-ABI)"""
+    import ctypes as C
+    import subprocess
+    from dojo_jl_b200 import capi
+    names = ["DojoBodyDesc", "DojoJointElementDesc", "DojoJointDesc", "DojoContactDesc", "DojoMechanismDesc", "DojoSolverOptions", "DojoEnvSpec"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "dojo_b200.h")}"', "int main(void) {"]
+    for n in names:
+        st = getattr(capi, n)
+        lines.append(f'  printf("{n} %zu\\n", sizeof({n}));')
+        for f, _ in st._fields_:
+            lines.append(f'  printf("{n}.{f} %zu\\n", offsetof({n}, {f}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        st = getattr(capi, n)
+        assert int(out[n]) == C.sizeof(st), n
+        for f, _ in st._fields_:
+            assert int(out[f"{n}.{f}"]) == getattr(st, f).offset, (n, f)
