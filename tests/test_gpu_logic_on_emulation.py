@@ -3,7 +3,7 @@ place of the GPU stepper (tests/hostemu/adapter.py): their Python logic and thei
 functions run against libdojo_b200.so.
 
 Emulating 64 environments x 40 steps on CPU fibers takes minutes, so only the shortest case runs by default; the others run with
-DOJO_EMULATE_GPU_TESTS=1 (all of them passed at the end of round 1: 7 passed in 11 min)."""
+DOJO_EMULATE_GPU_TESTS=1 (they passed at the end of round 1: the seven short cases in 11 min, the quadruped parity case in 11 min more; the ant case was not run)."""
 import os
 
 import pytest
@@ -56,3 +56,11 @@ def test_step_rollout_and_gradient_parity(emulated_stepper, case):
 def test_contact_models_step_and_gradient_parity(emulated_stepper, name, ct):
     import test_zzzz_gpu_contact_models as G
     G.test_step_and_gradient_parity(name, ct)
+
+
+@slow
+@pytest.mark.parametrize("name,B,T,scale", [("quadruped", 64, 30, 2.0), ("ant", 96, 25, 1.0)])
+def test_step_parity_of_the_baseline_models(emulated_stepper, name, B, T, scale):
+    """tests/test_gpu_parity.py::test_step_parity (ten minutes and more per case on CPU fibers)"""
+    import test_gpu_parity as G
+    G._compare_rollout(name, B, T, seed=7, scale=scale)
