@@ -28,9 +28,11 @@ and then returns batched results.  All compute happens in libdojo_b200.so on the
 Deviations (documented switches):
   * step returns the TRUE next state (x3, v25, q3, w25) -- the mechanism's internal state after step! -- unless
     literal_q1=True (the reference's return value advances the configuration twice, Q1);
-  * gradients are the consistent IFT gradients at the solution (Q2);
-  * "Excessive angular velocity" (solver/line_search.jl:18-20) raises RuntimeError for a single environment, as the
-    reference's error(); in a batch it is reported per environment in `status` (code 2).
+  * gradients are the consistent IFT gradients at the solution unless literal_q2=True (get_maximal_gradients! builds the data
+    Jacobian AFTER update_state! but solves against the KKT matrix assembled before it, Q2);
+  * "Excessive angular velocity" (solver/line_search.jl:18-20): status code 2 is reserved for it, but the reference's test can
+    never fire -- candidate_step! clips |w|^2 to (3.9/h^2)^2 / |w|^2 < 3.9/h^2 before line_search! compares it with 3.91/h^2
+     -- so no path produces it; _check_single keeps the mapping to the reference's error().
 """
 from typing import Callable, Optional
 
@@ -38,7 +40,7 @@ import numpy as np
 
 from . import capi
 from .mechanism import Mechanism
-from .solver import DOJO_FLAG_Q1_LITERAL_RETURN, STATUS, BatchedStepper
+from .solver import DOJO_FLAG_Q1_LITERAL_RETURN, DOJO_FLAG_Q2_LITERAL_GRADIENTS, STATUS, BatchedStepper
 
 SolverOptions = capi.solver_options
 
@@ -99,15 +101,17 @@ def simulate(mechanism: Mechanism, steps: int, z0=None, control: Optional[Callab
     return (Zf, traj) if record else Zf
 
 
-def get_maximal_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0):
+def get_maximal_gradients(mechanism: Mechanism, z, u, opts=None, device: int = 0, literal_q2: bool = False):
     """get_maximal_gradients!(mechanism, z, u; opts) -> (jacobian_state [12Nb x 12Nb], jacobian_control [12Nb x nu]);
-    batched inputs give [B, 12Nb, 12Nb] and [B, 12Nb, nu]."""
+    batched inputs give [B, 12Nb, 12Nb] and [B, 12Nb, nu].  literal_q2=True reproduces the reference's literal result (data
+    Jacobian and chain rule at the state shifted by update_state!, gradients/state.jl:69-76); the default is the consistent
+    implicit-function-theorem gradient."""
     z = np.asarray(z, dtype=float)
     single = z.ndim == 1
     Z = np.atleast_2d(z)
     U = np.atleast_2d(np.asarray(u, dtype=float))
     s = _stepper(mechanism, Z.shape[0], device)
-    _, Fz, Fu, status, _ = s.step_grad(Z, U, opts)
+    _, Fz, Fu, status, _ = s.step_grad(Z, U, opts, flags=DOJO_FLAG_Q2_LITERAL_GRADIENTS if literal_q2 else 0)
     if single:
         _check_single(status)
         return Fz[0], Fu[0]

@@ -26,9 +26,10 @@ using namespace dj;
 // dojo_step_kernel<GRAD> (StepArgs): dojo_step_kernel.cuh; the DJ_ANY_CONTACT compilation of the same source lives in
 // dojo_b200_cm.cu and is reached through these two entry points
 extern "C" __attribute__((visibility("hidden"))) const void* dojo_cm_step_kernel(int grad);
-static const void* step_kernel_fn(bool any_contact, bool grad) {
+static const void* step_kernel_fn(bool any_contact, bool grad, bool plan_smem) {
   if (any_contact) return dojo_cm_step_kernel(grad ? 1 : 0);
-  return grad ? (const void*)dojo_step_kernel<true> : (const void*)dojo_step_kernel<false>;
+  if (plan_smem && !getenv("DOJO_B200_GENERIC_PLAN")) return grad ? (const void*)dojo_step_kernel<true, true> : (const void*)dojo_step_kernel<false, true>;
+  return grad ? (const void*)dojo_step_kernel<true, false> : (const void*)dojo_step_kernel<false, false>;
 }
 
 // Longest-processing-time-first order.  The cost of an environment's step is proportional to its Newton-iteration count
@@ -97,6 +98,14 @@ struct DojoHandle {
   int32_t *d_status = nullptr, *d_iters = nullptr;
   double *p_in = nullptr, *p_out = nullptr;  // pinned
   cudaStream_t stream = nullptr;
+  // one call in flight per handle: the work queue counter, completion lists, staging and scratch buffers belong to the handle.
+  // Calls on DIFFERENT streams are ordered behind each other through this event (enter_call / leave_call), so that an async call
+  // on a caller stream followed by a call on another stream (or by a synchronous call, which runs on `stream`) cannot race on them.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  double *d_rollU = nullptr, *d_rollTraj = nullptr;  // grow-only staging of dojo_rollout (host-pointer calls)
+  size_t rollU_bytes = 0, rollTraj_bytes = 0;
   int64_t launches = 0;
   bool any_contact = false;                       // the mechanism needs the DJ_ANY_CONTACT kernels (dojo_b200_cm.cu): it has ...
   bool orthant_contact = false;                   // ... an ImpactContact / LinearContact
@@ -116,6 +125,16 @@ static std::string g_create_error;
       return DOJO_ECUDA;                                                                   \
     }                                                                                      \
   } while (0)
+
+// Ordering of calls that use the handle's scratch (see DojoHandle::ev_last).  Free when every call uses the same stream.
+static void enter_call(DojoHandle* h, cudaStream_t s) {
+  if (h->has_last && h->last_stream != s && h->ev_last) cudaStreamWaitEvent(s, h->ev_last, 0);
+}
+static void leave_call(DojoHandle* h, cudaStream_t s) {
+  if (!h->ev_last) return;
+  cudaEventRecord(h->ev_last, s);
+  h->last_stream = s; h->has_last = true;
+}
 
 extern "C" void dojo_default_options(DojoSolverOptions* o) {
   o->rtol = 1.0e-6; o->btol = 1.0e-4; o->ls_scale = 0.5; o->max_iter = 50; o->max_ls = 10;
@@ -518,6 +537,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   ok = ok && cudaMalloc((void**)&h->d_prof, (32 + 2 * (size_t)max_batch) * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long)) == cudaSuccess &&
        cudaMemset(h->d_prof + 31, 0xff, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming) == cudaSuccess;
   // environments per CTA ("slots"): as many arenas as fit, at most 256 threads (the register file holds 256 threads at 255 registers)
   auto pick_slots = [&](size_t bytes) {
     int g = (int)std::min<size_t>((size_t)prop.sharedMemPerBlockOptin / bytes, (size_t)(256 / (32 * nw)));
@@ -530,16 +550,20 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   const bool smem_plan = !getenv("DOJO_B200_GLOBAL_PLAN");
   if (smem_plan && h->slots * h->arena_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off = (int)(h->slots * h->arena_bytes / sizeof(double));
   h->smem_fwd = h->slots * h->arena_bytes + (h->plan_smem_off >= 0 ? h->blob_bytes : 0);
-  h->k_fwd = step_kernel_fn(h->any_contact, false);
-  h->k_grad = step_kernel_fn(h->any_contact, true);
-  ok = ok && cudaFuncSetAttribute(h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fwd) == cudaSuccess;
+  h->k_fwd = step_kernel_fn(h->any_contact, false, h->plan_smem_off >= 0);
+  h->k_grad = step_kernel_fn(h->any_contact, true, false);  // re-selected below once the gradient configuration is known
+  // The attribute belongs to the kernel FUNCTION (per device), not to this handle: several handles (ant, pendulum, ...) share the
+  // four kernel symbols, so it is set to the device's opt-in maximum once and for all -- a handle created later with a smaller
+  // arena must not lower it under the launches of an earlier, larger one (tests/test_gpu_parity.py::test_two_handles_share_kernels).
+  ok = ok && cudaFuncSetAttribute(h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(h->k_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   const bool grad_fits = h->grad_bytes <= (size_t)prop.sharedMemPerBlockOptin;
   if (grad_fits) {
     h->slots_grad = pick_slots(h->grad_bytes);
     if (smem_plan && h->slots_grad * h->grad_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off_grad = (int)(h->slots_grad * h->grad_bytes / sizeof(double));
     h->smem_grad = h->slots_grad * h->grad_bytes + (h->plan_smem_off_grad >= 0 ? h->blob_bytes : 0);
-    ok = ok && cudaFuncSetAttribute(h->k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_grad) == cudaSuccess;
+    h->k_grad = step_kernel_fn(h->any_contact, true, h->plan_smem_off_grad >= 0);
+    ok = ok && cudaFuncSetAttribute(h->k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(h->k_grad, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   } else h->grad_bytes = 0;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
@@ -566,6 +590,8 @@ extern "C" int dojo_destroy(DojoHandle* h) {
   if (h->p_in) cudaFreeHost(h->p_in);
   if (h->p_out) cudaFreeHost(h->p_out);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
+  cudaFree(h->d_rollU); cudaFree(h->d_rollTraj);
   delete h;
   return DOJO_OK;
 }
@@ -610,10 +636,11 @@ static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   a.counter = h->d_counter;
   // LPT order from the previous call's iteration counts (only meaningful when the same batch is stepped again, which is what
   // simulation loops do; a stale order is harmless -- it is just an order)
+  enter_call(h, s);
   const bool lpt = h->lpt && B <= h->max_batch && B > h->sm_count * h->envs_per_sm * h->slots;
   a.order = lpt ? h->d_order : nullptr;
   a.prev_iters = (h->lpt && B <= h->max_batch) ? h->d_prev_iters : nullptr;
-  if (lpt) { dojo_order_kernel<<<1, 1024, 0, s>>>(h->d_prev_iters, B, h->d_order); h->launches += 1; }
+  if (lpt) { dojo_order_kernel<<<1, 1024, 0, s>>>(h->d_prev_iters, B, h->d_order); CUDA_TRY(h, cudaGetLastError()); h->launches += 1; }
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
@@ -623,6 +650,7 @@ static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   { void* kargs[1] = {(void*)&a}; CUDA_TRY(h, cudaLaunchKernel(h->k_fwd, dim3(grid), dim3(32 * h->nw * h->slots), kargs, h->smem_fwd, s)); }
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  leave_call(h, s);
   return DOJO_OK;
 }
 
@@ -722,6 +750,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.sol_raw = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
   a.Fz = nullptr; a.Fu = nullptr; a.Fc = nullptr; a.T = T; a.traj = dtraj; a.done_count = nullptr; a.done_list = nullptr;
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
+  enter_call(h, s);
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
   a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off;
@@ -730,6 +759,7 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   { void* kargs[1] = {(void*)&a}; CUDA_TRY(h, cudaLaunchKernel(h->k_fwd, dim3(grid), dim3(32 * h->nw * h->slots), kargs, h->smem_fwd, s)); }
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  leave_call(h, s);
   return DOJO_OK;
 }
 
@@ -759,18 +789,25 @@ extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B,
   const Plan& P = h->plan;
   const size_t zbytes = (size_t)B * P.nz * sizeof(double), ubytes = (size_t)B * P.nu * sizeof(double) * T;
   double *dU = nullptr, *dtraj = nullptr;
+  auto grow = [&](double** buf, size_t* have, size_t need) -> cudaError_t {  // grow-only: no allocation in steady state
+    if (*have >= need) return cudaSuccess;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    cudaFree(*buf); *buf = nullptr; *have = 0;
+    e = cudaMalloc((void**)buf, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+  };
   CUDA_TRY(h, cudaMemcpyAsync(h->d_Z, Z0, zbytes, cudaMemcpyHostToDevice, s));
-  if (U && P.nu > 0) { CUDA_TRY(h, cudaMalloc((void**)&dU, ubytes)); CUDA_TRY(h, cudaMemcpyAsync(dU, U, ubytes, cudaMemcpyHostToDevice, s)); }
-  if (Z_traj) CUDA_TRY(h, cudaMalloc((void**)&dtraj, zbytes * T));
+  if (U && P.nu > 0) { CUDA_TRY(h, grow(&h->d_rollU, &h->rollU_bytes, ubytes)); dU = h->d_rollU; CUDA_TRY(h, cudaMemcpyAsync(dU, U, ubytes, cudaMemcpyHostToDevice, s)); }
+  if (Z_traj) { CUDA_TRY(h, grow(&h->d_rollTraj, &h->rollTraj_bytes, zbytes * T)); dtraj = h->d_rollTraj; }
   rc = launch_rollout(h, opts, B, T, h->d_Z, dU, h->d_Zn, dtraj, h->d_status, s);
-  if (rc == DOJO_OK) {
-    cudaMemcpyAsync(Z_final, h->d_Zn, zbytes, cudaMemcpyDeviceToHost, s);
-    if (Z_traj) cudaMemcpyAsync(Z_traj, dtraj, zbytes * T, cudaMemcpyDeviceToHost, s);
-    if (status_any) cudaMemcpyAsync(status_any, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) { h->err = "dojo_rollout: CUDA failure"; rc = DOJO_ECUDA; }
-  }
-  cudaFree(dU); cudaFree(dtraj);
-  return rc;
+  if (rc != DOJO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(Z_final, h->d_Zn, zbytes, cudaMemcpyDeviceToHost, s));
+  if (Z_traj) CUDA_TRY(h, cudaMemcpyAsync(Z_traj, dtraj, zbytes * T, cudaMemcpyDeviceToHost, s));
+  if (status_any) CUDA_TRY(h, cudaMemcpyAsync(status_any, h->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return DOJO_OK;
 }
 
 // gradients: implemented in dojo_grad.cu
@@ -801,6 +838,7 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  enter_call(h, s);
   if (!h->d_gsol) {
     CUDA_TRY(h, cudaMalloc((void**)&h->d_gsol, (size_t)h->max_batch * h->plan.nres * sizeof(double)));
     CUDA_TRY(h, cudaMalloc((void**)&h->d_gstatus, (size_t)h->max_batch * sizeof(int32_t)));
@@ -846,6 +884,7 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   }
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  leave_call(h, s);
   return DOJO_OK;
 }
 
@@ -1020,10 +1059,12 @@ static int launch_kinjac(DojoHandle* h, int mode, int B, const double* dZ, const
   a.outM = mode == 0 ? out0 : nullptr; a.outN = mode == 1 ? out0 : nullptr;
   a.Gx = mode == 2 ? out0 : nullptr; a.Gu = mode == 2 ? out1 : nullptr;
   a.ws = h->d_kjws; a.mode = mode;
+  enter_call(h, s);
   if (mode == 0) CUDA_TRY(h, cudaMemsetAsync(out0, 0, (size_t)B * 2 * P.nu * 12 * P.Nb * sizeof(double), s));
   dojo_kinjac_kernel<<<std::min(B, h->kj_grid), 128, 0, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  leave_call(h, s);
   return DOJO_OK;
 }
 
@@ -1179,6 +1220,7 @@ static int env_step_impl(DojoHandle* h, const DojoSolverOptions* opts, const Doj
   a.S = dS; a.A = dA; a.Z = h->d_Z; a.U = h->d_U; a.Zn = h->d_Zn; a.sol = h->d_sol; a.Sn = dSn; a.reward = dreward; a.done = ddone;
   a.ret = dret; a.dead = ddead;
   const int threads = 128, grid = (B + threads - 1) / threads;
+  enter_call(h, s);
   dojo_env_pre_kernel<<<grid, threads, 0, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
@@ -1187,6 +1229,7 @@ static int env_step_impl(DojoHandle* h, const DojoSolverOptions* opts, const Doj
   dojo_env_post_kernel<<<grid, threads, 0, s>>>(a);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  leave_call(h, s);
   return DOJO_OK;
 }
 
@@ -1272,7 +1315,9 @@ extern "C" int dojo_step_record_async(DojoHandle* h, const DojoSolverOptions* op
   cudaStream_t s = (cudaStream_t)cuda_stream;
   rc = launch_forward(h, opts, B, dZ, dU, nullptr, dZn, h->d_sol, nullptr, dstatus, diters, 0, s);
   if (rc != DOJO_OK) return rc;
-  return launch_storage(h, B, dZ, dZn, dU, h->d_sol, dstorage, ddiag, s);
+  rc = launch_storage(h, B, dZ, dZn, dU, h->d_sol, dstorage, ddiag, s);
+  leave_call(h, s);  // the storage kernel reads the handle's solution buffer: later calls on other streams wait for it
+  return rc;
 }
 
 static int ensure_record_staging(DojoHandle* h) {

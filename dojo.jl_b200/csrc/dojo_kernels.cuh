@@ -1359,14 +1359,21 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
         }
         slot_sync(c);
       }
+      // The head of the next iteration (mehrotra.jl:26-30) tests exactly these violations (the candidate's, line_search.jl:22-30):
+      // decide here, before set_entries! -- the KKT blocks of a final iterate are never used (the gradient pass assembles its own).
+      if ((rvio != rvio) || (bvio != bvio)) { status = 3; break; }
+      if (ndone >= o.max_iter) break;
+      if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
       mode = 0; fk = 0.0;
       continue;  // set_entries! at the new iterate (mu = mutarget)
     }
     // mode 0: the system is assembled
     if (first) { rvio = rv; bvio = bv; first = false; }
     if ((rvio != rvio) || (bvio != bvio)) { status = 3; break; }
-    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
+    // `for n = 1:max_iter` tests convergence at the TOP of an iteration only (solver/mehrotra.jl:26-30): an iterate that meets the
+    // tolerances after the last iteration's line search is still :failed
     if (ndone >= o.max_iter) break;
+    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
     ndone += 1;
     for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.sav_off + t] = A[P.rhs_off + t];  // pull_residual!
     slot_sync(c);

@@ -69,7 +69,10 @@ DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
 #ifdef DJ_PROFILE
 __device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { return *((volatile unsigned long long*)(prof + 31)); }
 #endif
-template <bool GRAD>
+// PLAN_SMEM: the launch keeps its copy of the plan tables in shared memory (a.plan_smem_off >= 0), known at compile time, so that
+// every table pointer is derived from the shared-memory array and the table reads compile to LDS with immediate offsets instead of
+// generic loads (the generic variant, PLAN_SMEM = false, decides at run time and serves mechanisms whose tables do not fit).
+template <bool GRAD, bool PLAN_SMEM = false>
 __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(const StepArgs a) {
   extern __shared__ double arena[];
   __shared__ int s_env[8];
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   c.mu = 0.0;
   {
     const char* pb = a.plan_blob;
-    if (a.plan_smem_off >= 0) {  // one copy of the plan tables per CTA, shared by its slots
+    if (PLAN_SMEM || a.plan_smem_off >= 0) {  // one copy of the plan tables per CTA, shared by its slots
       int4* dst = reinterpret_cast<int4*>(arena + a.plan_smem_off);
       const int4* src = reinterpret_cast<const int4*>(a.plan_blob);
       for (int i = threadIdx.x; i < a.plan_bytes / 16; i += blockDim.x) dst[i] = src[i];
@@ -166,6 +169,20 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
       double rv, bv;
       c.mu = 0.0;
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
+      if (a.flags & DOJO_FLAG_Q2_LITERAL_GRADIENTS) {
+        // get_maximal_gradients! literally (gradients/state.jl:69-76): step! has already run update_state! (bodies/set.jl:22-36)
+        // when the data Jacobian is built -- (x2, q2) <- (x3, q3), (v15, w15) <- (v25, w25) -- while the KKT blocks assembled above
+        // (the matrix the reference reads back with full_matrix) belong to the unshifted final iterate
+        if (c.tid < P.Nb) {
+          const BodyDev& bd = c.bodies[c.tid];
+          Kin k = body_kin(c, c.tid, 0.0);
+          double* stp = c.A + bd.st_off;
+          st3(stp, k.x3);
+          stp[3] = k.q3.s; stp[4] = k.q3.x; stp[5] = k.q3.y; stp[6] = k.q3.z;
+          st3(c.A + bd.gb_off + 27, k.w);
+        }
+        slot_sync(c);
+      }
       status = a.status ? a.status[e] : 0;
       const size_t ng = 12 * (size_t)P.Nb;
       if (!gradients(c, a.Fz + (size_t)e * ng * ng, a.Fu + (size_t)e * ng * P.nu, a.Fc ? a.Fc + (size_t)e * ng * 5 * P.Ni : nullptr) && status == 0) status = 3;

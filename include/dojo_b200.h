@@ -38,10 +38,18 @@
  * copied inside the call.  The *_async variants take device pointers only and a cudaStream_t
  * (passed as void*), do not synchronise, and are what a resident-data caller uses.
  *
+ * Threading / streams: a handle is not thread-safe (the reference's Mechanism is single-threaded and mutable as well) and
+ * has ONE call in flight at a time: the work-queue counter, completion lists, staging and scratch buffers belong to the
+ * handle.  Calls issued on different streams (or an *_async call followed by a synchronous one, which runs on the
+ * handle's own stream) are therefore ordered behind each other by the library (an event wait on the later stream);
+ * use one handle per stream for concurrent batches.
+ *
  * Return value: 0 on success, negative DOJO_E* on API misuse / CUDA failure (message via
  * dojo_last_error).  Per-environment solver outcomes never abort the batch; they are reported in
  * status[B]: 0 success, 1 :failed (max_iter reached, src/solver/mehrotra.jl:13,30,72),
- * 2 excessive angular velocity (the reference throws: src/solver/line_search.jl:18-20),
+ * 2 excessive angular velocity (reserved: the reference throws at src/solver/line_search.jl:18-20, but its test
+ *   |w|^2 > 3.91/h^2 comes after candidate_step! has clipped |w|^2 > 3.9/h^2 down to (3.9/h^2)^2/|w|^2 < 3.9/h^2
+ *   (src/solver/line_search.jl:141-152), so the branch is unreachable in the reference and no path here produces it),
  * 3 non-finite iterate.
  */
 #ifndef DOJO_B200_H
@@ -66,6 +74,13 @@ extern "C" {
 
 /* flags */
 #define DOJO_FLAG_Q1_LITERAL_RETURN 1u /* reproduce step!'s double-advanced return value */
+/* dojo_step_grad*: reproduce what get_maximal_gradients!(mechanism, z, u) literally returns (SURVEY Q2,
+ * src/gradients/state.jl:69-76): step! shifts the state (update_state!, src/bodies/set.jl:22-36: x2 <- x3, q2 <- q3,
+ * v15 <- v25, w15 <- w25, input impulses cleared) BEFORE get_maximal_gradients builds the data Jacobian and the
+ * integrator chain rule, while `full_matrix(mechanism.system)` still holds the KKT entries of the unshifted final
+ * iterate (src/solver/mehrotra.jl:66-69).  Without the flag the consistent implicit-function-theorem gradient is
+ * returned (data Jacobian and KKT matrix at the same state), which is what test/data.jl and the documentation pin. */
+#define DOJO_FLAG_Q2_LITERAL_GRADIENTS 2u
 
 /* Body: src/bodies/constructor.jl:13-27 (mass, inertia) */
 typedef struct {

@@ -980,6 +980,16 @@ struct Oracle {
       s.wsol[0] = s.wsol[1] = s.w15;
     }
   }
+  // update_state! (bodies/set.jl:22-36)
+  void update_state() {
+    for (BodyS& s : bodies) {
+      s.x1 = s.x2; s.q1 = s.q2;
+      s.v15 = s.vsol[1]; s.w15 = s.wsol[1];
+      s.x2 = next_position(s.x2, s.vsol[1], h);
+      s.q2 = next_orientation(s.q2, s.wsol[1], h);
+      s.JF2 = V3(); s.Jt2 = V3();
+    }
+  }
   void set_external(const double* f) {
     for (int b = 0; b < Nb; ++b) {
       bodies[b].Fext = f ? vec3(f + 6 * b) : V3();
@@ -2184,6 +2194,9 @@ int oracle_step_grad(void* h, const DojoSolverOptions* opts, const double* z, co
   int it = 0;
   int st = o->step(*opts, z, u, fext, z_next, nullptr, &it, flags);
   if (iters) *iters = it;
+  // DOJO_FLAG_Q2_LITERAL_GRADIENTS: get_maximal_gradients! = step! (incl. update_state!) THEN get_maximal_gradients (gradients/state.jl:69-76);
+  // the KKT matrix `A` keeps the entries of the last set_entries! (the unshifted final iterate, solver/mehrotra.jl:66-69)
+  if (flags & DOJO_FLAG_Q2_LITERAL_GRADIENTS) o->update_state();
   if (!o->maximal_gradients(Fz, Fu, use_factor != 0)) return DOJO_STATUS_NONFINITE;
   return st;
 }

@@ -119,7 +119,7 @@ class Oracle:
         self.L.oracle_step_batch(self.h, C.byref(opts or self.opts), B, _d(Z), _d(U), None, _d(Zn), None, capi.iptr(st), capi.iptr(it), flags)
         return Zn, st, it
 
-    def step_grad(self, z, u, opts=None, use_factor=False):
+    def step_grad(self, z, u, opts=None, use_factor=False, flags=0):
         z = np.ascontiguousarray(z, dtype=float)
         u = np.ascontiguousarray(u, dtype=float)
         ns = 12 * self.mech.Nb
@@ -128,7 +128,7 @@ class Oracle:
         Fu = np.empty((ns, self.nu), order="F")
         it = np.zeros(1, dtype=np.int32)
         st = self.L.oracle_step_grad(self.h, C.byref(opts or self.opts), _d(z), _d(u), None, _d(zn),
-                                     Fz.ctypes.data_as(capi.c_double_p), Fu.ctypes.data_as(capi.c_double_p), capi.iptr(it), 0, int(use_factor))
+                                     Fz.ctypes.data_as(capi.c_double_p), Fu.ctypes.data_as(capi.c_double_p), capi.iptr(it), flags, int(use_factor))
         return zn, Fz, Fu, st, int(it[0])
 
     def contact_data_jacobian(self):

@@ -30,7 +30,7 @@ class EmuStepper:
 
     def step_grad(self, Z, U=None, opts=None, flags=0, out=None):
         Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=float)
-        return self.em.step_grad(Z, self._u(U, Z.shape[0]), opts, slots=2, slots_grad=1 if self.mech.Nb > 13 else 2)
+        return self.em.step_grad(Z, self._u(U, Z.shape[0]), opts, slots=2, slots_grad=1 if self.mech.Nb > 13 else 2, flags=flags)
 
     def rollout(self, Z0, U=None, T=1, opts=None, record=False):
         Z0 = np.ascontiguousarray(np.atleast_2d(Z0), dtype=float)

@@ -58,7 +58,7 @@ class HostEmu:
         self.L.hostemu_step(self.h, C.byref(o), B, T, _p(Z), _p(U), _p(fext), _p(Zn), _p(sol), _p(st), _p(it), flags, slots, int(smem_plan), grid, _p(traj))
         return (Zn, st, it, sol, traj) if record else (Zn, st, it, sol)
 
-    def step_grad(self, Z, U=None, opts=None, slots=1, slots_grad=1, smem_plan=True, publish_order=True, contact=False):
+    def step_grad(self, Z, U=None, opts=None, slots=1, slots_grad=1, smem_plan=True, publish_order=True, contact=False, flags=0):
         """dojo_step_grad (contact=True: dojo_step_grad_contact).  Returns (Z_next, Fz [B, 12Nb, 12Nb], Fu [B, 12Nb, nu][, Fc [B, 12Nb, 5Ni]],
         status, iters)."""
         Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
@@ -70,10 +70,13 @@ class HostEmu:
         st, it = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
         o = opts if opts is not None else capi.solver_options()
         Fc = np.empty((B, 5 * self.mech.Ni, ng)) if contact else None
+        self.L.hostemu_set_grad_flags(C.c_uint32(flags))
         rc = self.L.hostemu_step_grad(self.h, C.byref(o), B, _p(Z), _p(U), _p(Zn), _p(Fz), _p(Fu), _p(st), _p(it), slots, slots_grad, int(smem_plan),
                                       int(publish_order), _p(Fc))
         if rc != 0:
+            self.L.hostemu_set_grad_flags(C.c_uint32(0))
             raise RuntimeError("the gradient workspace does not fit for this mechanism")
+        self.L.hostemu_set_grad_flags(C.c_uint32(0))
         if contact:
             return Zn, Fz.transpose(0, 2, 1), Fu.transpose(0, 2, 1), Fc.transpose(0, 2, 1), st, it
         return Zn, Fz.transpose(0, 2, 1), Fu.transpose(0, 2, 1), st, it

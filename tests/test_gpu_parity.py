@@ -334,3 +334,34 @@ def test_full_size_invariants_quadruped():
     ok = sg == 0
     assert np.isfinite(Fz[ok]).all() and np.isfinite(Fu[ok]).all()
     assert np.array_equal(Zp, Zg[perm]) and np.array_equal(Fzp, Fz[perm]) and np.array_equal(Fup, Fu[perm])
+
+
+@pytest.mark.parametrize("name", ["ant", "quadruped"])
+def test_q2_literal_gradients(name):
+    """DOJO_FLAG_Q2_LITERAL_GRADIENTS: what get_maximal_gradients!(mechanism, z, u) literally returns (gradients/state.jl:69-76: data
+    Jacobian after update_state!, KKT matrix from before it) against the oracle's literal restatement; same forward step as without."""
+    from dojo_jl_b200.solver import BatchedStepper, DOJO_FLAG_Q2_LITERAL_GRADIENTS
+    from oracle.oracle import Oracle
+    mech = dj.get_mechanism(name)
+    rng = np.random.default_rng(43)
+    B = 24
+    Z = jittered_states(mech, B, rng)
+    stepper, oracle = BatchedStepper(mech, B), Oracle(mech)
+    for _ in range(5):
+        Z, _, _ = stepper.step(Z, random_inputs(mech, B, rng))
+    U = random_inputs(mech, B, rng)
+    Zn, Fz, Fu, sg, ig = stepper.step_grad(Z, U, flags=DOJO_FLAG_Q2_LITERAL_GRADIENTS)
+    Zc, Fzc, Fuc, _, _ = stepper.step_grad(Z, U)
+    assert np.array_equal(Zn, Zc)
+    errs, diff = [], []
+    for e in range(B):
+        _, Fzo, Fuo, so, io = oracle.step_grad(Z[e], U[e], flags=DOJO_FLAG_Q2_LITERAL_GRADIENTS)
+        if so != 0 or sg[e] != 0 or io != ig[e]:
+            continue
+        sz, su = max(1.0, np.abs(Fzo).max()), max(1.0, np.abs(Fuo).max())
+        errs.append(max(np.abs(Fz[e] - Fzo).max() / sz, np.abs(Fu[e] - Fuo).max() / su))
+        diff.append(np.abs(Fz[e] - Fzc[e]).max() / sz)
+    errs = np.array(errs)
+    assert len(errs) >= B // 2
+    assert np.median(errs) < 1e-7 and errs.max() < 1e-2, errs
+    assert np.median(diff) > 1e-4  # the literal result is a different matrix
