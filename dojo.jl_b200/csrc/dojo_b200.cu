@@ -51,6 +51,36 @@ __global__ void dojo_order_kernel(const int32_t* __restrict__ prev_iters, int B,
 }
 
 
+// Closes a step of dojo_step_gather_async on the receiving side: returns once every CTA of every rank has counted itself in on this
+// rank's counter (dojo_step_kernel signals after its last environment), i.e. once the gathered buffer holds the next states of all
+// ranks.  A peer that never arrives (crashed process) must not hang the GPU: after ~10 s the kernel gives up and flags status[0].
+__global__ void dojo_gather_wait_kernel(const unsigned long long* flag, unsigned long long target, int32_t* status) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= target) break;
+    __nanosleep(500);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) { if (status) status[0] = DOJO_STATUS_NONFINITE; break; }
+  }
+  __threadfence_system();
+}
+
+struct DojoGather {
+  DojoHandle* h = nullptr;
+  int world = 1, rank = 0, B = 0;
+  double* buf = nullptr;                 // [nz x B x world] on this device
+  unsigned long long* flag = nullptr;    // CTAs (of all ranks, all steps so far) that have delivered into buf
+  double* peer_buf[DOJO_MAX_GATHER_RANKS] = {};
+  unsigned long long* peer_flag[DOJO_MAX_GATHER_RANKS] = {};
+  bool opened[DOJO_MAX_GATHER_RANKS] = {};
+  bool connected = false;
+  unsigned long long expected = 0;       // value of `flag` when every rank has finished the steps issued so far
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------------
@@ -71,8 +101,9 @@ struct DojoHandle {
   cudaStream_t copy_stream = nullptr;
   int grad_chunk = 0;
   char* d_blob = nullptr;  // plan tables (one contiguous upload)
-  int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0}, blob_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
+  int plan_smem_bytes = 0, plan_smem_bytes_grad = 0, plan_smem_mask = 0, plan_smem_mask_grad = 0;  // prefix of the blob kept in shared memory / tables inside it
   int* d_counter = nullptr;
   int* d_kin_order = nullptr;      // joints root -> leaves (minimal -> maximal map)
   double *d_X = nullptr, *d_Xn = nullptr;  // minimal-state staging [2 nu x max_batch]
@@ -284,8 +315,8 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     const int slot_len = (J.flags & JF_FULL) ? kSlotC : kSlot;  // full joints: force(3) torque(3) K(6x6), like a contact
     J.slot_c = a; a += slot_len;
     if (J.parent >= 0) { J.slot_p = a; a += slot_len; } else J.slot_p = -1;
-    J.Lc_off = a; a += 6 * J.ne;
-    if (J.parent >= 0) { J.Gp_off = a; a += 6 * J.ne; } else J.Gp_off = -1;
+    J.Lc_off = a; a += 6 * joint_nq(J);
+    if (J.parent >= 0) { J.Gp_off = a; a += 6 * joint_nq(J); } else J.Gp_off = -1;
     J.lim_off = a; a += ((J.flags & JF_FULL) ? 2 * kLim : kLim) * J.nb2_r;  // full: aP(6) aC(6) tP(6) tC(6) per limited axis
   }
   for (int c = 0; c < Ni; ++c) {  // contact records survive the assembly (used by condense / recover)
@@ -300,11 +331,12 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   for (int b = 0; b < Nb; ++b) { bodies[b].D_off = a; a += 36; }
   for (int j = 0; j < Ne; ++j) {
     JointDev& J = joints[j];
-    J.D_off = a; a += J.ne * J.ne;
-    J.Uc_off = a; a += 6 * J.ne;
+    const int nq = joint_nq(J);
+    J.D_off = a; a += nq * nq;
+    J.Uc_off = a; a += 6 * nq;
     if (J.parent >= 0) {
-      J.Up_off = a; a += 6 * J.ne;
-      J.Lp_off = a; a += 6 * J.ne;
+      J.Up_off = a; a += 6 * nq;
+      J.Lp_off = a; a += 6 * nq;
       // body-body coupling exists with dampers and with (condensed) joint limits
       if (J.damper_r != 0.0 || J.nb2_r > 0 || (J.flags & JF_TRA_DAMPER)) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
     } else { J.Up_off = J.Lp_off = J.BBpc_off = J.BBcp_off = -1; }
@@ -324,7 +356,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   std::vector<int> ucol;
   {
     int r = 0;
-    for (int j = 0; j < Ne; ++j) { joints[j].r_off = r; r += joints[j].ne; }
+    for (int j = 0; j < Ne; ++j) { joints[j].r_off = r; r += joint_nq(joints[j]); }
     for (int b = 0; b < Nb; ++b) { bodies[b].r_off = r; r += 6; }
     P.n_red = r;
     P.ncol = 12 * Nb + nu;
@@ -337,7 +369,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
       for (int c = 0; c < Ni; ++c) { contacts[c].gc_off = g; g += 36; }
       for (int j = 0; j < Ne; ++j) {
         JointDev& J = joints[j];
-        J.gj_off = g; g += 12 * J.ne + 144 + 12 * (J.nfree_t + J.nfree_r);
+        J.gj_off = g; g += 12 * joint_nq(J) + 144 + 12 * (J.nfree_t + J.nfree_r);
         if (J.parent >= 0) { J.gv_off = g; g += 6 * P.ch; } else J.gv_off = -1;
       }
       P.gvec_off = g; g += P.n_red * P.ch;
@@ -424,9 +456,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
           s.gfold_off = (int)ilist.size();
           for (int f : gfold) ilist.push_back(f);
           int ij = -1, ip = -1;
-          if (J.ne > 0) {
+          if (joint_nq(J) > 0) {
             ij = s.nnb++;
-            s.nb[ij].n = J.ne; s.nb[ij].vec_off = J.sol_off; s.nb[ij].r_off = J.r_off; s.nb[ij].gv_off = -1; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+            s.nb[ij].n = joint_nq(J); s.nb[ij].vec_off = J.sol_off; s.nb[ij].r_off = J.r_off; s.nb[ij].gv_off = -1; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
           }
           if (J.parent >= 0 && J.BBpc_off >= 0) {
             ip = s.nnb++;
@@ -436,22 +468,22 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
           if (ij >= 0) s.tgt[ij][ij] = J.D_off;
           if (ip >= 0) s.tgt[ip][ip] = J.S_off;
           if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off; s.tgt[ip][ij] = J.Lp_off; }
-          h.height = hb; h.group = -1; h.cost = 4.0 + J.ne * 0.3;
+          h.height = hb; h.group = -1; h.cost = 4.0 + joint_nq(J) * 0.3;
           hs.push_back(h);
         }
         int hj = hb;
-        if (J.ne > 0) {  // the parent joint: neighbour = parent body
+        if (joint_nq(J) > 0) {  // the parent joint: neighbour = parent body
           HStep h; std::memset(&h, 0, sizeof(h));
           ElimStep& s = h.s;
-          s.d_off = J.D_off; s.n = J.ne; s.vec_off = J.sol_off; s.r_off = J.r_off; s.nnb = 0;
+          s.d_off = J.D_off; s.n = joint_nq(J); s.vec_off = J.sol_off; s.r_off = J.r_off; s.nnb = 0;
           if (J.parent >= 0) {
             const BodyDev& Pb = bodies[J.parent];
             s.nnb = 1;
-            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].r_off = Pb.r_off; s.nb[0].gv_off = J.gv_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = J.ne; s.nb[0].U_row = 0;
+            s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].r_off = Pb.r_off; s.nb[0].gv_off = J.gv_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = joint_nq(J); s.nb[0].U_row = 0;
             s.tgt[0][0] = J.S_off;
           }
           hj = hb + 1;
-          h.height = hj; h.group = -1; h.cost = 2.0 + J.ne * 0.4;
+          h.height = hj; h.group = -1; h.cost = 2.0 + joint_nq(J) * 0.4;
           hs.push_back(h);
         }
         return hj;
@@ -511,10 +543,16 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     const void* src[8] = {bodies.data(), joints.data(), contacts.data(), steps.data(), sched.data(), ilist.data(), roles.data(), ucol.data()};
     const size_t len[8] = {sizeof(BodyDev) * Nb, sizeof(JointDev) * Ne, sizeof(ContactDev) * Ni, sizeof(ElimStep) * steps.size(), sizeof(int) * sched.size(),
                            sizeof(int) * ilist.size(), sizeof(WarpRole) * roles.size(), sizeof(int) * ucol.size()};
-    for (int k = 0; k < 8; ++k) {
+    // physical order: the tables walked by the serial phases of the solver (elimination steps, schedule, lists, roles) first, the
+    // per-node descriptors (read by one lane per node) last, so that a PREFIX of the blob can ride in shared memory when the whole
+    // does not fit behind the arenas (quadruped: 4 x 56.7 KB leave 5.6 KB)
+    const int order[8] = {3, 4, 5, 6, 7, 0, 2, 1};
+    for (int q = 0; q < 8; ++q) {
+      const int k = order[q];
       h->blob_off[k] = (int)blob.size();
       blob.insert(blob.end(), (const char*)src[k], (const char*)src[k] + len[k]);
       blob.resize((blob.size() + 15) & ~size_t(15), 0);
+      h->blob_end[k] = (int)blob.size();
     }
     h->blob_bytes = (int)blob.size();
   }
@@ -548,22 +586,38 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   h->slots = pick_slots(h->arena_bytes);
   // the plan tables ride along in shared memory when they fit behind the arenas
   const bool smem_plan = !getenv("DOJO_B200_GLOBAL_PLAN");
-  if (smem_plan && h->slots * h->arena_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off = (int)(h->slots * h->arena_bytes / sizeof(double));
-  h->smem_fwd = h->slots * h->arena_bytes + (h->plan_smem_off >= 0 ? h->blob_bytes : 0);
-  h->k_fwd = step_kernel_fn(h->any_contact, false, h->plan_smem_off >= 0);
+  // largest prefix of the blob (whole tables) that fits behind `n` arenas of `bytes` (32 bytes of static shared memory are reserved)
+  auto plan_prefix = [&](int n, size_t bytes, int* off, int* pbytes, int* mask) {
+    *off = -1; *pbytes = 0; *mask = 0;
+    if (!smem_plan) return;
+    const size_t room = (size_t)prop.sharedMemPerBlockOptin - 64 - n * bytes;
+    for (int k = 0; k < 8; ++k)
+      if ((size_t)h->blob_end[k] <= room) { *mask |= 1 << k; *pbytes = std::max(*pbytes, h->blob_end[k]); }
+    for (int k = 0; k < 8; ++k)  // a prefix: drop tables that start beyond the copied bytes (cannot happen with the ordered blob, kept for safety)
+      if (((*mask >> k) & 1) && h->blob_end[k] > *pbytes) *mask &= ~(1 << k);
+    if (*mask) *off = (int)(n * bytes / sizeof(double));
+  };
+  plan_prefix(h->slots, h->arena_bytes, &h->plan_smem_off, &h->plan_smem_bytes, &h->plan_smem_mask);
+  h->smem_fwd = h->slots * h->arena_bytes + h->plan_smem_bytes;
+  h->k_fwd = step_kernel_fn(h->any_contact, false, h->plan_smem_mask == 0xff);
   h->k_grad = step_kernel_fn(h->any_contact, true, false);  // re-selected below once the gradient configuration is known
   // The attribute belongs to the kernel FUNCTION (per device), not to this handle: several handles (ant, pendulum, ...) share the
   // four kernel symbols, so it is set to the device's opt-in maximum once and for all -- a handle created later with a smaller
   // arena must not lower it under the launches of an earlier, larger one (tests/test_gpu_parity.py::test_two_handles_share_kernels).
-  ok = ok && cudaFuncSetAttribute(h->k_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) == cudaSuccess;
+  auto max_dynamic_smem = [&](const void* fn) {  // opt-in maximum minus the kernel's static shared memory
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { ok = false; return; }
+    ok = ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) == cudaSuccess;
+  };
+  max_dynamic_smem(h->k_fwd);
   ok = ok && cudaFuncSetAttribute(h->k_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   const bool grad_fits = h->grad_bytes <= (size_t)prop.sharedMemPerBlockOptin;
   if (grad_fits) {
     h->slots_grad = pick_slots(h->grad_bytes);
-    if (smem_plan && h->slots_grad * h->grad_bytes + h->blob_bytes <= (size_t)prop.sharedMemPerBlockOptin) h->plan_smem_off_grad = (int)(h->slots_grad * h->grad_bytes / sizeof(double));
-    h->smem_grad = h->slots_grad * h->grad_bytes + (h->plan_smem_off_grad >= 0 ? h->blob_bytes : 0);
-    h->k_grad = step_kernel_fn(h->any_contact, true, h->plan_smem_off_grad >= 0);
-    ok = ok && cudaFuncSetAttribute(h->k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) == cudaSuccess;
+    plan_prefix(h->slots_grad, h->grad_bytes, &h->plan_smem_off_grad, &h->plan_smem_bytes_grad, &h->plan_smem_mask_grad);
+    h->smem_grad = h->slots_grad * h->grad_bytes + h->plan_smem_bytes_grad;
+    h->k_grad = step_kernel_fn(h->any_contact, true, h->plan_smem_mask_grad == 0xff);
+    max_dynamic_smem(h->k_grad);
     ok = ok && cudaFuncSetAttribute(h->k_grad, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
   } else h->grad_bytes = 0;
   if (!ok) { g_create_error = std::string("dojo_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); dojo_destroy(h); return DOJO_ECUDA; }
@@ -628,8 +682,16 @@ static Options make_options(const DojoSolverOptions* o) {
 // [hostemu:options:end]
 
 static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn, double* dsol,
-                          double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s, int* done_count = nullptr, int* done_list = nullptr) {
+                          double* dsol_raw, int32_t* dstatus, int32_t* diters, uint32_t flags, cudaStream_t s, int* done_count = nullptr, int* done_list = nullptr,
+                          DojoGather* g = nullptr) {
   StepArgs a;
+  a.n_peers = 0; a.gather_off = 0;
+  if (g) {
+    if (!g->connected || g->h != h || B != g->B) { h->err = "dojo_step_gather_async: gather not connected / made for another handle / B differs from B_local"; return DOJO_EINVAL; }
+    a.n_peers = g->world;
+    a.gather_off = (long long)g->rank * g->B * h->plan.nz;
+    for (int r = 0; r < g->world; ++r) { a.peer_buf[r] = g->peer_buf[r]; a.peer_flag[r] = g->peer_flag[r]; }
+  }
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = dsol; a.sol_raw = dsol_raw; a.status = dstatus; a.iters = diters; a.flags = flags;
   a.Fz = nullptr; a.Fu = nullptr; a.Fc = nullptr; a.T = 1; a.traj = nullptr; a.done_count = done_count; a.done_list = done_list;
@@ -644,12 +706,13 @@ static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   a.prof = h->d_prof;
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
-  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off;
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off; a.plan_smem_bytes = h->plan_smem_bytes; a.plan_smem_mask = h->plan_smem_mask;
   for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
   { void* kargs[1] = {(void*)&a}; CUDA_TRY(h, cudaLaunchKernel(h->k_fwd, dim3(grid), dim3(32 * h->nw * h->slots), kargs, h->smem_fwd, s)); }
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
+  if (g) g->expected += (unsigned long long)g->world * (unsigned long long)grid;  // every rank launches the same grid (same B_local, same device type)
   leave_call(h, s);
   return DOJO_OK;
 }
@@ -750,10 +813,11 @@ static int launch_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B, i
   a.Z = dZ0; a.U = dU; a.Fext = nullptr; a.Zn = dZf; a.sol = nullptr; a.sol_raw = nullptr; a.status = dstatus; a.iters = nullptr; a.flags = 0;
   a.Fz = nullptr; a.Fu = nullptr; a.Fc = nullptr; a.T = T; a.traj = dtraj; a.done_count = nullptr; a.done_list = nullptr;
   a.counter = h->d_counter; a.prof = h->d_prof; a.order = nullptr; a.prev_iters = nullptr;
+  a.n_peers = 0; a.gather_off = 0;
   enter_call(h, s);
   CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->arena_bytes / sizeof(double));
-  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off;
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off; a.plan_smem_bytes = h->plan_smem_bytes; a.plan_smem_mask = h->plan_smem_mask;
   for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots - 1) / h->slots, h->sm_count * h->envs_per_sm);
   { void* kargs[1] = {(void*)&a}; CUDA_TRY(h, cudaLaunchKernel(h->k_fwd, dim3(grid), dim3(32 * h->nw * h->slots), kargs, h->smem_fwd, s)); }
@@ -816,7 +880,7 @@ extern "C" int dojo_rollout(DojoHandle* h, const DojoSolverOptions* opts, int B,
 // solution + IFT solves) in the larger-arena configuration.  Running the Newton loop inside the gradient configuration
 // (two slots per CTA) made it twice as slow.  dZn must not alias dZ (the gradient kernel re-reads the input state).
 static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn,
-                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
+                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream, DojoGather* g = nullptr);
 extern "C" int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
                                     double* dZn, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
   return step_grad_impl(h, opts, B, dZ, dU, dFext, dZn, dFz, dFu, nullptr, dstatus, diters, flags, cuda_stream);
@@ -833,7 +897,7 @@ extern "C" int dojo_step_grad_contact_async(DojoHandle* h, const DojoSolverOptio
   return step_grad_impl(h, opts, B, dZ, dU, dFext, dZn, dFz, dFu, dFc, dstatus, diters, flags, cuda_stream);
 }
 static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext, double* dZn,
-                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+                          double* dFz, double* dFu, double* dFc, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream, DojoGather* g) {
   if (!h || B <= 0 || B > h->max_batch || !dZ || !dZn || !dFz || !dFu || dZ == dZn) { if (h) h->err = "dojo_step_grad_async: bad arguments (B <= max_batch, dZn != dZ)"; return DOJO_EINVAL; }
   if (!h->grad_bytes) { h->err = "dojo_step_grad_async: the gradient workspace does not fit in shared memory for this mechanism"; return DOJO_ENOMEM; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
@@ -856,17 +920,18 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
     CUDA_TRY(h, cudaMemsetAsync(h->d_done, 0, 2 * sizeof(int), s));                 // [0] finished count, [1] gradient work queue
     CUDA_TRY(h, cudaMemsetAsync(h->d_done + 2, 0xff, (size_t)B * sizeof(int), s));  // -1 = not finished yet
   }
-  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, h->d_gsol, st, diters, flags, s, done_count, done_list);
+  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, h->d_gsol, st, diters, flags, s, done_count, done_list, g);
   if (rc != DOJO_OK) return rc;
   StepArgs a;
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
   a.Z = dZ; a.U = dU; a.Fext = dFext; a.Zn = dZn; a.sol = nullptr; a.sol_raw = h->d_gsol; a.status = st; a.iters = nullptr; a.flags = flags;
   a.Fz = dFz; a.Fu = dFu; a.Fc = dFc; a.T = 1; a.traj = nullptr; a.done_count = nullptr; a.done_list = done_list;
+  a.n_peers = 0; a.gather_off = 0;
   a.counter = overlap ? h->d_done + 1 : h->d_counter; a.order = nullptr; a.prev_iters = nullptr;
   a.prof = h->d_prof;
   if (!overlap) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
   a.slot_stride = (int)(h->grad_bytes / sizeof(double));
-  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off_grad;
+  a.plan_blob = h->d_blob; a.plan_bytes = h->blob_bytes; a.plan_smem_off = h->plan_smem_off_grad; a.plan_smem_bytes = h->plan_smem_bytes_grad; a.plan_smem_mask = h->plan_smem_mask_grad;
   for (int k = 0; k < 8; ++k) a.plan_off[k] = h->blob_off[k];
   int grid = std::min((B + h->slots_grad - 1) / h->slots_grad, h->sm_count * h->envs_per_sm_grad);
   if (overlap) {
@@ -886,6 +951,91 @@ static int step_grad_impl(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   h->launches += 1;
   leave_call(h, s);
   return DOJO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Multi-GPU exchange of the next states, fused into the step (include/dojo_b200.h)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int dojo_gather_create(DojoHandle* h, int world, int rank, int B_local, DojoGather** out) {
+  if (!h || !out || world < 1 || world > DOJO_MAX_GATHER_RANKS || rank < 0 || rank >= world || B_local <= 0 || B_local > h->max_batch) {
+    if (h) h->err = "dojo_gather_create: bad arguments (1 <= world <= 8, B_local <= max_batch)";
+    return DOJO_EINVAL;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  DojoGather* g = new DojoGather();
+  g->h = h; g->world = world; g->rank = rank; g->B = B_local;
+  const size_t bytes = (size_t)world * B_local * h->plan.nz * sizeof(double);
+  if (cudaMalloc((void**)&g->buf, bytes) != cudaSuccess || cudaMalloc((void**)&g->flag, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(g->buf, 0, bytes) != cudaSuccess || cudaMemset(g->flag, 0, sizeof(unsigned long long)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    h->err = std::string("dojo_gather_create: ") + cudaGetErrorString(cudaGetLastError());
+    cudaFree(g->buf); cudaFree(g->flag); delete g;
+    return DOJO_ECUDA;
+  }
+  if (world == 1) { g->peer_buf[0] = g->buf; g->peer_flag[0] = g->flag; g->connected = true; }
+  *out = g;
+  return DOJO_OK;
+}
+extern "C" int dojo_gather_export(DojoGather* g, void* handle_out) {
+  if (!g || !handle_out) return DOJO_EINVAL;
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) <= DOJO_GATHER_HANDLE_BYTES, "descriptor size");
+  cudaIpcMemHandle_t hb, hf;
+  CUDA_TRY(g->h, cudaSetDevice(g->h->device));
+  CUDA_TRY(g->h, cudaIpcGetMemHandle(&hb, g->buf));
+  CUDA_TRY(g->h, cudaIpcGetMemHandle(&hf, g->flag));
+  std::memset(handle_out, 0, DOJO_GATHER_HANDLE_BYTES);
+  std::memcpy(handle_out, &hb, sizeof(hb));
+  std::memcpy((char*)handle_out + sizeof(hb), &hf, sizeof(hf));
+  return DOJO_OK;
+}
+extern "C" int dojo_gather_connect(DojoGather* g, const void* all_handles) {
+  if (!g || !all_handles) return DOJO_EINVAL;
+  CUDA_TRY(g->h, cudaSetDevice(g->h->device));
+  for (int r = 0; r < g->world; ++r) {
+    if (r == g->rank) { g->peer_buf[r] = g->buf; g->peer_flag[r] = g->flag; continue; }
+    cudaIpcMemHandle_t hb, hf;
+    const char* src = (const char*)all_handles + (size_t)r * DOJO_GATHER_HANDLE_BYTES;
+    std::memcpy(&hb, src, sizeof(hb));
+    std::memcpy(&hf, src + sizeof(hb), sizeof(hf));
+    CUDA_TRY(g->h, cudaIpcOpenMemHandle((void**)&g->peer_buf[r], hb, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(g->h, cudaIpcOpenMemHandle((void**)&g->peer_flag[r], hf, cudaIpcMemLazyEnablePeerAccess));
+    g->opened[r] = true;
+  }
+  g->connected = true;
+  return DOJO_OK;
+}
+extern "C" double* dojo_gather_buffer(DojoGather* g) { return g ? g->buf : nullptr; }
+extern "C" int dojo_gather_destroy(DojoGather* g) {
+  if (!g) return DOJO_OK;
+  cudaSetDevice(g->h->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < g->world; ++r)
+    if (g->opened[r]) { cudaIpcCloseMemHandle(g->peer_buf[r]); cudaIpcCloseMemHandle(g->peer_flag[r]); }
+  cudaFree(g->buf); cudaFree(g->flag);
+  delete g;
+  return DOJO_OK;
+}
+static int gather_close_step(DojoHandle* h, DojoGather* g, int32_t* dstatus, cudaStream_t s) {
+  dojo_gather_wait_kernel<<<1, 32, 0, s>>>(g->flag, g->expected, dstatus);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  leave_call(h, s);
+  return DOJO_OK;
+}
+extern "C" int dojo_step_gather_async(DojoHandle* h, DojoGather* g, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU, const double* dFext,
+                                      double* dZn, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream) {
+  if (!h || !g || B <= 0 || !dZ || !dZn) { if (h) h->err = "dojo_step_gather_async: bad arguments"; return DOJO_EINVAL; }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = launch_forward(h, opts, B, dZ, dU, dFext, dZn, nullptr, nullptr, dstatus, diters, flags, (cudaStream_t)cuda_stream, nullptr, nullptr, g);
+  if (rc != DOJO_OK) return rc;
+  return gather_close_step(h, g, dstatus, (cudaStream_t)cuda_stream);
+}
+extern "C" int dojo_step_grad_gather_async(DojoHandle* h, DojoGather* g, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU,
+                                           const double* dFext, double* dZn, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags,
+                                           void* cuda_stream) {
+  if (!h || !g) { if (h) h->err = "dojo_step_grad_gather_async: bad arguments"; return DOJO_EINVAL; }
+  int rc = step_grad_impl(h, opts, B, dZ, dU, dFext, dZn, dFz, dFu, nullptr, dstatus, diters, flags, cuda_stream, g);
+  if (rc != DOJO_OK) return rc;
+  return gather_close_step(h, g, dstatus, (cudaStream_t)cuda_stream);
 }
 
 // Host- or device-pointer entry.  Host buffers are processed in chunks (the Jacobians are large: (12Nb)^2 doubles per env).

@@ -220,7 +220,7 @@ DJ_DEV void grad_contact_param_rhs(Ctx& c, int idx, int p, double* v) {
 //              (a perturbation d of q2 moves the attitude of q1 by R(m(-w))' d).
 // Returns the force to add to p_t.  Limits: the slack rows move with theta = a.e(x3, q3); condensed like the solver's rows.
 DJ_DEV V3 grad_joint_tra(Ctx& c, const JointDev& jd, const Kin& ka, const Kin& kb, const JointGeom& g2, const JointGeom& g3, const M33& Ma,
-                         const M33& Mb, const double* so, double* BPp, double* BPc, double* BCp, double* BCc) {
+                         const M33& Mb, const double* so, double* BPp, double* BPc, double* BCp, double* BCc, double* RJp, double* RJc) {
   const Plan& P = *c.P;
   double* A = c.A;
   V3 extra = v3zero();
@@ -268,10 +268,14 @@ DJ_DEV V3 grad_joint_tra(Ctx& c, const JointDev& jd, const Kin& ka, const Kin& k
         V3 ai = ld3(jd.At + 3 * i);
         const int is_u = ne + i, is_l = ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
         extra += (so[ig_l] - so[ig_u]) * ai;
-        const double kk = (so[ig_u] + kReg) / (so[is_u] + kReg) + (so[ig_l] + kReg) / (so[is_l] + kReg);
+        const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);  // kept / condensed side as in the solver
+        const double kk = ls.kI;
         V3 apx = vtmul(ai, g3.Xp), apq = vtmul(ai, QtpM), acx = vtmul(ai, g3.Xc), acq = vtmul(ai, QtcM);
         const double ap[6] = {apx.x, apx.y, apx.z, apq.x, apq.y, apq.z}, ac[6] = {acx.x, acx.y, acx.z, acq.x, acq.y, acq.z};
         const double* lim = A + jd.lim_off + 2 * kLim * i;
+        const int q = ne + i;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { RJp[q * 6 + r] = (ls.sg * ls.gA) * ap[r]; RJc[q * 6 + r] = (ls.sg * ls.gA) * ac[r]; }
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -290,15 +294,16 @@ DJ_DEV V3 grad_joint_tra(Ctx& c, const JointDev& jd, const Kin& ka, const Kin& k
 }
 #endif
 
-// record layout of a joint (doubles): RJp[ne*6] RJc[ne*6] BPp[36] BPc[36] BCp[36] BCc[36] Up[6*nu] Uc[6*nu]
+// record layout of a joint (doubles): RJp[nq*6] RJc[nq*6] BPp[36] BPc[36] BCp[36] BCc[36] Up[6*nu] Uc[6*nu]   (nq = joint_nq: the
+// node's rows = ne equality rows + one kept limit dual per limited axis)
 DJ_DEV void grad_joint(Ctx& c, int idx) {
   const Plan& P = *c.P;
   double* A = c.A;
   const JointDev& jd = c.joints[idx];
-  const int ne = jd.ne, nuj = jd.nfree_t + jd.nfree_r;
+  const int ne = jd.ne, nq = joint_nq(jd), nuj = jd.nfree_t + jd.nfree_r;
   double* RJp = A + jd.gj_off;
-  double* RJc = RJp + 6 * ne;
-  double* BPp = RJc + 6 * ne;
+  double* RJc = RJp + 6 * nq;
+  double* BPp = RJc + 6 * nq;
   double* BPc = BPp + 36;
   double* BCp = BPc + 36;
   double* BCc = BCp + 36;
@@ -346,7 +351,7 @@ DJ_DEV void grad_joint(Ctx& c, int idx) {
     if (i < jd.nb2_r) pr += (so[ne + jd.nb_r + jd.nb2_r + i] - so[ne + jd.nb_r + i]) * ld3(jd.Ar + 3 * i);
   }
 #ifdef DJ_ANY_CONTACT
-  if (jd.flags) pt += grad_joint_tra(c, jd, ka, kb, g2, g3, Ma, Mb, so, BPp, BPc, BCp, BCc);
+  if (jd.flags) pt += grad_joint_tra(c, jd, ka, kb, g2, g3, Ma, Mb, so, BPp, BPc, BCp, BCc, RJp, RJc);
 #endif
   // translational impulses (translational/impulses.jl:9-45):  F_p = -Ra p, F_c = Ra p, tau_p = p x (e + pa), tau_c = pb x (Rb' Ra p)
   {
@@ -451,11 +456,16 @@ DJ_DEV void grad_joint(Ctx& c, int idx) {
         V3 ai = ld3(jd.Ar + 3 * i);
         V3 ap = vtmul(ai, Tp), ac = vtmul(ai, Tc);
         const int is_u = ne + i, is_l = ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-        double kk = (so[ig_u] + kReg) / (so[is_u] + kReg) + (so[ig_l] + kReg) / (so[is_l] + kReg);
+        // a data column enters the slack rows with rs = -sg (ap.dphi_a + ac.dphi_b): the condensed side gives -k_I t (.) on the body rows
+        // as in the solver, the kept side the right-hand side -gamma_A' rs_A = sg gamma_A' (.) of its own row ne + i (limit_side)
+        const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);
         const double* lim = A + jd.lim_off + kLim * i;
         V3 tP = ld3(lim + 6), tC = ld3(lim + 9);
-        add_block33(BPp, 6, 3, 3, outer(tP, ap), -kk); add_block33(BPc, 6, 3, 3, outer(tP, ac), -kk);
-        add_block33(BCp, 6, 3, 3, outer(tC, ap), -kk); add_block33(BCc, 6, 3, 3, outer(tC, ac), -kk);
+        add_block33(BPp, 6, 3, 3, outer(tP, ap), -ls.kI); add_block33(BPc, 6, 3, 3, outer(tP, ac), -ls.kI);
+        add_block33(BCp, 6, 3, 3, outer(tC, ap), -ls.kI); add_block33(BCc, 6, 3, 3, outer(tC, ac), -ls.kI);
+        const int q = ne + i;
+        st3(RJp + q * 6, v3zero()); st3(RJp + q * 6 + 3, (ls.sg * ls.gA) * ap);
+        st3(RJc + q * 6, v3zero()); st3(RJc + q * 6 + 3, (ls.sg * ls.gA) * ac);
       }
     }
   }
@@ -511,19 +521,21 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int ch, int col, int lane) {
       const int cc = k < 3 ? k : k - 3;
       const JointDev& pj = c.joints[bd.pjoint];
       {  // parent joint: this body is the child
-        const double* RJc = A + pj.gj_off + 6 * pj.ne;
-        const double* BPc = RJc + 6 * pj.ne + 36;
+        const int pnq = joint_nq(pj);
+        const double* RJc = A + pj.gj_off + 6 * pnq;
+        const double* BPc = RJc + 6 * pnq + 36;
         const double* BCc = BPc + 72;
-        for (int r = 0; r < pj.ne; ++r) V[(pj.r_off + r) * ch + lane] += RJc[r * 6 + cc];
+        for (int r = 0; r < pnq; ++r) V[(pj.r_off + r) * ch + lane] += RJc[r * 6 + cc];
         add_col6(V, ch, lane, bd.r_off, BCc, 6, cc);
         if (pj.parent >= 0) add_col6(V, ch, lane, c.bodies[pj.parent].r_off, BPc, 6, cc);
       }
       for (int q = 0; q < bd.cj_cnt; ++q) {  // child joints: this body is the parent
         const JointDev& cj = c.joints[c.ilist[bd.cj_off + q]];
+        const int cnq = joint_nq(cj);
         const double* RJp = A + cj.gj_off;
-        const double* BPp = RJp + 12 * cj.ne;
+        const double* BPp = RJp + 12 * cnq;
         const double* BCp = BPp + 72;
-        for (int r = 0; r < cj.ne; ++r) V[(cj.r_off + r) * ch + lane] += RJp[r * 6 + cc];
+        for (int r = 0; r < cnq; ++r) V[(cj.r_off + r) * ch + lane] += RJp[r * 6 + cc];
         add_col6(V, ch, lane, bd.r_off, BPp, 6, cc);
         add_col6(V, ch, lane, c.bodies[cj.child].r_off, BCp, 6, cc);
       }
@@ -540,7 +552,7 @@ DJ_DEV void grad_build_rhs(Ctx& c, double* V, int ch, int col, int lane) {
     const int ui = col - 12 * P.Nb;
     const JointDev& jd = c.joints[c.ucol[2 * ui]];
     const int dof = c.ucol[2 * ui + 1], nuj = jd.nfree_t + jd.nfree_r;
-    const double* Up = A + jd.gj_off + 12 * jd.ne + 144;
+    const double* Up = A + jd.gj_off + 12 * joint_nq(jd) + 144;
     const double* Uc = Up + 6 * nuj;
     if (jd.parent >= 0) add_col6(V, ch, lane, c.bodies[jd.parent].r_off, Up, nuj, dof);
     add_col6(V, ch, lane, c.bodies[jd.child].r_off, Uc, nuj, dof);

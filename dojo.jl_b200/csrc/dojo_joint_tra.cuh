@@ -117,7 +117,9 @@ DJ_DEV void eval_joint_tra(Ctx& c, const JointDev& jd, double f, const Kin& ka, 
         if (JAC) {
           V3 aPl = P.h * vtmul(ai, g3.Xp), aPa = vtmul(ai, QtpE), aCl = P.h * vtmul(ai, g3.Xc), aCa = vtmul(ai, QtcE);
           st3(lim, aPl); st3(lim + 3, aPa); st3(lim + 6, aCl); st3(lim + 9, aCa);
-          const double kk = (gu + kReg) / (su + kReg) + (gl + kReg) / (sl + kReg);
+          // kept side / condensed side exactly as for the rotational limits (dojo_kernels.cuh limit_side, dojo_plan.h joint_nq)
+          const LimitSide ls = limit_side(su, sl, gu, gl);
+          const double kk = ls.kI;
           const double tP[6] = {tPl.x, tPl.y, tPl.z, tPa.x, tPa.y, tPa.z}, tC[6] = {tCl.x, tCl.y, tCl.z, tCa.x, tCa.y, tCa.z};
           const double aP[6] = {aPl.x, aPl.y, aPl.z, aPa.x, aPa.y, aPa.z}, aC[6] = {aCl.x, aCl.y, aCl.z, aCa.x, aCa.y, aCa.z};
 #pragma unroll
@@ -129,27 +131,44 @@ DJ_DEV void eval_joint_tra(Ctx& c, const JointDev& jd, double f, const Kin& ka, 
               B6pc[r * 6 + q] += kk * tP[r] * aC[q];
               B6cp[r * 6 + q] += kk * tC[r] * aP[q];
             }
+          const int n = joint_nq(jd), q = jd.ne + i;
+          double* D = A + jd.D_off;
+          double* Uc = A + jd.Uc_off;
+          double* Lcw = A + jd.Lc_off;
+          D[q * n + q] = ls.sA;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { Uc[q * 6 + r] = (-ls.sg * ls.gA) * aC[r]; Lcw[r * n + q] = ls.sg * tC[r]; }
+          if (jd.parent >= 0) {
+            double* Up = A + jd.Up_off;
+            double* Gpw = A + jd.Gp_off;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { Up[q * 6 + r] = (-ls.sg * ls.gA) * aP[r]; Gpw[r * n + q] = -ls.sg * tP[r]; }
+          }
         }
       }
     }
   }
 }
 
-DJ_DEV void condense_joint_tra(Ctx& c, const JointDev& jd, const double* x) {
+DJ_DEV void condense_joint_tra(Ctx& c, const JointDev& jd, double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
   V3 pl = v3zero(), pa = v3zero(), cl = v3zero(), ca = v3zero();
   const double* so = A + P.sol_off + jd.sol_off;
-  const double* xr = x + jd.sol_off;
+  double* xr = x + jd.sol_off;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nb2_r) {
       const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
-      double c0 = (xr[is_u] - gu * xr[ig_u]) / su - (xr[is_l] - gl * xr[ig_l]) / sl;
+      const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);
+      const double rc_u = xr[is_u], rc_l = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
+      const double cI = ((ls.up ? rc_l : rc_u) - ls.gI * (ls.up ? rs_l : rs_u)) / ls.sI;
+      const double w = ls.sg * cI;
       const double* lim = A + jd.lim_off + 2 * kLim * i;
-      pl -= c0 * ld3(lim + 12); pa -= c0 * ld3(lim + 15);
-      cl -= c0 * ld3(lim + 18); ca -= c0 * ld3(lim + 21);
+      pl += w * ld3(lim + 12); pa += w * ld3(lim + 15);
+      cl += w * ld3(lim + 18); ca += w * ld3(lim + 21);
+      xr[is_u] = (ls.up ? rc_u : rc_l) - ls.gA * (ls.up ? rs_u : rs_l);
+      if (!ls.up) xr[is_l] = rc_u;
     }
   }
   double* sc = A + jd.slot_c;
@@ -169,15 +188,16 @@ DJ_DEV void recover_joint_tra(Ctx& c, const JointDev& jd, double* x) {
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nb2_r) {
       const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
+      const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);
       const double* lim = A + jd.lim_off + 2 * kLim * i;
-      double adw = dot(ld3(lim), vp) + dot(ld3(lim + 3), wp) + dot(ld3(lim + 6), vc) + dot(ld3(lim + 9), wc);
-      double rc_u = xr[is_u], rc_l = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
-      double ds_u = rs_u - adw, ds_l = rs_l + adw;
+      const double adw = dot(ld3(lim), vp) + dot(ld3(lim + 3), wp) + dot(ld3(lim + 6), vc) + dot(ld3(lim + 9), wc);
+      const double dgA = xr[is_u], rcI = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
+      const double ds_u = rs_u - adw, ds_l = rs_l + adw;
+      const double dgI = (rcI - ls.gI * (ls.up ? ds_l : ds_u)) / ls.sI;
       xr[is_u] = ds_u;
       xr[is_l] = ds_l;
-      xr[ig_u] = (rc_u - gu * ds_u) / su;
-      xr[ig_l] = (rc_l - gl * ds_l) / sl;
+      xr[ig_u] = ls.up ? dgA : dgI;
+      xr[ig_l] = ls.up ? dgI : dgA;
     }
   }
 }

@@ -218,6 +218,20 @@ DJ_DEV void rotvec_attitude_jacobians(const JointDev& jd, const JointGeom& g, M3
 }
 
 DJ_DEV void write_slot(double* s, V3 f, V3 t, const M33& K) { st3(s, f); st3(s + 3, t); stm33(s + 6, K); }
+// Which side of a limited axis keeps its dual in the joint's node (dojo_plan.h joint_nq), from the current iterate (s, gamma >= 0):
+// the smaller REG-shifted slack.  sA, gA: shifted slack / dual of the kept side, sg = +1 (upper) / -1 (lower); kI = gamma'/s' of the
+// condensed side.  Evaluated identically by the assembly, the right-hand-side condensation and the recovery of one iteration.
+struct LimitSide { bool up; double sA, gA, sg, sI, gI, kI; };
+DJ_DEV LimitSide limit_side(double su, double sl, double gu, double gl) {
+  LimitSide r;
+  const double su1 = su + kReg, sl1 = sl + kReg, gu1 = gu + kReg, gl1 = gl + kReg;
+  r.up = su1 <= sl1;
+  r.sA = r.up ? su1 : sl1; r.gA = r.up ? gu1 : gl1; r.sg = r.up ? 1.0 : -1.0;
+  r.sI = r.up ? sl1 : su1; r.gI = r.up ? gl1 : gu1;
+  r.kI = r.gI / r.sI;
+  return r;
+}
+
 #ifdef DJ_ANY_CONTACT
 #include "dojo_joint_tra.cuh"  // translational springs / dampers / limits (only in the compilation that serves such mechanisms)
 #endif
@@ -282,7 +296,9 @@ DJ_DEV void prologue_joint(Ctx& c, int j, const double* __restrict__ u) {
     const M33& X = par ? g.Xp : g.Xc;
     const M33& Qt = par ? g.Qtp : g.Qtc;
     const M33& Qr = par ? g.Qrp : g.Qrc;
-    const int n = jd.ne;
+    const int n = joint_nq(jd);
+    for (int q = jd.ne; q < n; ++q)  // columns of the kept limit duals: written at every assembly (the kept side can change)
+      for (int r = 0; r < 6; ++r) G[r * n + q] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if (i < jd.nl_t) {  // translational lambda column i
@@ -577,7 +593,7 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
   bool coupled = false;
   Kin ka = body_kin(c, jd.parent, f), kb = body_kin(c, jd.child, f);
   JointGeom g = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
-  const int n = jd.ne;
+  const int n = joint_nq(jd);  // rows of the joint's node: ne equality multipliers + one kept limit dual per limited axis
   double* rr = res + jd.sol_off;
   const double* so = sol + jd.sol_off;
   const double* dd = dl + jd.sol_off;
@@ -654,12 +670,27 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
         if (JAC) {
           V3 aP = vtmul(ai, Tp), aC = vtmul(ai, Tc);
           st3(lim, aP); st3(lim + 3, aC);
-          double kk = (gu + kReg) / (su + kReg) + (gl + kReg) / (sl + kReg);
-          // body rows gain  t kk (aP.dw_p + aC.dw_c)  =>  D_parent += kk tP aP', (p,c) += kk tP aC', ...
-          Kaa = Kaa - kk * outer(tP, aP);
-          Kcc = Kcc - kk * outer(tC, aC);
-          Bpc = Bpc + kk * outer(tP, aC);
-          Bcp = Bcp + kk * outer(tC, aP);
+          // Kept side A = the smaller slack (dojo_plan.h joint_nq): after ds_A = rs_A - sg a.dw its complementarity row reads
+          //   s_A' dgamma_A - sg gamma_A' a.dw = rc_A - gamma_A' rs_A          (sg = +1 upper, -1 lower)
+          // and is the node's row ne + i; the bodies see dgamma_A through the column sg t.  The other side I is condensed:
+          //   dgamma_I = c_I + sg_I k_I a.dw,  k_I = gamma_I'/s_I'  =>  body rows gain  k_I t (aP.dw_p + aC.dw_c).
+          const LimitSide ls = limit_side(su, sl, gu, gl);
+          Kaa = Kaa - ls.kI * outer(tP, aP);
+          Kcc = Kcc - ls.kI * outer(tC, aC);
+          Bpc = Bpc + ls.kI * outer(tP, aC);
+          Bcp = Bcp + ls.kI * outer(tC, aP);
+          const int q = jd.ne + i;
+          D[q * n + q] = ls.sA;
+          st3(Uc + q * 6, v3zero()); st3(Uc + q * 6 + 3, (-ls.sg * ls.gA) * aC);
+          if (Up) { st3(Up + q * 6, v3zero()); st3(Up + q * 6 + 3, (-ls.sg * ls.gA) * aP); }
+          double* Lcw = A + jd.Lc_off;
+          Lcw[0 * n + q] = 0.0; Lcw[1 * n + q] = 0.0; Lcw[2 * n + q] = 0.0;
+          Lcw[3 * n + q] = ls.sg * tC.x; Lcw[4 * n + q] = ls.sg * tC.y; Lcw[5 * n + q] = ls.sg * tC.z;
+          if (jd.parent >= 0) {  // pristine parent map G = -L (Lp is refreshed from it below)
+            double* Gpw = A + jd.Gp_off;
+            Gpw[0 * n + q] = 0.0; Gpw[1 * n + q] = 0.0; Gpw[2 * n + q] = 0.0;
+            Gpw[3 * n + q] = -ls.sg * tP.x; Gpw[4 * n + q] = -ls.sg * tP.y; Gpw[5 * n + q] = -ls.sg * tP.z;
+          }
         }
       }
     }
@@ -677,7 +708,7 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
     const double* Lc = A + jd.Lc_off;
     const double* Gp = (jd.parent >= 0) ? A + jd.Gp_off : nullptr;
     double ac[6] = {0, 0, 0, 0, 0, 0}, ap[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < jd.ne; ++i) {  // equality columns only: the limit duals act through (gl - gu) t above
       double e = so[i];
       if (f != 0.0) e += f * dd[i];
 #pragma unroll
@@ -826,7 +857,7 @@ DJ_DEV void recover_contact(Ctx& c, int idx, double* x) {
 #pragma unroll
   for (int r = 0; r < 8; ++r) x[cd.sol_off + r] = y[r];
 }
-DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
+DJ_DEV void condense_joint(Ctx& c, int idx, double* x) {
   const Plan& P = *c.P;
   double* A = c.A;
   const JointDev& jd = c.joints[idx];
@@ -835,16 +866,22 @@ DJ_DEV void condense_joint(Ctx& c, int idx, const double* x) {
 #endif
   V3 tp = v3zero(), tc = v3zero();
   const double* so = A + P.sol_off + jd.sol_off;
-  const double* xr = x + jd.sol_off;
+  double* xr = x + jd.sol_off;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nb2_r) {
       const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
-      double c0 = (xr[is_u] - gu * xr[ig_u]) / su - (xr[is_l] - gl * xr[ig_l]) / sl;
+      const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);
+      const double rc_u = xr[is_u], rc_l = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
+      // condensed side I: dgamma_I = c_I + sg_I k_I a.dw;  the body rows carry sg_I t dgamma_I  =>  rhs -= sg_I c_I t
+      const double cI = ((ls.up ? rc_l : rc_u) - ls.gI * (ls.up ? rs_l : rs_u)) / ls.sI;
+      const double w = ls.sg * cI;  // sg_I = -sg
       const double* lim = A + jd.lim_off + kLim * i;
-      tp -= c0 * ld3(lim + 6);  // body rows: t (dg_u - dg_l) moves to the right-hand side
-      tc -= c0 * ld3(lim + 9);
+      tp += w * ld3(lim + 6);
+      tc += w * ld3(lim + 9);
+      // kept side A: right-hand side of its row (position ne + i of the node); rc of the condensed side is kept at is_l for recover
+      xr[is_u] = (ls.up ? rc_u : rc_l) - ls.gA * (ls.up ? rs_u : rs_l);
+      if (!ls.up) xr[is_l] = rc_u;
     }
   }
   double* sc = A + jd.slot_c;
@@ -867,15 +904,16 @@ DJ_DEV void recover_joint(Ctx& c, int idx, double* x) {
   for (int i = 0; i < 3; ++i) {
     if (i < jd.nb2_r) {
       const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i, ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
-      double su = so[is_u] + kReg, sl = so[is_l] + kReg, gu = so[ig_u] + kReg, gl = so[ig_l] + kReg;
+      const LimitSide ls = limit_side(so[is_u], so[is_l], so[ig_u], so[ig_l]);
       const double* lim = A + jd.lim_off + kLim * i;
-      double adw = dot(ld3(lim), wp) + dot(ld3(lim + 3), wc);
-      double rc_u = xr[is_u], rc_l = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
-      double ds_u = rs_u - adw, ds_l = rs_l + adw;
+      const double adw = dot(ld3(lim), wp) + dot(ld3(lim + 3), wc);
+      const double dgA = xr[is_u], rcI = xr[is_l], rs_u = xr[ig_u], rs_l = xr[ig_l];
+      const double ds_u = rs_u - adw, ds_l = rs_l + adw;
+      const double dgI = (rcI - ls.gI * (ls.up ? ds_l : ds_u)) / ls.sI;
       xr[is_u] = ds_u;
       xr[is_l] = ds_l;
-      xr[ig_u] = (rc_u - gu * ds_u) / su;
-      xr[ig_l] = (rc_l - gl * ds_l) / sl;
+      xr[ig_u] = ls.up ? dgA : dgI;
+      xr[ig_l] = ls.up ? dgI : dgA;
     }
   }
 }

@@ -41,6 +41,24 @@ DJ_LA bool block_inverse_nopivot_t(double* A, int ld, int l, unsigned mask) {
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
+#ifdef DJ_BLOCK_PIVOT  // opt-in build variant; measured (128 ant environments in hard contact, rtol = btol = 1e-10 / 1e-12): no gain
+    // in convergence over the unpivoted elimination once the joint limits are no longer condensed through 1 / s (dojo_plan.h joint_nq)
+    // partial (row) pivoting inside the block: the lane that owns column k picks the largest remaining entry of its column, every
+    // lane of the group swaps the two rows of its own column.  Row operations on [A | I] leave A^-1 in the right half as before.
+    if (k + 1 < N) {
+      int p = k;
+      double best = fabs(a[k]);
+#pragma unroll
+      for (int r = k + 1; r < N; ++r) {
+        const double v = fabs(a[r]);
+        if (v > best) { best = v; p = r; }
+      }
+      p = __shfl_sync(mask, p, k, 16);
+#pragma unroll
+      for (int r = k + 1; r < N; ++r)
+        if (r == p) { const double t = a[k]; a[k] = a[r]; a[r] = t; }
+    }
+#endif
     double piv = __shfl_sync(mask, a[k], k, 16);
     if (!(fabs(piv) > 1e-300) || !(fabs(piv) < 1e300)) ok = false;
     double akk = a[k] * (1.0 / piv);

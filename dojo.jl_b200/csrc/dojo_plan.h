@@ -42,7 +42,7 @@ struct BodyDev {
 struct JointDev {
   int parent, child;  // body indices, parent = -1 for the origin
   int n, sol_off;     // impulse dimension / offset inside the solution vector
-  int ne;             // equality multipliers nl_t + nl_r: the joint's node in the condensed KKT system
+  int ne;             // equality multipliers nl_t + nl_r; the joint's node in the condensed KKT system has joint_nq() = ne + nb2_r rows
   int nl_t, nl_r, nb2_r, nb_r;  // constrained axes (tra, rot), rotational limits Nb/2 and Nb
   // DEVICE layout of the joint's entries in sol / rhs / sav:  [ tra eq (nl_t) | rot eq (nl_r) | s (nb_r) | gamma (nb_r) ]
   // (the reference orders them [tra eq | s | gamma | rot eq]; the permutation is applied when `sol` is written out)
@@ -52,8 +52,8 @@ struct JointDev {
   double pa[3], pb[3], qoff[4];
   double Ct[9], At[9], Cr[9], Ar[9];  // constraint / nullspace masks, zero-padded to 3 rows (joints/joint.jl:56-64)
   double spring_r, damper_r, spring_off_r[3], lo[3], hi[3];
-  int D_off;                    // ne x ne (limit slacks / duals are condensed out analytically)
-  int Uc_off, Lc_off;           // (joint,child) n x 6, rewritten every assembly ; (child,joint) 6 x n = -G_c, constant over the
+  int D_off;                    // nq x nq, nq = joint_nq(): equality rows + one kept limit dual per limited axis
+  int Uc_off, Lc_off;           // (joint,child) nq x 6, rewritten every assembly ; (child,joint) 6 x nq = -G_c, constant over the
                                 // solve and never written by the factorisation (lives in the constant region of the arena)
   int Up_off, Lp_off, Gp_off;   // same for the parent body (-1 when the parent is the origin); Lp is consumed by the
                                 // factorisation and refreshed from the pristine impulse map Gp at every assembly
@@ -82,6 +82,13 @@ static_assert(sizeof(JointDev) == 568, "JointDev layout is part of the kernels' 
 #else
 #define DJ_PLAN_FN inline
 #endif
+// Size of the joint's node in the condensed KKT system: its ne equality multipliers plus ONE dual per limited axis.  Of the two
+// limit sides of an axis (upper / lower) the one nearer to its bound -- the smaller slack, the only one that can be active -- keeps
+// its dual as an explicit unknown (a row with diagonal s, like an equality row with diagonal REG); its slack and the whole other side
+// are condensed out analytically.  Condensing BOTH sides (division by the active slack s -> 0) put terms of size gamma / s on the body
+// rows and lost the dynamics there to rounding (linear residual ~3e-9, no convergence below rtol ~1e-8); the reference eliminates the
+// bodies BEFORE the joint node, which is what keeping the active dual in the joint node reproduces.
+DJ_PLAN_FN int joint_nq(const JointDev& j) { return j.ne + j.nb2_r; }
 DJ_PLAN_FN const double* joint_tra_params(const JointDev& j) { return j.Ct + 3 * j.nl_t; }
 DJ_PLAN_FN double* joint_tra_params(JointDev& j) { return j.Ct + 3 * j.nl_t; }
 

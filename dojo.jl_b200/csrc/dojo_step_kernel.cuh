@@ -36,28 +36,41 @@ struct StepArgs {
   int32_t* prev_iters;  // Newton iterations of the previous call per environment (predicts the cost of the next one)
   const char* plan_blob;  // plan tables, one contiguous blob: [bodies | joints | contacts | steps | sched | ilist | roles | ucol]
   int plan_bytes, plan_off[8];
-  int plan_smem_off;    // >= 0: doubles from the start of dynamic shared memory where the CTA keeps its copy of the blob
+  int plan_smem_off;    // >= 0: doubles from the start of dynamic shared memory where the CTA keeps its copy of the blob ...
+  int plan_smem_bytes;  // ... of which the first plan_smem_bytes bytes are copied (the blob starts with the tables of the serial phases:
+  int plan_smem_mask;   // steps, sched, ilist, roles); bit k set: table k lies inside that prefix and is read from shared memory
   int slot_stride;      // doubles between the arenas of two slots of a CTA
   int T;                // time steps fused in this launch (rollouts: every environment is advanced T steps by one CTA)
   double* traj;         // nullable [T][B][nz]: state after every step
   unsigned long long* prof;  // DJ_PROFILE builds: cycle counters [eval_jac, eval_ls, factorize, solve, misc]
+  // Multi-GPU exchange fused into the step (dojo_step_gather_async): besides Zn the epilogue writes every environment's
+  // next state straight into the gathered buffer of every rank -- peer-mapped memory (CUDA IPC over NVLink / NVSwitch), this rank's
+  // slice starts at gather_off doubles -- and every CTA signals the ranks when its share is out.  n_peers = 0: no exchange.
+  int n_peers;
+  long long gather_off;
+  double* peer_buf[DOJO_MAX_GATHER_RANKS];
+  unsigned long long* peer_flag[DOJO_MAX_GATHER_RANKS];
 };
 
 // epilogue: update_state! + get_next_state (bodies/set.jl:22-36, mechanism/get.jl:126-134).  The default output is the
 // mechanism's state after the step, (x3, v25, q3, w25); DOJO_FLAG_Q1_LITERAL_RETURN reproduces step!'s literal return
 // value, which advances the configuration a second time.
-DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal) {
+DJ_DEV void epilogue(Ctx& c, double* __restrict__ zn, bool q1_literal, int n_peers = 0, double* const* peer = nullptr, long long peer_off = 0) {
   const Plan& P = *c.P;
   if (c.tid < P.Nb) {
     Kin k = body_kin(c, c.tid, 0.0);
     V3 x3 = k.x3;
     Quat q3 = k.q3;
     if (q1_literal) { x3 = x3 + P.h * k.v; q3 = qmul(q3, qmap(k.w, P.h)); }
+    const double v[13] = {x3.x, x3.y, x3.z, k.v.x, k.v.y, k.v.z, q3.s, q3.x, q3.y, q3.z, k.w.x, k.w.y, k.w.z};
     double* o = zn + 13 * c.tid;
-    o[0] = x3.x; o[1] = x3.y; o[2] = x3.z;
-    o[3] = k.v.x; o[4] = k.v.y; o[5] = k.v.z;
-    o[6] = q3.s; o[7] = q3.x; o[8] = q3.y; o[9] = q3.z;
-    o[10] = k.w.x; o[11] = k.w.y; o[12] = k.w.z;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) o[i] = v[i];
+    for (int r = 0; r < n_peers; ++r) {  // posted writes into the peers' gathered buffers (this rank's own copy included)
+      double* po = peer[r] + peer_off + 13 * c.tid;
+#pragma unroll
+      for (int i = 0; i < 13; ++i) po[i] = v[i];
+    }
   }
 }
 
@@ -90,22 +103,25 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   c.sd = 0;
   c.mu = 0.0;
   {
-    const char* pb = a.plan_blob;
-    if (PLAN_SMEM || a.plan_smem_off >= 0) {  // one copy of the plan tables per CTA, shared by its slots
+    const char* gb = a.plan_blob;
+    const char* sb = nullptr;
+    if (PLAN_SMEM || a.plan_smem_off >= 0) {  // one copy of the plan tables (or of their hot prefix) per CTA, shared by its slots
       int4* dst = reinterpret_cast<int4*>(arena + a.plan_smem_off);
       const int4* src = reinterpret_cast<const int4*>(a.plan_blob);
-      for (int i = threadIdx.x; i < a.plan_bytes / 16; i += blockDim.x) dst[i] = src[i];
+      for (int i = threadIdx.x; i < a.plan_smem_bytes / 16; i += blockDim.x) dst[i] = src[i];
       __syncthreads();
-      pb = reinterpret_cast<const char*>(dst);
+      sb = reinterpret_cast<const char*>(dst);
     }
-    c.bodies = reinterpret_cast<const BodyDev*>(pb + a.plan_off[0]);
-    c.joints = reinterpret_cast<const JointDev*>(pb + a.plan_off[1]);
-    c.contacts = reinterpret_cast<const ContactDev*>(pb + a.plan_off[2]);
-    c.steps = reinterpret_cast<const ElimStep*>(pb + a.plan_off[3]);
-    c.sched = reinterpret_cast<const int*>(pb + a.plan_off[4]);
-    c.ilist = reinterpret_cast<const int*>(pb + a.plan_off[5]);
-    c.roles = reinterpret_cast<const WarpRole*>(pb + a.plan_off[6]);
-    c.ucol = reinterpret_cast<const int*>(pb + a.plan_off[7]);
+#define DJ_TABLE(k) ((PLAN_SMEM || (sb && ((a.plan_smem_mask >> (k)) & 1))) ? sb + a.plan_off[k] : gb + a.plan_off[k])
+    c.bodies = reinterpret_cast<const BodyDev*>(DJ_TABLE(0));
+    c.joints = reinterpret_cast<const JointDev*>(DJ_TABLE(1));
+    c.contacts = reinterpret_cast<const ContactDev*>(DJ_TABLE(2));
+    c.steps = reinterpret_cast<const ElimStep*>(DJ_TABLE(3));
+    c.sched = reinterpret_cast<const int*>(DJ_TABLE(4));
+    c.ilist = reinterpret_cast<const int*>(DJ_TABLE(5));
+    c.roles = reinterpret_cast<const WarpRole*>(DJ_TABLE(6));
+    c.ucol = reinterpret_cast<const int*>(DJ_TABLE(7));
+#undef DJ_TABLE
   }
 #ifdef DJ_PROFILE
   c.t_eval_jac = c.t_eval_ls = c.t_fact = c.t_solve = c.t_misc = c.t_align = c.t_cone = c.t_center = c.t_rolewait = 0; c.t_last = clock64();
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
         worst = max(worst, status);
         // state after this step: the trajectory slot if recorded, else the output buffer (re-read by the next step from L2)
         double* zo = (a.traj ? a.traj + ((size_t)t * a.B + e) * P.nz : a.Zn + (size_t)e * P.nz);
-        epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0);
+        epilogue(c, zo, (a.flags & DOJO_FLAG_Q1_LITERAL_RETURN) != 0, (t + 1 == a.T) ? a.n_peers : 0, a.peer_buf, a.gather_off + (long long)e * P.nz);
         if (t + 1 < a.T) { __threadfence_block(); slot_sync(c); z = zo; }
       }
       if (a.traj) {  // final state also goes to Zn
@@ -231,6 +247,15 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     slot_sync(c);
   }
   while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
+  if (!GRAD && a.n_peers > 0) {
+    // every environment of this CTA has been written to the peers: make the writes visible system-wide, then count this CTA in on
+    // every rank (the receiving side waits for all CTAs of all ranks, dojo_gather_wait_kernel).  The barrier above orders the other
+    // threads' stores before thread 0's fence (fence cumulativity).
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      for (int r = 0; r < a.n_peers; ++r) atomicAdd_system(a.peer_flag[r], 1ull);
+    }
+  }
   // a gradient grid that started early (programmatic dependent launch) does not complete before the forward grid has
   if (GRAD) asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef DJ_PROFILE

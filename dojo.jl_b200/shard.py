@@ -42,3 +42,89 @@ def scatter_check(batch: int, world: int) -> np.ndarray:
         lo, hi = shard_bounds(batch, world, r)
         owner[lo:hi] = r
     return owner
+
+
+class StateGather:
+    """The one exchange of the path (every rank receives the next states of the whole batch), for one process per GPU.
+
+    fused = True : dojo_step_gather_async -- the step kernel writes every environment's next state straight into the gathered buffer
+                   of every rank (peer memory mapped with CUDA IPC over NVLink / NVSwitch), overlapping the exchange with the solve
+                   and its tail; a small wait kernel closes the step.  The IPC descriptors are exchanged once with torch.distributed.
+    fused = False: fallback when peer mapping is unavailable (or DOJO_B200_GATHER=nccl): one NCCL all-gather per step on a side
+                   stream behind the kernel.
+    """
+
+    def __init__(self, stepper, B_local, nz, rank, world, dist, device):
+        import os
+        import torch
+        self.stepper, self.B, self.nz, self.rank, self.world, self.dist, self.dev = stepper, B_local, nz, rank, world, dist, device
+        self.g = None
+        self.fused = False
+        self.why = ""
+        ok = torch.zeros(1, dtype=torch.int32, device=device)
+        if os.environ.get("DOJO_B200_GATHER", "p2p") != "nccl":
+            try:
+                self.g = stepper.gather_create(world, rank, B_local)
+                mine = torch.frombuffer(bytearray(stepper.gather_export(self.g)), dtype=torch.uint8).to(device)
+                allh = torch.empty(world * 128, dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(allh, mine)
+                stepper.gather_connect(self.g, bytes(allh.cpu().numpy().tobytes()))
+                ok += 1
+            except Exception as ex:  # e.g. CUDA IPC not permitted in this container
+                self.why = f"{type(ex).__name__}: {ex}"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
+        self.fused = bool(ok.item() == 1)
+        if self.fused:
+            ptr = stepper.gather_buffer(self.g)
+            self.Zall = _wrap_device_buffer(ptr, (world * B_local, nz), device)
+        else:
+            self.Zall = torch.empty((world * B_local, nz), dtype=torch.float64, device=device)
+            self.side = torch.cuda.Stream(device=device)
+            self.ev = torch.cuda.Event()
+            self.done = torch.cuda.Event()
+
+    def step(self, dZ, dU, dZn, opts, dstatus=None, diters=None, stream=0):
+        self.stepper.step_gather_device(self.g, dZ, dU, dZn, self.B, opts, dstatus=dstatus, diters=diters, stream=stream)
+
+    def step_grad(self, dZ, dU, dZn, dFz, dFu, opts, dstatus=None, diters=None, stream=0):
+        self.stepper.step_grad_gather_device(self.g, dZ, dU, dZn, dFz, dFu, self.B, opts, dstatus=dstatus, diters=diters, stream=stream)
+
+    def exchange(self, z_local, stream):
+        """NCCL fallback: all-gather behind the kernel; the launching stream waits for it (the step ends with the gathered buffer filled)."""
+        import torch
+        self.ev.record(stream)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev)
+            self.dist.all_gather_into_tensor(self.Zall, z_local)
+            self.done.record(self.side)
+        stream.wait_event(self.done)
+
+    def exchange_host(self, z_local_host, z_all_host):
+        """End-to-end leg of bench.py: the local next states are on the host already; gather them on the device and bring the whole
+        batch to the host of every rank."""
+        import torch
+        zl = torch.from_numpy(z_local_host).to(self.dev, non_blocking=True)
+        tmp = self.Zall if not self.fused else torch.empty_like(self.Zall)
+        self.dist.all_gather_into_tensor(tmp, zl)
+        torch.from_numpy(z_all_host).copy_(tmp, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def describe(self):
+        return {"kind": "fused peer writes (CUDA IPC over NVLink, dojo_step_gather_async)" if self.fused else "NCCL all_gather_into_tensor behind the kernel (side stream)",
+                "bytes_per_rank_per_step": 8 * self.B * self.nz * (self.world - 1), "fallback_reason": self.why or None}
+
+    def close(self):
+        if self.g is not None:
+            self.stepper.gather_destroy(self.g)
+            self.g = None
+
+
+def _wrap_device_buffer(ptr, shape, device):
+    """torch view of a device buffer owned by the library (no copy): __cuda_array_interface__."""
+    import torch
+
+    class _Buf:
+        pass
+    b = _Buf()
+    b.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+    return torch.as_tensor(b, device=device)

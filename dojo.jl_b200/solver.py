@@ -26,7 +26,9 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
            "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_env_policy_rollout", "dojo_update_params", "dojo_num_contact_data", "dojo_step_grad_contact",
-           "dojo_step_grad_contact_async", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record"]
+           "dojo_step_grad_contact_async", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record",
+           "dojo_gather_create", "dojo_gather_export", "dojo_gather_connect", "dojo_gather_buffer", "dojo_gather_destroy", "dojo_step_gather_async",
+           "dojo_step_grad_gather_async"]
 
 _lib = None
 
@@ -109,6 +111,20 @@ def load_library():
     L.dojo_step_record_async.restype = C.c_int
     L.dojo_simulate_record.argtypes = [vp, op, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.dojo_simulate_record.restype = C.c_int
+    L.dojo_gather_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.dojo_gather_create.restype = C.c_int
+    L.dojo_gather_export.argtypes = [vp, vp]
+    L.dojo_gather_export.restype = C.c_int
+    L.dojo_gather_connect.argtypes = [vp, vp]
+    L.dojo_gather_connect.restype = C.c_int
+    L.dojo_gather_buffer.argtypes = [vp]
+    L.dojo_gather_buffer.restype = vp
+    L.dojo_gather_destroy.argtypes = [vp]
+    L.dojo_gather_destroy.restype = C.c_int
+    L.dojo_step_gather_async.argtypes = [vp, vp, op, C.c_int, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.dojo_step_gather_async.restype = C.c_int
+    L.dojo_step_grad_gather_async.argtypes = [vp, vp, op, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.dojo_step_grad_gather_async.restype = C.c_int
     _lib = L
     return L
 
@@ -473,3 +489,36 @@ class BatchedStepper:
         rc = self.L.dojo_step_grad_async(self.h, C.byref(o), int(B), _p(dZ), _p(dU), None, _p(dZn), _p(dFz), _p(dFu), _p(dstatus), _p(diters), flags,
                                          C.c_void_p(int(stream)))
         self._check(rc, "dojo_step_grad_async")
+
+    # ---- multi-GPU: the exchange of the next states fused into the step (include/dojo_b200.h)
+    def gather_create(self, world: int, rank: int, B_local: int):
+        g = C.c_void_p()
+        self._check(self.L.dojo_gather_create(self.h, int(world), int(rank), int(B_local), C.byref(g)), "dojo_gather_create")
+        return g
+
+    def gather_export(self, g) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.L.dojo_gather_export(g, buf), "dojo_gather_export")
+        return buf.raw
+
+    def gather_connect(self, g, all_handles: bytes):
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        self._check(self.L.dojo_gather_connect(g, buf), "dojo_gather_connect")
+
+    def gather_buffer(self, g) -> int:
+        return int(self.L.dojo_gather_buffer(g) or 0)
+
+    def gather_destroy(self, g):
+        self.L.dojo_gather_destroy(g)
+
+    def step_gather_device(self, g, dZ: int, dU: Optional[int], dZn: int, B: int, opts=None, dstatus=None, diters=None, flags: int = 0, stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_gather_async(self.h, g, C.byref(o), int(B), _p(dZ), _p(dU), None, _p(dZn), _p(dstatus), _p(diters), flags, C.c_void_p(int(stream)))
+        self._check(rc, "dojo_step_gather_async")
+
+    def step_grad_gather_device(self, g, dZ: int, dU: Optional[int], dZn: int, dFz: int, dFu: int, B: int, opts=None, dstatus=None, diters=None, flags: int = 0,
+                                stream: int = 0):
+        o = opts if opts is not None else capi.solver_options()
+        rc = self.L.dojo_step_grad_gather_async(self.h, g, C.byref(o), int(B), _p(dZ), _p(dU), None, _p(dZn), _p(dFz), _p(dFu), _p(dstatus), _p(diters), flags,
+                                                C.c_void_p(int(stream)))
+        self._check(rc, "dojo_step_grad_gather_async")

@@ -200,6 +200,34 @@ int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, co
                          double* dFu, int32_t* dstatus, int32_t* diters, uint32_t flags,
                          void* cuda_stream);
 
+/* ---- Multi-GPU: environments shard over the GPUs of a box, one process + one handle per GPU -------------------------
+ * The reference is single-process; BASELINE.json's north_star asks for ONE exchange per step: every rank receives the next states
+ * of the whole batch.  It is fused into the step kernel: each environment's next state is written, as soon as it is solved, straight
+ * into the gathered buffer of every rank (peer memory mapped through CUDA IPC: NVLink / NVSwitch posted writes), so the exchange
+ * overlaps the solve and its tail instead of following the kernel as a collective.  No NCCL is involved; a Julia host binds these
+ * like every other entry point.
+ *   dojo_gather_create   allocates this rank's gathered buffer [13Nb x B_local x world] (rank r's slice at r * B_local) + a counter
+ *   dojo_gather_export   the 128-byte IPC descriptor of this rank (exchange them with any host-side all-gather: MPI, torch.distributed ...)
+ *   dojo_gather_connect  maps the buffers of all ranks (descriptors in rank order, world x 128 bytes)
+ *   dojo_step_gather_async / dojo_step_grad_gather_async
+ *                        dojo_step_async / dojo_step_grad_async + the exchange; on return of the stream work the gathered buffer of THIS
+ *                        rank holds the next states of all ranks (a small wait kernel closes the step: it returns once every CTA of
+ *                        every rank has signalled; it gives up after ~10 s and reports DOJO_STATUS_NONFINITE in status[0] if a peer died)
+ * All ranks must call with the same B_local and the same sequence of steps. */
+#define DOJO_MAX_GATHER_RANKS 8
+#define DOJO_GATHER_HANDLE_BYTES 128
+typedef struct DojoGather DojoGather;
+int dojo_gather_create(DojoHandle* h, int world, int rank, int B_local, DojoGather** out);
+int dojo_gather_export(DojoGather* g, void* handle_out /* DOJO_GATHER_HANDLE_BYTES */);
+int dojo_gather_connect(DojoGather* g, const void* all_handles /* world x DOJO_GATHER_HANDLE_BYTES, rank order */);
+double* dojo_gather_buffer(DojoGather* g); /* device pointer, [13Nb x (world * B_local)] */
+int dojo_gather_destroy(DojoGather* g);
+int dojo_step_gather_async(DojoHandle* h, DojoGather* g, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU,
+                           const double* dFext, double* dZ_next, int32_t* dstatus, int32_t* diters, uint32_t flags, void* cuda_stream);
+int dojo_step_grad_gather_async(DojoHandle* h, DojoGather* g, const DojoSolverOptions* opts, int B, const double* dZ, const double* dU,
+                                const double* dFext, double* dZ_next, double* dFz, double* dFu, int32_t* dstatus, int32_t* diters,
+                                uint32_t flags, void* cuda_stream);
+
 /* get_contact_gradients(mechanism) (src/gradients/contact.jl:1-55; data blocks src/gradients/data.jl:152-192): step! and the
  * gradients with respect to the contact data theta_c = [friction_coefficient; contact_radius; contact_origin(3)] of every
  * contact, next to the state / control gradients (the reference returns jacobian_state with jacobian_contact):

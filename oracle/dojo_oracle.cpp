@@ -2188,6 +2188,34 @@ void oracle_step_batch_threads(const DojoMechanismDesc* d, const DojoSolverOptio
   }
   for (auto& th : pool) th.join();
 }
+// step! + get_maximal_gradients for a batch on `nthreads` threads (bench.py --impl reference --mode grad).  Fz / Fu may be null: the
+// Jacobians are then computed into per-thread scratch and dropped (12Nb x 12Nb doubles per environment do not fit a host buffer at
+// benchmark batch sizes); use_factor selects the block-LDU back-solve instead of the reference's dense solmat \ datamat.
+void oracle_step_grad_batch_threads(const DojoMechanismDesc* d, const DojoSolverOptions* opts, int B, const double* Z, const double* U, double* Zn,
+                                    double* Fz, double* Fu, int32_t* status, int32_t* iters, int nthreads, int use_factor, uint32_t flags) {
+  nthreads = std::max(1, std::min(nthreads, B));
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t) {
+    pool.emplace_back([=]() {
+      Oracle o(*d);
+      int lo = (int)((long long)B * t / nthreads), hi = (int)((long long)B * (t + 1) / nthreads);
+      const int nz = 13 * o.Nb;
+      const size_t ns = 12 * (size_t)o.Nb;
+      std::vector<double> fz(ns * ns), fu(ns * (size_t)o.nu);
+      for (int e = lo; e < hi; ++e) {
+        int it = 0;
+        int st = o.step(*opts, Z + (size_t)e * nz, U + (size_t)e * o.nu, nullptr, Zn + (size_t)e * nz, nullptr, &it, flags);
+        if (flags & DOJO_FLAG_Q2_LITERAL_GRADIENTS) o.update_state();
+        double* pz = Fz ? Fz + (size_t)e * ns * ns : fz.data();
+        double* pu = Fu ? Fu + (size_t)e * ns * o.nu : fu.data();
+        if (!o.maximal_gradients(pz, pu, use_factor != 0) && st == 0) st = DOJO_STATUS_NONFINITE;
+        if (status) status[e] = st;
+        if (iters) iters[e] = it;
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+}
 int oracle_step_grad(void* h, const DojoSolverOptions* opts, const double* z, const double* u, const double* fext, double* z_next,
                      double* Fz, double* Fu, int32_t* iters, uint32_t flags, int use_factor) {
   Oracle* o = static_cast<Oracle*>(h);

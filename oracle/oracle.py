@@ -48,6 +48,7 @@ def lib():
         L.oracle_step.restype = C.c_int
         L.oracle_step_batch.argtypes = [vp, op, C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_uint32]
         L.oracle_step_batch_threads.argtypes = [C.POINTER(capi.DojoMechanismDesc), op, C.c_int, dp, dp, dp, ip, ip, C.c_int]
+        L.oracle_step_grad_batch_threads.argtypes = [C.POINTER(capi.DojoMechanismDesc), op, C.c_int, dp, dp, dp, dp, dp, ip, ip, C.c_int, C.c_int, C.c_uint32]
         L.oracle_step_grad.argtypes = [vp, op, dp, dp, dp, dp, dp, dp, ip, C.c_uint32, C.c_int]
         L.oracle_step_grad.restype = C.c_int
         L.oracle_set_state.argtypes = [vp, dp, dp, dp]
@@ -277,3 +278,23 @@ def step_batch_threads(mech, Z, U, opts=None, nthreads=1):
     o = opts if opts is not None else capi.solver_options()
     L.oracle_step_batch_threads(C.byref(desc), C.byref(o), B, _d(Z), _d(U), _d(Zn), capi.iptr(st), capi.iptr(it), int(nthreads))
     return Zn, st, it
+
+
+def step_grad_batch_threads(mech, Z, U, opts=None, nthreads=1, keep=False, use_factor=False, flags=0):
+    """step! + get_maximal_gradients for a batch on `nthreads` C++ threads.  keep=False drops the Jacobians (timing only).
+    Returns (Zn, status, iters[, Fz [B, 12Nb, 12Nb] column-major per environment, Fu])."""
+    L = lib()
+    desc, _keep = capi.flatten(mech)
+    Z = np.ascontiguousarray(Z, dtype=float)
+    U = np.ascontiguousarray(U, dtype=float)
+    B = Z.shape[0]
+    ns = 12 * mech.Nb
+    Zn = np.empty_like(Z)
+    st = np.zeros(B, dtype=np.int32)
+    it = np.zeros(B, dtype=np.int32)
+    Fz = np.empty((B, ns, ns)) if keep else None
+    Fu = np.empty((B, mech.nu, ns)) if keep else None
+    o = opts if opts is not None else capi.solver_options()
+    L.oracle_step_grad_batch_threads(C.byref(desc), C.byref(o), B, _d(Z), _d(U), _d(Zn), _d(Fz), _d(Fu), capi.iptr(st), capi.iptr(it), int(nthreads),
+                                     int(use_factor), int(flags))
+    return (Zn, st, it, Fz, Fu) if keep else (Zn, st, it)

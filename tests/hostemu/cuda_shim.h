@@ -233,6 +233,8 @@ template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return 
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
+template <class T> inline T atomicAdd_system(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline void __threadfence_block() {}
 inline void __nanosleep(unsigned) { emu::yield(); }
 inline long long clock64() { return 0; }

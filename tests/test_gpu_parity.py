@@ -17,12 +17,13 @@ from conftest import jittered_states, random_inputs
 
 pytestmark = pytest.mark.gpu
 
-TOL_SAME_PATH = 1e-6
+TOL_SAME_PATH = 1e-6    # every same-iteration environment (3.3e-7 measured once in 3072 ant environments in hard contact) ...
+TOL_SAME_Q99 = 1e-9     # ... and 99 % of them (SURVEY.md 8c asks for 1e-9; the median is ~1e-13)
 # environments that take a different number of Newton iterations on the two paths (a rounding-level flip of a convergence /
 # line-search comparison) stop on different iterates of the same central path: with the reference defaults (rtol 1e-6, btol 1e-4)
 # their next states differ by up to ~1e-2 in the velocity of a light link (measured on B200, quadruped: 7.7e-3; kernel emulation
 # on the CPU: 4.6e-3, same step sequence), typically 1e-6 .. 1e-3
-TOL_SOLVER = 2e-2
+TOL_SOLVER = 5e-3
 
 
 def _contact_modes(mech, sol):
@@ -31,7 +32,7 @@ def _contact_modes(mech, sol):
     return s[:, :, 4] > s[:, :, 0]
 
 
-def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03, tol_same=TOL_SAME_PATH, tol_all=TOL_SOLVER):
+def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.01, tol_same=TOL_SAME_PATH, tol_all=TOL_SOLVER):
     from dojo_jl_b200.solver import BatchedStepper
     from oracle.oracle import Oracle
     mech = dj.get_mechanism(name)
@@ -40,6 +41,7 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03, tol_
     stepper = BatchedStepper(mech, B)
     oracle = Oracle(mech, opts)
     total = mismatched = 0
+    same_errs = []
     for t in range(T):
         U = random_inputs(mech, B, rng, scale)
         Zg, sg, ig, solg = stepper.step(Z, U, opts=opts, return_sol=True)
@@ -49,13 +51,15 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03, tol_
         for e in range(B):
             Zo[e], so[e], io[e], solo[e] = oracle.step(Z[e], U[e], return_sol=True)
         # an environment that runs out of Newton iterations on one path (:failed) while the other converges on its last
-        # iterations is a tolerance-edge event; it is counted in the mismatch budget, everything else must agree
+        # iterations is a tolerance-edge event (the two paths stagnate around the tolerance for dozens of iterations); it is counted in
+        # the mismatch budget, everything else must agree
         edge = (sg != so) & (np.maximum(ig, io) >= 45)
         assert ((sg == so) | edge).all(), f"{name} step {t}: status differs"
         conv = (so == 0) & (sg == 0)  # :failed environments end on an arbitrary unconverged iterate
         same = (ig == io) & conv
         err = np.abs(Zg - Zo).max(axis=1)
         assert err[same].max(initial=0.0) <= tol_same, f"{name} step {t}: {err[same].max()}"
+        same_errs.append(err[same])
         assert err[conv].max(initial=0.0) <= tol_all, f"{name} step {t}: {err[conv].max()}"
         if mech.Ni:
             assert (_contact_modes(mech, solg)[same] == _contact_modes(mech, solo)[same]).all()
@@ -63,7 +67,21 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.03, tol_
         mismatched += int((conv & (ig != io)).sum()) + int(edge.sum())
         Z = Zo
     assert mismatched <= max_mismatch * total, f"{name}: {mismatched}/{total} environments took a different iteration count"
+    same_errs = np.concatenate(same_errs)
+    assert np.quantile(same_errs, 0.99) <= TOL_SAME_Q99, f"{name}: 99 % quantile of the same-iteration error {np.quantile(same_errs, 0.99)}"
+    _record_stats(name, {"B": B, "T": T, "env_steps": total, "iteration_mismatches": mismatched, "max_err_same_iters": float(same_errs.max()),
+                         "q99_err_same_iters": float(np.quantile(same_errs, 0.99)), "median_err_same_iters": float(np.median(same_errs))})
     return mismatched, total
+
+
+def _record_stats(name, d):
+    """measured parity statistics next to the verdict of the test (gpurun_out/ is brought back from the GPU box)"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_stats.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **d}) + "\n")
 
 
 def test_pendulum_1000_steps():
@@ -101,13 +119,83 @@ def test_step_parity(name, B, T, scale):
 
 
 def test_step_parity_tight_tolerances():
-    """rtol = btol = 1e-8: both paths converge to the same solution, so ALL converged environments must agree to 5e-5
-    (TOL_SOLVER scaled by the tolerance ratio 1e-8 / 1e-6; 1.1e-5 observed on one ill-conditioned environment) whatever
-    their iteration counts (a count can differ by one when a violation lands within rounding of the tolerance).
-    1e-8 is the tightest supported setting of the CUDA path this round: its condensed no-pivot block LDU reaches a linear
-    residual of ~3e-9 on ant (the oracle's reference-order LDU ~2e-10, dense LU ~1e-15), see DESIGN.md §6."""
-    _compare_rollout("ant", 48, 12, seed=11, scale=1.0, opts=capi.solver_options(rtol=1e-8, btol=1e-8), max_mismatch=1.0,
-                     tol_same=1e-7, tol_all=5e-5)
+    """rtol = btol = 1e-10 (round 1 stalled below ~1e-8: both sides of every joint limit were condensed through 1 / s; the kept limit
+    dual now lives in the joint's node, dojo_plan.h joint_nq): the CUDA path converges wherever the oracle does -- identical status
+    for EVERY environment -- and all converged environments agree to 1e-6 whatever their iteration counts (the reference's own
+    conservation tests run at 1e-12, test/momentum.jl:154-218).  Same case on the CPU emulation: tests/test_tight_tolerances.py."""
+    from dojo_jl_b200.solver import BatchedStepper
+    from oracle.oracle import step_batch_threads
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(29)
+    B = 96
+    Z = jittered_states(mech, B, rng)
+    stepper = BatchedStepper(mech, B)
+    for _ in range(14):
+        Z, _, _ = stepper.step(Z, random_inputs(mech, B, rng, 1.0))
+    for tol in (1e-10, 1e-12):
+        opts = capi.solver_options(rtol=tol, btol=tol)
+        U = random_inputs(mech, B, rng, 1.0)
+        Zg, sg, ig = stepper.step(Z, U, opts=opts)
+        Zo, so, io = step_batch_threads(mech, Z, U, opts, 8)
+        conv = (so == 0) & (sg == 0)
+        assert conv.sum() >= B // 2
+        if tol == 1e-10:
+            assert np.array_equal(sg, so), (tol, np.where(sg != so)[0], ig[sg != so], io[sg != so])
+        else:  # at 1e-12 both paths sit on their rounding floor: a few environments may end on different sides of the tolerance
+            assert (sg != so).sum() <= max(2, B // 20), (tol, (sg != so).sum())
+        err = np.abs(Zg - Zo)[conv].max(axis=1)  # ill-conditioned contact solves amplify rounding: 1.1e-6 seen on one environment
+        assert err.max() < 1e-5 and np.quantile(err, 0.9) < 1e-8 and np.median(err) < 1e-10, (err.max(), np.quantile(err, 0.9), np.median(err))
+
+
+def test_two_handles_share_kernels():
+    """Handles of different mechanisms share the kernel symbols (the dynamic shared-memory attribute belongs to the function, not to
+    the handle): a small mechanism created after a large one must not break the large one's launches, in either order."""
+    from dojo_jl_b200.solver import BatchedStepper
+    ant, pend = dj.get_mechanism("ant"), dj.get_mechanism("pendulum")
+    rng = np.random.default_rng(47)
+    Za = jittered_states(ant, 8, rng)
+    Ua = random_inputs(ant, 8, rng)
+    s_ant = BatchedStepper(ant, 8)
+    ref = s_ant.step(Za, Ua)
+    s_pend = BatchedStepper(pend, 4)                      # created later, needs a few KB only
+    zp = s_pend.step(np.tile(pend.z0, (4, 1)), np.zeros((4, 1)))[0]
+    again = s_ant.step(Za, Ua)                            # the large handle still launches
+    assert all(np.array_equal(a, b) for a, b in zip(ref, again)) and np.isfinite(zp).all()
+    s_atlas = BatchedStepper(dj.get_mechanism("atlas"), 4)  # larger than both
+    atlas = dj.get_mechanism("atlas")
+    za = s_atlas.step(np.tile(atlas.z0, (4, 1)), np.zeros((4, atlas.nu)))[0]
+    assert np.isfinite(za).all()
+    assert all(np.array_equal(a, b) for a, b in zip(ref, s_ant.step(Za, Ua)))
+    g1 = s_ant.step_grad(Za, Ua)
+    s_pend.step_grad(np.tile(pend.z0, (4, 1)), np.zeros((4, 1)))
+    g2 = s_ant.step_grad(Za, Ua)
+    assert all(np.array_equal(a, b) for a, b in zip(g1, g2))
+
+
+def test_calls_on_different_streams_are_ordered():
+    """One call in flight per handle (include/dojo_b200.h): async calls issued on different streams are ordered by the library, so
+    two back-to-back steps on two streams give the results of the same steps issued on one stream."""
+    import torch
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(53)
+    B = 600
+    Z = torch.from_numpy(jittered_states(mech, 32, rng)[rng.integers(0, 32, B)]).cuda()
+    U = torch.from_numpy(random_inputs(mech, B, rng)).cuda()
+    st = BatchedStepper(mech, B)
+    Z1, Z2 = torch.empty_like(Z), torch.empty_like(Z)
+    s0 = torch.cuda.current_stream()
+    st.step_device(Z.data_ptr(), U.data_ptr(), Z1.data_ptr(), B, stream=s0.cuda_stream)
+    st.step_device(Z1.data_ptr(), U.data_ptr(), Z2.data_ptr(), B, stream=s0.cuda_stream)
+    torch.cuda.synchronize()
+    ref1, ref2 = Z1.clone(), Z2.clone()
+    Z1.zero_(); Z2.zero_()
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    st.step_device(Z.data_ptr(), U.data_ptr(), Z1.data_ptr(), B, stream=sa.cuda_stream)
+    st.step_device(Z1.data_ptr(), U.data_ptr(), Z2.data_ptr(), B, stream=sb.cuda_stream)  # consumes Z1 and the handle's work queue
+    torch.cuda.synchronize()
+    assert torch.equal(Z1, ref1) and torch.equal(Z2, ref2)
 
 
 def test_q1_literal_return_flag():
@@ -365,3 +453,33 @@ def test_q2_literal_gradients(name):
     assert len(errs) >= B // 2
     assert np.median(errs) < 1e-7 and errs.max() < 1e-2, errs
     assert np.median(diff) > 1e-4  # the literal result is a different matrix
+
+
+@pytest.mark.parametrize("name,B,sample", [("ant", 4096, 768), ("quadruped", 8192, 512)])
+def test_parity_on_the_benchmarked_states(name, B, sample):
+    """The batch bench.py TIMES (BASELINE C1: ant B = 4096 after its 20-step roll-in in hard contact; C2: quadruped B = 8192, stance
+    episodes), not jittered test states: a random subset against the oracle -- identical status, iteration count and contact-mode
+    bitmap (gamma_1 > s_1 per contact) for every sampled environment, states to the same-path tolerance.  (Round 1 allowed 3 % of
+    the environments a different iteration count; with the joint-limit duals in the joint node none of 4608 sampled environments
+    differed on B200.)  bench.py reports the same comparison as rates in its JSON line."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import bench
+    from parity_bench_states import compare
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism(name)
+    w = bench.WORKLOADS[name]
+    Z, rng = bench.synthetic_batch(mech, B, 0xD0D0 + 1, name)
+    steps = w["rollin"] + 3 if not w["episode"] else 5
+    U = bench.random_inputs(mech, rng, steps + 1, B, bench.SCALE[name])
+    st = BatchedStepper(mech, B)
+    for t in range(steps):
+        Z, _, _ = st.step(Z, U[t])
+    r = compare(mech, Z, U[steps], st, sample, seed=1)
+    _record_stats("bench_states_" + name, r)
+    assert r["status_mismatch"] == 0 and r["contact_mode_mismatch_all_converged"] == 0, r
+    assert r["iters_mismatch"] <= max(1, sample // 200), r          # <= 0.5 %
+    assert r["max_abs_dz_same_iters"] <= TOL_SAME_PATH and r["median_abs_dz_same_iters"] <= 1e-11, r
