@@ -116,14 +116,15 @@ function Dojo.step!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opt
     return Zn
 end
 
-"batched get_maximal_gradients!"
-function Dojo.get_maximal_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+"batched get_maximal_gradients!.  literal_q2 = true reproduces what the single-environment get_maximal_gradients! literally returns (data
+ Jacobian built after update_state!, gradients/state.jl:69-76; DOJO_FLAG_Q2_LITERAL_GRADIENTS); the default is the consistent IFT gradient."
+function Dojo.get_maximal_gradients!(mech::Mechanism, Z::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}(), literal_q2 = false)
     h = handle(mech); B = size(Z, 2)
     Zn = similar(Z); Fz = zeros(h.ng, h.ng, B); Fu = zeros(h.ng, h.nu, B)
     status = zeros(Int32, B); iters = zeros(Int32, B)
     rc = ccall((:dojo_step_grad, LIB), Cint,
                (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32),
-               h.ptr, COptions(opts), B, Z, U, C_NULL, Zn, Fz, Fu, status, iters, 0)
+               h.ptr, COptions(opts), B, Z, U, C_NULL, Zn, Fz, Fu, status, iters, literal_q2 ? 2 : 0)
     rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
     return Fz, Fu
 end
@@ -245,6 +246,37 @@ function rollout(mech::Mechanism, Z0::Matrix{Float64}, U::Array{Float64,3}; opts
     rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
     return Zf, traj
 end
+
+# ---- multi-GPU: one Julia process per GPU (e.g. MPI.jl ranks or Distributed workers); the exchange of the next states is fused into
+# the step kernel (peer writes over NVLink, include/dojo_b200.h "Multi-GPU"): no NCCL.jl needed.  `allgather_bytes` is any host-side
+# all-gather of a 128-byte blob per rank (MPI.Allgather, a shared file, ...), used ONCE at set-up.
+mutable struct Gather
+    ptr::Ptr{Cvoid}; world::Int; rank::Int; B::Int
+end
+function Gather(mech::Mechanism, world::Integer, rank::Integer, B_local::Integer, allgather_bytes::Function)
+    h = handle(mech); g = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:dojo_gather_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), h.ptr, world, rank, B_local, g)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    mine = zeros(UInt8, 128)
+    ccall((:dojo_gather_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g[], mine) == 0 || error("dojo_gather_export")
+    all = allgather_bytes(mine)::Vector{UInt8}                       # world * 128 bytes, rank order
+    ccall((:dojo_gather_connect, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), g[], all) == 0 ||
+        error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    gd = Gather(g[], world, rank, B_local)
+    finalizer(x -> ccall((:dojo_gather_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), gd)
+    return gd
+end
+"step! of this rank's shard (device pointers, e.g. CuArray pointers) + exchange: afterwards `gathered(g)` on every rank holds the next
+ states of all ranks, 13Nb x (world * B_local)"
+function step_gather!(mech::Mechanism, g::Gather, dZ::Ptr{Float64}, dU::Ptr{Float64}, dZn::Ptr{Float64}; opts = SolverOptions{Float64}(), stream = C_NULL)
+    h = handle(mech)
+    rc = ccall((:dojo_step_gather_async, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32, Ptr{Cvoid}),
+               h.ptr, g.ptr, COptions(opts), g.B, dZ, dU, C_NULL, dZn, C_NULL, C_NULL, 0, stream)
+    rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
+    return nothing
+end
+gathered(g::Gather) = ccall((:dojo_gather_buffer, LIB), Ptr{Float64}, (Ptr{Cvoid},), g.ptr)   # device pointer
 
 "B = 1 drop-in for mehrotra!(mechanism; opts): runs the step on the GPU and writes vsol / wsol back into the Mechanism"
 function mehrotra_gpu!(mech::Mechanism; opts = SolverOptions{Float64}())

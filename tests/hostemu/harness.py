@@ -58,6 +58,21 @@ class HostEmu:
         self.L.hostemu_step(self.h, C.byref(o), B, T, _p(Z), _p(U), _p(fext), _p(Zn), _p(sol), _p(st), _p(it), flags, slots, int(smem_plan), grid, _p(traj))
         return (Zn, st, it, sol, traj) if record else (Zn, st, it, sol)
 
+    def step_gather(self, Z, U, rank, bufs, flags, slots=2, grid=2, opts=None):
+        """dojo_step_gather_async for one rank: bufs[r] = gathered buffer of rank r [world * B, nz], flags[r] = its counter (uint64[1])."""
+        Z = np.ascontiguousarray(np.atleast_2d(Z), dtype=np.float64)
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        B, world = Z.shape[0], len(bufs)
+        Zn = np.empty_like(Z)
+        st, it = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        pb = (C.c_void_p * world)(*[b.ctypes.data for b in bufs])
+        pf = (C.c_void_p * world)(*[f.ctypes.data for f in flags])
+        o = opts if opts is not None else capi.solver_options()
+        self.L.hostemu_step_gather.argtypes = [_vp, C.POINTER(capi.DojoSolverOptions), _ip, _vp, _vp, _vp, _vp, _vp, _ip, _ip, _vp, _vp, _ip, _ip]
+        rc = self.L.hostemu_step_gather(self.h, C.byref(o), B, _p(Z), _p(U), _p(Zn), _p(st), _p(it), world, rank, pb, pf, slots, grid)
+        assert rc == 0
+        return Zn, st, it
+
     def step_grad(self, Z, U=None, opts=None, slots=1, slots_grad=1, smem_plan=True, publish_order=True, contact=False, flags=0):
         """dojo_step_grad (contact=True: dojo_step_grad_contact).  Returns (Z_next, Fz [B, 12Nb, 12Nb], Fu [B, 12Nb, nu][, Fc [B, 12Nb, 5Ni]],
         status, iters)."""

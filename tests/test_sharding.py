@@ -42,3 +42,29 @@ def test_all_gather_states_gloo_world2(batch):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, batch, 13, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_fused_gather_kernel_side_on_the_emulation():
+    """dojo_step_gather_async, kernel side (the CUDA IPC mapping and the wait kernel need GPUs: tests/test_zz_gpu_gather.py): two
+    "ranks" step their shards on the CPU emulation of the step kernel; each rank's epilogue writes into BOTH gathered buffers, every
+    CTA counts itself in on both counters.  Afterwards both buffers hold [shard 0 | shard 1] and both counters the number of CTAs."""
+    import dojo_jl_b200 as dj
+    from conftest import jittered_states, random_inputs
+    from hostemu.harness import HostEmu
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(61)
+    B, world, grid = 5, 2, 2
+    emu = HostEmu(mech)
+    bufs = [np.full((world * B, mech.nz), np.nan) for _ in range(world)]
+    flags = [np.zeros(1, dtype=np.uint64) for _ in range(world)]
+    outs = []
+    for r in range(world):
+        Z, U = jittered_states(mech, B, rng), random_inputs(mech, B, rng)
+        Zn, st, it = emu.step_gather(Z, U, r, bufs, flags, slots=2, grid=grid)
+        Zref, st2, it2, _ = emu.step(Z, U, slots=2, grid=grid)
+        assert np.array_equal(Zn, Zref) and np.array_equal(it, it2)  # the exchange does not change the step
+        outs.append(Zn)
+    full = np.concatenate(outs)
+    for r in range(world):
+        assert np.array_equal(bufs[r], full)
+        assert int(flags[r][0]) == world * grid

@@ -3,7 +3,8 @@
 # Dumps, for pendulum / ant / quadruped / atlas and the widened models (contact types, translational springs / dampers / limits):
 # the flattened mechanism (same fields as include/dojo_b200.h, with explicit
 # name -> index maps because the body order is Dict-hash order), N random (z, u), and the reference results
-# z_next (true and Q1-literal), the solution vector, iteration counts, full_matrix(system) and get_maximal_gradients.
+# z_next (true and Q1-literal), the solution vector, iteration counts, full_matrix(system) and get_maximal_gradients (consistent: right
+# after mehrotra!; literal: get_maximal_gradients!, i.e. after update_state!).  Loader: tests/test_julia_fixtures.py.
 using Dojo, DojoEnvironments, JSON, Random, LinearAlgebra
 include(joinpath(@__DIR__, "..", "ext", "DojoB200.jl"))
 out = length(ARGS) > 0 ? ARGS[1] : "fixtures"; mkpath(out)
@@ -31,8 +32,9 @@ for (name, kw, tag) in configs
         solmat = Dojo.full_matrix(m1.system)
         Fz, Fu = Dojo.get_maximal_gradients(m1)
         znext_q1 = step!(deepcopy(mech), z, u)
+        Fz_lit, Fu_lit = get_maximal_gradients!(deepcopy(mech), z, u)   # the literal result (data Jacobian after update_state!, SURVEY Q2)
         push!(cases, Dict("z" => z, "u" => u, "status" => String(status), "sol" => sol, "z_next" => znext_true, "z_next_q1" => znext_q1,
-                          "solmat" => vec(solmat), "Fz" => vec(Fz), "Fu" => vec(Fu)))
+                          "solmat" => vec(solmat), "Fz" => vec(Fz), "Fu" => vec(Fu), "Fz_literal" => vec(Fz_lit), "Fu_literal" => vec(Fu_lit)))
         z = znext_true
     end
     open(joinpath(out, "$(tag).json"), "w") do io
