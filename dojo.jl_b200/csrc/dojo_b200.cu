@@ -101,6 +101,7 @@ struct DojoHandle {
   cudaStream_t copy_stream = nullptr;
   int grad_chunk = 0;
   char* d_blob = nullptr;  // plan tables (one contiguous upload)
+  int nsteps = 0;  // elimination steps of the block LDU
   int blob_bytes = 0, blob_off[8] = {0, 0, 0, 0, 0, 0, 0, 0}, blob_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_smem_off = -1, plan_smem_off_grad = -1;  // doubles; -1: the tables stay in global memory
   int plan_smem_bytes = 0, plan_smem_bytes_grad = 0, plan_smem_mask = 0, plan_smem_mask_grad = 0;  // prefix of the blob kept in shared memory / tables inside it
@@ -338,7 +339,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
       J.Up_off = a; a += 6 * nq;
       J.Lp_off = a; a += 6 * nq;
       // body-body coupling exists with dampers and with (condensed) joint limits
-      if (J.damper_r != 0.0 || J.nb2_r > 0 || (J.flags & JF_TRA_DAMPER)) { J.BBpc_off = a; a += 36; J.BBcp_off = a; a += 36; } else { J.BBpc_off = J.BBcp_off = -1; }
+      // (rotational terms touch the angular rows only: 3 x 6 and 3 x 3; translational dampers / limits need the full blocks)
+      const bool bb_full = (J.flags & JF_FULL) != 0;
+      if (J.damper_r != 0.0 || J.nb2_r > 0 || (J.flags & JF_TRA_DAMPER)) { J.BBpc_off = a; a += bb_full ? 36 : 18; J.BBcp_off = a; a += bb_full ? 36 : 9; } else { J.BBpc_off = J.BBcp_off = -1; }
     } else { J.Up_off = J.Lp_off = J.BBpc_off = J.BBcp_off = -1; }
   }
   P.mat_len = a - P.mat_off;
@@ -459,15 +462,20 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
           if (joint_nq(J) > 0) {
             ij = s.nnb++;
             s.nb[ij].n = joint_nq(J); s.nb[ij].vec_off = J.sol_off; s.nb[ij].r_off = J.r_off; s.nb[ij].gv_off = -1; s.nb[ij].fwd_abs = -1; s.nb[ij].L_off = J.Uc_off; s.nb[ij].U_off = J.Lc_off; s.nb[ij].U_k = 6; s.nb[ij].U_row = 0;
+            s.nb[ij].ld = joint_nq(J); s.nb[ij].row0 = 0;
           }
+          int r0 = 0;  // first row of the parent body the coupling reaches: 3 (angular rows only) unless the joint carries full blocks
           if (J.parent >= 0 && J.BBpc_off >= 0) {
             ip = s.nnb++;
             const BodyDev& Pb = bodies[J.parent];
-            s.nb[ip].n = 6; s.nb[ip].vec_off = Pb.sol_off; s.nb[ip].r_off = Pb.r_off; s.nb[ip].gv_off = J.gv_off; s.nb[ip].fwd_abs = J.S_off + 36; s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6; s.nb[ip].U_row = 0;
+            r0 = (J.flags & JF_FULL) ? 0 : 3;
+            s.nb[ip].n = 6 - r0; s.nb[ip].vec_off = Pb.sol_off + r0; s.nb[ip].r_off = Pb.r_off + r0; s.nb[ip].gv_off = J.gv_off; s.nb[ip].fwd_abs = J.S_off + 36 + r0;
+            s.nb[ip].L_off = J.BBpc_off; s.nb[ip].U_off = J.BBcp_off; s.nb[ip].U_k = 6 - r0; s.nb[ip].U_row = r0;
+            s.nb[ip].ld = 6; s.nb[ip].row0 = r0;
           }
           if (ij >= 0) s.tgt[ij][ij] = J.D_off;
-          if (ip >= 0) s.tgt[ip][ip] = J.S_off;
-          if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off; s.tgt[ip][ij] = J.Lp_off; }
+          if (ip >= 0) s.tgt[ip][ip] = J.S_off + 7 * r0;                                  // rows / columns r0.. of the 6 x 6 scratch
+          if (ij >= 0 && ip >= 0) { s.tgt[ij][ip] = J.Up_off + r0; s.tgt[ip][ij] = J.Lp_off + r0 * joint_nq(J); }  // columns r0.. of (joint, parent); rows r0.. of (parent, joint)
           h.height = hb; h.group = -1; h.cost = 4.0 + joint_nq(J) * 0.3;
           hs.push_back(h);
         }
@@ -480,6 +488,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
             const BodyDev& Pb = bodies[J.parent];
             s.nnb = 1;
             s.nb[0].n = 6; s.nb[0].vec_off = Pb.sol_off; s.nb[0].r_off = Pb.r_off; s.nb[0].gv_off = J.gv_off; s.nb[0].fwd_abs = J.S_off + 36; s.nb[0].L_off = J.Lp_off; s.nb[0].U_off = J.Up_off; s.nb[0].U_k = joint_nq(J); s.nb[0].U_row = 0;
+            s.nb[0].ld = 6; s.nb[0].row0 = 0;
             s.tgt[0][0] = J.S_off;
           }
           hj = hb + 1;
@@ -521,6 +530,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     }
   }
   P.nphase = nphase;
+  h->nsteps = (int)steps.size();
   // [hostemu:tables:end]
 
   // ---- device resources
@@ -658,6 +668,17 @@ extern "C" int dojo_num_grad_state(const DojoHandle* h) { return 12 * h->plan.Nb
 extern "C" int dojo_shared_bytes_per_env(const DojoHandle* h) { return (int)h->arena_bytes; }
 extern "C" int64_t dojo_launch_count(const DojoHandle* h) { return h->launches; }
 // debugging aid (DJ_PROFILE builds): cycle counters accumulated by thread 0 of every CTA; out[5]
+// launch configuration chosen by dojo_create (diagnostics: tools/prof_one.py prints it): [slots, slots_grad, gradient chunk width,
+// arena bytes, gradient arena bytes, dynamic smem forward, dynamic smem gradient, plan-in-smem mask forward, mask gradient, paired
+// line-search trials, elimination phases, elimination steps, plan blob bytes, warps per environment, resident CTAs / SM fwd, grad]
+extern "C" int dojo_debug_config(const DojoHandle* h, int* out) {
+  if (!h || !out) return DOJO_EINVAL;
+  const int v[16] = {h->slots, h->slots_grad, h->plan.ch, (int)h->arena_bytes, (int)h->grad_bytes, (int)h->smem_fwd, (int)h->smem_grad,
+                     h->plan_smem_mask, h->plan_smem_mask_grad, h->plan.ls_pair, h->plan.nphase, h->nsteps, h->blob_bytes, h->nw, h->envs_per_sm,
+                     h->envs_per_sm_grad};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return DOJO_OK;
+}
 extern "C" int dojo_debug_cycles(DojoHandle* h, unsigned long long* out) {
   cudaMemcpy(out, h->d_prof, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(h->d_prof, 0, 32 * sizeof(unsigned long long));

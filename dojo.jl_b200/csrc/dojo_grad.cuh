@@ -596,7 +596,7 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0, int n
       for (int j = 0; j < st.nnb; ++j) {
         const ElimNb& nb = st.nb[j];
         const double* L = A + nb.L_off;
-        double* tgt = nb.gv_off >= 0 ? A + nb.gv_off + gvo : V + nb.r_off * ch;
+        double* tgt = nb.gv_off >= 0 ? A + nb.gv_off + gvo + nb.row0 * ch : V + nb.r_off * ch;  // row0: sub-range of the parent's scratch rows
         for (int i = 0; i < nb.n; ++i) {
           double acc = 0.0;
 #pragma unroll
@@ -620,11 +620,11 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0, int n
         const ElimNb& nb = st.nb[j];
         const double* U = A + nb.U_off;
         const double* xj = V + nb.r_off * ch;
-        for (int kk = 0; kk < nb.n; ++kk) {
+        for (int kk = 0; kk < nb.n; ++kk) {  // M_{c,nb} holds the rows [U_row, U_row + U_k) of c (all of them unless the coupling is angular only)
           double xv = xj[kk * ch + lane];
 #pragma unroll
           for (int r = 0; r < 6; ++r)
-            if (r < st.n) t[r] -= U[r * nb.n + kk] * xv;
+            if (r >= nb.U_row && r < nb.U_row + nb.U_k) t[r] -= U[(r - nb.U_row) * nb.n + kk] * xv;
         }
       }
       const double* Dc = A + st.d_off;

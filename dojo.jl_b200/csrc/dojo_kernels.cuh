@@ -796,14 +796,16 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
   }
 #endif
   if (JAC && coupled && jd.parent >= 0 && jd.BBpc_off >= 0) {
+    // the coupling touches the angular rows / columns only: (parent angular rows, child) is stored 3 x 6, (child angular rows,
+    // parent angular columns) 3 x 3 (dojo_plan.h ElimNb::row0); the linear columns of the former stay zero until the factorisation
     double* Mpc = A + jd.BBpc_off;
     double* Mcp = A + jd.BBcp_off;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int j2 = 0; j2 < 3; ++j2) {
-        Mpc[(3 + i) * 6 + 3 + j2] = Bpc.m[i][j2];
-        Mcp[(3 + i) * 6 + 3 + j2] = Bcp.m[i][j2];
+        Mpc[i * 6 + 3 + j2] = Bpc.m[i][j2];
+        Mcp[i * 3 + j2] = Bcp.m[i][j2];
       }
   }
   write_slot(A + jd.slot_c + c.sd, fl_c, fa_c, Kcc);
@@ -1073,7 +1075,7 @@ DJ_DEV bool factorize(Ctx& c) {
       DJ_FTICK(c, f_rm)
       for (int i = 0; i < st.nnb; ++i)
         for (int j = 0; j < st.nnb; ++j)                                                                  // M_ij -= L~_ic M_cj
-          schur_update(A + st.tgt[i][j], A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
+          schur_update(A + st.tgt[i][j], st.nb[j].ld, A + st.nb[i].L_off + st.nb[j].U_row, st.n, A + st.nb[j].U_off, st.nb[i].n, st.nb[j].U_k,
                        st.nb[j].n, l, mask);
       DJ_FTICK(c, f_schur)
     }

@@ -118,14 +118,14 @@ __device__ __noinline__ void right_multiply_generic(double* L, const double* Din
   __syncwarp(mask);
 }
 
-// C (ni x nj, ld = nj) -= A (ni x k, ld = lda) * B (k x nj, ld = nj)
-__device__ __noinline__ void schur_generic(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int l, unsigned mask) {
+// C (ni x nj, ld = ldc) -= A (ni x k, ld = lda) * B (k x nj, ld = nj)
+__device__ __noinline__ void schur_generic(double* C, int ldc, const double* A, int lda, const double* B, int ni, int k, int nj, int l, unsigned mask) {
   const int total = ni * nj;
   for (int e = l; e < total; e += 16) {
     int i = e / nj, j = e - i * nj;
     double acc = 0.0;
     for (int t = 0; t < k; ++t) acc += A[i * lda + t] * B[t * nj + j];
-    C[e] -= acc;
+    C[i * ldc + j] -= acc;
   }
   __syncwarp(mask);
 }
@@ -161,7 +161,7 @@ DJ_LA void right_multiply_t(double* L, const double* Dinv, int l, unsigned mask)
   __syncwarp(mask);
 }
 
-template <int NI, int K, int NJ>
+template <int NI, int K, int NJ, int LDC = NJ>
 DJ_LA void schur_t(double* C, const double* A, int lda, const double* B, int l, unsigned mask) {
   constexpr int SPR = (NJ + kStrip - 1) / kStrip;
   constexpr int NS = NI * SPR;
@@ -178,7 +178,7 @@ DJ_LA void schur_t(double* C, const double* A, int lda, const double* B, int l, 
     }
 #pragma unroll
     for (int c = 0; c < kStrip; ++c)
-      if (js + c < NJ) C[i * NJ + js + c] -= acc[c];
+      if (js + c < NJ) C[i * LDC + js + c] -= acc[c];
   }
   __syncwarp(mask);
 }
@@ -190,13 +190,17 @@ DJ_DEV void right_multiply_inplace(double* L, const double* Dinv, int m, int n, 
     default: right_multiply_generic(L, Dinv, m, n, l, mask);
   }
 }
-#define DJ_SC_CASE(NI, K, NJ) case ((NI) * 32 + (K)) * 32 + (NJ): schur_t<NI, K, NJ>(C, A, lda, B, l, mask); return;
-DJ_DEV void schur_update(double* C, const double* A, int lda, const double* B, int ni, int k, int nj, int l, unsigned mask) {
-  switch ((ni * 32 + k) * 32 + nj) {
+// ldc = nj (a whole block) or 6 (three columns of a block that belongs to a body: the angular part, dojo_plan.h ElimNb::ld)
+#define DJ_SC_CASE(NI, K, NJ) case (((NI) * 32 + (K)) * 32 + (NJ)) * 8 + (NJ): schur_t<NI, K, NJ>(C, A, lda, B, l, mask); return;
+#define DJ_SC_CASE_LD6(NI, K, NJ) case (((NI) * 32 + (K)) * 32 + (NJ)) * 8 + 6: schur_t<NI, K, NJ, 6>(C, A, lda, B, l, mask); return;
+DJ_DEV void schur_update(double* C, int ldc, const double* A, int lda, const double* B, int ni, int k, int nj, int l, unsigned mask) {
+  switch (((ni * 32 + k) * 32 + nj) * 8 + ldc) {
     DJ_SC_CASE(6, 6, 6)
     DJ_SC_CASE(5, 6, 5) DJ_SC_CASE(5, 6, 6) DJ_SC_CASE(6, 6, 5) DJ_SC_CASE(6, 5, 6)
     DJ_SC_CASE(3, 6, 3) DJ_SC_CASE(3, 6, 6) DJ_SC_CASE(6, 6, 3) DJ_SC_CASE(6, 3, 6)
-    default: schur_generic(C, A, lda, B, ni, k, nj, l, mask);
+    // body-body coupling through the angular rows (limits / dampers): (joint, parent) columns 3..5, (parent, joint) rows 3..5, parent diagonal
+    DJ_SC_CASE_LD6(6, 3, 3) DJ_SC_CASE_LD6(5, 3, 3) DJ_SC_CASE_LD6(3, 3, 3) DJ_SC_CASE(3, 6, 5)
+    default: schur_generic(C, ldc, A, lda, B, ni, k, nj, l, mask);
   }
 }
 

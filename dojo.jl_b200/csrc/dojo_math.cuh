@@ -7,6 +7,7 @@
 // rotation matrices and the *attitude* (body-frame) perturbation q (x) (1, d): see DESIGN.md §"Closed forms".
 #pragma once
 #include <math.h>
+#include <string.h>
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define DJ_DEV __device__ __forceinline__
@@ -216,8 +217,23 @@ DJ_DEV double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// fmax that propagates NaN like Julia's max (so a non-finite iterate is detected, not silently dropped)
-DJ_DEV double nanmax(double a, double b) { return (a != a || b != b) ? (a + b) : fmax(a, b); }
+// max that propagates NaN like Julia's max (so a non-finite iterate is detected, not silently dropped).  Every caller passes
+// magnitudes (|x|, or the result of an earlier nanmax starting from +0): for non-negative doubles the IEEE-754 bit patterns are
+// ordered like the values, and a NaN (sign cleared by fabs) has a larger pattern than +Inf -- so the 64-bit INTEGER maximum of the
+// two patterns is the NaN-propagating maximum: four integer instructions instead of two DSETP + DADD + the fp64 min/max emulation
+// (the violations are reduced with this in every residual evaluation; 4 % of the forward kernel's instructions before).
+DJ_DEV double nanmax(double a, double b) {
+#ifdef __CUDA_ARCH__
+  const long long ia = __double_as_longlong(a), ib = __double_as_longlong(b);
+  return __longlong_as_double(ia > ib ? ia : ib);
+#else
+  long long ia, ib;
+  memcpy(&ia, &a, 8); memcpy(&ib, &b, 8);
+  const long long im = ia > ib ? ia : ib;
+  double r; memcpy(&r, &im, 8);
+  return r;
+#endif
+}
 DJ_DEV double warp_nanmax(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));

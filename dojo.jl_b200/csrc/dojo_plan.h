@@ -57,7 +57,8 @@ struct JointDev {
                                 // solve and never written by the factorisation (lives in the constant region of the arena)
   int Up_off, Lp_off, Gp_off;   // same for the parent body (-1 when the parent is the origin); Lp is consumed by the
                                 // factorisation and refreshed from the pristine impulse map Gp at every assembly
-  int BBpc_off, BBcp_off;       // (parent,child) / (child,parent) 6x6 blocks, -1 without dampers
+  int BBpc_off, BBcp_off;       // body-body coupling through rotational limits / dampers, -1 without: (parent angular rows, child) 3 x 6
+                                // and (child angular rows, parent angular columns) 3 x 3; JF_FULL joints: full 6 x 6 blocks
   int slot_c, slot_p;           // contribution slots for the child / parent body (slot_p = -1 for the origin)
   int S_off;                    // scratch record receiving this joint's (and its child body's) updates of the parent body
   // gradient pass
@@ -114,6 +115,11 @@ struct ElimNb {
   int L_off;        // M_{nb,c}: n_nb x n_c   (overwritten by M_{nb,c} * Dinv_c)
   int U_off, U_k;   // M_{c,nb}: rows [U_row, U_row + U_k) of c, U_k x n_nb (never written by the factorisation)
   int U_row;
+  // A neighbour may stand for a SUB-RANGE of rows of its node: the parent body of a joint with rotational limits / dampers couples to
+  // the child body through its three angular rows only (round 2: those body-body blocks are stored 3 x 6 / 3 x 3 instead of 6 x 6 with
+  // exact zeros).  n, vec_off, r_off, fwd_abs and the tgt offsets below then address the sub-range directly;
+  int ld;           // leading dimension of the blocks whose COLUMNS belong to this neighbour's node (its full dimension: 6 for a body)
+  int row0;         // first row of the node covered by this neighbour (0, or 3 for the angular rows); only the gradient pass needs it
 };
 struct ElimStep {
   int d_off, n, vec_off;

@@ -1685,6 +1685,7 @@ struct Oracle {
   }
 
   // ---------------------------------------------------------------- mehrotra! (solver/mehrotra.jl:9-73)
+  int force_iters = -1;
   int mehrotra(const DojoSolverOptions& opts, int* iters_out) {
     for (ContactS& c : contacts)  // reset! (contacts/constraints.jl:79-86), neutral = [1,1,0,0]
       for (int idx = 0; idx < 2; ++idx) for (int i = 0; i < c.nh; ++i) { c.gam[idx][i] = c.neutral(i); c.s[idx][i] = c.neutral(i); }
@@ -1713,7 +1714,9 @@ struct Oracle {
     int n_done = 0;
     for (int n = 1; n <= opts.max_iter; ++n) {
       trace.push_back(rvio); trace.push_back(bvio); trace.push_back(alpha); trace.push_back(mutarget);
-      if ((rvio < opts.rtol) && (bvio < opts.btol)) { status = DOJO_STATUS_SUCCESS; break; }
+      // force_iters >= 0 (test hook, tests/test_gpu_parity.py): run EXACTLY that many Newton iterations -- the convergence test is skipped
+      // before, and taken for granted after -- so that the iterate of a path that stopped one comparison earlier / later can be reproduced
+      if (force_iters >= 0 ? (n > force_iters) : ((rvio < opts.rtol) && (bvio < opts.btol))) { status = DOJO_STATUS_SUCCESS; break; }
       n_done = n;
       // affine search direction (Quirk Q3: the rhs carries the previous mutarget)
       res_saved = rhs;                                   // pull_residual!
@@ -2142,6 +2145,7 @@ int oracle_num_residual(void* h) { return static_cast<Oracle*>(h)->nres; }
 int oracle_num_input(void* h) { return static_cast<Oracle*>(h)->nu; }
 int oracle_is_tree(void* h) { return static_cast<Oracle*>(h)->tree_ok ? 1 : 0; }
 void oracle_set_solver_mode(void* h, int mode) { static_cast<Oracle*>(h)->solver_mode = mode; }
+void oracle_set_force_iters(void* h, int n) { static_cast<Oracle*>(h)->force_iters = n; }
 void oracle_elimination_order(void* h, int32_t* out) {
   Oracle* o = static_cast<Oracle*>(h);
   for (size_t i = 0; i < o->elim_order.size(); ++i) out[i] = o->elim_order[i];

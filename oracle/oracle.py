@@ -43,6 +43,7 @@ def lib():
         dp, ip, vp = capi.c_double_p, capi.c_int32_p, C.c_void_p
         op = C.POINTER(capi.DojoSolverOptions)
         L.oracle_set_solver_mode.argtypes = [vp, C.c_int]
+        L.oracle_set_force_iters.argtypes = [vp, C.c_int]
         L.oracle_elimination_order.argtypes = [vp, ip]
         L.oracle_step.argtypes = [vp, op, dp, dp, dp, dp, dp, ip, C.c_uint32]
         L.oracle_step.restype = C.c_int
@@ -108,6 +109,15 @@ class Oracle:
         it = np.zeros(1, dtype=np.int32)
         st = self.L.oracle_step(self.h, C.byref(opts or self.opts), _d(z), _d(u), _d(fext), _d(zn), _d(sol), capi.iptr(it), flags)
         return (zn, st, int(it[0]), sol) if return_sol else (zn, st, int(it[0]))
+
+    def step_forced(self, z, u, iters, opts=None):
+        """step! with EXACTLY `iters` Newton iterations (the convergence test is skipped): the iterate a path reaches when a rounding-level
+        flip of the convergence comparison makes it stop one iteration earlier / later than this oracle would."""
+        self.L.oracle_set_force_iters(self.h, int(iters))
+        try:
+            return self.step(z, u, opts=opts)
+        finally:
+            self.L.oracle_set_force_iters(self.h, -1)
 
     def step_batch(self, Z, U, opts=None, flags=0):
         """Z [B x 13Nb], U [B x nu] (row = environment, i.e. the column-major [feature x B] buffer)."""

@@ -19,11 +19,15 @@ pytestmark = pytest.mark.gpu
 
 TOL_SAME_PATH = 1e-6    # every same-iteration environment (3.3e-7 measured once in 3072 ant environments in hard contact) ...
 TOL_SAME_Q99 = 1e-9     # ... and 99 % of them (SURVEY.md 8c asks for 1e-9; the median is ~1e-13)
-# environments that take a different number of Newton iterations on the two paths (a rounding-level flip of a convergence /
-# line-search comparison) stop on different iterates of the same central path: with the reference defaults (rtol 1e-6, btol 1e-4)
-# their next states differ by up to ~1e-2 in the velocity of a light link (measured on B200, quadruped: 7.7e-3; kernel emulation
-# on the CPU: 4.6e-3, same step sequence), typically 1e-6 .. 1e-3
-TOL_SOLVER = 5e-3
+# Environments that take a different number of Newton iterations on the two paths: a rounding-level flip of the convergence
+# comparison (rvio < rtol && bvio < btol) makes one path stop one iterate earlier / later on the SAME central path.  Consecutive
+# iterates near convergence differ by up to ~1e-2 with the reference defaults (rtol 1e-6, btol 1e-4; e.g. ant at rest: iterate 6 vs 7
+# = 8.1e-3, iterate 7 vs 8 = 7.5e-4), so a fixed bound on |z_gpu - z_oracle| says nothing there.  Instead the oracle is re-run with
+# EXACTLY the device's iteration count (Oracle.step_forced, a test hook that skips the convergence test) and must then agree like a
+# same-iteration environment (TOL_SAME_PATH).  What that does not explain -- a flipped line-search comparison earlier in the solve,
+# i.e. a different path -- is counted separately, must stay below TOL_SOLVER and below MAX_PATH_FLIPS of the environment-steps.
+TOL_SOLVER = 2e-2
+MAX_PATH_FLIPS = 0.002
 
 
 def _contact_modes(mech, sol):
@@ -40,8 +44,8 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.01, tol_
     Z = jittered_states(mech, B, rng) if mech.Nb > 1 else np.tile(mech.z0, (B, 1))
     stepper = BatchedStepper(mech, B)
     oracle = Oracle(mech, opts)
-    total = mismatched = 0
-    same_errs, conv_errs, problems = [], [], []
+    total = mismatched = path_flips = 0
+    same_errs, conv_errs, problems, forced_errs = [], [], [], []
     for t in range(T):
         U = random_inputs(mech, B, rng, scale)
         Zg, sg, ig, solg = stepper.step(Z, U, opts=opts, return_sol=True)
@@ -63,8 +67,15 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.01, tol_
             problems.append(f"{name} step {t}: same-iteration error {err[same].max()} > {tol_same}")
         same_errs.append(err[same])
         conv_errs.append(err[conv])
-        if err[conv].max(initial=0.0) > tol_all:
-            problems.append(f"{name} step {t}: converged-environment error {err[conv].max()} > {tol_all}")
+        for e in np.nonzero(conv & (ig != io))[0]:  # the oracle's iterate after exactly the device's number of iterations
+            zf, _, _ = oracle.step_forced(Z[e], U[e], int(ig[e]))
+            ef = float(np.abs(Zg[e] - zf).max())
+            forced_errs.append(ef)
+            if ef > tol_same:  # not a flip of the convergence test: a different path
+                path_flips += 1
+                if err[e] > tol_all:
+                    problems.append(f"{name} step {t}: environment {e} took {ig[e]} / {io[e]} iterations and differs by {err[e]} > {tol_all} "
+                                    f"({ef} from the oracle's iterate {ig[e]})")
         if mech.Ni and not (_contact_modes(mech, solg)[same] == _contact_modes(mech, solo)[same]).all():
             problems.append(f"{name} step {t}: contact-mode bitmap differs")
         total += B
@@ -73,9 +84,11 @@ def _compare_rollout(name, B, T, seed, scale, opts=None, max_mismatch=0.01, tol_
     same_errs, conv_errs = np.concatenate(same_errs), np.concatenate(conv_errs)
     _record_stats(name, {"B": B, "T": T, "env_steps": total, "iteration_mismatches": mismatched, "max_err_same_iters": float(same_errs.max()),
                          "q99_err_same_iters": float(np.quantile(same_errs, 0.99)), "median_err_same_iters": float(np.median(same_errs)),
-                         "max_err_converged": float(conv_errs.max()), "problems": problems[:6]})
+                         "max_err_converged": float(conv_errs.max()), "path_flips": path_flips,
+                         "max_err_vs_oracle_iterate_of_same_count": float(max(forced_errs, default=0.0)), "problems": problems[:6]})
     assert not problems, problems[:6]
     assert mismatched <= max_mismatch * total, f"{name}: {mismatched}/{total} environments took a different iteration count"
+    assert path_flips <= max(1, MAX_PATH_FLIPS * total), f"{name}: {path_flips}/{total} environments left the oracle's path"
     assert np.quantile(same_errs, 0.99) <= TOL_SAME_Q99, f"{name}: 99 % quantile of the same-iteration error {np.quantile(same_errs, 0.99)}"
     return mismatched, total
 

@@ -36,4 +36,5 @@ for t in range(pre + steps):
         s.step_device(Za.data_ptr(), U[t].data_ptr(), Zb.data_ptr(), B, dstatus=stt.data_ptr(), diters=it.data_ptr(), stream=st)
     Za, Zb = Zb, Za
 e1.record(); torch.cuda.synchronize()
+print("   config:", s.launch_config)
 print(f"{name} {kw} B={B} {mode}: {e0.elapsed_time(e1)/steps:.3f} ms/step  {B*steps/e0.elapsed_time(e1)*1e3:.0f} env-steps/s  mean iters {float(it.float().mean()):.2f}  failed {int((stt!=0).sum())}  pre-steps {pre}  smem/env {s.shared_bytes_per_env}")
