@@ -620,11 +620,19 @@ DJ_DEV void grad_solve_columns(Ctx& c, double* V, int ch, int gvo, int c0, int n
         const ElimNb& nb = st.nb[j];
         const double* U = A + nb.U_off;
         const double* xj = V + nb.r_off * ch;
-        for (int kk = 0; kk < nb.n; ++kk) {  // M_{c,nb} holds the rows [U_row, U_row + U_k) of c (all of them unless the coupling is angular only)
-          double xv = xj[kk * ch + lane];
+        if (nb.U_row == 0) {  // M_{c,nb} holds all st.n rows of c
+          for (int kk = 0; kk < nb.n; ++kk) {
+            double xv = xj[kk * ch + lane];
 #pragma unroll
-          for (int r = 0; r < 6; ++r)
-            if (r >= nb.U_row && r < nb.U_row + nb.U_k) t[r] -= U[(r - nb.U_row) * nb.n + kk] * xv;
+            for (int r = 0; r < 6; ++r)
+              if (r < st.n) t[r] -= U[r * nb.n + kk] * xv;
+          }
+        } else {  // angular coupling only (dojo_plan.h ElimNb::row0): rows 3..5 of c, stored 3 x n_nb
+          for (int kk = 0; kk < nb.n; ++kk) {
+            double xv = xj[kk * ch + lane];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) t[3 + r] -= U[r * nb.n + kk] * xv;
+          }
         }
       }
       const double* Dc = A + st.d_off;

@@ -1225,6 +1225,22 @@ DJ_DEV double cone_line_search(Ctx& c, double tau_ort, double tau_soc) {
   const WarpRole& role = c.roles[c.warp];
   double a = 1.0;
   for (int p = 0; p < role.npass; ++p) {
+#ifndef DJ_ANY_CONTACT
+    // NonlinearContact: the slack cone and the dual cone of a contact are two independent (orthant, second-order cone) pairs with the
+    // same formulas -- two lanes per contact, lane 2k the slacks, lane 2k + 1 the duals (half the chain of divisions / square roots)
+    if (role.type[p] == ROLE_CONTACT && role.count[p] <= 16) {
+      const int ci = c.lane >> 1;
+      if (ci < role.count[p]) {
+        const ContactDev& cd = c.contacts[role.first[p] + ci];
+        const int o = cd.sol_off + 4 * (c.lane & 1);
+        const double* v = sol + o;
+        const double* dv = dl + o;
+        a = fmin(a, ort_step(v[0], dv[0], tau_ort));
+        a = fmin(a, soc_step(v[1], v[2], v[3], dv[1], dv[2], dv[3], tau_soc));
+      }
+      continue;
+    }
+#endif
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_CONTACT) {

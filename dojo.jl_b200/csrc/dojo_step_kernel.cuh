@@ -108,8 +108,31 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     if (PLAN_SMEM || a.plan_smem_off >= 0) {  // one copy of the plan tables (or of their hot prefix) per CTA, shared by its slots
       int4* dst = reinterpret_cast<int4*>(arena + a.plan_smem_off);
       const int4* src = reinterpret_cast<const int4*>(a.plan_blob);
+#ifndef DJ_HOSTEMU
+      // TMA bulk staging: ONE thread issues one asynchronous bulk copy global -> shared (cp.async.bulk, 16-byte aligned on both sides, the
+      // blob is padded to 16-byte multiples) that completes on an mbarrier; every thread of the CTA then waits on that barrier's phase 0.
+      __shared__ __align__(8) unsigned long long s_plan_bar;
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_plan_bar);
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the initialised barrier visible to the async (TMA) proxy
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)a.plan_smem_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+      }
+      {
+        unsigned done = 0;
+        while (!done)
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+      }
+#else
       for (int i = threadIdx.x; i < a.plan_smem_bytes / 16; i += blockDim.x) dst[i] = src[i];
       __syncthreads();
+#endif
       sb = reinterpret_cast<const char*>(dst);
     }
 #define DJ_TABLE(k) ((PLAN_SMEM || (sb && ((a.plan_smem_mask >> (k)) & 1))) ? sb + a.plan_off[k] : gb + a.plan_off[k])

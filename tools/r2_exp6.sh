@@ -2,6 +2,9 @@
 # round 2, call 2: compact body-body blocks + integer nanmax; full GPU suite; configs; LPT on / off; 2-GPU gather check is a separate call
 mkdir -p gpurun_out
 {
+echo "== guarded first launch (TMA bulk staging of the plan tables is new)"
+timeout 180 python tools/prof_one.py ant 256 2 fwd || { echo "FIRST LAUNCH FAILED"; exit 1; }
+timeout 180 python tools/prof_one.py quadruped 256 2 grad
 echo "== timing"
 python tools/prof_one.py ant 4096 8 fwd
 DOJO_B200_LPT=0 python tools/prof_one.py ant 4096 8 fwd
