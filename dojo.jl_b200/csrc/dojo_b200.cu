@@ -350,6 +350,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     const int first_slot = Ne > 0 ? joints[0].slot_c : P.mat_off;
     const int span = P.mat_off - first_slot;
     P.ls_pair = (nw == 2 && Nb <= 16 && Ne <= 16 && Ni <= 16 && span + nres <= P.mat_len && !getenv("DOJO_B200_NO_LS_PAIR")) ? 1 : 0;
+    // two lanes per joint in set_entries! (eval_joint_pair): mechanisms with NonlinearContact and rotational joint terms only (the kernel
+    // also requires <= 16 joints in the pass)
+    P.jpair = (!h->any_contact && !getenv("DOJO_B200_NO_JOINT_PAIR")) ? 1 : 0;
     P.ls_slot_delta = span;
     P.ls_res2_off = P.mat_off + span;
   }

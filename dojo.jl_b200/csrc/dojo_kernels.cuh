@@ -812,6 +812,202 @@ DJ_DEV void eval_joint(Ctx& c, int idx, double f, double* res, double& rv, doubl
   if (jd.parent >= 0) write_slot(A + jd.slot_p + c.sd, fl_p, fa_p, Kaa);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// set_entries! of one joint on TWO lanes (round 2): lane 2k evaluates the CHILD side of joint k, lane 2k + 1 the PARENT side, with
+// one instruction stream -- everything that differs between the sides is data (signs, selected matrices, table offsets), not control
+// flow.  The joint pass is the longest lane-serial stretch of the assembly (~3 500 instructions per lane, the other warp waits for
+// it half of the time, profiles/README.md); both lanes still need the kinematics of both bodies and the relative rotation, but each
+// forms only ITS body's attitude Jacobian E, products with E, rows of (joint, body), angular blocks and impulse sums.  The two things
+// a side needs from the other -- the limit row a' of the other body and the damper block of the other body -- travel through
+// pair shuffles.  Same formulas, term by term, as eval_joint<true>(f = 0) (the set of floating-point operations per output is
+// unchanged); used when a joint pass has at most 16 joints (ant, quadruped) and the mechanism has only NonlinearContact and rotational
+// joint terms (Plan::jpair, set by dojo_create), otherwise one lane per joint as before.
+// ------------------------------------------------------------------------------------------------------------
+DJ_DEV M33 select33(bool p, const M33& a, const M33& b) {
+  M33 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.m[i][j] = p ? a.m[i][j] : b.m[i][j];
+  return r;
+}
+DJ_DEV V3 select3(bool p, V3 a, V3 b) { return V3{p ? a.x : b.x, p ? a.y : b.y, p ? a.z : b.z}; }
+DJ_DEV V3 pair_swap3(unsigned pm, V3 v) { return V3{__shfl_xor_sync(pm, v.x, 1), __shfl_xor_sync(pm, v.y, 1), __shfl_xor_sync(pm, v.z, 1)}; }
+DJ_DEV M33 pair_swap33(unsigned pm, const M33& a) {
+  M33 r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.m[i][j] = __shfl_xor_sync(pm, a.m[i][j], 1);
+  return r;
+}
+
+DJ_DEV void eval_joint_pair(Ctx& c, int idx, const bool par, double* res, double& rv, double& bv) {
+  const Plan& P = *c.P;
+  double* A = c.A;
+  const double* sol = A + P.sol_off;
+  const JointDev& jd = c.joints[idx];
+  const unsigned pm = 3u << (c.lane & ~1);     // the two lanes of this joint
+  const bool act = !(par && jd.parent < 0);    // parent side of a joint to the origin: computes along, stores nothing
+  const double sg_x = par ? -1.0 : 1.0;        // X = +-Ra', conj of the velocity-map perturbation, sign of the (., other) damper block
+  Kin ka = body_kin(c, jd.parent, 0.0), kb = body_kin(c, jd.child, 0.0);  // (their E members are never read: dead code)
+  JointGeom g = joint_geom(jd, ka.x3, ka.q3, ka.R3, kb.x3, kb.q3, kb.R3);
+  const V3 wm = select3(par, ka.w, kb.w);
+  const M33 E = attitude_velocity_jacobian(wm, P.h);  // of THIS side's body
+  const M33 Qt = select33(par, g.Qtp, g.Qtc), Qr = select33(par, g.Qrp, g.Qrc);
+  const M33 X = sg_x * g.Xc;  // Xc = Ra', Xp = -Ra'
+  const M33 QtE = Qt * E, QrE = Qr * E;
+  V3 fl = v3zero(), fa = v3zero();
+  M33 K = m33zero(), Bx = m33zero();  // D_mine -= K ; (mine, other) angular block
+  bool coupled = false;
+  const int n = joint_nq(jd);
+  double* rr = res + jd.sol_off;
+  const double* so = sol + jd.sol_off;
+  const bool pa = par && act;                     // (an inactive parent lane reads the child's tables: harmless, nothing is stored)
+  double* U = A + (pa ? jd.Up_off : jd.Uc_off);   // (joint, this body) n x 6
+  double* D = A + jd.D_off;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nl_t) {
+      V3 ci = ld3(jd.Ct + 3 * i);
+      double gi = dot(ci, g.et);
+      rv = nanmax(rv, fabs(gi));
+      if (!par) { rr[i] = -gi; D[i * n + i] = kReg; }
+      if (act) { st3(U + i * 6, P.h * vtmul(ci, X)); st3(U + i * 6 + 3, vtmul(ci, QtE)); }
+    }
+  }
+  V3 er = qvec(g.qr);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < jd.nl_r) {
+      V3 ci = ld3(jd.Cr + 3 * i);
+      const int row = jd.nl_t + i;
+      double gi = dot(ci, er);
+      rv = nanmax(rv, fabs(gi));
+      if (!par) { rr[row] = -gi; D[row * n + row] = kReg; }
+      if (act) { st3(U + row * 6, v3zero()); st3(U + row * 6 + 3, vtmul(ci, QrE)); }
+    }
+  }
+  double* mapm = A + (pa ? jd.Gp_off : jd.Lc_off);  // pristine impulse map of this side: parent G_p, child L_c = -G_c
+  if (jd.nb2_r > 0) {  // rotational limits (joints/limits.jl:1-29), see eval_joint
+    V3 rvq = rotation_vector(g.qr);
+    M33 T;  // d rotation_vector(qr) / d attitude of this body (rotvec_attitude_jacobians, one side), times E
+    {
+      M34 drv = drotation_vector_dq(g.qr);
+      V3 vr = qvec(g.qr);
+      M33 Rofft = transpose(rotmat(ldq(jd.qoff)));
+      V3 srow = select3(par, vtmul(vr, Rofft), -vr);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        V3 dv = v3(drv.m[i][1], drv.m[i][2], drv.m[i][3]);
+        V3 r1 = drv.m[i][0] * srow + vtmul(dv, Qr);
+        T.m[i][0] = r1.x; T.m[i][1] = r1.y; T.m[i][2] = r1.z;
+      }
+      T = T * E;
+    }
+    coupled = true;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < jd.nb2_r) {
+        V3 ai = ld3(jd.Ar + 3 * i);
+        double th = dot(ai, rvq);
+        const int is_u = jd.ne + i, is_l = jd.ne + jd.nb2_r + i;
+        const int ig_u = is_u + jd.nb_r, ig_l = is_l + jd.nb_r;
+        const double su = so[is_u], sl = so[is_l], gu = so[ig_u], gl = so[ig_l];
+        bv = nanmax(bv, nanmax(fabs(su * gu), fabs(sl * gl)));
+        if (!par) {
+          rr[is_u] = -(su * gu - c.mu);
+          rr[is_l] = -(sl * gl - c.mu);
+          rr[ig_u] = -(su - (jd.hi[i] - th));
+          rr[ig_l] = -(sl - (th - jd.lo[i]));
+        }
+        double* lim = A + jd.lim_off + kLim * i;
+        const V3 tm = ld3(lim + (par ? 6 : 9));  // tP / tC
+        fa += (gl - gu) * tm;
+        const V3 am = vtmul(ai, T);              // aP / aC
+        if (act) st3(lim + (par ? 0 : 3), am);
+        const V3 ao = pair_swap3(pm, am);        // the other body's row
+        const LimitSide ls = limit_side(su, sl, gu, gl);
+        K = K - ls.kI * outer(tm, am);
+        Bx = Bx + ls.kI * outer(tm, ao);
+        const int q = jd.ne + i;
+        if (!par) D[q * n + q] = ls.sA;
+        if (act) {
+          st3(U + q * 6, v3zero()); st3(U + q * 6 + 3, (-ls.sg * ls.gA) * am);
+          const V3 col = (sg_x * ls.sg) * tm;   // L_c column +sg tC, G_p column -sg tP
+          mapm[0 * n + q] = 0.0; mapm[1 * n + q] = 0.0; mapm[2 * n + q] = 0.0;
+          mapm[3 * n + q] = col.x; mapm[4 * n + q] = col.y; mapm[5 * n + q] = col.z;
+        }
+      }
+    }
+  }
+  {  // impulses of the equality multipliers on this body: child -L_c lambda, parent +G_p lambda
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < jd.ne; ++i) {
+      const double e = so[i];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) acc[r] += mapm[r * n + i] * e;
+    }
+    fl += (-sg_x) * v3(acc[0], acc[1], acc[2]);
+    fa += (-sg_x) * v3(acc[3], acc[4], acc[5]);
+    if (jd.parent >= 0) {  // refresh the parent-side lower block from the pristine copy: the two lanes share the copy
+      double* Lp = A + jd.Lp_off;
+      const double* Gp = A + jd.Gp_off;
+      for (int i = (par ? 1 : 0); i < 6 * n; i += 2) Lp[i] = -Gp[i];
+    }
+  }
+  if (jd.damper_r != 0.0 && jd.nfree_r > 0) {  // rotational damper, see eval_joint
+    Quat r = qmul(qinv(ka.q2), kb.q2);
+    Quat ma = qmap(ka.w, P.h), mb = qmap(kb.w, P.h);
+    Quat left = qmul(mb, qinv(r));
+    Quat rest = qmul(qmul(qinv(r), qconj(ma)), r);
+    Quat wq = qmul(mb, rest);
+    V3 rvd = rotation_vector(wq);
+    M33 AtA = m33zero();
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < jd.nfree_r) { V3 a = ld3(jd.Ar + 3 * i); AtA = AtA + outer(a, a); }
+    M33 Roff = rotmat(ldq(jd.qoff));
+    M33 Rr = rotmat(r);
+    M33 B = jd.damper_r * (Roff * AtA);
+    V3 ta = B * rvd;
+    V3 tb = (-1.0) * tmul(Rr, ta);
+    fa += select3(par, ta, tb);
+    coupled = true;
+    M34 drv = drotation_vector_dq(wq);
+    // d w / d (this body's angular velocity): the perturbed velocity map dm sits between Xq and Yq,
+    //   parent: w = left (x) conj(ma) (x) r  ->  left (x) conj(dm) (x) r ;   child: w = mb (x) rest  ->  dm (x) rest
+    const double m0 = par ? ma.s : mb.s;
+    const Quat Xq = par ? left : Quat{1.0, 0.0, 0.0, 0.0};
+    const Quat Yq = par ? r : rest;
+    M33 dw;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const double hv = sg_x * 0.5 * P.h;  // conj() flips the vector part on the parent side
+      Quat dm = Quat{-(0.25 * P.h * P.h) * comp(wm, kx) / m0, kx == 0 ? hv : 0.0, kx == 1 ? hv : 0.0, kx == 2 ? hv : 0.0};
+      Quat cq = qmul(qmul(Xq, dm), Yq);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dw.m[i][kx] = drv.m[i][0] * cq.s + drv.m[i][1] * cq.x + drv.m[i][2] * cq.y + drv.m[i][3] * cq.z;
+    }
+    const M33 Km = B * dw;                  // parent: Ka = d tau_a / d w_a ; child: Kb = d tau_a / d w_b
+    const M33 Ko = pair_swap33(pm, Km);     // the other side's block
+    const M33 Rrt = transpose(Rr);
+    // parent: Kaa += Ka, Bpc -= Kb ;  child: Kcc -= Rr' Kb, Bcp += Rr' Ka
+    const M33 N = select33(par, m33ident(), Rrt);
+    K = K + (-sg_x) * (N * Km);
+    Bx = Bx + sg_x * (N * Ko);
+  }
+  if (coupled && jd.parent >= 0 && jd.BBpc_off >= 0) {  // (parent angular rows, child) 3 x 6 ; (child angular rows, parent angular columns) 3 x 3
+    double* M = A + (par ? jd.BBpc_off + 3 : jd.BBcp_off);
+    const int ldm = par ? 6 : 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j2 = 0; j2 < 3; ++j2) M[i * ldm + j2] = Bx.m[i][j2];
+  }
+  if (act) write_slot(A + (par ? jd.slot_p : jd.slot_c), fl, fa, K);
+}
+
 // condense_rhs / recover: the per-solve halves of the analytic condensation.  `x` is a right-hand side in solution
 // ordering.  condense_rhs writes each node's contribution to its bodies' rows into the slots (gathered by the bodies
 // right after); recover overwrites the condensed-out entries of x with the step (ds, dgamma) once dv is known.
@@ -932,6 +1128,10 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
     slot_sync(c);
   }
   for (int p = 0; p < role.npass; ++p) {
+    if (JAC && role.type[p] == ROLE_JOINT && P.jpair && role.count[p] <= 16) {  // set_entries! of the joints on two lanes each (f = 0)
+      if ((c.lane >> 1) < role.count[p]) eval_joint_pair(c, role.first[p] + (c.lane >> 1), (c.lane & 1) != 0, res, rv, bv);
+      continue;
+    }
     const int idx = role_item(role, p, c.lane);
     if (idx < 0) continue;
     if (role.type[p] == ROLE_BODY) eval_body<JAC>(c, idx, f, res);
