@@ -353,6 +353,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     // two lanes per joint in set_entries! (eval_joint_pair): mechanisms with NonlinearContact and rotational joint terms only (the kernel
     // also requires <= 16 joints in the pass)
     P.jpair = (!h->any_contact && !getenv("DOJO_B200_NO_JOINT_PAIR")) ? 1 : 0;
+    P.ls_assist = getenv("DOJO_B200_NO_LS_ASSIST") ? 0 : 1;
     P.ls_slot_delta = span;
     P.ls_res2_off = P.mat_off + span;
   }
@@ -603,7 +604,7 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   auto plan_prefix = [&](int n, size_t bytes, int* off, int* pbytes, int* mask) {
     *off = -1; *pbytes = 0; *mask = 0;
     if (!smem_plan) return;
-    const size_t room = (size_t)prop.sharedMemPerBlockOptin - 64 - n * bytes;
+    const size_t room = (size_t)prop.sharedMemPerBlockOptin - 1024 - n * bytes;  // 1 KB: static shared memory of the kernel (mailbox, mbarrier)
     for (int k = 0; k < 8; ++k)
       if ((size_t)h->blob_end[k] <= room) { *mask |= 1 << k; *pbytes = std::max(*pbytes, h->blob_end[k]); }
     for (int k = 0; k < 8; ++k)  // a prefix: drop tables that start beyond the copied bytes (cannot happen with the ordered blob, kept for safety)

@@ -68,6 +68,14 @@ struct Ctx {
   int sd;                         // offset added to contribution-slot addresses (second trial of a paired line-search pass)
   int bar;                        // named barrier of the slot (1 + slot index); barrier 0 is the CTA-wide alignment barrier
   double mu;
+  // slots of the CTA: this slot's index, their number, the arena of slot 0 and the distance between arenas; CTA-wide mailbox in
+  // static shared memory (s_int / s_dbl, layout below); parity of the next alignment; whether this slot is the OWNER of a
+  // line search that the drained slots of the CTA assist (ls_assist_loop)
+  int slot, nslots, slot_stride;
+  double* arena0;
+  int* s_int;
+  double* s_dbl;
+  int apar, assist;
 #ifdef DJ_PROFILE
   long long t_eval_jac, t_eval_ls, t_fact, t_solve, t_misc, t_align, t_cone, t_center, t_rolewait, t_last;
   long long f_fold, f_inv, f_rm, f_schur, f_bar, f_last;
@@ -89,9 +97,34 @@ DJ_DEV void slot_sync(const Ctx& c) { hostemu_bar_sync(c.bar, c.nthreads); }
 DJ_DEV void slot_sync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "r"(c.nthreads) : "memory"); }
 #endif
 
-// CTA-wide alignment barrier (barrier 0); returns whether any slot of the CTA still has work.  Slots that ran out of
-// environments keep arriving here (with live = false) until every slot is done.
-DJ_DEV bool cta_align(bool live) { return __syncthreads_or(live ? 1 : 0) != 0; }
+// CTA-wide mailbox (static shared memory of the kernel):
+//   s_int[0..7]   environment dequeued by slot k                      s_int[8 + 8 p + k]  slot k is live, alignment parity p
+//   s_int[24]     line-search request: 1 = evaluate, 0 = released     s_int[25]           first trial index of the pass
+//   s_dbl[0], [1] step length of that first trial, mu                 s_dbl[2 + 2 t], [3 + 2 t]  violations (rv, bv) of trial t < 16
+constexpr int kMaxAssistTrials = 16;
+struct AlignInfo { int n_live, owner; };
+// CTA-wide alignment barrier (barrier 0): how many slots of the CTA still have work (and the last of them).  Slots that ran out of
+// environments keep arriving here (with live = false) until every slot is done.  The flags are double-buffered by the parity of the
+// call: a slot can only be two alignments ahead of another one after the barrier in between, which that one passes after its reads.
+DJ_DEV AlignInfo cta_align(Ctx& c, bool live) {
+  int* fl = c.s_int + 8 + 8 * c.apar;
+  c.apar ^= 1;
+  if (c.tid == 0) fl[c.slot] = live ? 1 : 0;
+  __syncthreads();
+  AlignInfo r;
+  r.n_live = 0; r.owner = -1;
+  for (int q = 0; q < c.nslots; ++q)
+    if (fl[q]) { r.n_live++; r.owner = q; }
+  return r;
+}
+// The owner of an assisted line search lets the helpers go (they wait at the CTA barrier for the next request): on every path that
+// leaves the Newton iteration, and when a trial has been accepted.
+DJ_DEV void assist_release(Ctx& c) {
+  if (!c.assist) return;
+  if (c.tid == 0) c.s_int[24] = 0;
+  __syncthreads();
+  c.assist = 0;
+}
 
 // slot-wide reductions (deterministic: per-warp shuffles, then a fixed-order combine of the nw partials)
 DJ_DEV void block_nanmax2(const Ctx& c, double& a, double& b) {
@@ -1187,7 +1220,10 @@ DJ_DEV void evaluate(Ctx& c, double f, int res_off, double& rvio, double& bvio) 
 // scratch vector and its contribution slots to a shadow copy, both inside the matrix region, which is dead between the
 // solves and the next assembly.  A pass with both halves busy costs about the same as a single trial; an environment that stalls (ten trials per
 // iteration) needs five passes instead of ten, one rejection costs no extra pass.
-DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, double& rvB, double& bvB) {
+// `W` is the arena that receives everything this evaluation writes (trial residuals, contribution slots, reduction scratch): the
+// slot's own arena, or -- when a drained slot evaluates trials of another slot's environment (ls_assist_loop) -- the helper's arena
+// while c.A points at the owner's (iterate, direction, per-step constants: read only).
+DJ_DEV void evaluate_ls(Ctx& c, double* W, double fk, bool pair, double& rvA, double& bvA, double& rvB, double& bvB) {
   const Plan& P = *c.P;
   double* A = c.A;
   const WarpRole& role = c.roles[c.warp];
@@ -1196,8 +1232,8 @@ DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, 
   const int ln = pl ? (c.lane & 15) : c.lane;
   const bool on = (half == 0) || pair;
   const double f = half ? 0.5 * fk : fk;
-  double* res = A + (half ? P.ls_res2_off : P.sav_off);
-  c.sd = half ? P.ls_slot_delta : 0;
+  double* res = W + (half ? P.ls_res2_off : P.sav_off);
+  c.sd = (int)(W - A) + (half ? P.ls_slot_delta : 0);
   double rv = 0.0, bv = 0.0;
   for (int p = 0; p < role.npass; ++p) {
     const int idx = on ? role_item(role, p, ln) : -1;
@@ -1231,7 +1267,7 @@ DJ_DEV void evaluate_ls(Ctx& c, double fk, bool pair, double& rvA, double& bvA, 
     rv = nanmax(rv, __shfl_xor_sync(0xffffffffu, rv, 16));
     bv = nanmax(bv, __shfl_xor_sync(0xffffffffu, bv, 16));
   }
-  double* red = A + P.red_off;
+  double* red = W + P.red_off;
   if ((c.lane & 15) == 0) { red[4 * c.warp + 2 * (c.lane >> 4)] = rv; red[4 * c.warp + 2 * (c.lane >> 4) + 1] = bv; }
   slot_sync(c);
   rvA = red[0]; bvA = red[1]; rvB = red[2]; bvB = red[3];
@@ -1579,18 +1615,48 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       // alignment point: the environments hosted by this CTA start every Newton iteration together, so that their warps run
       // the same (large, straight-line) code at the same time and share its instruction fetches
       DJ_TICK(c, t_misc)
-      cta_align(true);
+      {
+        // When this is the only slot of the CTA that still has an environment (the tail of a launch), the drained slots evaluate
+        // further line-search trials of this iteration at the same time (ls_assist_loop): an environment that stalls needs ten
+        // trials per iteration, and it is the latency of such environments that ends a per-step launch.
+        const AlignInfo ai = cta_align(c, true);
+        c.assist = (P.ls_assist && ai.n_live == 1 && c.nslots > 1 && o.max_ls <= kMaxAssistTrials) ? 1 : 0;
+      }
       DJ_TICK(c, t_align)
       evaluate<true>(c, 0.0, P.rhs_off, rv, bv);
     } else {
       // trials are evaluated two at a time (k at fk, k + 1 at fk / 2); the second one is used only if the first is rejected
       pair = (P.ls_pair != 0) && (ls_k + 1 < o.max_ls);
-      evaluate_ls(c, fk, pair, rv, bv, rv2, bv2);
+      if (c.assist) {  // post the pass: the helpers take the trials behind this slot's own
+        if (c.tid == 0) { c.s_int[24] = 1; c.s_int[25] = ls_k; c.s_dbl[0] = fk; c.s_dbl[1] = c.mu; }
+        __syncthreads();
+      }
+      evaluate_ls(c, A, fk, pair, rv, bv, rv2, bv2);
+      if (c.assist) {
+        if (c.tid == 0) {
+          c.s_dbl[2 + 2 * ls_k] = rv; c.s_dbl[3 + 2 * ls_k] = bv;
+          if (pair) { c.s_dbl[4 + 2 * ls_k] = rv2; c.s_dbl[5 + 2 * ls_k] = bv2; }
+        }
+        __syncthreads();
+      }
     }
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
     if (mode == 1) {
       // line_search! (solver/line_search.jl:1-34): trial k uses alpha / 2^k, accept unless both violations grow
-      if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) {
+      if (c.assist) {
+        // the pass evaluated the trials ls_k .. ls_k + ntr - 1 (this slot's own and the helpers'): same rule, same order
+        const int per = (P.ls_pair != 0) ? 2 : 1;
+        const int ntr = min(per * c.nslots, o.max_ls - ls_k);
+        bool accepted = false;
+        for (int j = 0; j < ntr; ++j) {
+          rv = c.s_dbl[2 + 2 * ls_k]; bv = c.s_dbl[3 + 2 * ls_k];
+          if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) { fk *= 0.5; ls_k += 1; continue; }
+          accepted = true;
+          break;
+        }
+        if (!accepted) continue;  // next pass
+        assist_release(c);
+      } else if ((rv > rvio) && (bv > bvio) && (ls_k + 1 < o.max_ls)) {
         fk *= 0.5; ls_k += 1;
         if (!pair) continue;
         rv = rv2; bv = bv2;  // trial k + 1 was evaluated in the same pass
@@ -1625,16 +1691,16 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
     }
     // mode 0: the system is assembled
     if (first) { rvio = rv; bvio = bv; first = false; }
-    if ((rvio != rvio) || (bvio != bvio)) { status = 3; break; }
+    if ((rvio != rvio) || (bvio != bvio)) { status = 3; assist_release(c); break; }
     // `for n = 1:max_iter` tests convergence at the TOP of an iteration only (solver/mehrotra.jl:26-30): an iterate that meets the
     // tolerances after the last iteration's line search is still :failed
-    if (ndone >= o.max_iter) break;
-    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; break; }
+    if (ndone >= o.max_iter) { assist_release(c); break; }
+    if ((rvio < o.rtol) && (bvio < o.btol)) { status = 0; assist_release(c); break; }
     ndone += 1;
     for (int t = c.tid; t < P.nres; t += c.nthreads) A[P.sav_off + t] = A[P.rhs_off + t];  // pull_residual!
     slot_sync(c);
     DJ_TICK(c, t_misc)
-    if (!factorize(c)) { status = 3; break; }
+    if (!factorize(c)) { status = 3; assist_release(c); break; }
     DJ_TICK(c, t_fact)
     double alpha = 1.0;
     for (int pass = 0; pass < 2; ++pass) {  // pass 0: affine direction (Quirk Q3: rhs carries the previous mutarget); pass 1: corrected
@@ -1665,6 +1731,39 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
   }
   *iters = ndone;
   return status;
+}
+
+// A drained slot of a CTA whose only remaining environment belongs to slot `owner` (the tail of a launch): evaluate line-search trials
+// of that environment until the owner releases the iteration.  The owner posts a pass (first trial index, its step length, mu) and
+// takes the first `per` trials itself; helper `rank` >= 1 takes the trials k0 + per rank .. with the same halvings of the step length
+// the owner would apply (exact: powers of two), reading the owner's arena and writing residuals, contribution slots and reduction
+// scratch into its own (evaluate_ls, `W`).  The residual evaluations are the ones the owner would have run in later passes, so the
+// accepted trial and its violations -- all the line search hands on -- are bit-identical with and without helpers.
+DJ_DEV void ls_assist_loop(Ctx& c, const Options& o, int owner, int rank) {
+  const Plan& P = *c.P;
+  double* own = c.A;
+  const int per = (P.ls_pair != 0) ? 2 : 1;
+  for (;;) {
+    __syncthreads();  // a pass has been posted, or the iteration released
+    if (c.s_int[24] == 0) break;
+    const int k0 = c.s_int[25] + per * rank;
+    if (k0 < o.max_ls) {
+      double f = c.s_dbl[0];
+      for (int q = 0; q < per * rank; ++q) f *= 0.5;
+      c.mu = c.s_dbl[1];
+      const bool pair = (per == 2) && (k0 + 1 < o.max_ls);
+      double rv, bv, rv2, bv2;
+      c.A = c.arena0 + (size_t)owner * c.slot_stride;
+      evaluate_ls(c, own, f, pair, rv, bv, rv2, bv2);
+      c.A = own;
+      if (c.tid == 0) {
+        c.s_dbl[2 + 2 * k0] = rv; c.s_dbl[3 + 2 * k0] = bv;
+        if (pair) { c.s_dbl[4 + 2 * k0] = rv2; c.s_dbl[5 + 2 * k0] = bv2; }
+      }
+    }
+    __syncthreads();  // results of the pass are in the mailbox
+  }
+  c.mu = 0.0;
 }
 
 }  // namespace dj

@@ -143,6 +143,7 @@ struct Plan {
   // paired line-search trials (every role pass has <= 16 nodes): the second trial of a pass writes its contribution slots at
   // [slot + ls_slot_delta] and its residual at ls_res2_off, both inside the matrix region
   int ls_pair, ls_slot_delta, ls_res2_off;
+  int ls_assist;  // drained slots of a CTA evaluate line-search trials of its last live environment (ls_assist_loop)
   int jpair;    // set_entries! of a joint on two lanes (child side / parent side) when a joint pass has at most 16 joints (eval_joint_pair)
   double h, input_scaling, g[3];
   // arena layout (doubles)

@@ -88,7 +88,7 @@ __device__ __forceinline__ unsigned long long k_t0g(unsigned long long* prof) { 
 template <bool GRAD, bool PLAN_SMEM = false>
 __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(const StepArgs a) {
   extern __shared__ double arena[];
-  __shared__ int s_env[8];
+  __shared__ __align__(8) int s_env[128];  // CTA-wide mailbox, layout: dojo_kernels.cuh (cta_align)
   // a CTA hosts a.slots environments at a time; slot k is served by threads [k * 32 nw, (k + 1) * 32 nw)
   const int slot_threads = 32 * a.plan.nw;
   const int slot = threadIdx.x / slot_threads;
@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
   c.bar = 1 + slot;
   c.sd = 0;
   c.mu = 0.0;
+  c.slot = slot; c.nslots = blockDim.x / slot_threads; c.slot_stride = a.slot_stride; c.arena0 = arena;
+  c.s_int = s_env; c.s_dbl = reinterpret_cast<double*>(s_env + 32);
+  c.apar = 0; c.assist = 0;
   {
     const char* gb = a.plan_blob;
     const char* sb = nullptr;
@@ -269,7 +272,12 @@ __global__ void __launch_bounds__(DJ_LB_THREADS, DJ_LB_BLOCKS) dojo_step_kernel(
     }
     slot_sync(c);
   }
-  while (cta_align(false)) {}  // keep the alignment barrier of the Newton loop matched until every slot has drained
+  for (;;) {  // keep the alignment barrier of the Newton loop matched until every slot has drained
+    const AlignInfo ai = cta_align(c, false);
+    if (ai.n_live == 0) break;
+    // one environment left in this CTA: help its line search (same condition as the owner evaluates in mehrotra())
+    if (!GRAD && P.ls_assist && ai.n_live == 1 && a.opts.max_ls <= kMaxAssistTrials) ls_assist_loop(c, a.opts, ai.owner, slot < ai.owner ? slot + 1 : slot);
+  }
   if (!GRAD && a.n_peers > 0) {
     // every environment of this CTA has been written to the peers: make the writes visible system-wide, then count this CTA in on
     // every rank (the receiving side waits for all CTAs of all ranks, dojo_gather_wait_kernel).  The barrier above orders the other

@@ -88,7 +88,7 @@ inline void run_cta(unsigned block, unsigned grid, int nthreads, size_t smem_byt
   State& s = S();
   s.block = block; s.grid = grid; s.nthreads = nthreads; s.body = body;
   s.smem.assign(smem_bytes / sizeof(double) + 2, 0.0);
-  s.sstatic.assign(64, 0);
+  s.sstatic.assign(128, 0);
   s.bars.clear();
   s.or_val[0] = s.or_val[1] = 0;
   if ((int)s.fibers.size() < nthreads) s.fibers.resize(nthreads);
