@@ -502,3 +502,31 @@ def test_parity_on_the_benchmarked_states(name, B, sample):
     assert r["status_mismatch"] == 0 and r["contact_mode_mismatch_all_converged"] == 0, r
     assert r["iters_mismatch"] <= max(1, sample // 200), r          # <= 0.5 %
     assert r["max_abs_dz_same_iters"] <= TOL_SAME_PATH and r["median_abs_dz_same_iters"] <= 1e-11, r
+
+
+def test_results_do_not_depend_on_the_work_queue_order(monkeypatch):
+    """The order in which the environments are dequeued (least likely to stall last, DOJO_B200_LPT) and the line-search assist of the
+    drained slots (DOJO_B200_NO_LS_ASSIST) only change WHEN an environment is computed: states, status, iteration counts and solution
+    vectors are bit-identical under every setting (B large enough for the order to be used and for the launch to have a tail)."""
+    from dojo_jl_b200.solver import BatchedStepper
+    mech = dj.get_mechanism("ant")
+    rng = np.random.default_rng(41)
+    B = 1500
+    Z = jittered_states(mech, B, rng)
+    ref = None
+    for env in ({}, {"DOJO_B200_LPT": "0"}, {"DOJO_B200_LPT": "2"}, {"DOJO_B200_NO_LS_ASSIST": "1"}):
+        for k in ("DOJO_B200_LPT", "DOJO_B200_NO_LS_ASSIST"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        stepper = BatchedStepper(mech, B)
+        Zs, outs = Z, []
+        r2 = np.random.default_rng(43)
+        for _ in range(6):  # a few steps into contact, where stalls and line-search retries happen
+            Zs, st, it, sol = stepper.step(Zs, random_inputs(mech, B, r2, 1.0), return_sol=True)
+            outs += [Zs, st, it, sol]
+        stepper.close()
+        if ref is None:
+            ref = outs
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(ref, outs)), env
