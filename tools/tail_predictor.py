@@ -9,10 +9,14 @@ oracle (same seeds as bench.py), then scores, for steps 22..29, how well quantit
 environments that will take >= 30 iterations: AUC per feature, and recall of the long environments inside the first wave (592 of 4096
 = 14.5 % of the queue) for single features and for a gradient-boosted classifier trained on the first half of the steps.
 
-Result (round 2): the previous step's iteration count has AUC 0.46 (1 - 3 of ~35 long environments were long one step earlier);
-the best physical features are "nearly at rest" ones -- kinetic energy, largest contact normal velocity -- at AUC ~0.72, recall@14.5 %
-0.26 - 0.35 (chance: 0.145); the classifier reaches 0.31 on held-out steps.  Stalls are transient and not predictable from the state:
-the tail is bounded by the latency of one stalled environment, not by the order of the queue.
+Result (round 2): the previous step's iteration count has AUC 0.54 (1 - 3 of ~35 long environments were long one step earlier);
+the best physical features are "nearly at rest" ones -- kinetic energy, largest contact normal velocity: a sticking contact with zero
+tangential velocity is the degenerate point of the friction cone -- at AUC ~0.73, recall inside the first wave 0.26 - 0.35 (chance:
+0.145); the classifier reaches 0.33 on held-out steps.  Nobody can start the long environments FIRST with that.  But the order only has
+to keep them from starting LAST: the second part of the script list-schedules the measured iteration counts on 592 slots -- index /
+random / previous-iterations order end at 10.3 - 10.4 (arbitrary units, ideal 6.3, longest environment 4.9), ascending kinetic energy
+(the environments least likely to stall last) at 8.8, an oracle longest-first order at 6.8.  That key is what dojo_risk_key_kernel
+computes (dojo.jl_b200/csrc/dojo_b200.cu); measured on B200: ant B = 4096 per-step 9.2 -> 8.1 ms.
 """
 import os
 import sys
@@ -93,6 +97,34 @@ def main():
         v = np.concatenate(F[k])
         a = auc(v, y)
         print(f"  {k:30s} AUC {max(a, 1 - a):.3f} ({'low' if a < 0.5 else 'high'} first)   recall inside the first wave {recall_first_wave(v if a >= 0.5 else -v, y, B, frac):.3f}")
+    # list scheduling of the measured work on 592 slots under different orders of the queue (duration ~ iterations; stalled
+    # environments a little more for their extra line-search passes)
+    import heapq
+
+    def makespan(dur, order, m=592):
+        h = [0.0] * m
+        end = 0.0
+        for e in order:
+            t = heapq.heappop(h) + dur[e]
+            end = max(end, t)
+            heapq.heappush(h, t)
+        return end
+    sims = {}
+    for si, t in enumerate(range(22, T)):
+        dur = 0.087 * rec[t][3].astype(float)
+        dur[rec[t][2] != 0] *= 1.12
+        kin = F["kinetic"][si]
+        key = np.clip(np.floor(2 * np.log2(np.maximum(kin, 1e-300))) + 88, 0, 127)
+        orders = {"index order": np.arange(B), "random": np.random.default_rng(t).permutation(B), "previous iterations, descending": np.argsort(-rec[t - 1][3], kind="stable"),
+                  "kinetic energy, ascending (half-octave buckets)": np.argsort(key, kind="stable"),
+                  "energy key minus previous iterations / 2 (dojo_risk_key_kernel)": np.argsort(2 * key - rec[t - 1][3], kind="stable"),
+                  "oracle: longest first": np.argsort(-dur, kind="stable")}
+        for k, o in orders.items():
+            sims.setdefault(k, []).append(makespan(dur, o))
+        sims.setdefault("(ideal: total work / 592)", []).append(dur.sum() / 592)
+    print("simulated makespan of one step [ms], mean over steps 22..29:")
+    for k, v in sims.items():
+        print(f"  {k:66s} {np.mean(v):6.2f}")
     try:
         from sklearn.ensemble import GradientBoostingClassifier
         X = np.stack([np.concatenate(F[k]) for k in F], 1)
