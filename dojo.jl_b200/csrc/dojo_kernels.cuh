@@ -1348,7 +1348,6 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
   double* x = A + vec_off;
   const int lane = c.lane;
   const int half = lane >> 4, l = lane & 15;  // one elimination step per half-warp, as in factorize()
-  const unsigned mask = 0xffffu << (16 * half);
   const int sub = l >> 3, li = l & 7;         // forward substitution: lanes [0,8) of the group serve nb[0], [8,16) nb[1]
   const WarpRole& role = c.roles[c.warp];
   // condense the right-hand side of the contact / joint-limit rows onto the body rows
@@ -1371,60 +1370,63 @@ DJ_DEV void solve(Ctx& c, int vec_off) {
     }
   }
   slot_sync(c);
+  // The two halves of a warp take two steps of a phase with one instruction stream.  Both halves run the same number of loop
+  // iterations (a half without a step of its own looks at its partner's and stores nothing), so the warp stays converged and the
+  // intra-step synchronisation is the plain full-warp one: a __syncwarp / shuffle whose member mask DIFFERS between the lanes of one
+  // instruction (one 16-lane mask per half) is split into groups with MATCH.ANY by the compiler (3.7 % of the forward kernel's stall
+  // samples sat on those sequences, profiles/README.md).
   for (int ph = 0; ph < P.nphase; ++ph) {  // forward: z_i -= L~_ic z_c
     const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
-    for (int s = s0 + half; s < s0 + sn; s += 2) {
-      const ElimStep& st = c.steps[s];
+    for (int it = 0; 2 * it < sn; ++it) {
+      const bool act = 2 * it + half < sn;
+      const ElimStep& st = c.steps[s0 + 2 * it + (act ? half : 0)];
       double* xc = x + st.vec_off;
-      if (st.fold_cnt > 0) {  // fold (and clear) the children's forward updates of this body
-        if (l < st.n) {
-          double acc = xc[l];
-          for (int k = 0; k < st.fold_cnt; ++k) {
-            double* v = A + c.ilist[st.fold_off + k] + 36;
-            acc += v[l];
-            v[l] = 0.0;
-          }
-          xc[l] = acc;
+      if (act && st.fold_cnt > 0 && l < st.n) {  // fold (and clear) the children's forward updates of this body
+        double acc = xc[l];
+        for (int k = 0; k < st.fold_cnt; ++k) {
+          double* v = A + c.ilist[st.fold_off + k] + 36;
+          acc += v[l];
+          v[l] = 0.0;
         }
-        __syncwarp(mask);
+        xc[l] = acc;
       }
-      if (sub < st.nnb && li < st.nb[sub].n) {
+      __syncwarp();
+      if (act && sub < st.nnb && li < st.nb[sub].n) {
         const ElimNb& nb = st.nb[sub];
         const double* L = A + nb.L_off + li * st.n;
         const double acc = dot6(L, xc, st.n);
         double* tgt = nb.fwd_abs >= 0 ? A + nb.fwd_abs : x + nb.vec_off;
         tgt[li] -= acc;
       }
-      __syncwarp(mask);
+      __syncwarp();
     }
     slot_sync(c);
   }
   for (int ph = P.nphase - 1; ph >= 0; --ph) {  // backward: x_c = D_c^-1 (z_c - sum_j M_cj x_j)
     const int s0 = c.sched[2 * (ph * P.nw + c.warp)], sn = c.sched[2 * (ph * P.nw + c.warp) + 1];
     // same pairing as the forward sweep, last pair first (the steps of one phase are independent)
-    for (int s = s0 + half + 2 * ((sn - 1 - half) >> 1); s >= s0 + half && sn > half; s -= 2) {
-      const ElimStep& st = c.steps[s];
+    for (int it = (sn + 1) / 2 - 1; it >= 0; --it) {
+      const bool act = 2 * it + half < sn;
+      const ElimStep& st = c.steps[s0 + 2 * it + (act ? half : 0)];
       const double* Dc = A + st.d_off;
       double* xc = x + st.vec_off;
-      if (st.nnb > 0) {
-        if (l < st.n) {
-          double acc = 0.0;
-          for (int j = 0; j < st.nnb; ++j) {
-            const ElimNb& nb = st.nb[j];
-            int r = l - nb.U_row;
-            if (r >= 0 && r < nb.U_k) {
-              acc += dot6(A + nb.U_off + r * nb.n, x + nb.vec_off, nb.n);
-            }
+      if (act && st.nnb > 0 && l < st.n) {
+        double acc = 0.0;
+        for (int j = 0; j < st.nnb; ++j) {
+          const ElimNb& nb = st.nb[j];
+          int r = l - nb.U_row;
+          if (r >= 0 && r < nb.U_k) {
+            acc += dot6(A + nb.U_off + r * nb.n, x + nb.vec_off, nb.n);
           }
-          xc[l] -= acc;
         }
-        __syncwarp(mask);
+        xc[l] -= acc;
       }
+      __syncwarp();
       double acc = 0.0;
-      if (l < st.n) acc = dot6(Dc + l * st.n, xc, st.n);
-      __syncwarp(mask);
-      if (l < st.n) xc[l] = acc;
-      __syncwarp(mask);
+      if (act && l < st.n) acc = dot6(Dc + l * st.n, xc, st.n);
+      __syncwarp();
+      if (act && l < st.n) xc[l] = acc;
+      __syncwarp();
     }
     slot_sync(c);
   }
