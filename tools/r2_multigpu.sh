@@ -17,5 +17,5 @@ for ln in open('gpurun_out/bench_r2_n8.json'):
     for k, r in l['sub_records'].items():
         print(k, {q: r.get(q) for q in ('value', 'ms_per_step', 'mean_newton_iters', 'failed_rate', 'error')}, 'e2e', r.get('e2e', {}).get('value'), r.get('gather'))
 PY
-} > gpurun_out/r2_exp8.log 2>&1
-tail -c 4000 gpurun_out/r2_exp8.log
+} > gpurun_out/r2_multigpu.log 2>&1
+tail -c 4000 gpurun_out/r2_multigpu.log
