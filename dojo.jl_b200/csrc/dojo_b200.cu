@@ -320,7 +320,12 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   const int nres = off;
 
   // ---- warps per environment
-  int nw = 2;  // measured on B200 (ant, quadruped, atlas): 2 warps per environment beat 1, 4 and 8
+  // 2 warps per environment (measured on B200 for ant / quadruped: 2 beat 1, 4 and 8).  Mechanisms with more than 16 nodes of a kind
+  // (atlas: 31 bodies, 31 joints, 20 contacts) get 4: their arena only lets two environments share an SM (4 of the 8 warps the
+  // register file holds), and with every role pass split in two halves of <= 16 nodes they can pair line-search trials on the
+  // half-warps and assemble a joint on two lanes like the small mechanisms (round 2; atlas is where the solver stalls most:
+  // 7.5 % of its environment-steps run into max_iter with ten line-search trials per iteration).
+  int nw = (std::max(Nb, std::max(Ne, Ni)) > 16) ? 4 : 2;
   if (const char* e = getenv("DOJO_B200_WARPS")) nw = atoi(e);
   if (nw != 1 && nw != 2 && nw != 4 && nw != 8) nw = 2;
   h->nw = nw;
@@ -377,7 +382,9 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
   {  // paired line-search trials: shadow of the slot region + a second residual vector inside the (then dead) matrix region
     const int first_slot = Ne > 0 ? joints[0].slot_c : P.mat_off;
     const int span = P.mat_off - first_slot;
-    P.ls_pair = (nw == 2 && Nb <= 16 && Ne <= 16 && Ni <= 16 && span + nres <= P.mat_len && !getenv("DOJO_B200_NO_LS_PAIR")) ? 1 : 0;
+    // (every role pass must fit a half-warp: all of a kind on one warp with <= 16 nodes at 2 warps, halves of <= 32 at 4 warps)
+    const int per_pass = (nw == 4) ? 32 : 16;
+    P.ls_pair = ((nw == 2 || nw == 4) && Nb <= per_pass && Ne <= per_pass && Ni <= per_pass && span + nres <= P.mat_len && !getenv("DOJO_B200_NO_LS_PAIR")) ? 1 : 0;
     // two lanes per joint in set_entries! (eval_joint_pair): mechanisms with NonlinearContact and rotational joint terms only (the kernel
     // also requires <= 16 joints in the pass)
     P.jpair = (!h->any_contact && !getenv("DOJO_B200_NO_JOINT_PAIR")) ? 1 : 0;
@@ -450,7 +457,12 @@ extern "C" int dojo_create(const DojoMechanismDesc* d, int device, int max_batch
     };
     if (nw == 1) { add(0, ROLE_BODY, 0, Nb); add(0, ROLE_CONTACT, 0, Ni); add(0, ROLE_JOINT, 0, Ne); }
     else if (nw == 2) { add(0, ROLE_BODY, 0, Nb); add(0, ROLE_CONTACT, 0, Ni); add(1, ROLE_JOINT, 0, Ne); }
-    else if (nw == 4) { add(0, ROLE_BODY, 0, Nb); add(1, ROLE_CONTACT, 0, Ni); int hj = (Ne + 1) / 2; add(2, ROLE_JOINT, 0, hj); add(3, ROLE_JOINT, hj, Ne - hj); }
+    else if (nw == 4) {  // halves of every kind: bodies + contacts on warps 0 / 1, joints on warps 2 / 3 (every pass <= 16 nodes for <= 32 of a kind)
+      const int hb = (Nb + 1) / 2, hc = (Ni + 1) / 2, hj = (Ne + 1) / 2;
+      add(0, ROLE_BODY, 0, hb); add(0, ROLE_CONTACT, 0, hc);
+      add(1, ROLE_BODY, hb, Nb - hb); add(1, ROLE_CONTACT, hc, Ni - hc);
+      add(2, ROLE_JOINT, 0, hj); add(3, ROLE_JOINT, hj, Ne - hj);
+    }
     else {
       int hb = (Nb + 1) / 2, hc = (Ni + 1) / 2, qj = (Ne + 3) / 4;
       add(0, ROLE_BODY, 0, hb); add(1, ROLE_BODY, hb, Nb - hb);

@@ -103,6 +103,15 @@ DJ_DEV void slot_sync(const Ctx& c) { asm volatile("bar.sync %0, %1;" ::"r"(c.ba
 //   s_dbl[0], [1] step length of that first trial, mu                 s_dbl[2 + 2 t], [3 + 2 t]  violations (rv, bv) of trial t < 16
 constexpr int kMaxAssistTrials = 16;
 struct AlignInfo { int n_live, owner; };
+// Every CTA-wide barrier of the Newton loop is THIS instruction: live slots reach it from mehrotra(), drained slots from the loop at the
+// end of the kernel, helpers from ls_assist_loop().  Different bar.sync instructions on barrier 0 would match as well (sm_70+ counts
+// arrivals per barrier resource, not per instruction), but one shared call site keeps the pattern within what CUDA C++ documents for
+// __syncthreads() and what compute-sanitizer's synccheck accepts.
+#ifdef DJ_HOSTEMU
+DJ_DEV void cta_barrier() { __syncthreads(); }
+#else
+__device__ __noinline__ void cta_barrier() { __syncthreads(); }
+#endif
 // CTA-wide alignment barrier (barrier 0): how many slots of the CTA still have work (and the last of them).  Slots that ran out of
 // environments keep arriving here (with live = false) until every slot is done.  The flags are double-buffered by the parity of the
 // call: a slot can only be two alignments ahead of another one after the barrier in between, which that one passes after its reads.
@@ -110,7 +119,7 @@ DJ_DEV AlignInfo cta_align(Ctx& c, bool live) {
   int* fl = c.s_int + 8 + 8 * c.apar;
   c.apar ^= 1;
   if (c.tid == 0) fl[c.slot] = live ? 1 : 0;
-  __syncthreads();
+  cta_barrier();
   AlignInfo r;
   r.n_live = 0; r.owner = -1;
   for (int q = 0; q < c.nslots; ++q)
@@ -122,7 +131,7 @@ DJ_DEV AlignInfo cta_align(Ctx& c, bool live) {
 DJ_DEV void assist_release(Ctx& c) {
   if (!c.assist) return;
   if (c.tid == 0) c.s_int[24] = 0;
-  __syncthreads();
+  cta_barrier();
   c.assist = 0;
 }
 
@@ -1631,7 +1640,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
       pair = (P.ls_pair != 0) && (ls_k + 1 < o.max_ls);
       if (c.assist) {  // post the pass: the helpers take the trials behind this slot's own
         if (c.tid == 0) { c.s_int[24] = 1; c.s_int[25] = ls_k; c.s_dbl[0] = fk; c.s_dbl[1] = c.mu; }
-        __syncthreads();
+        cta_barrier();
       }
       evaluate_ls(c, A, fk, pair, rv, bv, rv2, bv2);
       if (c.assist) {
@@ -1639,7 +1648,7 @@ DJ_DEV int mehrotra(Ctx& c, const Options& o, int* iters) {
           c.s_dbl[2 + 2 * ls_k] = rv; c.s_dbl[3 + 2 * ls_k] = bv;
           if (pair) { c.s_dbl[4 + 2 * ls_k] = rv2; c.s_dbl[5 + 2 * ls_k] = bv2; }
         }
-        __syncthreads();
+        cta_barrier();
       }
     }
     if (mode == 0) { DJ_TICK(c, t_eval_jac) } else { DJ_TICK(c, t_eval_ls) }
@@ -1746,7 +1755,7 @@ DJ_DEV void ls_assist_loop(Ctx& c, const Options& o, int owner, int rank) {
   double* own = c.A;
   const int per = (P.ls_pair != 0) ? 2 : 1;
   for (;;) {
-    __syncthreads();  // a pass has been posted, or the iteration released
+    cta_barrier();  // a pass has been posted, or the iteration released
     if (c.s_int[24] == 0) break;
     const int k0 = c.s_int[25] + per * rank;
     if (k0 < o.max_ls) {
@@ -1763,7 +1772,7 @@ DJ_DEV void ls_assist_loop(Ctx& c, const Options& o, int owner, int rank) {
         if (pair) { c.s_dbl[4 + 2 * k0] = rv2; c.s_dbl[5 + 2 * k0] = bv2; }
       }
     }
-    __syncthreads();  // results of the pass are in the mailbox
+    cta_barrier();  // results of the pass are in the mailbox
   }
   c.mu = 0.0;
 }
