@@ -98,7 +98,9 @@ __global__ void dojo_gather_wait_kernel(const unsigned long long* flag, unsigned
 struct DojoGather {
   DojoHandle* h = nullptr;
   int world = 1, rank = 0, B = 0;
-  double* buf = nullptr;                 // [nz x B x world] on this device
+  double* buf = nullptr;                 // 2 x [nz x B x world] on this device: steps alternate between the two halves (see dojo_gather_buffer)
+  size_t half = 0;                       // doubles per half
+  int parity = 0, last = 0;              // half the NEXT step writes / half the most recent step wrote
   unsigned long long* flag = nullptr;    // CTAs (of all ranks, all steps so far) that have delivered into buf
   double* peer_buf[DOJO_MAX_GATHER_RANKS] = {};
   unsigned long long* peer_flag[DOJO_MAX_GATHER_RANKS] = {};
@@ -755,7 +757,8 @@ static int launch_forward(DojoHandle* h, const DojoSolverOptions* opts, int B, c
   if (g) {
     if (!g->connected || g->h != h || B != g->B) { h->err = "dojo_step_gather_async: gather not connected / made for another handle / B differs from B_local"; return DOJO_EINVAL; }
     a.n_peers = g->world;
-    a.gather_off = (long long)g->rank * g->B * h->plan.nz;
+    a.gather_off = (long long)((size_t)g->parity * g->half) + (long long)g->rank * g->B * h->plan.nz;
+    g->last = g->parity; g->parity ^= 1;
     for (int r = 0; r < g->world; ++r) { a.peer_buf[r] = g->peer_buf[r]; a.peer_flag[r] = g->peer_flag[r]; }
   }
   a.plan = h->plan; a.opts = make_options(opts); a.B = B;
@@ -1039,7 +1042,12 @@ extern "C" int dojo_gather_create(DojoHandle* h, int world, int rank, int B_loca
   CUDA_TRY(h, cudaSetDevice(h->device));
   DojoGather* g = new DojoGather();
   g->h = h; g->world = world; g->rank = rank; g->B = B_local;
-  const size_t bytes = (size_t)world * B_local * h->plan.nz * sizeof(double);
+  // Two halves, used alternately: a rank that has closed step t may start step t + 1 -- and write its slice into the other ranks'
+  // buffers -- while a slower rank is still READING the gathered states of step t; step t + 1 therefore goes to the other half, and
+  // the half of step t is only written again by step t + 2, which no rank starts before every rank has finished step t + 1 (issued
+  // behind its readers of step t in stream order).
+  g->half = (size_t)world * B_local * h->plan.nz;
+  const size_t bytes = 2 * g->half * sizeof(double);
   if (cudaMalloc((void**)&g->buf, bytes) != cudaSuccess || cudaMalloc((void**)&g->flag, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMemset(g->buf, 0, bytes) != cudaSuccess || cudaMemset(g->flag, 0, sizeof(unsigned long long)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     h->err = std::string("dojo_gather_create: ") + cudaGetErrorString(cudaGetLastError());
@@ -1078,7 +1086,7 @@ extern "C" int dojo_gather_connect(DojoGather* g, const void* all_handles) {
   g->connected = true;
   return DOJO_OK;
 }
-extern "C" double* dojo_gather_buffer(DojoGather* g) { return g ? g->buf : nullptr; }
+extern "C" double* dojo_gather_buffer(DojoGather* g) { return g ? g->buf + (size_t)g->last * g->half : nullptr; }
 extern "C" int dojo_gather_destroy(DojoGather* g) {
   if (!g) return DOJO_OK;
   cudaSetDevice(g->h->device);

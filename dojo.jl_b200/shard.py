@@ -75,19 +75,28 @@ class StateGather:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
         self.fused = bool(ok.item() == 1)
         if self.fused:
-            ptr = stepper.gather_buffer(self.g)
-            self.Zall = _wrap_device_buffer(ptr, (world * B_local, nz), device)
+            # the library alternates between two halves of the gathered buffer (dojo_gather_buffer = the half of the most recent step)
+            self._views = {}
+            self._refresh()
         else:
             self.Zall = torch.empty((world * B_local, nz), dtype=torch.float64, device=device)
             self.side = torch.cuda.Stream(device=device)
             self.ev = torch.cuda.Event()
             self.done = torch.cuda.Event()
 
+    def _refresh(self):
+        ptr = int(self.stepper.gather_buffer(self.g))
+        if ptr not in self._views:
+            self._views[ptr] = _wrap_device_buffer(ptr, (self.world * self.B, self.nz), self.dev)
+        self.Zall = self._views[ptr]  # gathered states of the most recent step (valid until the step after the next one is issued)
+
     def step(self, dZ, dU, dZn, opts, dstatus=None, diters=None, stream=0):
         self.stepper.step_gather_device(self.g, dZ, dU, dZn, self.B, opts, dstatus=dstatus, diters=diters, stream=stream)
+        self._refresh()
 
     def step_grad(self, dZ, dU, dZn, dFz, dFu, opts, dstatus=None, diters=None, stream=0):
         self.stepper.step_grad_gather_device(self.g, dZ, dU, dZn, dFz, dFu, self.B, opts, dstatus=dstatus, diters=diters, stream=stream)
+        self._refresh()
 
     def exchange(self, z_local, stream):
         """NCCL fallback: all-gather behind the kernel; the launching stream waits for it (the step ends with the gathered buffer filled)."""

@@ -276,7 +276,7 @@ function step_gather!(mech::Mechanism, g::Gather, dZ::Ptr{Float64}, dU::Ptr{Floa
     rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
     return nothing
 end
-gathered(g::Gather) = ccall((:dojo_gather_buffer, LIB), Ptr{Float64}, (Ptr{Cvoid},), g.ptr)   # device pointer
+gathered(g::Gather) = ccall((:dojo_gather_buffer, LIB), Ptr{Float64}, (Ptr{Cvoid},), g.ptr)   # device pointer of the most recent step's gathered states (two alternating halves: ask after every step)
 
 "B = 1 drop-in for mehrotra!(mechanism; opts): runs the step on the GPU and writes vsol / wsol back into the Mechanism"
 function mehrotra_gpu!(mech::Mechanism; opts = SolverOptions{Float64}())

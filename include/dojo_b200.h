@@ -213,6 +213,10 @@ int dojo_step_grad_async(DojoHandle* h, const DojoSolverOptions* opts, int B, co
  *                        dojo_step_async / dojo_step_grad_async + the exchange; on return of the stream work the gathered buffer of THIS
  *                        rank holds the next states of all ranks (a small wait kernel closes the step: it returns once every CTA of
  *                        every rank has signalled; it gives up after ~10 s and reports DOJO_STATUS_NONFINITE in status[0] if a peer died)
+ *   dojo_gather_buffer   the gathered states of the MOST RECENT step call.  The buffer has two halves that consecutive steps use
+ *                        alternately (a fast rank may already be writing step t + 1 into its peers while a slow rank still reads
+ *                        step t): call it after every step; work that reads it must be issued on the step's stream before the next
+ *                        step call, and the states of step t stay valid until step t + 2 is issued.
  * All ranks must call with the same B_local and the same sequence of steps. */
 #define DOJO_MAX_GATHER_RANKS 8
 #define DOJO_GATHER_HANDLE_BYTES 128

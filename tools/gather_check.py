@@ -31,6 +31,7 @@ def main():
     Za, Zb, Zp = torch.from_numpy(Z0).to(dev), torch.empty((B, mech.nz), dtype=torch.float64, device=dev), torch.empty((B, mech.nz), dtype=torch.float64, device=dev)
     ref_all = torch.empty((world * B, mech.nz), dtype=torch.float64, device=dev)
     ok = g.fused
+    prev_view, prev_ref = None, None
     for t in range(T):
         st.step_device(Za.data_ptr(), U[t].data_ptr(), Zp.data_ptr(), B, stream=stream.cuda_stream)          # plain step
         dist.all_gather_into_tensor(ref_all, Zp)
@@ -38,6 +39,11 @@ def main():
             g.step(Za.data_ptr(), U[t].data_ptr(), Zb.data_ptr(), None, stream=stream.cuda_stream)           # fused step + exchange
             torch.cuda.synchronize()
             ok = ok and torch.equal(Zb, Zp) and torch.equal(g.Zall, ref_all)
+            # the gathered states of the PREVIOUS step are still intact (steps alternate between two halves of the buffer, so that a fast
+            # rank writing step t + 1 cannot overwrite what a slow rank still reads of step t)
+            if prev_view is not None:
+                ok = ok and torch.equal(prev_view, prev_ref) and prev_view.data_ptr() != g.Zall.data_ptr()
+            prev_view, prev_ref = g.Zall, ref_all.clone()
         else:
             Zb.copy_(Zp)
         Za, Zb = Zb, Za
