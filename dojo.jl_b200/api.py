@@ -149,14 +149,15 @@ def maximal_to_minimal(mechanism: Mechanism, z, device: int = 0):
     return X[0] if z.ndim == 1 else X
 
 
-def step_minimal_coordinates(mechanism: Mechanism, x, u, opts=None, device: int = 0):
+def step_minimal_coordinates(mechanism: Mechanism, x, u, opts=None, device: int = 0, literal: bool = False):
     """step_minimal_coordinates!(mechanism, x, u; opts) -> x_next (what DojoEnvironments.step! calls); for a batch also
-    (status, iters).  The maximal states stay on the device between the three launches."""
+    (status, iters).  The maximal states stay on the device between the three launches.  literal = True returns what the reference
+    literally returns (step!'s return value advances the configuration a second time) instead of the state after the step."""
     x = np.asarray(x, dtype=float)
     single = x.ndim == 1
     X = np.atleast_2d(x)
     U = np.atleast_2d(np.asarray(u, dtype=float))
-    Xn, status, iters = _stepper(mechanism, X.shape[0], device).step_minimal(X, U, opts)
+    Xn, status, iters = _stepper(mechanism, X.shape[0], device).step_minimal(X, U, opts, flags=1 if literal else 0)
     if single:
         _check_single(status)
         return Xn[0]

@@ -1231,8 +1231,14 @@ extern "C" int dojo_maximal_to_minimal(DojoHandle* h, int B, const double* Z, do
 
 // step_minimal_coordinates! (simulation/step.jl:42-61): minimal -> maximal, step!, maximal -> minimal; three launches on one
 // stream, the maximal states never leave the device.  X, U, X_next: host or device pointers (all of the same kind).
+extern "C" int dojo_step_minimal_flags(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U, double* X_next, int32_t* status,
+                                       int32_t* iters, uint32_t flags);
 extern "C" int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U, double* X_next, int32_t* status,
                                  int32_t* iters) {
+  return dojo_step_minimal_flags(h, opts, B, X, U, X_next, status, iters, 0);
+}
+extern "C" int dojo_step_minimal_flags(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U, double* X_next, int32_t* status,
+                                       int32_t* iters, uint32_t flags) {
   if (!h || B <= 0 || B > h->max_batch || !X || !X_next) { if (h) h->err = "dojo_step_minimal: bad arguments"; return DOJO_EINVAL; }
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc = ensure_staging(h);
@@ -1250,7 +1256,8 @@ extern "C" int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, i
     dX = h->d_X; dU = (U && P.nu > 0) ? h->d_U : nullptr; dXn = h->d_Xn;
   }
   rc = launch_kin(h, true, B, dX, h->d_Z, s);
-  if (rc == DOJO_OK) rc = launch_forward(h, opts, B, h->d_Z, dU, nullptr, h->d_Zn, nullptr, nullptr, dev ? status : h->d_status, dev ? iters : h->d_iters, 0, s);
+  if (rc == DOJO_OK) rc = launch_forward(h, opts, B, h->d_Z, dU, nullptr, h->d_Zn, nullptr, nullptr, dev ? status : h->d_status, dev ? iters : h->d_iters,
+                                            flags & DOJO_FLAG_Q1_LITERAL_RETURN, s);
   if (rc == DOJO_OK) rc = launch_kin(h, false, B, h->d_Zn, dXn, s);
   if (rc != DOJO_OK) return rc;
   if (!dev) {

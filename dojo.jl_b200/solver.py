@@ -23,7 +23,7 @@ EXPORTS = ["dojo_default_options", "dojo_create", "dojo_destroy", "dojo_last_err
            "dojo_num_residual", "dojo_num_grad_state", "dojo_shared_bytes_per_env", "dojo_step", "dojo_step_async",
            "dojo_step_grad", "dojo_step_grad_async", "dojo_rollout", "dojo_rollout_async", "dojo_launch_count",
            "dojo_num_minimal", "dojo_minimal_to_maximal", "dojo_maximal_to_minimal", "dojo_minimal_to_maximal_async",
-           "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
+           "dojo_maximal_to_minimal_async", "dojo_step_minimal", "dojo_step_minimal_flags", "dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian",
            "dojo_maximal_to_minimal_jacobian_async", "dojo_minimal_to_maximal_jacobian_async", "dojo_minimal_gradients", "dojo_env_num_state", "dojo_env_num_action", "dojo_env_step",
            "dojo_env_step_async", "dojo_env_reset", "dojo_env_rollout", "dojo_env_policy_rollout", "dojo_update_params", "dojo_num_contact_data", "dojo_step_grad_contact",
            "dojo_step_grad_contact_async", "dojo_step_record", "dojo_step_record_async", "dojo_simulate_record",
@@ -76,6 +76,8 @@ def load_library():
         getattr(L, name + "_async").restype = C.c_int
     L.dojo_step_minimal.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp]
     L.dojo_step_minimal.restype = C.c_int
+    L.dojo_step_minimal_flags.argtypes = [vp, op, C.c_int, vp, vp, vp, vp, vp, C.c_uint32]
+    L.dojo_step_minimal_flags.restype = C.c_int
     for name in ("dojo_maximal_to_minimal_jacobian", "dojo_minimal_to_maximal_jacobian"):
         getattr(L, name).argtypes = [vp, C.c_int, vp, vp]
         getattr(L, name).restype = C.c_int
@@ -303,15 +305,16 @@ class BatchedStepper:
         self._check(self.L.dojo_maximal_to_minimal(self.h, Z.shape[0], _p(Z), _p(X)), "dojo_maximal_to_minimal")
         return X
 
-    def step_minimal(self, X, U=None, opts=None):
-        """step_minimal_coordinates! (simulation/step.jl:42-61), batched.  Returns (X_next, status, iters)."""
+    def step_minimal(self, X, U=None, opts=None, flags: int = 0):
+        """step_minimal_coordinates! (simulation/step.jl:42-61), batched.  Returns (X_next, status, iters).  flags =
+        DOJO_FLAG_Q1_LITERAL_RETURN: the reference's literal return value in minimal coordinates."""
         X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
         B = X.shape[0]
         U = None if U is None else np.ascontiguousarray(np.atleast_2d(U), dtype=np.float64)
         Xn = np.empty_like(X)
         status, iters = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
         o = opts if opts is not None else capi.solver_options()
-        self._check(self.L.dojo_step_minimal(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(status), _p(iters)), "dojo_step_minimal")
+        self._check(self.L.dojo_step_minimal_flags(self.h, C.byref(o), B, _p(X), _p(U), _p(Xn), _p(status), _p(iters), C.c_uint32(flags)), "dojo_step_minimal")
         return Xn, status, iters
 
     def maximal_to_minimal_jacobian(self, Z):

@@ -167,12 +167,13 @@ function Dojo.maximal_to_minimal(mech::Mechanism, Z::Matrix{Float64})
 end
 
 "batched step_minimal_coordinates! (simulation/step.jl:42-61): what DojoEnvironments.step! calls"
-function Dojo.step_minimal_coordinates!(mech::Mechanism, X::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}())
+function Dojo.step_minimal_coordinates!(mech::Mechanism, X::Matrix{Float64}, U::Matrix{Float64}; opts = SolverOptions{Float64}(), literal::Bool = false)
     h = handle(mech); B = size(X, 2)
     Xn = similar(X); status = zeros(Int32, B); iters = zeros(Int32, B)
-    rc = ccall((:dojo_step_minimal, LIB), Cint,
-               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
-               h.ptr, COptions(opts), B, X, U, Xn, status, iters)
+    # literal = true: the value step_minimal_coordinates! of Dojo.jl literally returns (step! advances the configuration a second time)
+    rc = ccall((:dojo_step_minimal_flags, LIB), Cint,
+               (Ptr{Cvoid}, Ref{COptions}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, UInt32),
+               h.ptr, COptions(opts), B, X, U, Xn, status, iters, literal ? UInt32(1) : UInt32(0))
     rc == 0 || error(unsafe_string(ccall((:dojo_last_error, LIB), Cstring, (Ptr{Cvoid},), h.ptr)))
     return Xn
 end

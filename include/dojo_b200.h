@@ -271,6 +271,11 @@ int dojo_maximal_to_minimal_async(DojoHandle* h, int B, const double* dZ, double
  * states never leave the device.  X [2 nu x B], U [nu x B] (nullable), X_next [2 nu x B]; host or device pointers. */
 int dojo_step_minimal(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
                       double* X_next, int32_t* status, int32_t* iters);
+/* the same with `flags`: DOJO_FLAG_Q1_LITERAL_RETURN maps step!'s LITERAL return value (configuration advanced a second time)
+ * to minimal coordinates -- what step_minimal_coordinates! of the reference returns, src/simulation/step.jl:42-61 -- instead of the
+ * mechanism's state after the step */
+int dojo_step_minimal_flags(DojoHandle* h, const DojoSolverOptions* opts, int B, const double* X, const double* U,
+                            double* X_next, int32_t* status, int32_t* iters, uint32_t flags);
 
 /* Jacobians of the coordinate maps in attitude-reduced maximal coordinates ([x, v, phi, w] per body, 12 Nb):
  *   dojo_maximal_to_minimal_jacobian   maximal_to_minimal_jacobian(mechanism, z)   src/gradients/state.jl:9-56

@@ -415,6 +415,17 @@ def test_step_minimal_coordinates(name):
         zo, so, io = o.step(o.minimal_to_maximal(X[e]), U[e])
         if so == 0 and st[e] == 0 and io == it[e]:
             assert np.abs(Xn[e] - o.maximal_to_minimal(zo)).max() < 1e-6
+    # the reference's literal return value (step! advances the configuration a second time) in minimal coordinates:
+    # dojo_step_minimal_flags(DOJO_FLAG_Q1_LITERAL_RETURN) == maximal_to_minimal(step(..., flags = Q1))
+    from dojo_jl_b200.solver import DOJO_FLAG_Q1_LITERAL_RETURN
+    Xl, stl, itl = stepper.step_minimal(X, U, flags=DOJO_FLAG_Q1_LITERAL_RETURN)
+    Zl, _, _ = stepper.step(Z, U, flags=DOJO_FLAG_Q1_LITERAL_RETURN)
+    assert np.array_equal(Xl, stepper.maximal_to_minimal(Zl)) and np.array_equal(stl, st) and np.array_equal(itl, it)
+    assert np.abs(Xl - Xn).max() > 1e-6  # it IS a different state
+    for e in range(B):
+        zo, so, io = o.step(o.minimal_to_maximal(X[e]), U[e], flags=DOJO_FLAG_Q1_LITERAL_RETURN)
+        if so == 0 and st[e] == 0 and io == it[e]:
+            assert np.abs(Xl[e] - o.maximal_to_minimal(zo)).max() < 1e-6
 
 
 def test_full_size_invariants_quadruped():
